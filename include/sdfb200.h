@@ -1,0 +1,152 @@
+/* sdfb200 — C-ABI of the B200-native SdfLib hot paths (octree construction + bulk getDistance).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. Everything behind it
+ * is hand-written CUDA for sm_100a (sdflib_b200/csrc). The C++ mirror of the reference classes
+ * (include/SdfLib/*.h) and the Python host (sdflib_b200/) both sit on top of exactly these symbols.
+ *
+ * Reference interfaces replaced (all paths relative to the reference tree):
+ *   - sdflib::OctreeSdf ctor            include/SdfLib/OctreeSdf.h:156-172, src/sdf/OctreeSdf.cpp:18-86
+ *   - sdflib::ExactOctreeSdf ctor       include/SdfLib/ExactOctreeSdf.h:91-93, src/sdf/ExactOctreeSdf.cpp:7-31
+ *   - SdfFunction::getDistance (x2)     include/SdfLib/SdfFunction.h:29-36, src/sdf/OctreeSdf.cpp:93-152,
+ *                                       src/sdf/ExactOctreeSdf.cpp:38-320
+ *   - SdfFunction::saveToFile/loadFromFile  src/sdf/SdfFunction.cpp:9-79 (same .bin bytes)
+ *   - the Unity C exports               src/tools/SdfLibUnity/SdfExportFunc.h:16-58 (see sdfb200_unity.h)
+ *
+ * Error behaviour: every call returns SDFB200_OK (0) or a negative code and records a thread-local
+ * message retrievable with sdfb200_last_error(); the library never calls exit() (the reference's BVH
+ * does on an empty mesh) and never falls back to the CPU: without a CUDA device every compute entry
+ * point fails with SDFB200_ERR_CUDA.
+ */
+#ifndef SDFB200_H
+#define SDFB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFB200_VERSION 100
+
+enum {
+    SDFB200_OK = 0,
+    SDFB200_ERR_INVALID = -1,      /* bad argument (null pointer, depth out of range, empty mesh, ...) */
+    SDFB200_ERR_CUDA = -2,         /* CUDA runtime error / no device */
+    SDFB200_ERR_IO = -3,           /* file cannot be opened / truncated / unknown format */
+    SDFB200_ERR_UNSUPPORTED = -4   /* option of the reference API that is not built yet */
+};
+
+/* SdfFunction::SdfFormat (include/SdfLib/SdfFunction.h:16-22) */
+enum { SDFB200_FORMAT_GRID = 0, SDFB200_FORMAT_OCTREE = 1, SDFB200_FORMAT_EXACT_OCTREE = 2 };
+/* OctreeSdf::InitAlgorithm (include/SdfLib/OctreeSdf.h:23-28) */
+enum { SDFB200_ALG_UNIFORM = 0, SDFB200_ALG_NO_CONTINUITY = 1, SDFB200_ALG_CONTINUITY = 2 };
+/* OctreeSdf::TerminationRule (include/SdfLib/OctreeSdf.h:100-106) */
+enum { SDFB200_RULE_NONE = 0, SDFB200_RULE_TRAPEZOIDAL = 1, SDFB200_RULE_SIMPSONS = 2, SDFB200_RULE_BY_DISTANCE = 3 };
+
+/* sdfb200_query flags */
+enum {
+    SDFB200_QUERY_DEVICE_POINTERS = 1, /* xyz / dist / grad are device pointers on the handle's GPU */
+    SDFB200_QUERY_EXACT_ORDER = 2      /* evaluate the leaf polynomial in the reference's literal operation
+                                          order without FMA (bit-identical to the CPU reference); default is
+                                          the FMA Horner form, within 1e-5 of it */
+};
+
+typedef struct sdfb200_sdf sdfb200_sdf; /* opaque: host mirrors + device buffers of one SdfFunction */
+
+typedef struct sdfb200_info {
+    int32_t format;               /* SDFB200_FORMAT_* */
+    float box_min[3], box_max[3]; /* getGridBoundingBox() == getSampleArea() (cubified input box) */
+    int32_t start_grid_size;      /* getStartGridSize().x */
+    uint32_t max_depth;           /* getOctreeMaxDepth() */
+    /* OCTREE */
+    float value_range;            /* getOctreeValueRange() */
+    float min_border_value;       /* getOctreeMinBorderValue() */
+    /* EXACT_OCTREE */
+    uint32_t start_depth, min_triangles_in_leafs, max_triangles_in_leafs, max_triangles_encoded_in_leafs,
+        bit_encoding_start_depth, bits_per_index;
+    /* array sizes */
+    uint64_t octree_words;        /* OCTREE: #uint32 of mOctreeData; EXACT: #nodes (2 uint32 each) */
+    uint64_t triangle_sets_words; /* EXACT: #uint32 of mTrianglesSets */
+    uint64_t triangle_masks_bytes;/* EXACT: #bytes of mTrianglesMasks */
+    uint64_t num_triangles;       /* EXACT: #TriangleData (37 floats each) */
+    int32_t device;               /* CUDA device the structure lives on */
+} sdfb200_info;
+
+/* Timings of the last build on this handle, milliseconds (host wall clock around synchronised phases). */
+typedef struct sdfb200_build_stats {
+    double total_ms, triangle_data_ms, bvh_ms, upload_ms, levels_ms, layout_ms, download_ms;
+    uint64_t nodes_processed, leaves, samples_evaluated, kernel_launches;
+} sdfb200_build_stats;
+
+const char* sdfb200_last_error(void);
+int sdfb200_version(void);
+int sdfb200_device_count(void);        /* 0 when no CUDA device is visible */
+int sdfb200_set_device(int device);    /* device used by subsequent build/load calls of this thread */
+
+/* ---- construction (hot path 1) ----------------------------------------------------------------
+ * vertices: numVertices * 3 floats; indices: numIndices uint32 (3 per triangle); box6 = min xyz, max xyz.
+ * Same argument meaning as the reference constructors; numThreads keeps its layout-selecting meaning
+ * (< 2: single depth-first layout, >= 2: per-start-voxel layout, src/sdf/OctreeSdfDepthFirst.h:395-503). */
+int sdfb200_build_octree(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                         const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule, float param0,
+                         float param1, int initAlgorithm, uint32_t numThreads, sdfb200_sdf** out);
+int sdfb200_build_exact(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                        const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
+                        uint32_t numThreads, sdfb200_sdf** out);
+
+/* Sharded construction (one process per GPU). rank builds the start-depth voxels v with
+ * v % worldSize == rank' under the balanced assignment, and returns a handle that only holds that
+ * shard. sdfb200_shard_* export the shard as one flat device buffer for the caller's all-gather
+ * (NCCL through torch.distributed); sdfb200_assemble builds the complete structure from the gathered
+ * buffers on every rank. */
+int sdfb200_build_octree_shard(const float* vertices, uint32_t numVertices, const uint32_t* indices,
+                               uint32_t numIndices, const float* box6, uint32_t depth, uint32_t startDepth,
+                               int terminationRule, float param0, float param1, int initAlgorithm,
+                               uint32_t numThreads, uint32_t rank, uint32_t worldSize, sdfb200_sdf** out);
+int sdfb200_shard_words(const sdfb200_sdf* shard, uint64_t* outWords);
+int sdfb200_shard_export(const sdfb200_sdf* shard, uint32_t* devicePtr, uint64_t capacityWords);
+int sdfb200_assemble(sdfb200_sdf* shard, const uint32_t* gatheredDevicePtr, const uint64_t* wordsPerRank,
+                     uint32_t worldSize);
+
+/* ---- persistence (.bin, cereal PortableBinary layout of the reference) ------------------------ */
+int sdfb200_save(const sdfb200_sdf* sdf, const char* path);
+int sdfb200_load(const char* path, sdfb200_sdf** out);
+void sdfb200_free(sdfb200_sdf* sdf);
+
+/* ---- getters ---------------------------------------------------------------------------------- */
+int sdfb200_get_info(const sdfb200_sdf* sdf, sdfb200_info* out);
+int sdfb200_get_build_stats(const sdfb200_sdf* sdf, sdfb200_build_stats* out);
+/* OCTREE: capacity in uint32 words >= octree_words. EXACT: 2 * octree_words. */
+int sdfb200_get_octree_data(const sdfb200_sdf* sdf, uint32_t* out, uint64_t capacityWords);
+int sdfb200_get_exact_arrays(const sdfb200_sdf* sdf, uint32_t* triangleSets, uint8_t* triangleMasks,
+                             float* triangleData37);
+/* Device pointer of the structure arrays (OCTREE: mOctreeData) for zero-copy consumers. */
+int sdfb200_get_device_octree(const sdfb200_sdf* sdf, const uint32_t** outDevicePtr);
+
+/* ---- bulk getDistance (hot path 2) ------------------------------------------------------------
+ * xyz: n packed float3. dist: n floats. grad: NULL or n packed float3 (getDistance(p, grad)).
+ * Host pointers by default (copied through pinned staging inside the call); with
+ * SDFB200_QUERY_DEVICE_POINTERS they are device pointers and the call only enqueues the kernel on
+ * `cudaStream` (a cudaStream_t, NULL = default stream) without synchronising. */
+int sdfb200_query(sdfb200_sdf* sdf, const float* xyz, uint64_t n, float* dist, float* grad, int flags,
+                  void* cudaStream);
+
+/* Kernel-level entry points (used by the parity tests; each runs the same device function the
+ * builders use). All pointers are HOST pointers. */
+int sdfb200_triangle_data(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                          float* out37);
+int sdfb200_nearest_triangle(const float* vertices, uint32_t numVertices, const uint32_t* indices,
+                             uint32_t numIndices, const float* xyz, uint64_t n, uint32_t* outTriangle);
+int sdfb200_point_triangle(const float* tri37, const float* v123, const float* xyz, uint64_t n, int mode,
+                           float* outDist, float* outGrad);
+
+/* Fixture generator of the benchmark configs: PrimitivesFactory::getIsosphere
+ * (src/utils/PrimitivesFactory.cpp:19-104), same vertex/triangle order. Pass NULL outputs to query sizes. */
+int sdfb200_make_isosphere(uint32_t subdivisions, float* outVertices, uint32_t* outIndices, uint32_t* numVertices,
+                           uint32_t* numIndices);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFB200_H */

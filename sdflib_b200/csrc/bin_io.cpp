@@ -1,0 +1,110 @@
+// .bin persistence: byte-compatible with the reference's cereal PortableBinary archives
+// (src/sdf/SdfFunction.cpp:9-79). Layout, little endian:
+//   u8 1 | u32 format | 6 f32 box(min,max) | i32 startGridSize | ...
+//   OCTREE       (OctreeSdf.h:225):      u32 maxDepth | f32 valueRange | f32 minBorderValue | u64 n | n x u32
+//   EXACT_OCTREE (ExactOctreeSdf.h:141): u32 startDepth | u32 minTrianglesInLeafs | u32 maxTrianglesInLeafs |
+//       u32 maxTrianglesEncodedInLeafs | u32 bitEncodingStartDepth | u32 bitsPerIndex | u32 maxDepth |
+//       u64 n | n x (u32 childrenIndex, u32 trianglesArrayIndex) | u64 n | n x u32 sets | u64 n | n x u8 masks |
+//       u64 T | T x 37 f32 TriangleData (TriangleUtils.h:53)
+// Derived members (cell size, scratch sizes) are recomputed on load exactly as the reference does
+// (OctreeSdf.h:233-234, ExactOctreeSdf.h:149-153).
+#include <cstring>
+#include <fstream>
+
+#include "sdf_internal.h"
+
+namespace sdfb200 {
+
+namespace {
+template <class T> void put(std::ostream& os, const T& v) { os.write(reinterpret_cast<const char*>(&v), sizeof(T)); }
+template <class T> void get(std::istream& is, T& v) {
+    is.read(reinterpret_cast<char*>(&v), sizeof(T));
+    if (!is) throw Error(SDFB200_ERR_IO, "truncated .bin file");
+}
+template <class T> void putArray(std::ostream& os, const T* p, uint64_t n) {
+    put(os, n);
+    os.write(reinterpret_cast<const char*>(p), std::streamsize(n * sizeof(T)));
+}
+template <class T> void getArray(std::istream& is, std::vector<T>& v, uint64_t elemsPerCount = 1) {
+    uint64_t n = 0;
+    get(is, n);
+    if (n > (uint64_t(1) << 36)) throw Error(SDFB200_ERR_IO, "implausible array size in .bin file");
+    v.resize(size_t(n * elemsPerCount));
+    is.read(reinterpret_cast<char*>(v.data()), std::streamsize(v.size() * sizeof(T)));
+    if (!is) throw Error(SDFB200_ERR_IO, "truncated .bin file");
+}
+}  // namespace
+
+void saveBin(const sdfb200_sdf& s, const char* path) {
+    std::ofstream os(path, std::ios::out | std::ios::binary);
+    if (!os.is_open()) throw Error(SDFB200_ERR_IO, std::string("cannot open file ") + path);
+    put(os, uint8_t(1));
+    put(os, uint32_t(s.format));
+    for (int i = 0; i < 3; i++) put(os, s.boxMin[i]);
+    for (int i = 0; i < 3; i++) put(os, s.boxMax[i]);
+    put(os, int32_t(s.startGridSize));
+    if (s.format == SDFB200_FORMAT_OCTREE) {
+        put(os, s.maxDepth); put(os, s.valueRange); put(os, s.minBorderValue);
+        putArray(os, s.octree.data(), uint64_t(s.octree.size()));
+    } else {
+        put(os, s.startDepth); put(os, s.minTrisInLeafs); put(os, s.maxTrisInLeafs); put(os, s.maxTrisEncoded);
+        put(os, s.bitEncodingStartDepth); put(os, s.bitsPerIndex); put(os, s.maxDepth);
+        put(os, uint64_t(s.octree.size() / 2));
+        os.write(reinterpret_cast<const char*>(s.octree.data()), std::streamsize(s.octree.size() * 4));
+        putArray(os, s.sets.data(), uint64_t(s.sets.size()));
+        putArray(os, s.masks.data(), uint64_t(s.masks.size()));
+        putArray(os, s.tris.data(), uint64_t(s.tris.size()));
+    }
+    if (!os) throw Error(SDFB200_ERR_IO, std::string("write failed on ") + path);
+}
+
+void loadBin(sdfb200_sdf& s, const char* path) {
+    std::ifstream is(path, std::ios::binary);
+    if (!is.is_open()) throw Error(SDFB200_ERR_IO, std::string("cannot open file ") + path);
+    uint8_t littleEndian = 0;
+    uint32_t format = 0;
+    int32_t startGrid = 0;
+    get(is, littleEndian);
+    get(is, format);
+    if (littleEndian != 1) throw Error(SDFB200_ERR_IO, "big-endian archives are not supported");
+    if (format != SDFB200_FORMAT_OCTREE && format != SDFB200_FORMAT_EXACT_OCTREE)
+        throw Error(SDFB200_ERR_IO, "unknown or unsupported SdfFormat in file (only OCTREE and EXACT_OCTREE)");
+    s.format = int(format);
+    for (int i = 0; i < 3; i++) get(is, s.boxMin[i]);
+    for (int i = 0; i < 3; i++) get(is, s.boxMax[i]);
+    get(is, startGrid);
+    if (startGrid <= 0 || startGrid > 1024) throw Error(SDFB200_ERR_IO, "implausible start grid size");
+    s.startGridSize = startGrid;
+    if (format == SDFB200_FORMAT_OCTREE) {
+        get(is, s.maxDepth); get(is, s.valueRange); get(is, s.minBorderValue);
+        getArray(is, s.octree);
+    } else {
+        get(is, s.startDepth); get(is, s.minTrisInLeafs); get(is, s.maxTrisInLeafs); get(is, s.maxTrisEncoded);
+        get(is, s.bitEncodingStartDepth); get(is, s.bitsPerIndex); get(is, s.maxDepth);
+        getArray(is, s.octree, 2);
+        getArray(is, s.sets);
+        getArray(is, s.masks);
+        getArray(is, s.tris);
+    }
+    s.cellSize = (s.boxMax[0] - s.boxMin[0]) / float(s.startGridSize);
+}
+
+void uploadStructure(sdfb200_sdf& s) {
+    SDFB_CUDA(cudaGetDevice(&s.device));
+    s.dOctree.alloc(s.octree.size());
+    s.dOctree.upload(s.octree.data(), s.octree.size());
+    if (s.format == SDFB200_FORMAT_EXACT_OCTREE) {
+        // one zero pad word after the sets: the bit decoder always reads word w+1 (ExactOctreeSdf.cpp:73-77)
+        s.dSets.alloc(s.sets.size() + 1);
+        SDFB_CUDA(cudaMemsetAsync(s.dSets.p, 0, (s.sets.size() + 1) * 4));
+        s.dSets.upload(s.sets.data(), s.sets.size());
+        s.dMasks.alloc(s.masks.size() + 8);
+        SDFB_CUDA(cudaMemsetAsync(s.dMasks.p, 0, s.masks.size() + 8));
+        s.dMasks.upload(s.masks.data(), s.masks.size());
+        s.dTris.alloc(s.tris.size());
+        s.dTris.upload(s.tris.data(), s.tris.size());
+    }
+    SDFB_CUDA(cudaDeviceSynchronize());
+}
+
+}  // namespace sdfb200

@@ -1,0 +1,269 @@
+// The C-ABI of libsdfb200.so (include/sdfb200.h): argument checking, error translation, host<->device
+// staging. No compute happens here; every entry point that needs the GPU fails with SDFB200_ERR_CUDA
+// when no device is present — there is no CPU fallback.
+#include <cstring>
+#include <memory>
+#include <new>
+
+#include "sdf_internal.h"
+
+namespace sdfb200 {
+namespace {
+thread_local std::string gLastError;
+thread_local int gDevice = 0;
+}
+void setLastError(const std::string& msg) { gLastError = msg; }
+
+namespace {
+template <class F> int guarded(F&& f) {
+    try {
+        f();
+        return SDFB200_OK;
+    } catch (const Error& e) {
+        setLastError(e.what());
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        setLastError("out of host memory");
+        return SDFB200_ERR_INVALID;
+    } catch (const std::exception& e) {
+        setLastError(e.what());
+        return SDFB200_ERR_INVALID;
+    }
+}
+
+void requireDevice() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        throw Error(SDFB200_ERR_CUDA, "no CUDA device available (sdfb200 has no CPU fallback)");
+    }
+    SDFB_CUDA(cudaSetDevice(gDevice));
+}
+
+HostMesh checkedMesh(const float* v, uint32_t nv, const uint32_t* idx, uint32_t ni) {
+    if (!v || !idx) throw Error(SDFB200_ERR_INVALID, "null mesh pointer");
+    if (nv == 0 || ni < 3 || ni % 3 != 0) throw Error(SDFB200_ERR_INVALID, "empty mesh or index count not a multiple of 3");
+    for (uint32_t i = 0; i < ni; i++)
+        if (idx[i] >= nv) throw Error(SDFB200_ERR_INVALID, "triangle index out of range");
+    return HostMesh{reinterpret_cast<const f3*>(v), nv, idx, ni};
+}
+
+void checkBox(const float* b) {
+    if (!b) throw Error(SDFB200_ERR_INVALID, "null bounding box");
+    for (int i = 0; i < 3; i++)
+        if (!(b[i + 3] > b[i])) throw Error(SDFB200_ERR_INVALID, "bounding box max must exceed min on every axis");
+}
+}  // namespace
+}  // namespace sdfb200
+
+using namespace sdfb200;
+
+extern "C" {
+
+const char* sdfb200_last_error(void) { return gLastError.c_str(); }
+int sdfb200_version(void) { return SDFB200_VERSION; }
+
+int sdfb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sdfb200_set_device(int device) {
+    return guarded([&] {
+        int n = sdfb200_device_count();
+        if (device < 0 || device >= n) throw Error(SDFB200_ERR_INVALID, "device index out of range");
+        gDevice = device;
+        SDFB_CUDA(cudaSetDevice(device));
+    });
+}
+
+int sdfb200_build_octree_shard(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                               const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule, float param0,
+                               float param1, int initAlgorithm, uint32_t numThreads, uint32_t rank, uint32_t worldSize,
+                               sdfb200_sdf** out) {
+    return guarded([&] {
+        if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
+        *out = nullptr;
+        HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
+        checkBox(box6);
+        if (worldSize == 0 || rank >= worldSize) throw Error(SDFB200_ERR_INVALID, "rank/worldSize out of range");
+        if (initAlgorithm != SDFB200_ALG_NO_CONTINUITY)
+            throw Error(SDFB200_ERR_UNSUPPORTED, "only InitAlgorithm::NO_CONTINUITY is built (CONTINUITY / UNIFORM: see DESIGN.md)");
+        if (terminationRule < SDFB200_RULE_NONE || terminationRule > SDFB200_RULE_BY_DISTANCE)
+            throw Error(SDFB200_ERR_INVALID, "unknown termination rule");
+        requireDevice();
+        std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
+        buildOctreeOnDevice(*s, mesh, box6, depth, startDepth, terminationRule, param0, param1, numThreads, rank, worldSize);
+        *out = s.release();
+    });
+}
+
+int sdfb200_build_octree(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                         const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule, float param0,
+                         float param1, int initAlgorithm, uint32_t numThreads, sdfb200_sdf** out) {
+    return sdfb200_build_octree_shard(vertices, numVertices, indices, numIndices, box6, depth, startDepth, terminationRule,
+                                      param0, param1, initAlgorithm, numThreads, 0, 1, out);
+}
+
+int sdfb200_build_exact(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                        const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
+                        uint32_t numThreads, sdfb200_sdf** out) {
+    return guarded([&] {
+        if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
+        *out = nullptr;
+        HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
+        checkBox(box6);
+        requireDevice();
+        std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
+        buildExactOnDevice(*s, mesh, box6, maxDepth, startDepth, minTrianglesPerNode, numThreads);
+        *out = s.release();
+    });
+}
+
+int sdfb200_save(const sdfb200_sdf* sdf, const char* path) {
+    return guarded([&] {
+        if (!sdf || !path) throw Error(SDFB200_ERR_INVALID, "null argument");
+        saveBin(*sdf, path);
+    });
+}
+
+int sdfb200_load(const char* path, sdfb200_sdf** out) {
+    return guarded([&] {
+        if (!out || !path) throw Error(SDFB200_ERR_INVALID, "null argument");
+        *out = nullptr;
+        std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
+        loadBin(*s, path);   // file errors are reported even without a GPU
+        requireDevice();
+        uploadStructure(*s);
+        *out = s.release();
+    });
+}
+
+void sdfb200_free(sdfb200_sdf* sdf) { delete sdf; }
+
+int sdfb200_get_info(const sdfb200_sdf* s, sdfb200_info* o) {
+    return guarded([&] {
+        if (!s || !o) throw Error(SDFB200_ERR_INVALID, "null argument");
+        std::memset(o, 0, sizeof(*o));
+        o->format = s->format;
+        for (int i = 0; i < 3; i++) { o->box_min[i] = s->boxMin[i]; o->box_max[i] = s->boxMax[i]; }
+        o->start_grid_size = s->startGridSize;
+        o->max_depth = s->maxDepth;
+        o->value_range = s->valueRange;
+        o->min_border_value = s->minBorderValue;
+        o->start_depth = s->startDepth;
+        o->min_triangles_in_leafs = s->minTrisInLeafs;
+        o->max_triangles_in_leafs = s->maxTrisInLeafs;
+        o->max_triangles_encoded_in_leafs = s->maxTrisEncoded;
+        o->bit_encoding_start_depth = s->bitEncodingStartDepth;
+        o->bits_per_index = s->bitsPerIndex;
+        o->octree_words = s->format == SDFB200_FORMAT_OCTREE ? s->octree.size() : s->octree.size() / 2;
+        o->triangle_sets_words = s->sets.size();
+        o->triangle_masks_bytes = s->masks.size();
+        o->num_triangles = s->tris.size();
+        o->device = s->device;
+    });
+}
+
+int sdfb200_get_build_stats(const sdfb200_sdf* s, sdfb200_build_stats* o) {
+    return guarded([&] {
+        if (!s || !o) throw Error(SDFB200_ERR_INVALID, "null argument");
+        *o = s->stats;
+    });
+}
+
+int sdfb200_get_octree_data(const sdfb200_sdf* s, uint32_t* out, uint64_t capacityWords) {
+    return guarded([&] {
+        if (!s || !out) throw Error(SDFB200_ERR_INVALID, "null argument");
+        if (capacityWords < s->octree.size()) throw Error(SDFB200_ERR_INVALID, "output buffer too small");
+        std::memcpy(out, s->octree.data(), s->octree.size() * sizeof(uint32_t));
+    });
+}
+
+int sdfb200_get_exact_arrays(const sdfb200_sdf* s, uint32_t* sets, uint8_t* masks, float* tris37) {
+    return guarded([&] {
+        if (!s) throw Error(SDFB200_ERR_INVALID, "null argument");
+        if (s->format != SDFB200_FORMAT_EXACT_OCTREE) throw Error(SDFB200_ERR_INVALID, "not an ExactOctreeSdf");
+        if (sets) std::memcpy(sets, s->sets.data(), s->sets.size() * 4);
+        if (masks) std::memcpy(masks, s->masks.data(), s->masks.size());
+        if (tris37) std::memcpy(tris37, s->tris.data(), s->tris.size() * sizeof(TriData));
+    });
+}
+
+int sdfb200_get_device_octree(const sdfb200_sdf* s, const uint32_t** outDevicePtr) {
+    return guarded([&] {
+        if (!s || !outDevicePtr) throw Error(SDFB200_ERR_INVALID, "null argument");
+        *outDevicePtr = s->dOctree.p;
+    });
+}
+
+int sdfb200_query(sdfb200_sdf* s, const float* xyz, uint64_t n, float* dist, float* grad, int flags, void* cudaStream) {
+    return guarded([&] {
+        if (!s || (n && (!xyz || !dist))) throw Error(SDFB200_ERR_INVALID, "null argument");
+        if (n == 0) return;
+        if (!s->dOctree.p) throw Error(SDFB200_ERR_CUDA, "structure is not resident on a CUDA device");
+        SDFB_CUDA(cudaSetDevice(s->device));
+        cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
+        auto launch = [&](const float* dXyz, float* dDist, float* dGrad) {
+            if (s->format == SDFB200_FORMAT_OCTREE) {
+                if (flags & SDFB200_QUERY_EXACT_ORDER) launchOctreeQueryExact(*s, dXyz, n, dDist, dGrad, st);
+                else launchOctreeQueryFast(*s, dXyz, n, dDist, dGrad, st);
+            } else launchExactQuery(*s, dXyz, n, dDist, dGrad, st);
+        };
+        if (flags & SDFB200_QUERY_DEVICE_POINTERS) { launch(xyz, dist, grad); return; }
+        // host pointers: H2D of the points, kernel, D2H of the results, all on `st`
+        if (s->dPts.n < 3 * n) s->dPts.alloc(3 * n);
+        if (s->dDist.n < n) s->dDist.alloc(n);
+        if (grad && s->dGrad.n < 3 * n) s->dGrad.alloc(3 * n);
+        SDFB_CUDA(cudaMemcpyAsync(s->dPts.p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+        launch(s->dPts.p, s->dDist.p, grad ? s->dGrad.p : nullptr);
+        SDFB_CUDA(cudaMemcpyAsync(dist, s->dDist.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (grad) SDFB_CUDA(cudaMemcpyAsync(grad, s->dGrad.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        SDFB_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int sdfb200_shard_words(const sdfb200_sdf*, uint64_t*) {
+    setLastError("sharded construction is not built yet");
+    return SDFB200_ERR_UNSUPPORTED;
+}
+int sdfb200_shard_export(const sdfb200_sdf*, uint32_t*, uint64_t) {
+    setLastError("sharded construction is not built yet");
+    return SDFB200_ERR_UNSUPPORTED;
+}
+int sdfb200_assemble(sdfb200_sdf*, const uint32_t*, const uint64_t*, uint32_t) {
+    setLastError("sharded construction is not built yet");
+    return SDFB200_ERR_UNSUPPORTED;
+}
+
+int sdfb200_triangle_data(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices, float* out37) {
+    return guarded([&] {
+        if (!out37) throw Error(SDFB200_ERR_INVALID, "null output");
+        HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
+        std::vector<TriData> t = computeTriangleData(mesh);
+        std::memcpy(out37, t.data(), t.size() * sizeof(TriData));
+    });
+}
+
+int sdfb200_nearest_triangle(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                             const float* xyz, uint64_t n, uint32_t* outTriangle) {
+    return guarded([&] {
+        if (n && (!xyz || !outTriangle)) throw Error(SDFB200_ERR_INVALID, "null argument");
+        HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
+        requireDevice();
+        nearestTriangleOnDevice(mesh, xyz, n, outTriangle);
+    });
+}
+
+int sdfb200_point_triangle(const float* tri37, const float* v123, const float* xyz, uint64_t n, int mode, float* outDist,
+                           float* outGrad) {
+    return guarded([&] {
+        if (!tri37 || (n && (!xyz || !outDist))) throw Error(SDFB200_ERR_INVALID, "null argument");
+        requireDevice();
+        pointTriangleOnDevice(tri37, v123, xyz, n, mode, outDist, outGrad);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,272 @@
+#include "mesh_host.h"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <map>
+#include <utility>
+
+namespace sdfb200 {
+
+namespace {
+
+TriData makeTriData(f3 p1, f3 p2, f3 p3) {   // TriangleData ctor, include/SdfLib/utils/TriangleUtils.h:23-42
+    TriData d;
+    d.origin[0] = p1.x; d.origin[1] = p1.y; d.origin[2] = p1.z;
+    const f3 e12 = p2 - p1, e13 = p3 - p1;
+    const f3 sx = normalize3(e12);
+    const f3 crs = mk3(e12.y * e13.z - e13.y * e12.z, e12.z * e13.x - e13.z * e12.x, e12.x * e13.y - e13.x * e12.y);
+    const f3 sz = normalize3(crs);
+    const f3 sy = mk3(sz.y * sx.z - sx.y * sz.z, sz.z * sx.x - sx.z * sz.x, sz.x * sx.y - sx.x * sz.y);
+    // inverse of the matrix with columns (sx, sy, sz): cofactors times 1/det, det along the first row
+    const float m[3][3] = {{sx.x, sx.y, sx.z}, {sy.x, sy.y, sy.z}, {sz.x, sz.y, sz.z}};
+    const float c00 = m[1][1] * m[2][2] - m[2][1] * m[1][2];
+    const float c10 = m[0][1] * m[2][2] - m[2][1] * m[0][2];
+    const float c20 = m[0][1] * m[1][2] - m[1][1] * m[0][2];
+    const float inv = 1.0f / (+m[0][0] * c00 - m[1][0] * c10 + m[2][0] * c20);
+    d.T[0][0] = +c00 * inv;
+    d.T[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * inv;
+    d.T[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * inv;
+    d.T[0][1] = -c10 * inv;
+    d.T[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * inv;
+    d.T[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * inv;
+    d.T[0][2] = +c20 * inv;
+    d.T[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * inv;
+    d.T[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * inv;
+    auto unit2 = [](f3 v, float* out) {
+        const float tx = v.x * v.x, ty = v.y * v.y;
+        const float s = 1.0f / std::sqrt(tx + ty);
+        out[0] = v.x * s; out[1] = v.y * s;
+    };
+    unit2(matMul(d.T, p3 - p2), d.b);
+    unit2(matMul(d.T, p1 - p3), d.c);
+    d.v2 = matMul(d.T, p2 - p1).x;
+    const f3 l3 = matMul(d.T, p3 - p1);
+    d.v3[0] = l3.x; d.v3[1] = l3.y;
+    for (int k = 0; k < 3; k++) {
+        d.edgesNormal[k][0] = 0.f; d.edgesNormal[k][1] = 0.f; d.edgesNormal[k][2] = 1.f;
+        d.verticesNormal[k][0] = 0.f; d.verticesNormal[k][1] = 0.f; d.verticesNormal[k][2] = 1.f;
+    }
+    return d;
+}
+
+inline void st3(float* dst, f3 v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
+
+struct EdgeUse { uint64_t key; uint32_t corner; };   // key = min<<32 | max, corner = 3*t + k
+
+}  // namespace
+
+std::vector<TriData> computeTriangleData(const HostMesh& mesh) {
+    const uint32_t nT = mesh.numTriangles();
+    std::vector<TriData> tris(nT);
+    std::vector<f3> cornerContribution(size_t(nT) * 3);
+    std::vector<EdgeUse> uses(size_t(nT) * 3);
+
+    // Frames and per-corner angle * normal are pure per-triangle functions: parallel.
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < int64_t(nT); t++) {
+        const uint32_t* ix = mesh.idx + 3 * t;
+        tris[size_t(t)] = makeTriData(mesh.verts[ix[0]], mesh.verts[ix[1]], mesh.verts[ix[2]]);
+        const f3 n = triNormal(tris[size_t(t)]);
+        for (uint32_t k = 0; k < 3; k++) {
+            const uint32_t a = ix[k], b = ix[(k + 1) % 3], c = ix[(k + 2) % 3];
+            const float cosA = dot3(normalize3(mesh.verts[b] - mesh.verts[a]), normalize3(mesh.verts[c] - mesh.verts[a]));
+            const float angle = std::acos(gmin(gmax(cosA, -1.0f), 1.0f));
+            cornerContribution[size_t(3 * t + k)] = angle * n;
+            uses[size_t(3 * t + k)] = EdgeUse{(uint64_t(std::min(a, b)) << 32) | std::max(a, b), uint32_t(3 * t + k)};
+        }
+    }
+
+    // Edge pairing. The reference walks the corners in order through an ordered map: an edge seen
+    // while its key is stored pairs with the stored corner and both get n_t + n_t'; the key is then
+    // erased, so occurrences pair up (1st,2nd), (3rd,4th), ... and an odd one stays open. Sorting the
+    // uses by (edge, corner) reproduces exactly those pairs without the serial map.
+    std::sort(uses.begin(), uses.end(), [](const EdgeUse& x, const EdgeUse& y) {
+        return x.key != y.key ? x.key < y.key : x.corner < y.corner;
+    });
+    std::vector<EdgeUse> open;
+    for (size_t i = 0; i < uses.size();) {
+        size_t j = i;
+        while (j < uses.size() && uses[j].key == uses[i].key) j++;
+        size_t p = i;
+        for (; p + 1 < j; p += 2) {
+            const uint32_t first = uses[p].corner, second = uses[p + 1].corner;
+            const uint32_t t2 = first / 3, t = second / 3;
+            const f3 n = triNormal(tris[t]) + triNormal(tris[t2]);
+            st3(tris[t].edgesNormal[second % 3], matMul(tris[t].T, n));
+            st3(tris[t2].edgesNormal[first % 3], matMul(tris[t2].T, n));
+        }
+        if (p < j) open.push_back(uses[p]);
+        i = j;
+    }
+
+    // Angle-weighted vertex normals, accumulated in corner order (float addition order matters).
+    std::vector<f3> vNormal(mesh.nVerts, mk3(0.f, 0.f, 0.f));
+    for (size_t cix = 0; cix < size_t(nT) * 3; cix++) {
+        const uint32_t a = mesh.idx[cix];
+        vNormal[a] = vNormal[a] + cornerContribution[cix];
+    }
+
+    if (!open.empty()) {
+        // Non-manifold repair (src/utils/TriangleUtils.cpp:292-420): vertices of open edges that lie
+        // within 1e-5/extent of each other (found through two staggered 2048^3 hash grids) are merged
+        // with a union-find, open edges are re-paired under the merged ids, and merged vertices share
+        // the sum of their normals.
+        std::map<uint32_t, uint32_t> parentOf;
+        auto root = [&](uint32_t v) {
+            auto it = parentOf.find(v);
+            while (it != parentOf.end() && it->second != v) { v = it->second; it = parentOf.find(v); }
+            return v;
+        };
+        std::vector<uint32_t> nm;
+        for (const EdgeUse& e : open) { nm.push_back(uint32_t(e.key >> 32)); nm.push_back(uint32_t(e.key)); }
+        std::sort(nm.begin(), nm.end());
+        nm.erase(std::unique(nm.begin(), nm.end()), nm.end());
+        f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+        for (uint32_t i = 0; i < mesh.nVerts; i++) {
+            const f3 v = mesh.verts[i];
+            lo = mk3(gmin(lo.x, v.x), gmin(lo.y, v.y), gmin(lo.z, v.z));
+            hi = mk3(gmax(hi.x, v.x), gmax(hi.y, v.y), gmax(hi.z, v.z));
+        }
+        const f3 ext = hi - lo;
+        const float maxExt = gmax(ext.x, gmax(ext.y, ext.z));
+        const uint32_t res = 2048;
+        const float scale = float(res) / maxExt;
+        const float thr = float(1e-5 / double(maxExt));
+        const float sqThr = thr * thr;
+        auto cell = [&](f3 p, float off) {
+            const f3 q = (p - lo) * scale;
+            const int x = int(q.x + off), y = int(q.y + off), z = int(q.z + off);
+            return uint64_t(uint32_t(x + y * res + z * res * res));
+        };
+        std::map<uint64_t, std::vector<uint32_t>> grid[2];
+        for (uint32_t v : nm) { grid[0][cell(mesh.verts[v], 0.0f)].push_back(v); grid[1][cell(mesh.verts[v], 0.5f)].push_back(v); }
+        for (uint32_t v : nm)
+            for (int gsel = 0; gsel < 2; gsel++) {
+                auto it = grid[gsel].find(cell(mesh.verts[v], gsel ? 0.5f : 0.0f));
+                if (it == grid[gsel].end()) continue;
+                for (uint32_t u : it->second) {
+                    const f3 diff = mesh.verts[v] - mesh.verts[u];
+                    if (dot3(diff, diff) < sqThr) {
+                        const uint32_t p1 = root(v), p2 = root(u);
+                        if (v == p1) parentOf[p1] = p1;
+                        parentOf[p2] = p1;
+                        break;
+                    }
+                }
+            }
+        // open edges in key order (the reference iterates its ordered map)
+        std::map<std::pair<uint32_t, uint32_t>, uint32_t> merged;
+        for (const EdgeUse& e : open) {
+            const uint32_t a = root(uint32_t(e.key >> 32)), b = root(uint32_t(e.key));
+            auto ins = merged.insert(std::make_pair(std::make_pair(std::min(a, b), std::max(a, b)), e.corner));
+            if (!ins.second) {
+                const uint32_t t = e.corner / 3, t2 = ins.first->second / 3;
+                const f3 n = triNormal(tris[t]) + triNormal(tris[t2]);
+                st3(tris[t].edgesNormal[e.corner % 3], matMul(tris[t].T, n));
+                st3(tris[t2].edgesNormal[ins.first->second % 3], matMul(tris[t2].T, n));
+                merged.erase(ins.first);
+            }
+        }
+        for (uint32_t v : nm) { const uint32_t p = root(v); if (p != v) vNormal[p] = vNormal[p] + vNormal[v]; }
+        for (uint32_t v : nm) vNormal[v] = vNormal[root(v)];
+    }
+
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < int64_t(mesh.nIdx); i++)
+        st3(tris[size_t(i / 3)].verticesNormal[i % 3], matMul(tris[size_t(i / 3)].T, vNormal[mesh.idx[i]]));
+    return tris;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BVH (float64 bounding spheres, median split on the first vertex along the widest axis)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct BuildTri { double v[3][3]; int32_t id; };
+
+inline double sq3(const double* a, const double* b) {
+    const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
+    return x * x + y * y + z * z;
+}
+
+struct BvhBuilder {
+    std::vector<BuildTri>& bt;
+    std::vector<BvhNode>& nodes;
+
+    // sphere = where the bounding sphere of this subtree is stored (a child slot of the parent)
+    void build(int32_t nodeId, double* sphereCenter, double* sphereRadius, int32_t begin, int32_t end) {
+        const int32_t n = end - begin;
+        BvhNode& node = nodes[size_t(nodeId)];
+        if (n == 1) {
+            const BuildTri& t = bt[size_t(begin)];
+            double c[3];
+            for (int a = 0; a < 3; a++) c[a] = (t.v[0][a] + t.v[1][a] + t.v[2][a]) / 3.0;
+            const double r0 = std::sqrt(sq3(t.v[0], c)), r1 = std::sqrt(sq3(t.v[1], c)), r2 = std::sqrt(sq3(t.v[2], c));
+            for (int a = 0; a < 3; a++) sphereCenter[a] = c[a];
+            *sphereRadius = std::max(std::max(r0, r1), r2);
+            node.left = -1;
+            node.right = t.id;
+            return;
+        }
+        double top[3], bottom[3], c[3] = {0, 0, 0};
+        for (int a = 0; a < 3; a++) { top[a] = std::numeric_limits<double>::lowest(); bottom[a] = std::numeric_limits<double>::max(); }
+        for (int32_t i = begin; i < end; i++)
+            for (int k = 0; k < 3; k++)
+                for (int a = 0; a < 3; a++) {
+                    const double p = bt[size_t(i)].v[k][a];
+                    c[a] += p;
+                    top[a] = std::max(top[a], p);
+                    bottom[a] = std::min(bottom[a], p);
+                }
+        const double count = double(3 * n);
+        for (int a = 0; a < 3; a++) c[a] /= count;
+        int dim = 0;
+        for (int a = 1; a < 3; a++)
+            if (top[a] - bottom[a] > top[dim] - bottom[dim]) dim = a;
+        double r2 = 0.0;
+        for (int32_t i = begin; i < end; i++)
+            for (int k = 0; k < 3; k++) r2 = std::max(r2, sq3(c, bt[size_t(i)].v[k]));
+        for (int a = 0; a < 3; a++) sphereCenter[a] = c[a];
+        *sphereRadius = std::sqrt(r2);
+        // Same call as the reference: std::sort is not stable, and triangles sharing their first
+        // vertex tie on this key, so the library's comparison sequence is part of the result.
+        std::sort(bt.begin() + begin, bt.begin() + end,
+                  [dim](const BuildTri& x, const BuildTri& y) { return x.v[0][dim] < y.v[0][dim]; });
+        const int32_t mid = int32_t(0.5 * (begin + end));
+        node.left = nodeId + 1;
+        node.right = nodeId + 2 * (mid - begin);
+        const int32_t l = node.left, r = node.right;
+        double* lc = node.lc;
+        double* lr = &node.lr;
+        // the two halves are independent once sorted; nodes/bt are pre-sized, so tasks only touch
+        // disjoint ranges. The enclosing parallel region's barrier joins them.
+#pragma omp task firstprivate(l, lc, lr, begin, mid) if (n > 8192)
+        build(l, lc, lr, begin, mid);
+        build(r, node.rc, &node.rr, mid, end);
+    }
+};
+
+}  // namespace
+
+std::vector<BvhNode> buildBvh(const HostMesh& mesh) {
+    const uint32_t nT = mesh.numTriangles();
+    std::vector<BuildTri> bt(nT);
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < int64_t(nT); t++) {
+        bt[size_t(t)].id = int32_t(t);
+        for (int k = 0; k < 3; k++) {
+            const f3 p = mesh.verts[mesh.idx[3 * t + k]];
+            bt[size_t(t)].v[k][0] = double(p.x); bt[size_t(t)].v[k][1] = double(p.y); bt[size_t(t)].v[k][2] = double(p.z);
+        }
+    }
+    std::vector<BvhNode> nodes(size_t(2) * nT - 1);
+    double rootCenter[3], rootRadius;
+    BvhBuilder b{bt, nodes};
+#pragma omp parallel
+#pragma omp single
+    b.build(0, rootCenter, &rootRadius, 0, int32_t(nT));
+    return nodes;
+}
+
+}  // namespace sdfb200

@@ -1,0 +1,38 @@
+// Host-side mesh preprocessing of the product path: TriangleData precompute and the float64
+// bounding-sphere BVH whose traversal order defines the reference's nearest-triangle choice.
+// These are the serial set-up steps of the reference constructors; they stay on the host because
+// (a) vertex pseudo-normals use acosf, which must match the host libm bit for bit, and (b) the BVH
+// shape depends on std::sort's (unstable) tie order. Everything per-node / per-query runs on the GPU.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "tri_math.cuh"
+
+namespace sdfb200 {
+
+struct HostMesh {
+    const f3* verts; uint32_t nVerts;
+    const uint32_t* idx; uint32_t nIdx;
+    uint32_t numTriangles() const { return nIdx / 3; }
+};
+
+// reference: TriangleUtils::calculateMeshTriangleData, src/utils/TriangleUtils.cpp:7-428
+std::vector<TriData> computeTriangleData(const HostMesh& mesh);
+
+// Device-friendly BVH node: both child spheres + child links, 80 bytes, 16-byte aligned.
+// left < 0 marks a leaf and `right` is then the triangle id
+// (reference: tmd::TriangleMeshDistance::Node, TriangleMeshDistance.h:96-109).
+struct alignas(16) BvhNode {
+    double lc[3], lr;
+    double rc[3], rr;
+    int32_t left, right;
+    int32_t pad[2];
+};
+static_assert(sizeof(BvhNode) == 80, "BvhNode layout");
+
+// reference: tmd::TriangleMeshDistance::_build_tree, TriangleMeshDistance.h:421-490.
+// Node ids equal the reference's push order (pre-order: a subtree over n triangles owns 2n-1
+// consecutive ids), which lets independent subtrees be built by parallel host tasks.
+std::vector<BvhNode> buildBvh(const HostMesh& mesh);
+
+}  // namespace sdfb200

@@ -1,0 +1,727 @@
+// OctreeSdf construction on the GPU (hot path 1, tri-cubic variant).
+//
+// Replaces, behind sdfb200_build_octree, the reference's depth-first builder
+//   OctreeSdf::initOctree<VHQueries<TriCubicInterpolation>>   src/sdf/OctreeSdfDepthFirst.h:31-527
+//   VHQueries::calculateVerticesInfo                           include/SdfLib/TrianglesInfluence.h:952-996
+//   tmd::TriangleMeshDistance::_query                          libs/InteractiveComputerGraphics/.../TriangleMeshDistance.h:492-540
+//   TriCubicInterpolation::calculateCoefficients / interpolateValue  include/SdfLib/InterpolationMethods.h:292-439
+//   estimateErrorFunctionIntegralByTrapezoidRule               include/SdfLib/OctreeSdfUtils.h:60-85
+//   OctreeSdf::computeMinBorderValue                           src/sdf/OctreeSdf.cpp:155-230
+//
+// B200 design (not a translation of the CPU stack machine):
+//   * level-synchronous: one launch processes every candidate node of a depth; a warp owns a node,
+//     lanes 0..18 own its 19 sample points (BVH descent in float64 + signed distance/gradient in
+//     float32), then the whole warp fits the 64 Hermite coefficients and integrates the error;
+//   * subdividing nodes are compacted with an exclusive scan, children are written as 8 coalesced
+//     records (centre, 8 corner value quadruples) — no per-node heap, no stack;
+//   * the reference's array ORDER (a by-product of its stack discipline) is rebuilt afterwards from
+//     subtree sizes: bottom-up size pass, top-down offset pass, one emit pass that writes node words
+//     and recomputes leaf coefficients straight into their final position.
+// Arithmetic is bit-faithful to the CPU build (this TU is compiled with -fmad=false); the only
+// deliberate difference is that the reference's history-dependent 32^3 vertex cache is not emulated
+// (DESIGN.md "parity"), i.e. every sample asks the BVH afresh.
+#include <algorithm>
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "sdf_internal.h"
+
+namespace sdfb200 {
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr uint32_t kNoChild = 0xFFFFFFFFu;
+
+// lattice index L = x + 3y + 9z of the 19 mid-points, in the reference's sample order
+__constant__ int cSampleLattice[19] = {1, 3, 4, 5, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 19, 21, 22, 23, 25};
+
+// Non-zero entries of the 64x64 Hermite map W = H(x)H(x)H, row-major, columns ascending.
+struct alignas(16) HermiteTable {   // sizeof is a multiple of 16, so the word-wise copy below is exact
+    uint16_t rowStart[65];
+    uint8_t col[1000];
+    int8_t weight[1000];
+    uint8_t order[64];   // rows sorted by descending number of terms (load balance across lanes)
+};
+__constant__ HermiteTable cHermite;
+
+HermiteTable makeHermiteTable() {
+    static const int H[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {-3, -2, 3, -1}, {2, 1, -2, 1}};
+    static const int slot[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};
+    HermiteTable t;
+    int n = 0;
+    for (int row = 0; row < 64; row++) {
+        t.rowStart[row] = uint16_t(n);
+        const int i = row & 3, j = (row >> 2) & 3, k = row >> 4;
+        for (int c = 0; c < 8; c++)
+            for (int s = 0; s < 8; s++) {
+                const int w = H[i][2 * (c & 1) + slot[s][0]] * H[j][2 * ((c >> 1) & 1) + slot[s][1]] *
+                              H[k][2 * ((c >> 2) & 1) + slot[s][2]];
+                if (w != 0) { t.col[n] = uint8_t(c * 8 + s); t.weight[n] = int8_t(w); n++; }
+            }
+    }
+    t.rowStart[64] = uint16_t(n);
+    int o = 0;
+    for (int want : {64, 16, 4, 1})
+        for (int row = 0; row < 64; row++)
+            if (t.rowStart[row + 1] - t.rowStart[row] == want) t.order[o++] = uint8_t(row);
+    return t;
+}
+
+// ---- device helpers ------------------------------------------------------------------------------
+
+__device__ __forceinline__ d3 vertexD(const DeviceMesh& m, uint32_t v) {
+    const f3 p = m.verts[v];
+    return mkd(double(p.x), double(p.y), double(p.z));
+}
+
+// Nearest triangle id with the reference's traversal order: near child first, the far child is
+// re-tested against the running best when the near subtree is done, leaves replace the best only on
+// strict '<' against the re-squared running distance.
+__device__ uint32_t bvhNearest(const DeviceMesh& m, f3 pf) {
+    const d3 p = mkd(double(pf.x), double(pf.y), double(pf.z));
+    double best = DBL_MAX;
+    int bestTri = -1;
+    int stackNode[48];
+    double stackDist[48];
+    int sp = 0;
+    int cur = 0;
+    for (;;) {
+        const BvhNode nd = m.bvh[cur];
+        bool descend = false;
+        if (nd.left < 0) {
+            const uint32_t t = uint32_t(nd.right);
+            const double d2 = eberlySqDist(p, vertexD(m, m.idx[3 * t]), vertexD(m, m.idx[3 * t + 1]), vertexD(m, m.idx[3 * t + 2]));
+            if (d2 < best * best) { best = sqrt(d2); bestTri = nd.right; }
+        } else {
+            const d3 dl3 = p - mkd(nd.lc[0], nd.lc[1], nd.lc[2]);
+            const d3 dr3 = p - mkd(nd.rc[0], nd.rc[1], nd.rc[2]);
+            const double dl = sqrt(ddot(dl3, dl3)) - nd.lr;
+            const double dr = sqrt(ddot(dr3, dr3)) - nd.rr;
+            const bool leftFirst = dl < dr;
+            const int first = leftFirst ? nd.left : nd.right, second = leftFirst ? nd.right : nd.left;
+            const double dFirst = leftFirst ? dl : dr, dSecond = leftFirst ? dr : dl;
+            stackNode[sp] = second;
+            stackDist[sp] = dSecond;
+            sp++;
+            if (dFirst < best) { cur = first; descend = true; }
+        }
+        if (descend) continue;
+        bool found = false;
+        while (sp > 0) {
+            sp--;
+            if (stackDist[sp] < best) { cur = stackNode[sp]; found = true; break; }
+        }
+        if (!found) break;
+    }
+    return uint32_t(bestTri);
+}
+
+// TriCubicInterpolation::calculatePointValues: (signed distance, unit gradient) of the nearest triangle
+__device__ __forceinline__ float4 samplePoint(const DeviceMesh& m, f3 p) {
+    const uint32_t t = bvhNearest(m, p);
+    f3 g;
+    const float d = signedDistGradMesh(p, m.tris[t], m.verts[m.idx[3 * t]], m.verts[m.idx[3 * t + 1]], m.verts[m.idx[3 * t + 2]], g);
+    return make_float4(d, g.x, g.y, g.z);
+}
+
+// interpolateValue, scalar branch: acc = 0 + sum_n ((c_n * x^i) * y^j) * z^k, n ascending, left to right.
+__device__ __forceinline__ float polyValueExact(const float* c, float x, float y, float z) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int n = 0; n < 64; n++) {
+        float t = c[n];
+#pragma unroll
+        for (int a = 0; a < (n & 3); a++) t *= x;
+#pragma unroll
+        for (int a = 0; a < ((n >> 2) & 3); a++) t *= y;
+#pragma unroll
+        for (int a = 0; a < (n >> 4); a++) t *= z;
+        acc += t;
+    }
+    return acc;
+}
+
+// One Hermite row: left-to-right float sum of w * in[col] over the row's non-zero columns.
+// in[col] = corner value scaled by nodeSize^order (slots 4..7 are the always-zero mixed derivatives).
+__device__ __forceinline__ float hermiteRow(const HermiteTable& tab, int row, const float4* lattice, float nodeSize) {
+    const int b = tab.rowStart[row], e = tab.rowStart[row + 1];
+    float acc = 0.0f;
+    for (int i = b; i < e; i++) {
+        const int col = tab.col[i], c = col >> 3, s = col & 7;
+        // corner c = (x,y,z) bits -> lattice point (2x, 2y, 2z)
+        const float4 v = lattice[2 * (c & 1) + 6 * ((c >> 1) & 1) + 18 * (c >> 2)];
+        float in;
+        if (s == 0) in = v.x;
+        else if (s == 1) in = v.y * nodeSize;
+        else if (s == 2) in = v.z * nodeSize;
+        else if (s == 3) in = v.w * nodeSize;
+        else in = 0.0f;   // 0 * nodeSize^2 (or ^3) = +0
+        const float term = float(int(tab.weight[i])) * in;
+        acc = (i == b) ? term : acc + term;
+    }
+    return acc;
+}
+
+struct LevelView {
+    uint32_t count;
+    const float4* centerHalf;   // xyz centre, w half size
+    const float4* corners;      // 8 per node: (f, gx, gy, gz)
+    const uint32_t* coord;      // ix | iy << 10 | iz << 20 at this depth
+};
+
+// ---- kernels ---------------------------------------------------------------------------------------
+
+// Corner samples of the seed nodes (calculateVerticesInfo<8>, OctreeSdfDepthFirst.h:113-135)
+__global__ void seedCornersKernel(DeviceMesh mesh, const float4* centerHalf, float4* corners, uint32_t nSeeds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nSeeds * 8) return;
+    const float4 ch = centerHalf[i >> 3];
+    const f3 p = mk3(ch.x, ch.y, ch.z) + cornerDir(i & 7u) * ch.w;
+    corners[i] = samplePoint(mesh, p);
+}
+
+// One warp per candidate node of a level below maxDepth: 19 samples, fit, error integral, decision.
+template <bool kDecide>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+levelSampleKernel(DeviceMesh mesh, LevelView lv, float4* mids, uint32_t* subdivide, int rule, float sqThreshold, float decay) {
+    __shared__ HermiteTable tab;
+    __shared__ float4 lattice[kWarpsPerCta][27];
+    __shared__ float coeff[kWarpsPerCta][64];
+    __shared__ float terms[kWarpsPerCta][19];
+    if (kDecide) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&cHermite);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&tab);
+        for (uint32_t i = threadIdx.x; i < sizeof(HermiteTable) / 4; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t node = blockIdx.x * kWarpsPerCta + warp;
+    if (node >= lv.count) return;
+    const float4 ch = lv.centerHalf[node];
+    if (lane < 8) lattice[warp][2 * (lane & 1) + 6 * ((lane >> 1) & 1) + 18 * (lane >> 2)] = lv.corners[size_t(node) * 8 + lane];
+    if (lane < 19) {
+        const int L = cSampleLattice[lane];
+        const f3 rel = mk3(float(L % 3 - 1), float((L / 3) % 3 - 1), float(L / 9 - 1));
+        const f3 p = mk3(ch.x, ch.y, ch.z) + rel * ch.w;
+        const float4 v = samplePoint(mesh, p);
+        lattice[warp][L] = v;
+        mids[size_t(node) * 19 + lane] = v;
+    }
+    __syncwarp();
+    if (!kDecide) { if (lane == 0) subdivide[node] = 1u; return; }
+    const float nodeSize = 2.0f * ch.w;
+    coeff[warp][tab.order[lane]] = hermiteRow(tab, tab.order[lane], lattice[warp], nodeSize);
+    coeff[warp][tab.order[32 + lane]] = hermiteRow(tab, tab.order[32 + lane], lattice[warp], nodeSize);
+    __syncwarp();
+    if (lane < 19) {
+        const int L = cSampleLattice[lane];
+        const int lx = L % 3, ly = (L / 3) % 3, lz = L / 9;
+        const float v = polyValueExact(coeff[warp], 0.5f * float(lx), 0.5f * float(ly), 0.5f * float(lz));
+        const int centred = (lx == 1) + (ly == 1) + (lz == 1);
+        const float w = (centred == 1 ? 2.0f : (centred == 2 ? 4.0f : 8.0f)) / 64.0f;
+        const float truth = lattice[warp][L].x;
+        float d;
+        if (rule == SDFB200_RULE_BY_DISTANCE) d = gmax(gabs(truth - v) - decay * gabs(v), 0.0f);
+        else d = truth - v;
+        terms[warp][lane] = w * (d * d);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float value;
+        if (rule == SDFB200_RULE_NONE) value = INFINITY;
+        else {
+            value = terms[warp][0];
+            for (int s = 1; s < 19; s++) value += terms[warp][s];   // left-to-right, as the reference expression
+        }
+        subdivide[node] = (value < sqThreshold) ? 0u : 1u;
+    }
+}
+
+// Children of the subdividing nodes: 8 records each, corner values inherited from the 27-point lattice
+// (child c, corner k  <-  lattice point (c+k) per axis; OctreeSdfDepthFirst.h:225-336).
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+emitChildrenKernel(LevelView lv, const float4* mids, const uint32_t* subdivide, const uint32_t* scan, uint32_t* childOf,
+                   float4* nextCenterHalf, float4* nextCorners, uint32_t* nextCoord) {
+    __shared__ float4 lattice[kWarpsPerCta][27];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t node = blockIdx.x * kWarpsPerCta + warp;
+    if (node >= lv.count) return;
+    if (!subdivide[node]) { if (lane == 0) childOf[node] = kNoChild; return; }
+    const uint32_t base = scan[node] * 8u;
+    if (lane == 0) childOf[node] = base;
+    if (lane < 8) lattice[warp][2 * (lane & 1) + 6 * ((lane >> 1) & 1) + 18 * (lane >> 2)] = lv.corners[size_t(node) * 8 + lane];
+    if (lane < 19) lattice[warp][cSampleLattice[lane]] = mids[size_t(node) * 19 + lane];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int e = lane + 32 * r, c = e >> 3, k = e & 7;
+        const int L = ((c & 1) + (k & 1)) + 3 * (((c >> 1) & 1) + ((k >> 1) & 1)) + 9 * ((c >> 2) + (k >> 2));
+        nextCorners[size_t(base) * 8 + e] = lattice[warp][L];
+    }
+    if (lane < 8) {
+        const float4 ch = lv.centerHalf[node];
+        const float h = 0.5f * ch.w;
+        const f3 c = mk3(ch.x, ch.y, ch.z) + cornerDir(lane) * h;
+        nextCenterHalf[base + lane] = make_float4(c.x, c.y, c.z, h);
+        const uint32_t pc = lv.coord[node];
+        const uint32_t ix = ((pc & 1023u) << 1) | (lane & 1u), iy = (((pc >> 10) & 1023u) << 1) | ((lane >> 1) & 1u),
+                       iz = (((pc >> 20) & 1023u) << 1) | (uint32_t(lane) >> 2);
+        nextCoord[base + lane] = ix | (iy << 10) | (iz << 20);
+    }
+}
+
+// ---- exclusive scan of 0/1 flags (three small kernels; n is at most a few tens of millions) ----------
+constexpr int kScanBlock = 1024;
+__global__ void scanBlockSums(const uint32_t* in, uint32_t* blockSums, uint32_t n) {
+    __shared__ uint32_t warpSums[32];
+    const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+    uint32_t v = i < n ? in[i] : 0u;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t s = warpSums[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) blockSums[blockIdx.x] = s;
+    }
+}
+__global__ void scanOfBlockSums(uint32_t* blockSums, uint32_t nBlocks, uint32_t* total) {
+    // single CTA, sequential over chunks of 1024 block sums
+    __shared__ uint32_t buf[kScanBlock];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t start = 0; start < nBlocks; start += kScanBlock) {
+        const uint32_t i = start + threadIdx.x;
+        const uint32_t v = i < nBlocks ? blockSums[i] : 0u;
+        buf[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < kScanBlock; o <<= 1) {
+            const uint32_t add = threadIdx.x >= uint32_t(o) ? buf[threadIdx.x - o] : 0u;
+            __syncthreads();
+            buf[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (i < nBlocks) blockSums[i] = carry + buf[threadIdx.x] - v;   // exclusive
+        __syncthreads();
+        if (threadIdx.x == kScanBlock - 1) carry += buf[threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void scanFinalize(const uint32_t* in, const uint32_t* blockSums, uint32_t* out, uint32_t n) {
+    __shared__ uint32_t buf[kScanBlock];
+    const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+    const uint32_t v = i < n ? in[i] : 0u;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < kScanBlock; o <<= 1) {
+        const uint32_t add = threadIdx.x >= uint32_t(o) ? buf[threadIdx.x - o] : 0u;
+        __syncthreads();
+        buf[threadIdx.x] += add;
+        __syncthreads();
+    }
+    if (i < n) out[i] = blockSums[blockIdx.x] + buf[threadIdx.x] - v;
+}
+
+// ---- layout: subtree sizes bottom-up, block offsets top-down ---------------------------------------
+__global__ void leafSizesKernel(uint32_t* words, uint32_t* childOf, uint32_t n) {   // deepest level: every node is a leaf
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { words[i] = 64u; childOf[i] = kNoChild; }
+}
+__global__ void subtreeSizesKernel(const uint32_t* childOf, const uint32_t* nextWords, uint32_t* words, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = childOf[i];
+    uint32_t w = 64u;
+    if (c != kNoChild) {
+        w = 8u;
+        for (int k = 0; k < 8; k++) w += nextWords[c + k];
+    }
+    words[i] = w;
+}
+// children are laid out in the order the reference's stack pops them: 7 first
+__global__ void childOffsetsKernel(const uint32_t* childOf, const uint32_t* block, const uint32_t* nextWords,
+                                   uint32_t* nextSlot, uint32_t* nextBlock, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = childOf[i];
+    if (c == kNoChild) return;
+    const uint32_t b = block[i];
+    if (b == kNoChild) {   // subtree not owned by this rank
+        for (int k = 0; k < 8; k++) nextBlock[c + k] = kNoChild;
+        return;
+    }
+    uint32_t running = b + 8u;
+    for (int k = 7; k >= 0; k--) {
+        nextSlot[c + k] = b + uint32_t(k);
+        nextBlock[c + k] = running;
+        running += nextWords[c + k];
+    }
+}
+
+__device__ __forceinline__ uint32_t orderedFloat(float f) {   // monotone float -> uint mapping for atomicMin
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Final pass: node words, leaf coefficient blocks, value range and border minimum.
+// `out` is addressed relative to outBase (a shard writes only its own words).
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+emitWordsKernel(LevelView lv, const uint32_t* childOf, const uint32_t* slot, const uint32_t* block, uint32_t* out,
+                uint32_t depth, uint32_t* valueRangeBits, uint32_t* minBorderOrdered) {
+    __shared__ HermiteTable tab;
+    __shared__ float4 lattice[kWarpsPerCta][27];
+    __shared__ float coeff[kWarpsPerCta][64];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&cHermite);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&tab);
+        for (uint32_t i = threadIdx.x; i < sizeof(HermiteTable) / 4; i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t node = blockIdx.x * kWarpsPerCta + warp;
+    if (node >= lv.count) return;
+    const uint32_t b = block[node];
+    if (b == kNoChild) return;   // not owned
+    const uint32_t c = childOf[node];
+    if (c != kNoChild) { if (lane == 0) out[slot[node]] = b & kOctIndexMask; return; }
+    if (lane == 0) out[slot[node]] = (b & kOctIndexMask) | kLeafBit;
+    const float4 ch = lv.centerHalf[node];
+    float cornerAbs = 0.0f;
+    if (lane < 8) {
+        const float4 v = lv.corners[size_t(node) * 8 + lane];
+        lattice[warp][2 * (lane & 1) + 6 * ((lane >> 1) & 1) + 18 * (lane >> 2)] = v;
+        cornerAbs = gabs(v.x);
+    }
+    __syncwarp();
+    const float nodeSize = 2.0f * ch.w;
+    const int r0 = tab.order[lane], r1 = tab.order[32 + lane];
+    const float c0 = hermiteRow(tab, r0, lattice[warp], nodeSize), c1 = hermiteRow(tab, r1, lattice[warp], nodeSize);
+    coeff[warp][r0] = c0;
+    coeff[warp][r1] = c1;
+    __syncwarp();
+    reinterpret_cast<float*>(out)[b + lane] = coeff[warp][lane];
+    reinterpret_cast<float*>(out)[b + 32 + lane] = coeff[warp][32 + lane];
+    // mValueRange = max |corner distance| over leaves (OctreeSdfDepthFirst.h:358-361)
+    for (int o = 4; o > 0; o >>= 1) cornerAbs = fmaxf(cornerAbs, __shfl_down_sync(0xffffffffu, cornerAbs, o));
+    if (lane == 0 && !isnan(cornerAbs)) atomicMax(valueRangeBits, __float_as_uint(cornerAbs));
+    // computeMinBorderValue: polynomial at the leaf corners that lie on the unit-cube border
+    const uint32_t pc = lv.coord[node];
+    const uint32_t res = 1u << depth;
+    const uint32_t ix = pc & 1023u, iy = (pc >> 10) & 1023u, iz = pc >> 20;
+    const bool touches = ix == 0 || iy == 0 || iz == 0 || ix == res - 1 || iy == res - 1 || iz == res - 1;
+    if (touches && lane < 8) {
+        const float half = 0.5f / float(res);
+        const f3 pos = mk3((float(ix) + 0.5f) / float(res), (float(iy) + 0.5f) / float(res), (float(iz) + 0.5f) / float(res));
+        const f3 sp = pos + half * cornerDir(lane);
+        if (double(sp.x) < 1e-4 || double(sp.y) < 1e-4 || double(sp.z) < 1e-4 || double(sp.x) > double(1.0f) - 1e-4 ||
+            double(sp.y) > double(1.0f) - 1e-4 || double(sp.z) > double(1.0f) - 1e-4) {
+            const float v = polyValueExact(coeff[warp], float(lane & 1), float((lane >> 1) & 1), float(lane >> 2));
+            if (!isnan(v)) atomicMin(minBorderOrdered, orderedFloat(v));
+        }
+    }
+}
+
+__global__ void nearestKernel(DeviceMesh mesh, const f3* pts, uint64_t n, uint32_t* out) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = bvhNearest(mesh, pts[i]);
+}
+
+__global__ void pointTriangleKernel(const TriData* tri, const f3* w, const f3* pts, uint64_t n, int mode, float* outDist, f3* outGrad) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 g = mk3(0.f, 0.f, 0.f);
+    float d;
+    if (mode == 0) d = signedDistPointTriangle(pts[i], *tri);
+    else if (mode == 1) d = signedDistGradMesh(pts[i], *tri, w[0], w[1], w[2], g);
+    else if (mode == 2) d = signedDistGradSelf(pts[i], *tri, g);
+    else d = sqDistPointTriangle(pts[i], frameOf(*tri));
+    outDist[i] = d;
+    if (outGrad) outGrad[i] = g;
+}
+
+// ---- host orchestration --------------------------------------------------------------------------
+
+struct Level {
+    uint32_t count = 0;
+    DevBuf<float4> centerHalf, corners;
+    DevBuf<uint32_t> coord, childOf, words, slot, block;
+    void alloc(uint32_t n) {
+        count = n;
+        centerHalf.alloc(n); corners.alloc(size_t(n) * 8); coord.alloc(n); childOf.alloc(n); words.alloc(n); slot.alloc(n); block.alloc(n);
+    }
+    LevelView view() const { return LevelView{count, centerHalf.p, corners.p, coord.p}; }
+};
+
+inline uint32_t divUp(uint64_t a, uint64_t b) { return uint32_t((a + b - 1) / b); }
+
+double msSince(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void uploadHermite() {
+    static bool done[64] = {};
+    int dev = 0;
+    SDFB_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && done[dev]) return;
+    const HermiteTable t = makeHermiteTable();
+    SDFB_CUDA(cudaMemcpyToSymbol(cHermite, &t, sizeof(t)));
+    if (dev < 64) done[dev] = true;
+}
+
+void uploadMesh(MeshOnDevice& m, const HostMesh& mesh, const std::vector<TriData>& tris, const std::vector<BvhNode>* bvh) {
+    m.numTriangles = mesh.numTriangles();
+    m.verts.alloc(mesh.nVerts); m.verts.upload(mesh.verts, mesh.nVerts);
+    m.idx.alloc(mesh.nIdx); m.idx.upload(mesh.idx, mesh.nIdx);
+    m.tris.alloc(tris.size()); m.tris.upload(tris.data(), tris.size());
+    if (bvh) { m.bvh.alloc(bvh->size()); m.bvh.upload(bvh->data(), bvh->size()); }
+}
+
+}  // namespace
+
+void cubifyBox(sdfb200_sdf& s, const float* box6, uint32_t startDepth) {   // OctreeSdf.cpp:43-51
+    const f3 mn = mk3(box6[0], box6[1], box6[2]), mx = mk3(box6[3], box6[4], box6[5]);
+    const f3 size = mx - mn;
+    const float maxSize = gmax(gmax(size.x, size.y), size.z);
+    const f3 center = mn + 0.5f * size;
+    const f3 lo = center - mk3(0.5f * maxSize, 0.5f * maxSize, 0.5f * maxSize);
+    const f3 hi = center + mk3(0.5f * maxSize, 0.5f * maxSize, 0.5f * maxSize);
+    s.boxMin[0] = lo.x; s.boxMin[1] = lo.y; s.boxMin[2] = lo.z;
+    s.boxMax[0] = hi.x; s.boxMax[1] = hi.y; s.boxMax[2] = hi.z;
+    s.startGridSize = 1 << startDepth;
+    s.cellSize = maxSize / float(s.startGridSize);
+}
+
+void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+                         int rule, float param0, float param1, uint32_t numThreads, uint32_t rank, uint32_t world) {
+    const auto tStart = std::chrono::steady_clock::now();
+    sdfb200_build_stats& st = out.stats;
+    st = sdfb200_build_stats{};
+    if (depth > 10) throw Error(SDFB200_ERR_INVALID, "octree depth > 10 is not supported (node coordinates are packed in 3x10 bits)");
+    if (startDepth > depth) throw Error(SDFB200_ERR_INVALID, "startDepth must not exceed depth");
+    if (rule == SDFB200_RULE_SIMPSONS) throw Error(SDFB200_ERR_UNSUPPORTED, "SIMPSONS_RULE is not built yet");
+    out.format = SDFB200_FORMAT_OCTREE;
+    out.maxDepth = depth;
+    cubifyBox(out, box6, startDepth);
+    SDFB_CUDA(cudaGetDevice(&out.device));
+    uploadHermite();
+
+    // serial set-up steps of the reference, on the host (see mesh_host.h)
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<TriData> tris = computeTriangleData(mesh);
+    st.triangle_data_ms = msSince(t0);
+    t0 = std::chrono::steady_clock::now();
+    std::vector<BvhNode> bvh = buildBvh(mesh);
+    st.bvh_ms = msSince(t0);
+    t0 = std::chrono::steady_clock::now();
+    MeshOnDevice dm;
+    uploadMesh(dm, mesh, tris, &bvh);
+    SDFB_CUDA(cudaDeviceSynchronize());
+    st.upload_ms = msSince(t0);
+    const DeviceMesh dmesh = dm.view();
+
+    t0 = std::chrono::steady_clock::now();
+    const uint32_t d0 = std::min(startDepth, 1u);
+    const f3 boxMin = mk3(out.boxMin[0], out.boxMin[1], out.boxMin[2]);
+    const float boxSize = out.boxMax[0] - out.boxMin[0];
+    std::vector<std::unique_ptr<Level>> levels(depth + 1);
+
+    {   // seeds at depth d0 (OctreeSdfDepthFirst.h:113-135); centres in the reference's float arithmetic
+        const float h0 = float(0.5f * boxSize * std::pow(0.5f, d0));
+        const f3 c0 = boxMin + mk3(h0, h0, h0);
+        const uint32_t per = 1u << d0;
+        std::vector<float4> ch;
+        std::vector<uint32_t> coord;
+        for (uint32_t k = 0; k < per; k++)
+            for (uint32_t j = 0; j < per; j++)
+                for (uint32_t i = 0; i < per; i++) {
+                    const f3 c = c0 + (mk3(float(i), float(j), float(k)) * 2.0f) * h0;
+                    ch.push_back(make_float4(c.x, c.y, c.z, h0));
+                    coord.push_back(i | (j << 10) | (k << 20));
+                }
+        levels[d0].reset(new Level());
+        Level& L = *levels[d0];
+        L.alloc(uint32_t(ch.size()));
+        L.centerHalf.upload(ch.data(), ch.size());
+        L.coord.upload(coord.data(), coord.size());
+        seedCornersKernel<<<divUp(L.count * 8, 64), 64>>>(dmesh, L.centerHalf.p, L.corners.p, L.count);
+        st.kernel_launches++;
+        st.samples_evaluated += L.count * 8;
+    }
+
+    // sharding: at the start depth keep only the voxels this rank owns (others are marked unowned later)
+    DevBuf<float4> mids;
+    DevBuf<uint32_t> flags, scan, blockSums, total;
+    total.alloc(1);
+    for (uint32_t d = d0; d < depth; d++) {
+        Level& L = *levels[d];
+        if (L.count == 0) { levels[d + 1].reset(new Level()); continue; }
+        mids.alloc(size_t(L.count) * 19);
+        flags.alloc(L.count);
+        scan.alloc(L.count);
+        const uint32_t nBlocks = divUp(L.count, kScanBlock);
+        blockSums.alloc(nBlocks);
+        const uint32_t grid = divUp(L.count, kWarpsPerCta);
+        if (d >= startDepth)
+            levelSampleKernel<true><<<grid, kWarpsPerCta * 32>>>(dmesh, L.view(), mids.p, flags.p, rule, param0 * param0, param1);
+        else
+            levelSampleKernel<false><<<grid, kWarpsPerCta * 32>>>(dmesh, L.view(), mids.p, flags.p, rule, 0.0f, 0.0f);
+        scanBlockSums<<<nBlocks, kScanBlock>>>(flags.p, blockSums.p, L.count);
+        scanOfBlockSums<<<1, kScanBlock>>>(blockSums.p, nBlocks, total.p);
+        scanFinalize<<<nBlocks, kScanBlock>>>(flags.p, blockSums.p, scan.p, L.count);
+        st.kernel_launches += 4;
+        st.samples_evaluated += uint64_t(L.count) * 19;
+        uint32_t nSubdivide = 0;
+        SDFB_CUDA(cudaMemcpy(&nSubdivide, total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        levels[d + 1].reset(new Level());
+        Level& N = *levels[d + 1];
+        N.alloc(nSubdivide * 8);
+        emitChildrenKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), mids.p, flags.p, scan.p, L.childOf.p, N.centerHalf.p,
+                                                        N.corners.p, N.coord.p);
+        st.kernel_launches++;
+        st.nodes_processed += L.count;
+    }
+    SDFB_CUDA(cudaDeviceSynchronize());
+    st.levels_ms = msSince(t0);
+
+    // ---- layout --------------------------------------------------------------------------------
+    t0 = std::chrono::steady_clock::now();
+    {
+        Level& D = *levels[depth];
+        if (D.count) { leafSizesKernel<<<divUp(D.count, 256), 256>>>(D.words.p, D.childOf.p, D.count); st.kernel_launches++; }
+        st.nodes_processed += D.count;
+    }
+    for (int d = int(depth) - 1; d >= int(startDepth); d--) {
+        Level& L = *levels[size_t(d)];
+        if (!L.count) continue;
+        subtreeSizesKernel<<<divUp(L.count, 256), 256>>>(L.childOf.p, levels[size_t(d) + 1]->words.p, L.words.p, L.count);
+        st.kernel_launches++;
+    }
+    // roots = nodes of the start depth. Their order in the output follows the reference's drivers:
+    //   numThreads < 2 : one global stack, virtual levels popped 7-first (OctreeSdfDepthFirst.h:397-416)
+    //   numThreads >= 2: sub-octrees concatenated in start-grid index order (:471-503)
+    Level& R = *levels[startDepth];
+    const uint32_t G = uint32_t(out.startGridSize), G3 = G * G * G;
+    if (R.count != G3) throw Error(SDFB200_ERR_INVALID, "internal: start level is not a full grid");
+    std::vector<float4> rootCH(G3);
+    std::vector<uint32_t> rootCoord(G3), rootWords(G3);
+    R.centerHalf.download(rootCH.data(), G3);
+    R.coord.download(rootCoord.data(), G3);
+    R.words.download(rootWords.data(), G3);
+    SDFB_CUDA(cudaDeviceSynchronize());
+    std::vector<uint32_t> rootSlot(G3), order(G3), rootBlock(G3);
+    std::vector<uint64_t> key(G3);
+    for (uint32_t r = 0; r < G3; r++) {
+        const f3 f = (mk3(rootCH[r].x, rootCH[r].y, rootCH[r].z) - boxMin) / out.cellSize;   // :408-409
+        const int x = int(std::floor(f.x)), y = int(std::floor(f.y)), z = int(std::floor(f.z));
+        rootSlot[r] = uint32_t(z * int(G * G) + y * int(G) + x);
+        if (numThreads >= 2) key[r] = rootSlot[r];
+        else {
+            const uint32_t ix = rootCoord[r] & 1023u, iy = (rootCoord[r] >> 10) & 1023u, iz = rootCoord[r] >> 20;
+            uint64_t k = 0;
+            for (int b = int(startDepth) - 1; b >= 0; b--) {
+                const uint32_t c = ((ix >> b) & 1u) | (((iy >> b) & 1u) << 1) | (((iz >> b) & 1u) << 2);
+                k = (k << 3) | (7u - c);
+            }
+            key[r] = k;
+        }
+        order[r] = r;
+    }
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    // ownership (sharded build): the i-th root in layout order belongs to rank i % world. Every rank
+    // computes the same global offsets, but only needs the sizes of its own roots here; unowned roots
+    // get kNoChild as block and are skipped by the emit pass. Global offsets need all sizes, which a
+    // shard obtains from its peers (see sdfb200_build_octree_shard); with world == 1 they are local.
+    out.shardVoxelWords.assign(G3, 0u);
+    uint64_t running = G3;
+    std::vector<uint8_t> owned(G3, 0);
+    for (uint32_t i = 0; i < G3; i++) {
+        const uint32_t r = order[i];
+        owned[r] = (i % world) == rank;
+        rootBlock[r] = uint32_t(running);
+        running += rootWords[r];
+        out.shardVoxelWords[rootSlot[r]] = rootWords[r];
+    }
+    if (running > uint64_t(kOctIndexMask)) throw Error(SDFB200_ERR_INVALID, "octree exceeds the 30-bit index space of OctreeNode");
+    const uint64_t totalWords = running;
+    if (world > 1) for (uint32_t r = 0; r < G3; r++) if (!owned[r]) rootBlock[r] = kNoChild;
+    R.slot.upload(rootSlot.data(), G3);
+    R.block.upload(rootBlock.data(), G3);
+    for (uint32_t d = startDepth; d < depth; d++) {
+        Level& L = *levels[d];
+        Level& N = *levels[d + 1];
+        if (!L.count || !N.count) continue;
+        childOffsetsKernel<<<divUp(L.count, 256), 256>>>(L.childOf.p, L.block.p, N.words.p, N.slot.p, N.block.p, L.count);
+        st.kernel_launches++;
+    }
+    out.dOctree.alloc(totalWords);
+    SDFB_CUDA(cudaMemsetAsync(out.dOctree.p, 0, totalWords * sizeof(uint32_t)));
+    DevBuf<uint32_t> scalars(2);
+    const uint32_t scalarInit[2] = {0u, 0xFFFFFFFFu};
+    scalars.upload(scalarInit, 2);
+    for (uint32_t d = startDepth; d <= depth; d++) {
+        Level& L = *levels[d];
+        if (!L.count) continue;
+        emitWordsKernel<<<divUp(L.count, kWarpsPerCta), kWarpsPerCta * 32>>>(L.view(), L.childOf.p, L.slot.p, L.block.p, out.dOctree.p, d,
+                                                                              scalars.p, scalars.p + 1);
+        st.kernel_launches++;
+    }
+    uint32_t scalarOut[2];
+    scalars.download(scalarOut, 2);
+    SDFB_CUDA(cudaDeviceSynchronize());
+    st.layout_ms = msSince(t0);
+    {
+        float vr;
+        std::memcpy(&vr, &scalarOut[0], 4);
+        out.valueRange = vr;
+        const uint32_t o = scalarOut[1];
+        const uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+        float mb;
+        std::memcpy(&mb, &bits, 4);
+        out.minBorderValue = (o == 0xFFFFFFFFu) ? INFINITY : mb;
+    }
+    t0 = std::chrono::steady_clock::now();
+    out.octree.resize(totalWords);
+    out.dOctree.download(out.octree.data(), totalWords);
+    SDFB_CUDA(cudaDeviceSynchronize());
+    st.download_ms = msSince(t0);
+    out.isShard = world > 1;
+    out.shardRank = rank;
+    out.shardWorld = world;
+    st.total_ms = msSince(tStart);
+}
+
+void nearestTriangleOnDevice(const HostMesh& mesh, const float* xyz, uint64_t n, uint32_t* outTri) {
+    std::vector<TriData> tris = computeTriangleData(mesh);
+    std::vector<BvhNode> bvh = buildBvh(mesh);
+    MeshOnDevice dm;
+    uploadMesh(dm, mesh, tris, &bvh);
+    DevBuf<f3> pts(n);
+    DevBuf<uint32_t> out(n);
+    pts.upload(reinterpret_cast<const f3*>(xyz), n);
+    if (n) nearestKernel<<<divUp(n, 128), 128>>>(dm.view(), pts.p, n, out.p);
+    out.download(outTri, n);
+    SDFB_CUDA(cudaDeviceSynchronize());
+}
+
+void pointTriangleOnDevice(const float* tri37, const float* v123, const float* xyz, uint64_t n, int mode, float* outDist,
+                           float* outGrad) {
+    DevBuf<TriData> tri(1);
+    DevBuf<f3> w(3), pts(n), grad(outGrad ? n : 0);
+    DevBuf<float> dist(n);
+    tri.upload(reinterpret_cast<const TriData*>(tri37), 1);
+    const float zeros[9] = {0};
+    w.upload(reinterpret_cast<const f3*>(v123 ? v123 : zeros), 3);
+    pts.upload(reinterpret_cast<const f3*>(xyz), n);
+    if (n) pointTriangleKernel<<<divUp(n, 128), 128>>>(tri.p, w.p, pts.p, n, mode, dist.p, outGrad ? grad.p : nullptr);
+    dist.download(outDist, n);
+    if (outGrad) grad.download(reinterpret_cast<f3*>(outGrad), n);
+    SDFB_CUDA(cudaDeviceSynchronize());
+}
+
+}  // namespace sdfb200

@@ -1,0 +1,137 @@
+// Internal definitions shared by the translation units of libsdfb200.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sdfb200.h"
+#include "mesh_host.h"
+#include "tri_math.cuh"
+
+namespace sdfb200 {
+
+// ---- errors ------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+void setLastError(const std::string& msg);
+
+#define SDFB_CUDA(expr)                                                                                   \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            throw ::sdfb200::Error(SDFB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- device buffer -----------------------------------------------------------------------------
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; return *this; }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) SDFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void upload(const T* src, size_t count, cudaStream_t s = 0) {
+        if (count) SDFB_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T* dst, size_t count, cudaStream_t s = 0) const {
+        if (count) SDFB_CUDA(cudaMemcpyAsync(dst, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
+// ---- mesh on the device --------------------------------------------------------------------------
+struct DeviceMesh {
+    const f3* verts;
+    const uint32_t* idx;
+    const TriData* tris;
+    const BvhNode* bvh;   // may be null (exact builder does not need it)
+    uint32_t numTriangles;
+};
+
+struct MeshOnDevice {
+    DevBuf<f3> verts;
+    DevBuf<uint32_t> idx;
+    DevBuf<TriData> tris;
+    DevBuf<BvhNode> bvh;
+    uint32_t numTriangles = 0;
+    DeviceMesh view() const { return DeviceMesh{verts.p, idx.p, tris.p, bvh.p, numTriangles}; }
+};
+
+// octree node word encoding (reference: OctreeSdf::OctreeNode, include/SdfLib/OctreeSdf.h:39-98)
+constexpr uint32_t kLeafBit = 1u << 31;
+constexpr uint32_t kOctIndexMask = ~(3u << 30);
+constexpr uint32_t kExactIndexMask = ~(1u << 31);
+
+}  // namespace sdfb200
+
+// ---- the opaque handle -------------------------------------------------------------------------
+struct sdfb200_sdf {
+    int format = SDFB200_FORMAT_OCTREE;
+    int device = 0;
+    float boxMin[3] = {0, 0, 0}, boxMax[3] = {0, 0, 0};
+    int startGridSize = 0;
+    uint32_t maxDepth = 0;
+    float cellSize = 0.0f;
+    // OCTREE
+    float valueRange = 0.0f, minBorderValue = 0.0f;
+    // EXACT_OCTREE
+    uint32_t startDepth = 0, minTrisInLeafs = 0, maxTrisInLeafs = 0, maxTrisEncoded = 0, bitEncodingStartDepth = 0,
+             bitsPerIndex = 0;
+    // host mirrors (what the getters / .bin writer read)
+    std::vector<uint32_t> octree;   // OCTREE: words; EXACT: (childrenIndex, trianglesArrayIndex) pairs
+    std::vector<uint32_t> sets;
+    std::vector<uint8_t> masks;
+    std::vector<sdfb200::TriData> tris;
+    // device copies (what the query kernels read)
+    sdfb200::DevBuf<uint32_t> dOctree;
+    sdfb200::DevBuf<uint32_t> dSets;
+    sdfb200::DevBuf<uint8_t> dMasks;
+    sdfb200::DevBuf<sdfb200::TriData> dTris;
+    // staging for host-pointer queries
+    sdfb200::DevBuf<float> dPts, dDist, dGrad;
+    float* hPinned = nullptr;
+    size_t hPinnedFloats = 0;
+    // sharded build
+    bool isShard = false;
+    uint32_t shardRank = 0, shardWorld = 1;
+    sdfb200::DevBuf<uint32_t> dShardPayload;
+    std::vector<uint32_t> shardVoxelWords;   // per start voxel: subtree words (0 when not owned)
+    sdfb200_build_stats stats = {};
+
+    ~sdfb200_sdf() { if (hPinned) cudaFreeHost(hPinned); }
+};
+
+namespace sdfb200 {
+
+// octree_build.cu
+void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+                         int rule, float param0, float param1, uint32_t numThreads, uint32_t rank, uint32_t world);
+void nearestTriangleOnDevice(const HostMesh& mesh, const float* xyz, uint64_t n, uint32_t* outTri);
+void pointTriangleOnDevice(const float* tri37, const float* v123, const float* xyz, uint64_t n, int mode, float* outDist,
+                           float* outGrad);
+// octree_query.cu (two objects: fast = FMA Horner, exact = reference operation order)
+void launchOctreeQueryFast(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
+void launchOctreeQueryExact(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
+// exact_build.cu / exact_query.cu
+void buildExactOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
+                        uint32_t minTris, uint32_t numThreads);
+void launchExactQuery(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
+// bin_io.cpp
+void saveBin(const sdfb200_sdf& s, const char* path);
+void loadBin(sdfb200_sdf& s, const char* path);
+void uploadStructure(sdfb200_sdf& s);
+
+}  // namespace sdfb200
