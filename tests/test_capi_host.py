@@ -1,0 +1,120 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/sdfb200.h
+declares, validates arguments, reports errors as codes (never exits), and refuses to compute without
+a CUDA device (no CPU fallback). Host-side pieces (TriangleData precompute, fixtures) are checked
+against the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_bit_equal, golden, displaced_sphere
+
+
+def test_library_exports_every_declared_symbol(sdf):
+    header = open(os.path.join(ROOT, "include", "sdfb200.h")).read()
+    declared = set(re.findall(r"\b(sdfb200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    from sdflib_b200 import _capi
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    lib = sdf.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"libsdfb200.so does not export {name}"
+    assert lib.sdfb200_version() == 100
+
+
+def test_info_struct_layout_matches_header(sdf):
+    from sdflib_b200 import _capi
+    # int32 + 6 f32 + int32 + u32 + 2 f32 + 6 u32 (+pad) + 4 u64 + int32 (+pad)
+    assert C.sizeof(_capi.Info) == 112
+    assert C.sizeof(_capi.BuildStats) == 7 * 8 + 4 * 8
+
+
+def test_argument_validation_returns_codes(sdf):
+    from sdflib_b200 import _capi
+    L = sdf.lib()
+    v, i = sdf.meshes.isosphere(1)
+    box = np.float32([-2, -2, -2, 2, 2, 2])
+    h = C.c_void_p()
+    # null mesh
+    assert L.sdfb200_build_octree(None, 0, None, 0, _capi.ptr(box), 5, 3, 1, C.c_float(1e-3), C.c_float(0), 1, 1, C.byref(h)) == _capi.ERR_INVALID
+    assert b"mesh" in L.sdfb200_last_error()
+    # index out of range
+    bad = i.copy(); bad[5] = 10 ** 6
+    assert L.sdfb200_build_octree(_capi.ptr(v), len(v), _capi.ptr(bad), bad.size, _capi.ptr(box), 5, 3, 1, C.c_float(1e-3), C.c_float(0), 1, 1, C.byref(h)) == _capi.ERR_INVALID
+    # degenerate box
+    flat = np.float32([0, 0, 0, 1, 0, 1])
+    assert L.sdfb200_build_octree(_capi.ptr(v), len(v), _capi.ptr(i), i.size, _capi.ptr(flat), 5, 3, 1, C.c_float(1e-3), C.c_float(0), 1, 1, C.byref(h)) == _capi.ERR_INVALID
+    # options of the reference API that are not built yet are reported, not silently changed
+    assert L.sdfb200_build_octree(_capi.ptr(v), len(v), _capi.ptr(i), i.size, _capi.ptr(box), 5, 3, 1, C.c_float(1e-3), C.c_float(0), 2, 1, C.byref(h)) == _capi.ERR_UNSUPPORTED
+    assert h.value is None
+
+
+def test_file_errors(sdf, tmp_path):
+    from sdflib_b200 import _capi
+    L = sdf.lib()
+    h = C.c_void_p()
+    assert L.sdfb200_load(str(tmp_path / "missing.bin").encode(), C.byref(h)) == _capi.ERR_IO
+    p = tmp_path / "garbage.bin"
+    p.write_bytes(b"\x01\x07\x00\x00\x00" + b"\x00" * 40)
+    assert L.sdfb200_load(str(p).encode(), C.byref(h)) == _capi.ERR_IO
+    g = golden("small_structures.npz")
+    t = tmp_path / "truncated.bin"
+    t.write_bytes(g["octree_bin"].tobytes()[:1000])
+    assert L.sdfb200_load(str(t).encode(), C.byref(h)) == _capi.ERR_IO
+    # SdfFunction::loadFromFile returns nullptr on file errors (src/sdf/SdfFunction.cpp:47-51)
+    assert sdf.SdfFunction.loadFromFile(str(tmp_path / "missing.bin")) is None
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(sdf):
+    """Without a CUDA device construction and queries fail loudly with SDFB200_ERR_CUDA."""
+    from sdflib_b200 import _capi
+    v, i = sdf.meshes.isosphere(1)
+    with pytest.raises(sdf.SdfB200Error) as e:
+        sdf.OctreeSdf(sdf.Mesh(v, i), sdf.BoundingBox([-2, -2, -2], [2, 2, 2]), 4, 2)
+    assert e.value.code == _capi.ERR_CUDA
+    with pytest.raises(sdf.SdfB200Error) as e:
+        sdf.ExactOctreeSdf(sdf.Mesh(v, i), sdf.BoundingBox([-2, -2, -2], [2, 2, 2]), 4, 1, 16)
+    assert e.value.code in (_capi.ERR_CUDA, _capi.ERR_UNSUPPORTED)
+    assert sdf.device_count() == 0
+
+
+def test_host_triangle_data_matches_oracle(sdf, port):
+    """The product's sort-based edge pairing reproduces the reference's ordered-map walk bit for bit."""
+    from sdflib_b200 import _capi
+    for mesh in (displaced_sphere(3), (golden("kernels.npz")["tet_vertices"], golden("kernels.npz")["tet_indices"])):
+        v, i = mesh
+        out = np.empty((i.size // 3, 37), np.float32)
+        _capi.check(sdf.lib().sdfb200_triangle_data(_capi.ptr(_capi.f32(v)), len(v), _capi.ptr(_capi.u32(i)), i.size, _capi.ptr(out)))
+        assert_bit_equal(out, port.triangle_data(v, i), "TriangleData")
+
+
+def test_host_triangle_data_non_manifold(sdf, port):
+    """Open / duplicated-vertex meshes go through the non-manifold repair path (TriangleUtils.cpp:292-420)."""
+    from sdflib_b200 import _capi
+    v, i = displaced_sphere(2)
+    # duplicate the vertices of the first 40 triangles so their edges only pair after the merge step
+    i = i.copy()
+    extra = []
+    for t in range(40):
+        for k in range(3):
+            extra.append(v[i[3 * t + k]])
+            i[3 * t + k] = len(v) + len(extra) - 1
+    v2 = np.concatenate([v, np.float32(extra)])
+    out = np.empty((i.size // 3, 37), np.float32)
+    _capi.check(sdf.lib().sdfb200_triangle_data(_capi.ptr(v2), len(v2), _capi.ptr(i), i.size, _capi.ptr(out)))
+    assert_bit_equal(out, port.triangle_data(v2, i), "TriangleData (non-manifold)")
+
+
+def test_fixture_meshes(sdf, port):
+    for s in (0, 1, 2, 4):
+        v, i = sdf.meshes.isosphere(s)
+        pv, pi = port.isosphere(s)
+        assert_bit_equal(v, pv); assert np.array_equal(i, pi)
+        assert i.size // 3 == 20 * 4 ** s
+    v, i = sdf.meshes.config_mesh("M0")
+    assert i.size // 3 == 320
+    g = sdf.meshes.cell_centre_grid(np.float32([0, 0, 0, 1, 1, 1]), 4)
+    assert g.shape == (64, 3) and np.allclose(g[1] - g[0], [0.25, 0, 0]) and np.allclose(g[0], 0.125)

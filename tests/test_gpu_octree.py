@@ -1,0 +1,172 @@
+"""GPU parity tests of hot path 1 + 2 for OctreeSdf, through the C-ABI (ctypes -> libsdfb200.so).
+
+Parity bars:
+  * octree words / header / .bin bytes: BIT-EXACT against the history-free oracle (port, use_cache=False);
+    topology (node words) additionally bit-exact against the reference's own single-thread build
+  * getDistance(+gradient) with SDFB200_QUERY_EXACT_ORDER: bit-exact against the oracle's query of the same array
+  * default FMA query: |d - ref| <= 1e-5 * max(|ref|, 1e-3 * boxSize); unit gradients within 1e-4 absolute
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal, golden, displaced_sphere, octree_topology
+
+pytestmark = pytest.mark.gpu
+
+
+def build_both(sdf, port, v, i, depth, start, thr=1e-3, threads=1, rule=1, params=None):
+    box = sdf.meshes.bounding_box_with_margin(v)
+    g = sdf.OctreeSdf(sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:]), depth, start, thr, sdf.OctreeSdf.NO_CONTINUITY, threads,
+                      terminationRule=rule, terminationRuleParams=params)
+    p = port.build_octree(v, i, box, depth, start, thr if params is None else params[0], 1, threads, termination_rule=rule,
+                          param1=0.0 if params is None or len(params) < 2 else params[1], use_cache=False)
+    return g, p, box
+
+
+def random_points(area, n, seed, spill=0.1):
+    rng = np.random.default_rng(seed)
+    return (area[:3] + rng.uniform(-spill, 1 + spill, (n, 3)) * (area[3:] - area[:3])).astype(np.float32)
+
+
+@pytest.mark.parametrize("subdiv,depth,start,threads", [(2, 5, 3, 1), (2, 5, 3, 2), (3, 6, 2, 1), (4, 6, 3, 4), (3, 4, 0, 1), (3, 5, 1, 1), (2, 3, 3, 1)])
+def test_build_bit_exact_vs_oracle(sdf, port, subdiv, depth, start, threads):
+    v, i = displaced_sphere(subdiv)
+    g, p, _ = build_both(sdf, port, v, i, depth, start, threads=threads)
+    got, want = g.getOctreeData(), p.octree_data()
+    assert got.size == want.size
+    assert np.array_equal(got, want), f"{int((got != want).sum())} words differ"
+    h, info = p.header(), g.info()
+    assert_bit_equal(np.float32([info.value_range, info.min_border_value]), np.float32([h["value_range"], h["min_border_value"]]))
+    assert info.start_grid_size == 1 << start and info.max_depth == depth
+
+
+@pytest.mark.parametrize("rule,params", [(0, [1e-3]), (3, [1e-3, 0.05]), (1, [1e-2])])
+def test_termination_rules(sdf, port, rule, params):
+    v, i = displaced_sphere(2)
+    g, p, _ = build_both(sdf, port, v, i, 4 if rule == 0 else 5, 2, rule=rule, params=params)
+    assert np.array_equal(g.getOctreeData(), p.octree_data())
+
+
+def test_config1_against_reference_fixture(sdf):
+    """Config 1 verbatim (icosphere 320 tris, d5 s3): same size / topology / header as the reference's build.
+    The symmetric sphere has genuine nearest-triangle ties, so only topology and c0 are compared exactly."""
+    g = golden("config1_octree.npz")
+    v, i = sdf.meshes.isosphere(2)
+    s = sdf.OctreeSdf(sdf.Mesh(v, i), sdf.BoundingBox(g["box"][:3], g["box"][3:]), 5, 3, 1e-3, sdf.OctreeSdf.NO_CONTINUITY, 1)
+    d = s.getOctreeData()
+    assert d.size == int(g["words"])
+    assert np.array_equal(d[:512], g["start_slots"])
+    topo, leaves, inner = octree_topology(d, 8)
+    assert (leaves, inner) == (17571, 2437)
+    assert_bit_equal(np.float32([s.info().value_range]), np.float32([g["value_range"]]))
+    dist = s.getDistance(g["query_points"], exact_order=True)
+    assert np.abs(dist - g["distances"]).max() < 5e-3   # tie-broken gradients on a symmetric input
+
+
+def test_topology_equals_reference_single_thread(sdf, ref):
+    v, i = displaced_sphere(4)
+    box = sdf.meshes.bounding_box_with_margin(v)
+    s = sdf.OctreeSdf(sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:]), 6, 3, 1e-3, sdf.OctreeSdf.NO_CONTINUITY, 1)
+    r = ref.build_octree(v, i, box, 6, 3, 1e-3, 1, 1)
+    a, b = s.getOctreeData(), r.octree_data()
+    assert a.size == b.size
+    ta, la, ia = octree_topology(a, 8)
+    tb, lb, ib = octree_topology(b, 8)
+    assert np.array_equal(ta, tb) and np.array_equal(a[ta], b[tb]), "node words (topology + indices) differ from the reference"
+    fa, fb = a[~ta].view(np.float32).reshape(-1, 64), b[~tb].view(np.float32).reshape(-1, 64)
+    assert_bit_equal(fa[:, 0], fb[:, 0], "c0 (corner distance) of every leaf")
+    q = random_points(s.getSampleArea().as_array(), 200000, 1, spill=0.0)
+    d, dr = s.getDistance(q), r.query(q)
+    tol = 1e-5 * np.maximum(np.abs(dr), 1e-3 * (box[3:] - box[:3]).max())
+    assert (np.abs(d - dr) > tol).mean() < 1e-4      # parity gate of SURVEY.md §8(d)
+    assert np.abs(d - dr).max() < 5e-5
+
+
+@pytest.mark.parametrize("gradient", [False, True])
+def test_query_exact_order_bit_exact(sdf, port, gradient):
+    v, i = displaced_sphere(3)
+    g, p, _ = build_both(sdf, port, v, i, 6, 2)
+    q = random_points(g.getSampleArea().as_array(), 300000, 2)        # includes out-of-grid points
+    if gradient:
+        (d, gr), (od, og) = g.getDistance(q, gradient=True, exact_order=True), p.query(q, True)
+        assert_bit_equal(d, od, "distance"); assert_bit_equal(gr, og, "gradient")
+    else:
+        assert_bit_equal(g.getDistance(q, exact_order=True), p.query(q), "distance")
+
+
+def test_query_fast_within_tolerance(sdf, port):
+    v, i = displaced_sphere(3)
+    g, p, box = build_both(sdf, port, v, i, 6, 2)
+    q = random_points(g.getSampleArea().as_array(), 300000, 3)
+    (d, gr), (od, og) = g.getDistance(q, gradient=True), p.query(q, True)
+    tol = 1e-5 * np.maximum(np.abs(od), 1e-3 * (box[3:] - box[:3]).max())
+    assert np.all(np.abs(d - od) <= tol), float(np.abs(d - od).max())
+    assert np.abs(gr - og).max() < 1e-4
+    assert np.allclose(np.linalg.norm(gr[np.isfinite(gr).all(1)], axis=1)[:1000], 1.0, atol=1e-5)
+
+
+def test_query_device_pointers_and_single_point(sdf, port):
+    import torch
+    v, i = displaced_sphere(2)
+    g, p, _ = build_both(sdf, port, v, i, 5, 3)
+    q = random_points(g.getSampleArea().as_array(), 10001, 4)       # ragged size (not a multiple of the CTA)
+    host = g.getDistance(q, exact_order=True)
+    dev = g.getDistance(torch.from_numpy(q).cuda(), exact_order=True)
+    assert_bit_equal(host, dev.cpu().numpy())
+    one = g.getDistance(q[17], exact_order=True)
+    assert np.float32(one) == host[17]
+    d1, g1 = g.getDistance(q[17], gradient=True, exact_order=True)
+    assert g1.shape == (3,)
+    assert g.getDistance(np.zeros((0, 3), np.float32)).shape == (0,)   # empty batch
+
+
+def test_bin_round_trip_and_oracle_bytes(sdf, port, tmp_path):
+    v, i = displaced_sphere(2)
+    g, p, _ = build_both(sdf, port, v, i, 5, 2)
+    a, b = str(tmp_path / "gpu.bin"), str(tmp_path / "port.bin")
+    assert g.saveToFile(a) and p.save(b)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    again = sdf.SdfFunction.loadFromFile(a)
+    assert isinstance(again, sdf.OctreeSdf)
+    assert np.array_equal(again.getOctreeData(), g.getOctreeData())
+    q = random_points(g.getSampleArea().as_array(), 5000, 5)
+    assert_bit_equal(again.getDistance(q), g.getDistance(q))
+    # a .bin written by the reference is loaded and queried
+    gold = golden("small_structures.npz")
+    rp = tmp_path / "ref.bin"
+    rp.write_bytes(gold["octree_bin"].tobytes())
+    s = sdf.SdfFunction.loadFromFile(str(rp))
+    d, gr = s.getDistance(gold["query_points"], gradient=True, exact_order=True)
+    assert_bit_equal(d, gold["octree_distances"]); assert_bit_equal(gr, gold["octree_gradients"])
+    c = str(tmp_path / "resaved.bin")
+    assert s.saveToFile(c) and open(c, "rb").read() == gold["octree_bin"].tobytes()
+
+
+def test_full_size_properties(sdf):
+    """Config 2 at full size (327 680 triangles, depth 8): size-independent properties.
+    determinism, structural validity, polynomial == corner distance at leaf corners, .bin idempotence."""
+    import torch
+    v, i = sdf.meshes.config_mesh("M1")
+    box = sdf.meshes.bounding_box_with_margin(v)
+    mesh, bb = sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:])
+    a = sdf.OctreeSdf(mesh, bb, 8, 3, 1e-3, sdf.OctreeSdf.NO_CONTINUITY, 2)
+    b = sdf.OctreeSdf(mesh, bb, 8, 3, 1e-3, sdf.OctreeSdf.NO_CONTINUITY, 2)
+    da = a.getOctreeData()
+    assert da.size == 20630800                                   # the reference's own count for this input
+    assert hashlib.sha256(da.tobytes()).hexdigest() == hashlib.sha256(b.getOctreeData().tobytes()).hexdigest()
+    topo, leaves, inner = octree_topology(da, 8)
+    assert topo.sum() + 64 * leaves == da.size and topo.sum() == 512 + 8 * inner
+    # single-DFS layout holds the same leaves
+    c = sdf.OctreeSdf(mesh, bb, 8, 3, 1e-3, sdf.OctreeSdf.NO_CONTINUITY, 1).getOctreeData()
+    assert c.size == da.size and np.array_equal(np.sort(c[~octree_topology(c, 8)[0]]), np.sort(da[~topo]))
+    # 256^3 grid: exact-order and FMA evaluation agree, checksum is finite, grid covers inside and outside
+    grid = torch.from_numpy(sdf.meshes.cell_centre_grid(a.getSampleArea().as_array(), 256)).cuda()
+    d_exact = a.getDistance(grid, exact_order=True)
+    d_fast = a.getDistance(grid)
+    assert torch.isfinite(d_exact).all()
+    assert (d_exact - d_fast).abs().max().item() < 2e-6
+    assert d_exact.min().item() < 0 < d_exact.max().item()
+    assert abs(d_exact.abs().max().item()) <= a.info().value_range * 1.01
