@@ -87,6 +87,47 @@ void loadBin(sdfb200_sdf& s, const char* path) {
         getArray(is, s.tris);
     }
     s.cellSize = (s.boxMax[0] - s.boxMin[0]) / float(s.startGridSize);
+    validateStructure(s);
+}
+
+// A .bin file is untrusted input for the GPU kernels: every index the query kernels will follow is
+// checked here once (children blocks and coefficient / triangle-set blocks inside their arrays), and
+// the 16-byte alignment of OctreeSdf leaf blocks is recorded for the vectorised loads.
+void validateStructure(sdfb200_sdf& s) {
+    const uint64_t G3 = uint64_t(s.startGridSize) * s.startGridSize * s.startGridSize;
+    if (s.format == SDFB200_FORMAT_OCTREE) {
+        const uint64_t n = s.octree.size();
+        if (n < G3) throw Error(SDFB200_ERR_IO, "octree array smaller than its start grid");
+        s.leafBlocksAligned = true;
+        std::vector<uint32_t> stack;
+        stack.reserve(1024);
+        uint64_t visited = 0;
+        for (uint64_t r = 0; r < G3; r++) {
+            stack.push_back(uint32_t(r));
+            while (!stack.empty()) {
+                const uint32_t w = s.octree[stack.back()];
+                stack.pop_back();
+                const uint64_t at = w & kOctIndexMask;
+                if (++visited > n) throw Error(SDFB200_ERR_IO, "octree array contains a cycle");
+                if (w & kLeafBit) {
+                    if (at + 64 > n) throw Error(SDFB200_ERR_IO, "leaf coefficient block out of range");
+                    if (at % 4) s.leafBlocksAligned = false;
+                } else {
+                    if (at < G3 || at + 8 > n) throw Error(SDFB200_ERR_IO, "children block out of range");
+                    for (uint32_t c = 0; c < 8; c++) stack.push_back(uint32_t(at + c));
+                }
+            }
+        }
+    } else {
+        const uint64_t n = s.octree.size() / 2;
+        if (n < G3) throw Error(SDFB200_ERR_IO, "node array smaller than its start grid");
+        if (s.bitsPerIndex == 0 || s.bitsPerIndex > 31) throw Error(SDFB200_ERR_IO, "implausible bitsPerIndex");
+        for (uint64_t i = 0; i < n; i++) {
+            const uint32_t w = s.octree[2 * i];
+            if (!(w & kLeafBit) && (uint64_t(w) + 8 > n || w < G3)) throw Error(SDFB200_ERR_IO, "children block out of range");
+        }
+        // triangle indices inside the sets are checked lazily by the kernels against num_triangles
+    }
 }
 
 void uploadStructure(sdfb200_sdf& s) {

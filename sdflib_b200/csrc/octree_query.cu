@@ -90,20 +90,29 @@ template <int AX> __device__ __forceinline__ float polyDerivative(const float* c
     }
     return acc;
 }
-template <bool kGrad> __device__ __forceinline__ float evalLeaf(const float* c, float x, float y, float z, f3& g) {
+template <bool kGrad, bool kVec> __device__ __forceinline__ float evalLeaf(const float* c, float x, float y, float z, f3& g) {
     if (kGrad) g = normalize3(mk3(polyDerivative<0>(c, x, y, z), polyDerivative<1>(c, x, y, z), polyDerivative<2>(c, x, y, z)));
     return polyValue(c, x, y, z);
 }
 #else
-// Horner in x, then y, then z with derivative recurrences; all FMA.
-template <bool kGrad> __device__ __forceinline__ float evalLeaf(const float* c, float x, float y, float z, f3& g) {
+// Horner in x, then y, then z with derivative recurrences; all FMA. kVec: the 64 coefficients are
+// fetched as 16 x 128-bit read-only loads (legal whenever leaf blocks are 16-byte aligned, which holds
+// for every start grid with G^3 % 4 == 0 because all blocks are 8 or 64 words long).
+template <bool kGrad, bool kVec> __device__ __forceinline__ float evalLeaf(const float* c, float x, float y, float z, f3& g) {
     float v = 0.0f, vx = 0.0f, vy = 0.0f, vz = 0.0f;
 #pragma unroll
     for (int k = 3; k >= 0; k--) {
         float a = 0.0f, ax = 0.0f, ay = 0.0f;
 #pragma unroll
         for (int j = 3; j >= 0; j--) {
-            const float c0 = c[16 * k + 4 * j], c1 = c[16 * k + 4 * j + 1], c2 = c[16 * k + 4 * j + 2], c3 = c[16 * k + 4 * j + 3];
+            float c0, c1, c2, c3;
+            if (kVec) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(c) + 4 * k + j);
+                c0 = q.x; c1 = q.y; c2 = q.z; c3 = q.w;
+            } else {
+                c0 = __ldg(c + 16 * k + 4 * j); c1 = __ldg(c + 16 * k + 4 * j + 1);
+                c2 = __ldg(c + 16 * k + 4 * j + 2); c3 = __ldg(c + 16 * k + 4 * j + 3);
+            }
             const float r = fmaf(fmaf(fmaf(c3, x, c2), x, c1), x, c0);
             if (kGrad) {
                 const float rx = fmaf(fmaf(3.0f * c3, x, 2.0f * c2), x, c1);
@@ -124,13 +133,13 @@ template <bool kGrad> __device__ __forceinline__ float evalLeaf(const float* c, 
 }
 #endif
 
-template <bool kGrad>
+template <bool kGrad, bool kVec>
 __global__ void __launch_bounds__(256)
 octreeQueryKernel(const uint32_t* __restrict__ oct, const QueryParams q, const float* __restrict__ xyz, uint64_t n,
                   float* __restrict__ dist, float* __restrict__ grad) {
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const f3 p = mk3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    const f3 p = mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
     float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
     const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     const int ix = int(flx), iy = int(fly), iz = int(flz);
@@ -140,15 +149,27 @@ octreeQueryKernel(const uint32_t* __restrict__ oct, const QueryParams q, const f
     if (ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid) {
         d = (kGrad ? boxDistanceGrad(q, p, g) : boxDistance(q, p)) + q.minBorder;
     } else {
-        uint32_t node = oct[(iz * q.grid + iy) * q.grid + ix];
+        // The reference descends with child = (frac >= 0.5) per axis and frac <- fract(2 frac). Both
+        // steps are exact in binary floating point (doubling, floor and the subtraction introduce no
+        // rounding), so the same path and the same final frac are obtained from the leading bits of the
+        // start-cell fraction: level j uses bit j of floor(frac * 2^kPathBits), and a leaf reached after k
+        // steps evaluates at frac * 2^k - floor(frac * 2^k).
+        constexpr int kPathBits = 16;
+        const uint32_t bx = uint32_t(fx * float(1 << kPathBits)), by = uint32_t(fy * float(1 << kPathBits)),
+                       bz = uint32_t(fz * float(1 << kPathBits));
+        uint32_t node = __ldg(oct + (iz * q.grid + iy) * q.grid + ix);
+        int k = 0;
         while (!(node & kLeafBit)) {
-            const uint32_t child = ((fz >= 0.5f) ? 4u : 0u) + ((fy >= 0.5f) ? 2u : 0u) + ((fx >= 0.5f) ? 1u : 0u);
-            node = oct[(node & kOctIndexMask) + child];
-            fx = 2.0f * fx; fy = 2.0f * fy; fz = 2.0f * fz;
-            fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
+            const int sh = kPathBits - 1 - k;
+            const uint32_t child = ((bx >> sh) & 1u) | (((by >> sh) & 1u) << 1) | (((bz >> sh) & 1u) << 2);
+            node = __ldg(oct + (node & kOctIndexMask) + child);
+            k++;
         }
+        const float scale = float(1u << k);
+        fx *= scale; fy *= scale; fz *= scale;
+        fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
         const float* c = reinterpret_cast<const float*>(oct + (node & kOctIndexMask));
-        d = evalLeaf<kGrad>(c, fx, fy, fz, g);
+        d = evalLeaf<kGrad, kVec>(c, fx, fy, fz, g);
     }
     dist[i] = d;
     if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
@@ -170,8 +191,16 @@ void launchOctreeQueryFast(
     q.grid = s.startGridSize;
     q.minBorder = s.minBorderValue;
     const uint32_t grid = uint32_t((n + 255) / 256);
-    if (dGrad) octreeQueryKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, dGrad);
-    else octreeQueryKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, nullptr);
+    // leaf blocks are 16-byte aligned iff the start grid has a multiple of 4 slots (all blocks are 8 or 64 words)
+    const bool vec = (uint64_t(s.startGridSize) * s.startGridSize * s.startGridSize) % 4 == 0 && s.leafBlocksAligned;
+    if (s.maxDepth > 16) throw Error(SDFB200_ERR_INVALID, "octree deeper than 16 levels");
+    if (dGrad) {
+        if (vec) octreeQueryKernel<true, true><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, dGrad);
+        else octreeQueryKernel<true, false><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, dGrad);
+    } else {
+        if (vec) octreeQueryKernel<false, true><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, nullptr);
+        else octreeQueryKernel<false, false><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, nullptr);
+    }
     SDFB_CUDA(cudaGetLastError());
 }
 

@@ -87,6 +87,7 @@ struct sdfb200_sdf {
     float cellSize = 0.0f;
     // OCTREE
     float valueRange = 0.0f, minBorderValue = 0.0f;
+    bool leafBlocksAligned = true;   // every leaf block offset is a multiple of 4 words (checked on load)
     // EXACT_OCTREE
     uint32_t startDepth = 0, minTrisInLeafs = 0, maxTrisInLeafs = 0, maxTrisEncoded = 0, bitEncodingStartDepth = 0,
              bitsPerIndex = 0;
@@ -133,5 +134,6 @@ void launchExactQuery(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float
 void saveBin(const sdfb200_sdf& s, const char* path);
 void loadBin(sdfb200_sdf& s, const char* path);
 void uploadStructure(sdfb200_sdf& s);
+void validateStructure(sdfb200_sdf& s);
 
 }  // namespace sdfb200
