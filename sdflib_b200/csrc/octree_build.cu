@@ -27,6 +27,7 @@
 #include <cstring>
 #include <memory>
 
+#include "device_utils.cuh"
 #include "sdf_internal.h"
 
 namespace sdfb200 {
@@ -274,60 +275,6 @@ emitChildrenKernel(LevelView lv, const float4* mids, const uint32_t* subdivide, 
     }
 }
 
-// ---- exclusive scan of 0/1 flags (three small kernels; n is at most a few tens of millions) ----------
-constexpr int kScanBlock = 1024;
-__global__ void scanBlockSums(const uint32_t* in, uint32_t* blockSums, uint32_t n) {
-    __shared__ uint32_t warpSums[32];
-    const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
-    uint32_t v = i < n ? in[i] : 0u;
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t s = warpSums[threadIdx.x];
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-        if (threadIdx.x == 0) blockSums[blockIdx.x] = s;
-    }
-}
-__global__ void scanOfBlockSums(uint32_t* blockSums, uint32_t nBlocks, uint32_t* total) {
-    // single CTA, sequential over chunks of 1024 block sums
-    __shared__ uint32_t buf[kScanBlock];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t start = 0; start < nBlocks; start += kScanBlock) {
-        const uint32_t i = start + threadIdx.x;
-        const uint32_t v = i < nBlocks ? blockSums[i] : 0u;
-        buf[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < kScanBlock; o <<= 1) {
-            const uint32_t add = threadIdx.x >= uint32_t(o) ? buf[threadIdx.x - o] : 0u;
-            __syncthreads();
-            buf[threadIdx.x] += add;
-            __syncthreads();
-        }
-        if (i < nBlocks) blockSums[i] = carry + buf[threadIdx.x] - v;   // exclusive
-        __syncthreads();
-        if (threadIdx.x == kScanBlock - 1) carry += buf[threadIdx.x];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = carry;
-}
-__global__ void scanFinalize(const uint32_t* in, const uint32_t* blockSums, uint32_t* out, uint32_t n) {
-    __shared__ uint32_t buf[kScanBlock];
-    const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
-    const uint32_t v = i < n ? in[i] : 0u;
-    buf[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 1; o < kScanBlock; o <<= 1) {
-        const uint32_t add = threadIdx.x >= uint32_t(o) ? buf[threadIdx.x - o] : 0u;
-        __syncthreads();
-        buf[threadIdx.x] += add;
-        __syncthreads();
-    }
-    if (i < n) out[i] = blockSums[blockIdx.x] + buf[threadIdx.x] - v;
-}
-
 // ---- layout: subtree sizes bottom-up, block offsets top-down ---------------------------------------
 __global__ void leafSizesKernel(uint32_t* words, uint32_t* childOf, uint32_t n) {   // deepest level: every node is a leaf
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -458,12 +405,6 @@ struct Level {
     LevelView view() const { return LevelView{count, centerHalf.p, corners.p, coord.p}; }
 };
 
-inline uint32_t divUp(uint64_t a, uint64_t b) { return uint32_t((a + b - 1) / b); }
-
-double msSince(std::chrono::steady_clock::time_point t0) {
-    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-}
-
 void uploadHermite() {
     static bool done[64] = {};
     int dev = 0;
@@ -556,28 +497,22 @@ void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* bo
 
     // sharding: at the start depth keep only the voxels this rank owns (others are marked unowned later)
     DevBuf<float4> mids;
-    DevBuf<uint32_t> flags, scan, blockSums, total;
-    total.alloc(1);
+    DevBuf<uint32_t> flags, scan;
+    Scanner scanner;
     for (uint32_t d = d0; d < depth; d++) {
         Level& L = *levels[d];
         if (L.count == 0) { levels[d + 1].reset(new Level()); continue; }
         mids.alloc(size_t(L.count) * 19);
         flags.alloc(L.count);
         scan.alloc(L.count);
-        const uint32_t nBlocks = divUp(L.count, kScanBlock);
-        blockSums.alloc(nBlocks);
         const uint32_t grid = divUp(L.count, kWarpsPerCta);
         if (d >= startDepth)
             levelSampleKernel<true><<<grid, kWarpsPerCta * 32>>>(dmesh, L.view(), mids.p, flags.p, rule, param0 * param0, param1);
         else
             levelSampleKernel<false><<<grid, kWarpsPerCta * 32>>>(dmesh, L.view(), mids.p, flags.p, rule, 0.0f, 0.0f);
-        scanBlockSums<<<nBlocks, kScanBlock>>>(flags.p, blockSums.p, L.count);
-        scanOfBlockSums<<<1, kScanBlock>>>(blockSums.p, nBlocks, total.p);
-        scanFinalize<<<nBlocks, kScanBlock>>>(flags.p, blockSums.p, scan.p, L.count);
+        const uint32_t nSubdivide = scanner.run(flags.p, scan.p, L.count);
         st.kernel_launches += 4;
         st.samples_evaluated += uint64_t(L.count) * 19;
-        uint32_t nSubdivide = 0;
-        SDFB_CUDA(cudaMemcpy(&nSubdivide, total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         levels[d + 1].reset(new Level());
         Level& N = *levels[d + 1];
         N.alloc(nSubdivide * 8);
