@@ -122,6 +122,9 @@ void validateStructure(sdfb200_sdf& s) {
         const uint64_t n = s.octree.size() / 2;
         if (n < G3) throw Error(SDFB200_ERR_IO, "node array smaller than its start grid");
         if (s.bitsPerIndex == 0 || s.bitsPerIndex > 31) throw Error(SDFB200_ERR_IO, "implausible bitsPerIndex");
+        if (s.bitEncodingStartDepth < s.startDepth || s.bitEncodingStartDepth > s.maxDepth)
+            throw Error(SDFB200_ERR_IO, "bitEncodingStartDepth outside [startDepth, maxDepth]");
+        if (s.startGridSize != (1 << s.startDepth)) throw Error(SDFB200_ERR_IO, "start grid size does not match startDepth");
         for (uint64_t i = 0; i < n; i++) {
             const uint32_t w = s.octree[2 * i];
             if (!(w & kLeafBit) && (uint64_t(w) + 8 > n || w < G3)) throw Error(SDFB200_ERR_IO, "children block out of range");
@@ -144,6 +147,7 @@ void uploadStructure(sdfb200_sdf& s) {
         s.dMasks.upload(s.masks.data(), s.masks.size());
         s.dTris.alloc(s.tris.size());
         s.dTris.upload(s.tris.data(), s.tris.size());
+        prepareExactQuery(s);
     }
     SDFB_CUDA(cudaDeviceSynchronize());
 }

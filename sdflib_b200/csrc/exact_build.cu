@@ -1,0 +1,857 @@
+// ExactOctreeSdf construction on the GPU (hot path 1, exact variant).
+//
+// Replaces, behind sdfb200_build_exact, the reference's depth-first builder
+//   ExactOctreeSdf::initOctree<PerNodeRegionTrianglesInfluence>   include/SdfLib/ExactOctreeSdfDepthFirst.h:28-651
+//   PerNodeRegionTrianglesInfluence::filterTriangles                include/SdfLib/TrianglesInfluence.h:767-860  (HOT LOOP A)
+//   GJK::IsNearMinimize / findFurthestPoint                         src/utils/GJK.cpp:830-866, :715-738, :644-652
+//   PerNodeRegionTrianglesInfluence::calculateVerticesInfo          include/SdfLib/TrianglesInfluence.h:693-765  (HOT LOOP B)
+//   TriangleUtils::getSqDistPointAndTriangle                        include/SdfLib/utils/TriangleUtils.h:76-135
+//
+// B200 design (not a translation of the CPU stack machine):
+//   * level-synchronous and FLAT: the unit of work is a (node, parent-list entry) pair, not a node, so the
+//     250 000-triangle lists of interior nodes and the 129-triangle lists of surface nodes load the SMs
+//     equally. One launch filters every pair of a depth (Frank-Wolfe per thread), an exclusive scan of the
+//     keep flags gives the order-preserving compaction (lists stay ascending, as the reference's do);
+//   * HOT LOOP B: a CTA owns a 1024-entry chunk of one subdividing node's list; the chunk's index block is
+//     staged into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier) while the 19 sample
+//     points are set up, every lane gathers its triangles' 80-byte frames as 5 x 128-bit loads, keeps the 19
+//     running minima in registers and the CTA folds them with redux.sync (distance bits, then lowest list
+//     position among equals = the serial loop's first strict minimum) into one 64-bit atomicMin per sample;
+//   * the reference's post-order merge (children lists -> union list + 8 bit masks, only at depths >=
+//     maxDepth-2) is two flat passes over the stored keep flags — no 8-way merge loop;
+//   * array ORDER (stack discipline of the reference: block appended at first visit, children popped 7
+//     first, masks / union sets appended at the second visit) is rebuilt from subtree sizes: bottom-up size
+//     pass, top-down offset pass, emit passes for nodes / packed sets / masks.
+// Arithmetic is bit-faithful to the CPU build (this TU is compiled with -fmad=false); the reference's
+// history-dependent 32^3 vertex cache is not emulated (DESIGN.md "parity").
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "device_utils.cuh"
+#include "sdf_internal.h"
+
+namespace sdfb200 {
+
+namespace {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr int kChunk = 1024;          // list entries per CTA of the sample kernel
+constexpr int kSampleThreads = 256;
+constexpr uint64_t kNoKey = ~uint64_t(0);
+
+__constant__ int cMidLattice[19] = {1, 3, 4, 5, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 19, 21, 22, 23, 25};
+
+// ---- per-level node arrays -----------------------------------------------------------------------------
+struct LevelView {
+    uint32_t count;
+    uint32_t depth;
+    const float4* centerHalf;     // xyz centre, w half size
+    const uint32_t* info;         // 8 per node: nearest triangle of each corner (within the parent's list)
+    const uint32_t* parentLo;     // range of the parent's list inside the parent level's list array
+    const uint32_t* parentCnt;
+    const uint64_t* pairOff;      // count + 1: exclusive scan of parentCnt
+    const uint32_t* listLo;       // range of the node's own (filtered) list inside this level's list array
+    const uint32_t* listCnt;
+};
+
+__device__ __forceinline__ TriFrame loadFrame(const float4* __restrict__ frames, uint32_t t) {
+    const float4 a = __ldg(frames + 5 * size_t(t)), b = __ldg(frames + 5 * size_t(t) + 1), c = __ldg(frames + 5 * size_t(t) + 2),
+                 d = __ldg(frames + 5 * size_t(t) + 3), e = __ldg(frames + 5 * size_t(t) + 4);
+    TriFrame f;
+    f.ox = a.x; f.oy = a.y; f.oz = a.z; f.t00 = a.w;
+    f.t01 = b.x; f.t02 = b.y; f.t10 = b.z; f.t11 = b.w;
+    f.t12 = c.x; f.t20 = c.y; f.t21 = c.z; f.t22 = c.w;
+    f.bx = d.x; f.by = d.y; f.cx = d.z; f.cy = d.w;
+    f.v2 = e.x; f.v3x = e.y; f.v3y = e.z;
+    return f;
+}
+
+template <class T> __device__ __forceinline__ uint32_t lastLessEqual(const T* a, uint32_t n, T key) {
+    // largest i in [0, n) with a[i] <= key (a non-decreasing, a[0] <= key)
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] <= key) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- HOT LOOP A, part 1: region radii of a node (TrianglesInfluence.h:784-800) -------------------------
+// 64 threads per node: thread (i, c) evaluates the distance of corner c to the nearest triangle of corner i.
+__global__ void __launch_bounds__(256)
+regionKernel(const float4* __restrict__ frames, LevelView lv, float* __restrict__ region /* 72 per node */) {
+    const uint32_t node = blockIdx.x * 4 + (threadIdx.x >> 6);
+    if (node >= lv.count) return;   // whole 64-thread group leaves together (two full warps)
+    const uint32_t e = threadIdx.x & 63u, i = e >> 3, c = e & 7u;
+    const float4 ch = lv.centerHalf[node];
+    const TriFrame f = loadFrame(frames, lv.info[size_t(node) * 8 + i]);
+    const f3 p = mk3(ch.x, ch.y, ch.z) + cornerDir(c) * ch.w;
+    const float rho = sqrtf(sqDistPointTriangle(p, f));
+    float m = rho;
+    for (int o = 4; o > 0; o >>= 1) m = gmin(m, __shfl_xor_sync(0xffffffffu, m, o));   // groups of 8 lanes
+    region[size_t(node) * 72 + e] = rho - m;
+    if (c == 0) region[size_t(node) * 72 + 64 + i] = m;
+}
+
+// a9: Frank-Wolfe proximity test between the rounded box (8 corner spheres) and a triangle.
+__device__ __forceinline__ bool isNearMinimize(float half, const float* __restrict__ radius, f3 a, f3 b, f3 c, float thr) {
+    uint32_t iter = 0;
+    bool isNear = false;
+    const float sqThr = thr * thr;
+    f3 x = -a;
+    for (;;) {
+        const f3 g = normalize3(-x);
+        float best = dot3(mk3(-half, -half, -half), g) + radius[0];
+        uint32_t bi = 0;
+#pragma unroll
+        for (uint32_t i = 1; i < 8; i++) {
+            const float v = dot3(cornerDir(i) * half, g) + radius[i];
+            if (v > best) { best = v; bi = i; }
+        }
+        const f3 boxPoint = cornerDir(bi) * half + radius[bi] * g;
+        const f3 ng = -g;
+        const float d1 = dot3(a, ng), d2 = dot3(b, ng), d3v = dot3(c, ng);
+        const f3 triPoint = (d1 > d2) ? ((d1 > d3v) ? a : c) : ((d2 > d3v) ? b : c);
+        const f3 p = boxPoint - triPoint;
+        const float distToP = dot3(g, p - x);
+        const float distToO = dot3(g, -x);
+        const f3 dir = p - x;
+        const float d = dot3(dir, -x);
+        if (double(d) < 1.0e-5) return distToO <= distToP + thr;
+        x = x + dir * gmin(d / dot3(dir, dir), 1.0f);
+        isNear = dot3(x, x) < sqThr;
+        if (!(!isNear && distToO <= distToP + thr && ++iter < 15)) break;
+    }
+    return isNear || iter >= 15;
+}
+
+// ---- HOT LOOP A, part 2: one thread per (node, parent-list entry) pair ----------------------------------
+__global__ void __launch_bounds__(256)
+filterKernel(DeviceMesh mesh, LevelView lv, const uint32_t* __restrict__ parentList, const float* __restrict__ region,
+             uint8_t* __restrict__ flags, uint64_t numPairs) {
+    __shared__ uint32_t sNode;
+    const uint64_t p0 = uint64_t(blockIdx.x) * 256;
+    if (threadIdx.x == 0) sNode = lastLessEqual<uint64_t>(lv.pairOff, lv.count + 1, p0);
+    __syncthreads();
+    const uint64_t p = p0 + threadIdx.x;
+    if (p >= numPairs) return;
+    uint32_t node = sNode;
+    while (p >= lv.pairOff[node + 1]) node++;
+    const uint32_t j = uint32_t(p - lv.pairOff[node]);
+    const uint32_t t = parentList[lv.parentLo[node] + j];
+    const float4 ch = lv.centerHalf[node];
+    const f3 ctr = mk3(ch.x, ch.y, ch.z);
+    const f3 a = mesh.verts[mesh.idx[3 * size_t(t)]] - ctr, b = mesh.verts[mesh.idx[3 * size_t(t) + 1]] - ctr,
+             c = mesh.verts[mesh.idx[3 * size_t(t) + 2]] - ctr;
+    const f3 g = 0.3333333f * ((a + b) + c);
+    const uint32_t v = ((g.z > 0) ? 4u : 0u) + ((g.y > 0) ? 2u : 0u) + ((g.x > 0) ? 1u : 0u);
+    bool keep = lv.info[size_t(node) * 8 + v] == t;
+    if (!keep) {
+        float radius[8];
+        const float4 r0 = *reinterpret_cast<const float4*>(region + size_t(node) * 72 + v * 8);
+        const float4 r1 = *reinterpret_cast<const float4*>(region + size_t(node) * 72 + v * 8 + 4);
+        radius[0] = r0.x; radius[1] = r0.y; radius[2] = r0.z; radius[3] = r0.w;
+        radius[4] = r1.x; radius[5] = r1.y; radius[6] = r1.z; radius[7] = r1.w;
+        keep = isNearMinimize(ch.w, radius, a, b, c, region[size_t(node) * 72 + 64 + v]);
+    }
+    flags[p] = keep ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+compactKernel(LevelView lv, const uint32_t* __restrict__ parentList, const uint8_t* __restrict__ flags,
+              const uint32_t* __restrict__ pos, uint32_t* __restrict__ list, uint64_t numPairs) {
+    __shared__ uint32_t sNode;
+    const uint64_t p0 = uint64_t(blockIdx.x) * 256;
+    if (threadIdx.x == 0) sNode = lastLessEqual<uint64_t>(lv.pairOff, lv.count + 1, p0);
+    __syncthreads();
+    const uint64_t p = p0 + threadIdx.x;
+    if (p >= numPairs || !flags[p]) return;
+    uint32_t node = sNode;
+    while (p >= lv.pairOff[node + 1]) node++;
+    list[pos[p]] = parentList[lv.parentLo[node] + uint32_t(p - lv.pairOff[node])];
+}
+
+__global__ void listRangeKernel(const uint64_t* pairOff, const uint32_t* pos, uint64_t numPairs, uint32_t total, uint32_t* listLo,
+                                uint32_t* listCnt, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t a = pairOff[i], b = pairOff[i + 1];
+    const uint32_t lo = a < numPairs ? pos[a] : total, hi = b < numPairs ? pos[b] : total;
+    listLo[i] = lo;
+    listCnt[i] = hi - lo;
+}
+
+// terminal rule (ExactOctreeSdfDepthFirst.h:307-314) + chunk counts of the sample pass
+__global__ void decideKernel(const uint32_t* listCnt, uint32_t n, uint32_t depth, uint32_t startDepth, uint32_t maxDepth,
+                             uint32_t minTris, uint32_t* subdivide, uint32_t* chunks, uint32_t* maxTrisInLeafs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t cnt = listCnt[i];
+    const bool terminal = depth >= startDepth && cnt <= minTris;
+    const bool sub = !terminal && depth < maxDepth;
+    subdivide[i] = sub ? 1u : 0u;
+    chunks[i] = sub ? (cnt + kChunk - 1) / kChunk : 0u;
+    if (!sub) atomicMax(maxTrisInLeafs, cnt);
+}
+
+// ---- HOT LOOP B: nearest list entry for the kPts sample points of a node ---------------------------------
+// grid = total chunks; chunkOff (count + 1) maps a chunk to its node. best[node * kPts + s] receives
+// min over the list of (sqDist bits << 32 | list position).
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(uint32_t(__cvta_generic_to_shared(bar))), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(uint32_t(__cvta_generic_to_shared(bar))), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(uint32_t(__cvta_generic_to_shared(bar))), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared (16-byte aligned addresses and size)
+__device__ __forceinline__ void tmaLoad1d(void* smemDst, const void* gmemSrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     uint32_t(__cvta_generic_to_shared(smemDst))),
+                 "l"(gmemSrc), "r"(bytes), "r"(uint32_t(__cvta_generic_to_shared(bar)))
+                 : "memory");
+}
+
+template <int kPts>
+__global__ void __launch_bounds__(kSampleThreads)
+sampleKernel(const float4* __restrict__ frames, const float4* __restrict__ centerHalf, const uint32_t* __restrict__ list,
+             const uint32_t* __restrict__ listLo, const uint32_t* __restrict__ listCnt, const uint32_t* __restrict__ chunkOff,
+             uint32_t numNodes, unsigned long long* __restrict__ best) {
+    // The chunk's index block is fetched as the 16-byte aligned window that covers it: [winLo, winLo + winBytes)
+    __shared__ alignas(16) uint32_t sIdx[kChunk + 8];
+    __shared__ alignas(8) uint64_t sBar;
+    __shared__ float sPts[kPts][3];
+    __shared__ unsigned long long sKeys[kSampleThreads / 32][kPts];
+    __shared__ uint32_t sNode;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        sNode = lastLessEqual<uint32_t>(chunkOff, numNodes + 1, blockIdx.x);
+        mbarInit(&sBar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t node = sNode;
+    const uint32_t first = (blockIdx.x - chunkOff[node]) * kChunk;       // position of the chunk inside the node's list
+    const uint32_t cnt = min(uint32_t(kChunk), listCnt[node] - first);   // entries of this chunk
+    const size_t gFirst = size_t(listLo[node]) + first;                   // index of the first entry in `list`
+    const size_t winFirst = gFirst & ~size_t(3);                          // 16-byte aligned window start
+    const uint32_t skip = uint32_t(gFirst - winFirst);
+    const uint32_t winBytes = ((skip + cnt + 3u) & ~3u) * 4u;             // the list array is padded by 8 words
+    if (tid == 0) {
+        mbarExpectTx(&sBar, winBytes);
+        tmaLoad1d(sIdx, list + winFirst, winBytes, &sBar);
+    }
+    if (tid < kPts) {
+        const float4 ch = centerHalf[node];
+        f3 rel;
+        if (kPts == 8) rel = cornerDir(uint32_t(tid));
+        else {
+            const int L = cMidLattice[tid];
+            rel = mk3(float(L % 3 - 1), float((L / 3) % 3 - 1), float(L / 9 - 1));
+        }
+        const f3 p = mk3(ch.x, ch.y, ch.z) + rel * ch.w;
+        sPts[tid][0] = p.x; sPts[tid][1] = p.y; sPts[tid][2] = p.z;
+    }
+    __syncthreads();
+    mbarWait(&sBar, 0);
+
+    float bestD[kPts];
+    uint32_t bestJ[kPts];
+#pragma unroll
+    for (int s = 0; s < kPts; s++) { bestD[s] = INFINITY; bestJ[s] = kNone; }
+    for (uint32_t k = uint32_t(tid); k < cnt; k += kSampleThreads) {   // ascending positions per thread
+        const TriFrame f = loadFrame(frames, sIdx[skip + k]);
+#pragma unroll
+        for (int s = 0; s < kPts; s++) {
+            const float d = sqDistPointTriangle(mk3(sPts[s][0], sPts[s][1], sPts[s][2]), f);
+            if (d < bestD[s]) { bestD[s] = d; bestJ[s] = first + k; }
+        }
+    }
+    // fold: distance bits first (non-negative floats order like their bit patterns), then the lowest list
+    // position among the lanes that hold the minimum = first strict minimum of the serial ascending loop
+    unsigned long long mine = kNoKey;
+#pragma unroll
+    for (int s = 0; s < kPts; s++) {
+        const uint32_t bits = bestJ[s] == kNone ? 0xFFFFFFFFu : __float_as_uint(bestD[s]);
+        const uint32_t m = __reduce_min_sync(0xffffffffu, bits);
+        const uint32_t j = __reduce_min_sync(0xffffffffu, bits == m ? bestJ[s] : kNone);
+        if (lane == s) mine = (static_cast<unsigned long long>(m) << 32) | j;
+    }
+    if (lane < kPts) sKeys[warp][lane] = mine;
+    __syncthreads();
+    if (tid < kPts) {
+        unsigned long long k = sKeys[0][tid];
+#pragma unroll
+        for (int w = 1; w < kSampleThreads / 32; w++) k = min(k, sKeys[w][tid]);
+        if ((k >> 32) != 0xFFFFFFFFull) atomicMin(best + size_t(node) * kPts + tid, k);
+    }
+}
+
+// best keys -> triangle ids (0 when the list was empty: deterministic stand-in for the reference's untouched slot)
+__global__ void resolveKernel(const unsigned long long* best, const uint32_t* list, const uint32_t* listLo, uint32_t perNode,
+                              uint32_t* out, uint64_t n) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = best[i];
+    out[i] = (k == kNoKey) ? 0u : list[size_t(listLo[i / perNode]) + uint32_t(k & 0xFFFFFFFFull)];
+}
+
+// children of the subdividing nodes (ExactOctreeSdfDepthFirst.h:329-440): 64 threads per parent = (child c, corner k)
+__global__ void __launch_bounds__(256)
+childrenKernel(LevelView lv, const uint32_t* __restrict__ coord, const uint32_t* __restrict__ subdivide,
+               const uint32_t* __restrict__ childIdx, const uint32_t* __restrict__ midInfo, uint32_t* __restrict__ childOf,
+               float4* __restrict__ nCenterHalf, uint32_t* __restrict__ nInfo, uint32_t* __restrict__ nCoord,
+               uint32_t* __restrict__ nParent, uint32_t* __restrict__ nParentLo, uint32_t* __restrict__ nParentCnt) {
+    const uint32_t node = blockIdx.x * 4 + (threadIdx.x >> 6);
+    if (node >= lv.count) return;
+    const uint32_t e = threadIdx.x & 63u, c = e >> 3, k = e & 7u;
+    if (!subdivide[node]) { if (e == 0) childOf[node] = kNone; return; }
+    const uint32_t base = childIdx[node] * 8u;
+    if (e == 0) childOf[node] = base;
+    const uint32_t lx = (c & 1u) + (k & 1u), ly = ((c >> 1) & 1u) + ((k >> 1) & 1u), lz = (c >> 2) + (k >> 2);
+    uint32_t v;
+    if (lx != 1 && ly != 1 && lz != 1) v = lv.info[size_t(node) * 8 + ((lx >> 1) | ((ly >> 1) << 1) | ((lz >> 1) << 2))];
+    else {
+        const int L = int(lx + 3 * ly + 9 * lz);
+        // index of lattice point L among the 19 non-corner points (ascending L)
+        int s = 0;
+#pragma unroll
+        for (int q = 0; q < 19; q++) s += (cMidLattice[q] < L) ? 1 : 0;
+        v = midInfo[size_t(node) * 19 + s];
+    }
+    nInfo[size_t(base + c) * 8 + k] = v;
+    if (k == 0) {
+        const float4 ch = lv.centerHalf[node];
+        const float h = 0.5f * ch.w;
+        const f3 ctr = mk3(ch.x, ch.y, ch.z) + cornerDir(c) * h;
+        nCenterHalf[base + c] = make_float4(ctr.x, ctr.y, ctr.z, h);
+        const uint32_t pc = coord[node];
+        const uint32_t ix = ((pc & 1023u) << 1) | (c & 1u), iy = (((pc >> 10) & 1023u) << 1) | ((c >> 1) & 1u),
+                       iz = (((pc >> 20) & 1023u) << 1) | (c >> 2);
+        nCoord[base + c] = ix | (iy << 10) | (iz << 20);
+        nParent[base + c] = node;
+        nParentLo[base + c] = lv.listLo[node];
+        nParentCnt[base + c] = lv.listCnt[node];
+    }
+}
+
+// ---- post-order merge as flat passes (ExactOctreeSdfDepthFirst.h:189-286) ------------------------------------
+// member[g] (g = global index into this level's list array): bit c set iff entry g of an inner node's list
+// survives in child c's FINAL list (filtered, and merged if the child is itself inner).
+struct MergeChildView {
+    const uint64_t* pairOff;     // child level
+    const uint8_t* flags;        // child level keep flags per pair
+    const uint32_t* pos;         // child level list position per pair
+    const uint32_t* childOf;     // child level: kNone = leaf
+    const uint8_t* member;       // child level member bytes (null when the child level is the deepest one)
+};
+__global__ void __launch_bounds__(256)
+memberKernel(const uint32_t* __restrict__ listLo, const uint32_t* __restrict__ childOf, uint32_t numNodes, uint32_t listTotal,
+             MergeChildView ch, uint8_t* __restrict__ member, uint8_t* __restrict__ keep) {
+    __shared__ uint32_t sNode;
+    const uint32_t g0 = blockIdx.x * 256;
+    if (threadIdx.x == 0) sNode = lastLessEqual<uint32_t>(listLo, numNodes, g0);
+    __syncthreads();
+    const uint32_t g = g0 + threadIdx.x;
+    if (g >= listTotal) return;
+    uint32_t node = sNode;
+    while (node + 1 < numNodes && g >= listLo[node + 1]) node++;
+    uint32_t m = 0;
+    const uint32_t c0 = childOf[node];
+    if (c0 != kNone) {
+        const uint32_t j = g - listLo[node];
+#pragma unroll
+        for (uint32_t c = 0; c < 8; c++) {
+            const uint64_t pp = ch.pairOff[c0 + c] + j;
+            bool f = ch.flags[pp] != 0;
+            if (f && ch.member != nullptr && ch.childOf[c0 + c] != kNone) f = ch.member[ch.pos[pp]] != 0;
+            m |= f ? (1u << c) : 0u;
+        }
+    }
+    member[g] = uint8_t(m);
+    keep[g] = m ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+mergeCompactKernel(const uint32_t* __restrict__ list, const uint8_t* __restrict__ member, const uint32_t* __restrict__ mpos,
+                   uint32_t listTotal, uint32_t* __restrict__ mergedList, uint8_t* __restrict__ mergedMember) {
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    if (g >= listTotal || !member[g]) return;
+    mergedList[mpos[g]] = list[g];
+    mergedMember[mpos[g]] = member[g];
+}
+
+__global__ void mergedRangeKernel(const uint32_t* listLo, const uint32_t* listCnt, const uint32_t* mpos, uint32_t listTotal,
+                                  uint32_t mergedTotal, uint32_t* mergedLo, uint32_t* mergedCnt, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t a = listLo[i], b = a + listCnt[i];
+    const uint32_t lo = a < listTotal ? mpos[a] : mergedTotal, hi = b < listTotal ? mpos[b] : mergedTotal;
+    mergedLo[i] = lo;
+    mergedCnt[i] = hi - lo;
+}
+
+// ---- layout -----------------------------------------------------------------------------------------------
+struct LayoutView {   // per level
+    const uint32_t* childOf;
+    const uint32_t* listCnt;
+    const uint32_t* mergedCnt;   // null below/above the merge levels
+    uint32_t* nodeCnt;           // subtree sizes: nodes (8 per inner node)
+    uint32_t* setWords;          //                words of mTrianglesSets
+    uint32_t* maskBytes;         //                bytes of mTrianglesMasks
+    uint32_t* slot;              // where the node's own record lives
+    uint32_t* nodeBase;          // start of the subtree's regions in the three arrays
+    uint32_t* setBase;
+    uint32_t* maskBase;
+    uint32_t* ownMaskBase;       // start of the node's own 8 masks (after its inner children's)
+};
+
+__device__ __forceinline__ uint32_t packedSetWords(uint32_t n, uint32_t bits) {
+    return uint32_t((uint64_t(n) * bits + 31) / 32) + 2u;   // count word + packed indices + one zero pad word
+}
+
+__global__ void sizesKernel(LayoutView lv, LayoutView next, uint32_t n, uint32_t depth, uint32_t maxDepth, uint32_t bitEnc,
+                            uint32_t bits, uint32_t* maxEncoded) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c0 = lv.childOf[i];
+    uint32_t nodes = 0, sets = 0, masks = 0;
+    if (c0 == kNone) {
+        if (depth <= bitEnc) sets = packedSetWords(lv.listCnt[i], bits);
+    } else {
+        nodes = 8;
+        for (int c = 0; c < 8; c++) { nodes += next.nodeCnt[c0 + c]; sets += next.setWords[c0 + c]; masks += next.maskBytes[c0 + c]; }
+        if (depth >= bitEnc) {
+            const uint32_t m = lv.mergedCnt[i];
+            masks += 8u * ((m + 7u) / 8u);
+            if (depth == bitEnc) { sets = packedSetWords(m, bits); atomicMax(maxEncoded, m); }
+        }
+    }
+    lv.nodeCnt[i] = nodes;
+    lv.setWords[i] = sets;
+    lv.maskBytes[i] = masks;
+}
+
+// children regions in the order the reference's stack pops them: 7 first
+__global__ void offsetsKernel(LayoutView lv, LayoutView next, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c0 = lv.childOf[i];
+    if (c0 == kNone) return;
+    const uint32_t nb = lv.nodeBase[i];
+    if (nb == kNone) {   // subtree not owned by this rank
+        for (int c = 0; c < 8; c++) next.nodeBase[c0 + c] = kNone;
+        return;
+    }
+    uint32_t rn = nb + 8u, rs = lv.setBase[i], rm = lv.maskBase[i];
+    for (int c = 7; c >= 0; c--) {
+        next.slot[c0 + c] = nb + uint32_t(c);
+        next.nodeBase[c0 + c] = rn; rn += next.nodeCnt[c0 + c];
+        next.setBase[c0 + c] = rs;  rs += next.setWords[c0 + c];
+        next.maskBase[c0 + c] = rm; rm += next.maskBytes[c0 + c];
+    }
+    lv.ownMaskBase[i] = rm;
+}
+
+// node records: (childrenIndex | leaf, trianglesArrayIndex)
+__global__ void emitNodesKernel(LayoutView lv, uint32_t n, uint32_t depth, uint32_t bitEnc, uint32_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t nb = lv.nodeBase[i];
+    if (nb == kNone) return;
+    const uint32_t c0 = lv.childOf[i], slot = lv.slot[i];
+    out[2 * size_t(slot)] = c0 == kNone ? 0xFFFFFFFFu : (nb & kExactIndexMask);
+    if (depth <= bitEnc && (c0 == kNone || depth == bitEnc)) out[2 * size_t(slot) + 1] = lv.setBase[i];
+    if (c0 != kNone && depth >= bitEnc) {   // the second visit hands every child its mask offset
+        const uint32_t bytes = (lv.mergedCnt[i] + 7u) / 8u;
+        for (uint32_t c = 0; c < 8; c++) out[2 * size_t(nb + c) + 1] = lv.ownMaskBase[i] + c * bytes;
+    }
+}
+
+// packed sets: [count][MSB-first indices of `bits` bits][0]   (ExactOctreeSdfDepthFirst.h:263-280, :450-467)
+__global__ void __launch_bounds__(128)
+emitSetsKernel(LayoutView lv, uint32_t n, uint32_t depth, uint32_t bitEnc, uint32_t bits, const uint32_t* __restrict__ srcList,
+               const uint32_t* __restrict__ srcLo, const uint32_t* __restrict__ srcCnt, bool wantInner, uint32_t* __restrict__ sets) {
+    const uint32_t i = blockIdx.x;
+    if (i >= n || lv.nodeBase[i] == kNone) return;
+    const bool inner = lv.childOf[i] != kNone;
+    if (inner != wantInner) return;
+    if (inner && depth != bitEnc) return;
+    const uint32_t cnt = srcCnt[i];
+    const uint32_t* src = srcList + srcLo[i];
+    uint32_t* dst = sets + lv.setBase[i];
+    const uint32_t words = uint32_t((uint64_t(cnt) * bits + 31) / 32);
+    if (threadIdx.x == 0) { dst[0] = cnt; dst[1 + words] = 0u; }
+    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) {
+        const uint64_t bitLo = uint64_t(w) * 32;
+        uint32_t t = uint32_t(bitLo / bits);
+        uint32_t acc = 0;
+        for (; t < cnt; t++) {
+            const uint64_t start = uint64_t(t) * bits;
+            if (start >= bitLo + 32) break;
+            const uint32_t index = src[t];
+            // element occupies bits [start, start + bits) of the stream, MSB first
+            const int shift = int(bitLo + 32) - int(start + bits);   // > 0: shift left inside the word
+            acc |= shift >= 0 ? (index << shift) : (index >> (-shift));
+        }
+        dst[1 + w] = acc;
+    }
+}
+
+// 8 masks of an inner node at depth >= bitEnc: child c, byte b = member bits of merged entries 8b .. 8b+7, MSB first
+__global__ void __launch_bounds__(128)
+emitMasksKernel(LayoutView lv, uint32_t n, const uint32_t* __restrict__ mergedLo, const uint8_t* __restrict__ mergedMember,
+                uint8_t* __restrict__ masks) {
+    const uint32_t i = blockIdx.x;
+    if (i >= n || lv.nodeBase[i] == kNone || lv.childOf[i] == kNone) return;
+    const uint32_t cnt = lv.mergedCnt[i], bytes = (cnt + 7u) / 8u;
+    const uint8_t* mem = mergedMember + mergedLo[i];
+    uint8_t* dst = masks + lv.ownMaskBase[i];
+    for (uint32_t b = threadIdx.x; b < bytes; b += blockDim.x) {
+        uint32_t m[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) m[q] = (8 * b + q < cnt) ? mem[8 * b + q] : 0u;
+#pragma unroll
+        for (uint32_t c = 0; c < 8; c++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) v |= ((m[q] >> c) & 1u) << (7 - q);
+            dst[size_t(c) * bytes + b] = uint8_t(v);
+        }
+    }
+}
+
+__global__ void fillU64(unsigned long long* p, unsigned long long v, uint64_t n) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- host orchestration ------------------------------------------------------------------------------------
+struct Level {
+    uint32_t count = 0, depth = 0;
+    DevBuf<float4> centerHalf;
+    DevBuf<uint32_t> info, coord, parent, parentLo, parentCnt, listLo, listCnt, childOf, list, pos;
+    DevBuf<uint64_t> pairOff;
+    DevBuf<uint8_t> flags;
+    uint64_t numPairs = 0;
+    uint32_t listTotal = 0;
+    // merge levels
+    DevBuf<uint8_t> member, mergedMember;
+    DevBuf<uint32_t> mergedLo, mergedCnt, mergedList;
+    uint32_t mergedTotal = 0;
+    // layout
+    DevBuf<uint32_t> nodeCnt, setWords, maskBytes, slot, nodeBase, setBase, maskBase, ownMaskBase;
+
+    void allocNodes(uint32_t n, uint32_t d) {
+        count = n; depth = d;
+        centerHalf.alloc(n); info.alloc(size_t(n) * 8); coord.alloc(n); parent.alloc(n); parentLo.alloc(n); parentCnt.alloc(n);
+        listLo.alloc(n); listCnt.alloc(n); childOf.alloc(n); pairOff.alloc(size_t(n) + 1);
+    }
+    LevelView view() const {
+        return LevelView{count, depth, centerHalf.p, info.p, parentLo.p, parentCnt.p, pairOff.p, listLo.p, listCnt.p};
+    }
+    void allocLayout() {
+        nodeCnt.alloc(count); setWords.alloc(count); maskBytes.alloc(count); slot.alloc(count); nodeBase.alloc(count);
+        setBase.alloc(count); maskBase.alloc(count); ownMaskBase.alloc(count);
+    }
+    LayoutView layout() const {
+        return LayoutView{childOf.p, listCnt.p, mergedCnt.p, nodeCnt.p, setWords.p, maskBytes.p, slot.p,
+                          nodeBase.p, setBase.p, maskBase.p, ownMaskBase.p};
+    }
+};
+
+}  // namespace
+
+void cubifyBox(sdfb200_sdf& s, const float* box6, uint32_t startDepth);   // octree_build.cu
+
+void buildExactOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
+                        uint32_t minTris, uint32_t numThreads) {
+    const auto tStart = std::chrono::steady_clock::now();
+    sdfb200_build_stats& st = out.stats;
+    st = sdfb200_build_stats{};
+    if (maxDepth > 10) throw Error(SDFB200_ERR_INVALID, "octree depth > 10 is not supported (node coordinates are packed in 3x10 bits)");
+    if (maxDepth < startDepth + 2)
+        throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf needs maxDepth >= startDepth + 2 (the reference dereferences a null node otherwise)");
+    out.format = SDFB200_FORMAT_EXACT_OCTREE;
+    out.maxDepth = maxDepth;
+    out.startDepth = startDepth;
+    out.minTrisInLeafs = minTris;
+    out.bitEncodingStartDepth = maxDepth - 2;
+    cubifyBox(out, box6, startDepth);
+    SDFB_CUDA(cudaGetDevice(&out.device));
+    const uint32_t bitEnc = maxDepth - 2;
+
+    // ---- serial set-up of the reference, on the host ---------------------------------------------------
+    auto t0 = std::chrono::steady_clock::now();
+    out.tris = computeTriangleData(mesh);
+    const uint32_t nT = uint32_t(out.tris.size());
+    out.bitsPerIndex = uint32_t(int32_t(std::ceil(std::log2(float(nT)))));   // ExactOctreeSdfDepthFirst.h:61
+    const uint32_t bits = out.bitsPerIndex;
+    if (bits == 0 || bits > 31) throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf needs between 2 and 2^31 triangles");
+    std::vector<float4> frames(size_t(nT) * 5);
+    std::vector<uint32_t> all;
+    all.reserve(nT);
+    for (uint32_t t = 0; t < nT; t++) {
+        float tmp[20];
+        std::memcpy(tmp, &out.tris[t], 19 * sizeof(float));
+        tmp[19] = 0.0f;
+        std::memcpy(&frames[size_t(t) * 5], tmp, sizeof(tmp));
+        const f3 nrm = triNormal(out.tris[t]);
+        if (dot3(nrm, nrm) > 1e-3f) all.push_back(t);   // ExactOctreeSdfDepthFirst.h:106 (false for NaN)
+    }
+    st.triangle_data_ms = msSince(t0);
+    t0 = std::chrono::steady_clock::now();
+    DevBuf<f3> dVerts(mesh.nVerts);
+    DevBuf<uint32_t> dIdx(mesh.nIdx), dAll(all.size() + 8);
+    DevBuf<float4> dFrames(frames.size());
+    dVerts.upload(mesh.verts, mesh.nVerts);
+    dIdx.upload(mesh.idx, mesh.nIdx);
+    dFrames.upload(frames.data(), frames.size());
+    dAll.upload(all.data(), all.size());
+    SDFB_CUDA(cudaDeviceSynchronize());
+    st.upload_ms = msSince(t0);
+    const DeviceMesh dmesh{dVerts.p, dIdx.p, nullptr, nullptr, nT};
+
+    t0 = std::chrono::steady_clock::now();
+    const uint32_t d0 = std::min(startDepth, 1u);
+    const f3 boxMin = mk3(out.boxMin[0], out.boxMin[1], out.boxMin[2]);
+    const float boxSize = out.boxMax[0] - out.boxMin[0];
+    std::vector<std::unique_ptr<Level>> levels(maxDepth + 1);
+    ScannerT<uint32_t, uint32_t> scan32;
+    ScannerT<uint32_t, uint64_t> scan64;
+    ScannerT<uint8_t, uint32_t> scanFlags;
+    DevBuf<uint32_t> scalars(2);   // [0] maxTrianglesInLeafs, [1] maxTrianglesEncodedInLeafs
+    SDFB_CUDA(cudaMemset(scalars.p, 0, 8));
+    DevBuf<unsigned long long> best;
+    DevBuf<uint32_t> subdivide, chunks, childIdx, chunkOff, midInfo;
+    DevBuf<float> region;
+
+    auto runSample = [&](auto ptsTag, const Level& L, const uint32_t* list, const uint32_t* lo, const uint32_t* cnt,
+                         const uint32_t* chOff, uint32_t nChunks, uint32_t* outInfo) {
+        constexpr int kPts = decltype(ptsTag)::value;
+        const uint64_t nKeys = uint64_t(L.count) * kPts;
+        if (best.n < nKeys) best.alloc(nKeys);
+        fillU64<<<divUp(nKeys, 256), 256>>>(best.p, kNoKey, nKeys);
+        if (nChunks) sampleKernel<kPts><<<nChunks, kSampleThreads>>>(dFrames.p, L.centerHalf.p, list, lo, cnt, chOff, L.count, best.p);
+        resolveKernel<<<divUp(nKeys, 256), 256>>>(best.p, list, lo, kPts, outInfo, nKeys);
+        st.kernel_launches += 3;
+        SDFB_CUDA(cudaGetLastError());
+    };
+
+    {   // seeds at depth d0; corner info = nearest of ALL valid triangles (ExactOctreeSdfDepthFirst.h:113-150)
+        const float h0 = float(0.5f * boxSize * std::pow(0.5f, d0));
+        const f3 c0 = boxMin + mk3(h0, h0, h0);
+        const uint32_t per = 1u << d0;
+        std::vector<float4> ch;
+        std::vector<uint32_t> coord;
+        for (uint32_t k = 0; k < per; k++)
+            for (uint32_t j = 0; j < per; j++)
+                for (uint32_t i = 0; i < per; i++) {
+                    const f3 c = c0 + (mk3(float(i), float(j), float(k)) * 2.0f) * h0;
+                    ch.push_back(make_float4(c.x, c.y, c.z, h0));
+                    coord.push_back(i | (j << 10) | (k << 20));
+                }
+        levels[d0].reset(new Level());
+        Level& L = *levels[d0];
+        const uint32_t n = uint32_t(ch.size());
+        L.allocNodes(n, d0);
+        L.centerHalf.upload(ch.data(), n);
+        L.coord.upload(coord.data(), n);
+        std::vector<uint32_t> zero(n, 0u), cntAll(n, uint32_t(all.size())), chOff(n + 1);
+        const uint32_t perNode = divUp(all.size(), kChunk);
+        for (uint32_t i = 0; i <= n; i++) chOff[i] = i * perNode;
+        L.parent.upload(zero.data(), n);
+        L.parentLo.upload(zero.data(), n);
+        L.parentCnt.upload(cntAll.data(), n);
+        chunkOff.alloc(n + 1);
+        chunkOff.upload(chOff.data(), n + 1);
+        runSample(std::integral_constant<int, 8>(), L, dAll.p, L.parentLo.p, L.parentCnt.p, chunkOff.p, n * perNode, L.info.p);
+        st.samples_evaluated += uint64_t(n) * 8;
+    }
+
+    for (uint32_t d = d0; d <= maxDepth; d++) {
+        Level& L = *levels[d];
+        const uint32_t* parentList = d == d0 ? dAll.p : levels[d - 1]->list.p;
+        if (L.count == 0) {
+            if (d < maxDepth) { levels[d + 1].reset(new Level()); levels[d + 1]->depth = d + 1; }
+            L.list.alloc(8);
+            continue;
+        }
+        // HOT LOOP A
+        L.numPairs = scan64.run(L.parentCnt.p, L.pairOff.p, L.count, true);
+        // list positions are 32-bit (ScannerT<uint8_t, uint32_t> would wrap silently): bound them by the pair count
+        if (L.numPairs >= (uint64_t(1) << 32)) throw Error(SDFB200_ERR_INVALID, "more than 2^32 (node, triangle) pairs on one octree level");
+        if (region.n < size_t(L.count) * 72) region.alloc(size_t(L.count) * 72);
+        regionKernel<<<divUp(L.count, 4), 256>>>(dFrames.p, L.view(), region.p);
+        L.flags.alloc(L.numPairs + 1);
+        L.pos.alloc(L.numPairs + 1);
+        if (L.numPairs) filterKernel<<<divUp(L.numPairs, 256), 256>>>(dmesh, L.view(), parentList, region.p, L.flags.p, L.numPairs);
+        SDFB_CUDA(cudaGetLastError());
+        L.listTotal = L.numPairs ? scanFlags.run(L.flags.p, L.pos.p, L.numPairs) : 0u;
+        L.list.alloc(size_t(L.listTotal) + 8);   // + 8: the TMA window of the sample kernel may read past the end
+        SDFB_CUDA(cudaMemsetAsync(L.list.p + L.listTotal, 0, 8 * sizeof(uint32_t)));
+        if (L.numPairs) compactKernel<<<divUp(L.numPairs, 256), 256>>>(L.view(), parentList, L.flags.p, L.pos.p, L.list.p, L.numPairs);
+        listRangeKernel<<<divUp(L.count, 256), 256>>>(L.pairOff.p, L.pos.p, L.numPairs, L.listTotal, L.listLo.p, L.listCnt.p, L.count);
+        st.kernel_launches += 10;
+        st.nodes_processed += L.count;
+        st.samples_evaluated += L.numPairs;   // Frank-Wolfe runs
+        // terminal rule
+        subdivide.alloc(L.count); chunks.alloc(L.count); childIdx.alloc(L.count); chunkOff.alloc(size_t(L.count) + 1);
+        decideKernel<<<divUp(L.count, 256), 256>>>(L.listCnt.p, L.count, d, startDepth, maxDepth, minTris, subdivide.p, chunks.p, scalars.p);
+        if (d == maxDepth) { SDFB_CUDA(cudaMemsetAsync(L.childOf.p, 0xFF, size_t(L.count) * 4)); break; }
+        const uint32_t nSub = scan32.run(subdivide.p, childIdx.p, L.count);
+        const uint32_t nChunks = scan32.run(chunks.p, chunkOff.p, L.count, true);
+        // HOT LOOP B
+        midInfo.alloc(size_t(L.count) * 19);
+        runSample(std::integral_constant<int, 19>(), L, L.list.p, L.listLo.p, L.listCnt.p, chunkOff.p, nChunks, midInfo.p);
+        levels[d + 1].reset(new Level());
+        Level& N = *levels[d + 1];
+        N.allocNodes(nSub * 8, d + 1);
+        childrenKernel<<<divUp(L.count, 4), 256>>>(L.view(), L.coord.p, subdivide.p, childIdx.p, midInfo.p, L.childOf.p, N.centerHalf.p,
+                                                  N.info.p, N.coord.p, N.parent.p, N.parentLo.p, N.parentCnt.p);
+        st.kernel_launches += 8;
+        SDFB_CUDA(cudaGetLastError());
+        if (d + 1 < maxDepth) { L.flags.release(); L.pos.release(); }   // only the flags of levels maxDepth-1 and maxDepth feed the merge
+    }
+    SDFB_CUDA(cudaDeviceSynchronize());
+    st.levels_ms = msSince(t0);
+
+    // ---- post-order merge: levels maxDepth-1, then maxDepth-2 ------------------------------------------------
+    t0 = std::chrono::steady_clock::now();
+    DevBuf<uint8_t> keep;
+    DevBuf<uint32_t> mpos;
+    for (uint32_t d = maxDepth - 1; d + 1 > bitEnc; d--) {
+        Level& L = *levels[d];
+        Level& C = *levels[d + 1];
+        L.mergedLo.alloc(L.count); L.mergedCnt.alloc(L.count);
+        if (L.count == 0) continue;
+        L.member.alloc(size_t(L.listTotal) + 1); keep.alloc(size_t(L.listTotal) + 1); mpos.alloc(size_t(L.listTotal) + 1);
+        if (L.listTotal) {
+            MergeChildView cv{C.pairOff.p, C.flags.p, C.pos.p, C.childOf.p, d + 1 == maxDepth ? nullptr : C.member.p};
+            memberKernel<<<divUp(L.listTotal, 256), 256>>>(L.listLo.p, L.childOf.p, L.count, L.listTotal, cv, L.member.p, keep.p);
+            L.mergedTotal = scanFlags.run(keep.p, mpos.p, L.listTotal);
+        }
+        L.mergedList.alloc(size_t(L.mergedTotal) + 1); L.mergedMember.alloc(size_t(L.mergedTotal) + 1);
+        if (L.listTotal) mergeCompactKernel<<<divUp(L.listTotal, 256), 256>>>(L.list.p, L.member.p, mpos.p, L.listTotal, L.mergedList.p, L.mergedMember.p);
+        mergedRangeKernel<<<divUp(L.count, 256), 256>>>(L.listLo.p, L.listCnt.p, mpos.p, L.listTotal, L.mergedTotal, L.mergedLo.p, L.mergedCnt.p, L.count);
+        st.kernel_launches += 6;
+        SDFB_CUDA(cudaGetLastError());
+        if (d == 0) break;
+    }
+
+    // ---- layout: subtree sizes bottom-up ------------------------------------------------------------------------
+    for (int d = int(maxDepth); d >= int(startDepth); d--) {
+        Level& L = *levels[size_t(d)];
+        L.allocLayout();
+        if (!L.count) continue;
+        LayoutView next = d < int(maxDepth) ? levels[size_t(d) + 1]->layout() : LayoutView{};
+        sizesKernel<<<divUp(L.count, 256), 256>>>(L.layout(), next, L.count, uint32_t(d), maxDepth, bitEnc, bits, scalars.p + 1);
+        st.kernel_launches++;
+    }
+    Level& R = *levels[startDepth];
+    const uint32_t G = uint32_t(out.startGridSize), G3 = G * G * G;
+    if (R.count != G3) throw Error(SDFB200_ERR_INVALID, "internal: start level is not a full grid");
+    std::vector<float4> rootCH(G3);
+    std::vector<uint32_t> rootCoord(G3), rootNodes(G3), rootSets(G3), rootMasks(G3);
+    R.centerHalf.download(rootCH.data(), G3);
+    R.coord.download(rootCoord.data(), G3);
+    R.nodeCnt.download(rootNodes.data(), G3);
+    R.setWords.download(rootSets.data(), G3);
+    R.maskBytes.download(rootMasks.data(), G3);
+    SDFB_CUDA(cudaDeviceSynchronize());
+    std::vector<uint32_t> rootSlot(G3), order(G3), nodeBase(G3), setBase(G3), maskBase(G3);
+    std::vector<uint64_t> key(G3);
+    for (uint32_t r = 0; r < G3; r++) {
+        const f3 f = (mk3(rootCH[r].x, rootCH[r].y, rootCH[r].z) - boxMin) / out.cellSize;   // ExactOctreeSdfDepthFirst.h:505-506
+        const int x = int(std::floor(f.x)), y = int(std::floor(f.y)), z = int(std::floor(f.z));
+        rootSlot[r] = uint32_t(z * int(G * G) + y * int(G) + x);
+        if (numThreads >= 2) key[r] = rootSlot[r];   // per-voxel sub-octrees concatenated in start-grid order (:576-622)
+        else {                                       // one global stack: virtual levels popped 7-first (:497-511)
+            const uint32_t ix = rootCoord[r] & 1023u, iy = (rootCoord[r] >> 10) & 1023u, iz = rootCoord[r] >> 20;
+            uint64_t k = 0;
+            for (int b = int(startDepth) - 1; b >= 0; b--) {
+                const uint32_t c = ((ix >> b) & 1u) | (((iy >> b) & 1u) << 1) | (((iz >> b) & 1u) << 2);
+                k = (k << 3) | (7u - c);
+            }
+            key[r] = k;
+        }
+        order[r] = r;
+    }
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    uint64_t rn = G3, rs = 0, rm = 0;
+    for (uint32_t i = 0; i < G3; i++) {
+        const uint32_t r = order[i];
+        nodeBase[r] = uint32_t(rn); rn += rootNodes[r];
+        setBase[r] = uint32_t(rs);  rs += rootSets[r];
+        maskBase[r] = uint32_t(rm); rm += rootMasks[r];
+    }
+    if (rn > uint64_t(kExactIndexMask) || rs > 0xFFFFFFFFull || rm > 0xFFFFFFFFull)
+        throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf exceeds the 32-bit index space of its arrays");
+    R.slot.upload(rootSlot.data(), G3);
+    R.nodeBase.upload(nodeBase.data(), G3);
+    R.setBase.upload(setBase.data(), G3);
+    R.maskBase.upload(maskBase.data(), G3);
+    for (uint32_t d = startDepth; d < maxDepth; d++) {
+        Level& L = *levels[d];
+        Level& N = *levels[d + 1];
+        if (!L.count) continue;
+        offsetsKernel<<<divUp(L.count, 256), 256>>>(L.layout(), N.layout(), L.count);
+        st.kernel_launches++;
+    }
+    // ---- emit -----------------------------------------------------------------------------------------------------
+    out.dOctree.alloc(size_t(rn) * 2);
+    out.dSets.alloc(size_t(rs) + 1);
+    out.dMasks.alloc(size_t(rm) + 8);
+    SDFB_CUDA(cudaMemsetAsync(out.dOctree.p, 0, size_t(rn) * 8));
+    SDFB_CUDA(cudaMemsetAsync(out.dSets.p, 0, (size_t(rs) + 1) * 4));
+    SDFB_CUDA(cudaMemsetAsync(out.dMasks.p, 0, size_t(rm) + 8));
+    for (uint32_t d = startDepth; d <= maxDepth; d++) {
+        Level& L = *levels[d];
+        if (!L.count) continue;
+        emitNodesKernel<<<divUp(L.count, 256), 256>>>(L.layout(), L.count, d, bitEnc, out.dOctree.p);
+        if (d <= bitEnc) {
+            emitSetsKernel<<<L.count, 128>>>(L.layout(), L.count, d, bitEnc, bits, L.list.p, L.listLo.p, L.listCnt.p, false, out.dSets.p);
+            if (d == bitEnc)
+                emitSetsKernel<<<L.count, 128>>>(L.layout(), L.count, d, bitEnc, bits, L.mergedList.p, L.mergedLo.p, L.mergedCnt.p, true, out.dSets.p);
+        }
+        if (d >= bitEnc && d < maxDepth) emitMasksKernel<<<L.count, 128>>>(L.layout(), L.count, L.mergedLo.p, L.mergedMember.p, out.dMasks.p);
+        st.kernel_launches += 4;
+        SDFB_CUDA(cudaGetLastError());
+    }
+    uint32_t scalarOut[2];
+    scalars.download(scalarOut, 2);
+    SDFB_CUDA(cudaDeviceSynchronize());
+    out.maxTrisInLeafs = scalarOut[0];
+    out.maxTrisEncoded = scalarOut[1];
+    st.layout_ms = msSince(t0);
+
+    t0 = std::chrono::steady_clock::now();
+    out.octree.resize(size_t(rn) * 2);
+    out.sets.resize(size_t(rs));
+    out.masks.resize(size_t(rm));
+    out.dOctree.download(out.octree.data(), out.octree.size());
+    out.dSets.download(out.sets.data(), out.sets.size());
+    out.dMasks.download(out.masks.data(), out.masks.size());
+    out.dTris.alloc(out.tris.size());
+    out.dTris.upload(out.tris.data(), out.tris.size());
+    SDFB_CUDA(cudaDeviceSynchronize());
+    st.download_ms = msSince(t0);
+    levels.clear();   // release the builder's working set before the query-side pool is allocated
+    prepareExactQuery(out);
+    st.total_ms = msSince(tStart);
+}
+
+}  // namespace sdfb200

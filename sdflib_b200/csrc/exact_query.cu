@@ -1,0 +1,371 @@
+// Bulk ExactOctreeSdf::getDistance / getDistance(p, grad) (hot path 2, exact variant).
+//
+// Reference: src/sdf/ExactOctreeSdf.cpp:38-178 and :180-320 — descend to the node at
+// bitEncodingStartDepth, unpack its triangle set, filter it through the chain of per-child bit masks
+// down to the leaf, brute-force the nearest triangle (first strict minimum, ascending order), then
+// TriangleUtils::getSignedDistPointAndTriangle (include/SdfLib/utils/TriangleUtils.h:137-196, :292-376).
+//
+// B200 design: the per-query mask-chain decode of the reference is the same work for every query that
+// lands in a leaf, so it is done ONCE per leaf: prepareExactQuery() decodes the public arrays
+// (mOctreeData / mTrianglesSets / mTrianglesMasks — freshly built or loaded from a .bin) level by level
+// into a private pool of explicit per-leaf triangle lists with flat (node, entry) pair passes and scans.
+// The public arrays stay bit-identical to the reference; the query kernel walks the node array, then
+// streams its leaf's list: one query per thread, triangle frames fetched as 5 x 128-bit read-only loads
+// (neighbouring queries of a warp share the leaf, so the loads are warp-uniform broadcasts).
+// Compiled with -fmad=false: distances are bit-identical to the CPU reference.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+
+#include "device_utils.cuh"
+#include "sdf_internal.h"
+
+namespace sdfb200 {
+
+namespace {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+enum : uint32_t { kErrSetRange = 1, kErrMaskRange = 2, kErrTriangle = 4 };
+
+__device__ __forceinline__ uint32_t unpackIndex(const uint32_t* words, uint64_t bitIdx, uint32_t bits) {   // ExactOctreeSdf.cpp:73-77
+    const uint64_t w = bitIdx >> 5;
+    const uint32_t bit = uint32_t(bitIdx & 31u);
+    return ((words[w] << bit) >> (32 - bits)) | uint32_t(uint64_t(words[w + 1]) >> (64 - (bit + bits)));
+}
+
+template <class T> __device__ __forceinline__ uint32_t lastLessEqual(const T* a, uint32_t n, T key) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] <= key) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void framesFromTriData(const TriData* tris, float4* frames, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 5u) return;
+    const uint32_t t = i / 5u, q = i % 5u;
+    const float* src = reinterpret_cast<const float*>(tris + t) + 4 * q;
+    frames[i] = make_float4(src[0], src[1], src[2], q == 4 ? 0.0f : src[3]);
+}
+
+struct PublicView {
+    const uint32_t* nodes;   // (childrenIndex | leaf, trianglesArrayIndex) pairs
+    const uint32_t* sets;
+    const uint8_t* masks;
+    uint64_t numNodes, numSets, numMasks;
+    uint32_t numTriangles, bits, bitEnc;
+};
+
+// decoded-list length of every frontier node at depth <= bitEnc, and whether it has children
+__global__ void frontierCountsKernel(PublicView pv, const uint32_t* nodeIdx, uint32_t n, uint32_t depth, uint32_t* cnt,
+                                     uint32_t* inner, uint32_t* leafCnt, uint32_t* err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t w0 = pv.nodes[2 * size_t(nodeIdx[i])], w1 = pv.nodes[2 * size_t(nodeIdx[i]) + 1];
+    const bool leaf = (w0 & kLeafBit) != 0;
+    uint32_t c = 0;
+    if (leaf || depth == pv.bitEnc) {
+        if (uint64_t(w1) + 2 > pv.numSets) atomicOr(err, kErrSetRange);
+        else {
+            c = pv.sets[w1];
+            if (uint64_t(w1) + 2 + (uint64_t(c) * pv.bits + 31) / 32 > pv.numSets) { atomicOr(err, kErrSetRange); c = 0; }
+        }
+    }
+    cnt[i] = c;
+    inner[i] = leaf ? 0u : 1u;
+    leafCnt[i] = leaf ? c : 0u;
+}
+
+// unpack the packed set of every frontier node that owns one (CTA per node)
+__global__ void __launch_bounds__(128)
+unpackSetsKernel(PublicView pv, const uint32_t* nodeIdx, const uint64_t* lo, const uint32_t* cnt, uint32_t* dec, uint32_t* err) {
+    const uint32_t i = blockIdx.x;
+    const uint32_t c = cnt[i];
+    if (c == 0) return;
+    const uint32_t* words = pv.sets + pv.nodes[2 * size_t(nodeIdx[i]) + 1] + 1;
+    uint32_t* dst = dec + lo[i];
+    for (uint32_t t = threadIdx.x; t < c; t += blockDim.x) {
+        uint32_t tri = unpackIndex(words, uint64_t(t) * pv.bits, pv.bits);
+        if (tri >= pv.numTriangles) { atomicOr(err, kErrTriangle); tri = 0; }
+        dst[t] = tri;
+    }
+}
+
+// frontier below bitEnc: a node's list = its parent's decoded list filtered by the node's bit mask
+__global__ void maskRangeCheckKernel(PublicView pv, const uint32_t* nodeIdx, const uint32_t* parentCnt, uint32_t n, uint32_t* inner,
+                                     uint32_t* err) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t w0 = pv.nodes[2 * size_t(nodeIdx[i])], w1 = pv.nodes[2 * size_t(nodeIdx[i]) + 1];
+    if (uint64_t(w1) + (parentCnt[i] + 7u) / 8u > pv.numMasks) atomicOr(err, kErrMaskRange);
+    inner[i] = (w0 & kLeafBit) ? 0u : 1u;
+}
+__global__ void __launch_bounds__(256)
+maskFlagsKernel(PublicView pv, const uint32_t* nodeIdx, const uint64_t* pairOff, uint32_t n, uint64_t numPairs, uint8_t* flags) {
+    __shared__ uint32_t sNode;
+    const uint64_t p0 = uint64_t(blockIdx.x) * 256;
+    if (threadIdx.x == 0) sNode = lastLessEqual<uint64_t>(pairOff, n + 1, p0);
+    __syncthreads();
+    const uint64_t p = p0 + threadIdx.x;
+    if (p >= numPairs) return;
+    uint32_t node = sNode;
+    while (p >= pairOff[node + 1]) node++;
+    const uint32_t j = uint32_t(p - pairOff[node]);
+    const uint64_t at = uint64_t(pv.nodes[2 * size_t(nodeIdx[node]) + 1]) + (j >> 3);
+    const uint32_t byte = at < pv.numMasks ? pv.masks[at] : 0u;
+    flags[p] = (byte & (0x80u >> (j & 7u))) ? 1 : 0;
+}
+__global__ void __launch_bounds__(256)
+maskCompactKernel(const uint64_t* pairOff, const uint64_t* parentLo, uint32_t n, uint64_t numPairs, const uint8_t* flags,
+                  const uint32_t* pos, const uint32_t* parentDec, uint32_t* dec) {
+    __shared__ uint32_t sNode;
+    const uint64_t p0 = uint64_t(blockIdx.x) * 256;
+    if (threadIdx.x == 0) sNode = lastLessEqual<uint64_t>(pairOff, n + 1, p0);
+    __syncthreads();
+    const uint64_t p = p0 + threadIdx.x;
+    if (p >= numPairs || !flags[p]) return;
+    uint32_t node = sNode;
+    while (p >= pairOff[node + 1]) node++;
+    dec[pos[p]] = parentDec[parentLo[node] + (p - pairOff[node])];
+}
+__global__ void maskRangesKernel(const uint64_t* pairOff, const uint32_t* pos, uint64_t numPairs, uint32_t total, const uint32_t* inner,
+                                 uint64_t* lo, uint32_t* cnt, uint32_t* leafCnt, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t a = pairOff[i], b = pairOff[i + 1];
+    const uint32_t l = a < numPairs ? pos[a] : total, h = b < numPairs ? pos[b] : total;
+    lo[i] = l;
+    cnt[i] = h - l;
+    leafCnt[i] = inner[i] ? 0u : h - l;
+}
+
+__global__ void nextFrontierKernel(PublicView pv, const uint32_t* nodeIdx, const uint32_t* inner, const uint32_t* childSlot,
+                                   const uint64_t* lo, const uint32_t* cnt, uint32_t n, uint32_t* nNodeIdx, uint64_t* nParentLo,
+                                   uint32_t* nParentCnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !inner[i]) return;
+    const uint32_t c0 = pv.nodes[2 * size_t(nodeIdx[i])] & kExactIndexMask;
+    for (uint32_t c = 0; c < 8; c++) {
+        const uint32_t k = childSlot[i] * 8u + c;
+        nNodeIdx[k] = c0 + c;
+        nParentLo[k] = lo[i];
+        nParentCnt[k] = cnt[i];
+    }
+}
+
+// leaves of a frontier -> private pool (CTA per frontier node)
+__global__ void __launch_bounds__(128)
+leafPoolKernel(const uint32_t* nodeIdx, const uint32_t* inner, const uint64_t* lo, const uint32_t* cnt, const uint64_t* poolOff,
+               const uint32_t* dec, uint32_t* pool, uint64_t* leafLo, uint32_t* leafCnt) {
+    const uint32_t i = blockIdx.x;
+    if (inner[i]) return;
+    const uint32_t c = cnt[i];
+    const uint64_t dst = poolOff[i];
+    if (threadIdx.x == 0) { leafLo[nodeIdx[i]] = dst; leafCnt[nodeIdx[i]] = c; }
+    for (uint32_t t = threadIdx.x; t < c; t += blockDim.x) pool[dst + t] = dec[lo[i] + t];
+}
+
+__global__ void rebaseLeavesKernel(const uint32_t* nodeIdx, const uint32_t* inner, uint32_t n, uint64_t base, uint64_t* leafLo) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !inner[i]) leafLo[nodeIdx[i]] += base;
+}
+
+// ---- the query kernel -----------------------------------------------------------------------------------------
+struct ExactQueryParams {
+    float minx, miny, minz, maxx, maxy, maxz;
+    float cell;
+    int grid;
+    float outside;   // sqrt(3) * boxSize.x
+};
+
+__device__ __forceinline__ TriFrame loadFrame(const float4* __restrict__ frames, uint32_t t) {
+    const float4 a = __ldg(frames + 5 * size_t(t)), b = __ldg(frames + 5 * size_t(t) + 1), c = __ldg(frames + 5 * size_t(t) + 2),
+                 d = __ldg(frames + 5 * size_t(t) + 3), e = __ldg(frames + 5 * size_t(t) + 4);
+    TriFrame f;
+    f.ox = a.x; f.oy = a.y; f.oz = a.z; f.t00 = a.w;
+    f.t01 = b.x; f.t02 = b.y; f.t10 = b.z; f.t11 = b.w;
+    f.t12 = c.x; f.t20 = c.y; f.t21 = c.z; f.t22 = c.w;
+    f.bx = d.x; f.by = d.y; f.cx = d.z; f.cy = d.w;
+    f.v2 = e.x; f.v3x = e.y; f.v3y = e.z;
+    return f;
+}
+
+__device__ __forceinline__ float boxDistance(const ExactQueryParams& q, f3 p) {   // Mesh.h:42-46
+    const f3 size = mk3(q.maxx - q.minx, q.maxy - q.miny, q.maxz - q.minz);
+    const f3 center = mk3(q.minx, q.miny, q.minz) + 0.5f * size;
+    const f3 d = p - center;
+    const f3 h = 0.5f * size;
+    const f3 a = mk3(gabs(d.x) - h.x, gabs(d.y) - h.y, gabs(d.z) - h.z);
+    const f3 ap = mk3(gmax(a.x, 0.0f), gmax(a.y, 0.0f), gmax(a.z, 0.0f));
+    return sqrtf(dot3(ap, ap)) + gmin(gmax(a.x, gmax(a.y, a.z)), 0.0f);
+}
+
+template <bool kGrad>
+__global__ void __launch_bounds__(256)
+exactQueryKernel(const uint32_t* __restrict__ nodes, const uint64_t* __restrict__ leafLo, const uint32_t* __restrict__ leafCnt,
+                 const uint32_t* __restrict__ pool, const float4* __restrict__ frames, const TriData* __restrict__ tris,
+                 const ExactQueryParams q, const float* __restrict__ xyz, uint64_t n, float* __restrict__ dist,
+                 float* __restrict__ grad) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f3 p = mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+    float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const int ix = int(flx), iy = int(fly), iz = int(flz);
+    fx -= flx; fy -= fly; fz -= flz;
+    f3 g = mk3(0.0f, 0.0f, 0.0f);
+    float d;
+    if (ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid) {
+        d = boxDistance(q, p) + q.outside;   // the reference leaves the caller's gradient untouched here (zero-initialised by us)
+    } else {
+        uint32_t idx = uint32_t((iz * q.grid + iy) * q.grid + ix);
+        uint32_t w0 = __ldg(nodes + 2 * size_t(idx));
+        while (!(w0 & kLeafBit)) {   // roundFloat of ExactOctreeSdf.cpp:33-36 is a strict '>'
+            const uint32_t child = ((fz > 0.5f) ? 4u : 0u) + ((fy > 0.5f) ? 2u : 0u) + ((fx > 0.5f) ? 1u : 0u);
+            idx = (w0 & kExactIndexMask) + child;
+            w0 = __ldg(nodes + 2 * size_t(idx));
+            fx = 2.0f * fx; fy = 2.0f * fy; fz = 2.0f * fz;
+            fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
+        }
+        const uint32_t* lst = pool + leafLo[idx];
+        const uint32_t cnt = leafCnt[idx];
+        float best = INFINITY;
+        uint32_t bestTri = 0;
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t t = __ldg(lst + k);
+            const float sq = sqDistPointTriangle(p, loadFrame(frames, t));
+            if (sq < best) { best = sq; bestTri = t; }
+        }
+        d = kGrad ? signedDistGradSelf(p, tris[bestTri], g) : signedDistPointTriangle(p, tris[bestTri]);
+    }
+    dist[i] = d;
+    if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
+}
+
+}  // namespace
+
+// Decode the public arrays into the private per-leaf pool (see the header comment). Throws ERR_IO when the
+// arrays are inconsistent (untrusted .bin input).
+void prepareExactQuery(sdfb200_sdf& s) {
+    const uint32_t nT = uint32_t(s.tris.size());
+    const uint64_t numNodes = s.octree.size() / 2;
+    s.dFrames.alloc(size_t(nT) * 5);
+    if (nT) framesFromTriData<<<divUp(uint64_t(nT) * 5, 256), 256>>>(s.dTris.p, s.dFrames.p, nT);
+    s.dLeafLo.alloc(numNodes);
+    s.dLeafCnt.alloc(numNodes);
+    SDFB_CUDA(cudaMemsetAsync(s.dLeafLo.p, 0, numNodes * 8));
+    SDFB_CUDA(cudaMemsetAsync(s.dLeafCnt.p, 0, numNodes * 4));
+    PublicView pv{s.dOctree.p, s.dSets.p, s.dMasks.p, numNodes, s.sets.size(), s.masks.size(), nT, s.bitsPerIndex, s.bitEncodingStartDepth};
+    DevBuf<uint32_t> err(1);
+    SDFB_CUDA(cudaMemsetAsync(err.p, 0, 4));
+
+    struct Frontier {
+        uint32_t n = 0;
+        DevBuf<uint32_t> nodeIdx, cnt, inner, leafCnt, childSlot, parentCnt, dec, pos;
+        DevBuf<uint64_t> lo, parentLo, pairOff, poolOff;
+        DevBuf<uint8_t> flags;
+        uint64_t poolTotal = 0;
+        DevBuf<uint32_t> leafPool;   // this level's leaves, concatenated
+    };
+    ScannerT<uint32_t, uint32_t> scan32;
+    ScannerT<uint32_t, uint64_t> scan64;
+    ScannerT<uint8_t, uint32_t> scanFlags;
+    const uint64_t G3 = uint64_t(s.startGridSize) * s.startGridSize * s.startGridSize;
+    std::vector<std::unique_ptr<Frontier>> fr;
+    fr.emplace_back(new Frontier());
+    {
+        Frontier& F = *fr[0];
+        F.n = uint32_t(G3);
+        std::vector<uint32_t> ids(G3);
+        for (uint32_t i = 0; i < G3; i++) ids[i] = i;
+        F.nodeIdx.alloc(G3);
+        F.nodeIdx.upload(ids.data(), G3);
+        SDFB_CUDA(cudaDeviceSynchronize());
+    }
+    uint64_t poolTotal = 0;
+    for (uint32_t depth = s.startDepth; !fr.empty() && fr.back()->n > 0; depth++) {
+        if (depth > 32) throw Error(SDFB200_ERR_IO, "exact octree deeper than 32 levels");
+        Frontier& F = *fr.back();
+        const uint32_t n = F.n;
+        F.cnt.alloc(n); F.inner.alloc(n); F.leafCnt.alloc(n); F.childSlot.alloc(n); F.lo.alloc(size_t(n) + 1); F.poolOff.alloc(size_t(n) + 1);
+        if (depth <= s.bitEncodingStartDepth) {
+            frontierCountsKernel<<<divUp(n, 256), 256>>>(pv, F.nodeIdx.p, n, depth, F.cnt.p, F.inner.p, F.leafCnt.p, err.p);
+            const uint64_t total = scan64.run(F.cnt.p, F.lo.p, n, true);
+            if (total >= (uint64_t(1) << 32)) throw Error(SDFB200_ERR_IO, "decoded triangle sets of one level exceed 2^32 entries");
+            F.dec.alloc(total + 1);
+            unpackSetsKernel<<<n, 128>>>(pv, F.nodeIdx.p, F.lo.p, F.cnt.p, F.dec.p, err.p);
+        } else {
+            Frontier& P = *fr[fr.size() - 2];
+            maskRangeCheckKernel<<<divUp(n, 256), 256>>>(pv, F.nodeIdx.p, F.parentCnt.p, n, F.inner.p, err.p);
+            F.pairOff.alloc(size_t(n) + 1);
+            const uint64_t numPairs = scan64.run(F.parentCnt.p, F.pairOff.p, n, true);
+            if (numPairs >= (uint64_t(1) << 32)) throw Error(SDFB200_ERR_IO, "mask chain of one level exceeds 2^32 entries");
+            F.flags.alloc(numPairs + 1); F.pos.alloc(numPairs + 1);
+            uint32_t total = 0;
+            if (numPairs) {
+                maskFlagsKernel<<<divUp(numPairs, 256), 256>>>(pv, F.nodeIdx.p, F.pairOff.p, n, numPairs, F.flags.p);
+                total = scanFlags.run(F.flags.p, F.pos.p, numPairs);
+            }
+            F.dec.alloc(size_t(total) + 1);
+            if (numPairs) maskCompactKernel<<<divUp(numPairs, 256), 256>>>(F.pairOff.p, F.parentLo.p, n, numPairs, F.flags.p, F.pos.p, P.dec.p, F.dec.p);
+            maskRangesKernel<<<divUp(n, 256), 256>>>(F.pairOff.p, F.pos.p, numPairs, total, F.inner.p, F.lo.p, F.cnt.p, F.leafCnt.p, n);
+            F.flags.release(); F.pos.release();
+        }
+        SDFB_CUDA(cudaGetLastError());
+        // leaves -> this level's pool segment
+        F.poolTotal = scan64.run(F.leafCnt.p, F.poolOff.p, n, true);
+        F.leafPool.alloc(F.poolTotal + 1);
+        leafPoolKernel<<<n, 128>>>(F.nodeIdx.p, F.inner.p, F.lo.p, F.cnt.p, F.poolOff.p, F.dec.p, F.leafPool.p, s.dLeafLo.p, s.dLeafCnt.p);
+        // next frontier
+        const uint32_t nInner = scan32.run(F.inner.p, F.childSlot.p, n);
+        if (uint64_t(nInner) * 8 > numNodes) throw Error(SDFB200_ERR_IO, "exact octree node array contains a cycle");
+        std::unique_ptr<Frontier> N(new Frontier());
+        N->n = nInner * 8;
+        if (N->n) {
+            N->nodeIdx.alloc(N->n); N->parentLo.alloc(N->n); N->parentCnt.alloc(N->n);
+            nextFrontierKernel<<<divUp(n, 256), 256>>>(pv, F.nodeIdx.p, F.inner.p, F.childSlot.p, F.lo.p, F.cnt.p, n, N->nodeIdx.p,
+                                                       N->parentLo.p, N->parentCnt.p);
+        }
+        SDFB_CUDA(cudaGetLastError());
+        poolTotal += F.poolTotal;
+        if (fr.size() >= 2) fr[fr.size() - 2]->dec.release();   // the parent's decoded lists have been consumed
+        fr.emplace_back(std::move(N));
+    }
+    uint32_t hErr = 0;
+    SDFB_CUDA(cudaMemcpy(&hErr, err.p, 4, cudaMemcpyDeviceToHost));
+    if (hErr) throw Error(SDFB200_ERR_IO, std::string("inconsistent ExactOctreeSdf arrays:") + ((hErr & kErrSetRange) ? " set offset out of range" : "") +
+                                              ((hErr & kErrMaskRange) ? " mask offset out of range" : "") +
+                                              ((hErr & kErrTriangle) ? " triangle index out of range" : ""));
+    // concatenate the per-level segments; leafLo of a level's leaves is rebased by the segment start
+    s.dLeafPool.alloc(poolTotal + 1);
+    uint64_t base = 0;
+    for (auto& fp : fr) {
+        Frontier& F = *fp;
+        if (!F.n || !F.poolTotal) continue;
+        SDFB_CUDA(cudaMemcpyAsync(s.dLeafPool.p + base, F.leafPool.p, F.poolTotal * 4, cudaMemcpyDeviceToDevice));
+        if (base) rebaseLeavesKernel<<<divUp(F.n, 256), 256>>>(F.nodeIdx.p, F.inner.p, F.n, base, s.dLeafLo.p);
+        base += F.poolTotal;
+    }
+    SDFB_CUDA(cudaDeviceSynchronize());
+}
+
+void launchExactQuery(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st) {
+    if (n == 0) return;
+    if (!s.dLeafLo.p) throw Error(SDFB200_ERR_CUDA, "ExactOctreeSdf is not resident on a CUDA device");
+    ExactQueryParams q;
+    q.minx = s.boxMin[0]; q.miny = s.boxMin[1]; q.minz = s.boxMin[2];
+    q.maxx = s.boxMax[0]; q.maxy = s.boxMax[1]; q.maxz = s.boxMax[2];
+    q.cell = s.cellSize;
+    q.grid = s.startGridSize;
+    q.outside = sqrtf(3.0f) * (s.boxMax[0] - s.boxMin[0]);   // ExactOctreeSdf.cpp:48
+    const uint32_t grid = uint32_t((n + 255) / 256);
+    if (dGrad)
+        exactQueryKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, dGrad);
+    else
+        exactQueryKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, nullptr);
+    SDFB_CUDA(cudaGetLastError());
+}
+
+}  // namespace sdfb200

@@ -101,6 +101,11 @@ struct sdfb200_sdf {
     sdfb200::DevBuf<uint32_t> dSets;
     sdfb200::DevBuf<uint8_t> dMasks;
     sdfb200::DevBuf<sdfb200::TriData> dTris;
+    // private query-side copies of an EXACT_OCTREE (exact_query.cu): 80-byte triangle frames and the
+    // explicit per-leaf triangle lists decoded from sets + mask chains
+    sdfb200::DevBuf<float4> dFrames;
+    sdfb200::DevBuf<uint64_t> dLeafLo;
+    sdfb200::DevBuf<uint32_t> dLeafCnt, dLeafPool;
     // staging for host-pointer queries
     sdfb200::DevBuf<float> dPts, dDist, dGrad;
     float* hPinned = nullptr;
@@ -129,6 +134,7 @@ void launchOctreeQueryExact(const sdfb200_sdf& s, const float* dXyz, uint64_t n,
 // exact_build.cu / exact_query.cu
 void buildExactOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
                         uint32_t minTris, uint32_t numThreads);
+void prepareExactQuery(sdfb200_sdf& s);
 void launchExactQuery(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
 // bin_io.cpp
 void saveBin(const sdfb200_sdf& s, const char* path);
