@@ -95,19 +95,30 @@ int sdfb200_build_exact(const float* vertices, uint32_t numVertices, const uint3
                         const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
                         uint32_t numThreads, sdfb200_sdf** out);
 
-/* Sharded construction (one process per GPU). rank builds the start-depth voxels v with
- * v % worldSize == rank' under the balanced assignment, and returns a handle that only holds that
- * shard. sdfb200_shard_* export the shard as one flat device buffer for the caller's all-gather
- * (NCCL through torch.distributed); sdfb200_assemble builds the complete structure from the gathered
- * buffers on every rank. */
+/* Sharded construction (one process per GPU). The start-depth voxels ("roots") are the reference's
+ * own task decomposition (src/sdf/OctreeSdfDepthFirst.h:433-469, include/SdfLib/ExactOctreeSdfDepthFirst.h:534-574);
+ * root i of the layout order is built by rank i % worldSize. Protocol, identical on every rank:
+ *   1. sdfb200_build_*_shard      levels + subtree sizes of the own roots (GPU)
+ *   2. sdfb200_shard_sizes        K values per start-grid slot (K = 1 OCTREE: words; K = 3 EXACT: node records, set
+ *                                 words, mask bytes), 0 for roots of other ranks  -> caller all-reduces (SUM)
+ *   3. sdfb200_shard_finish       global offsets from all sizes; own blocks emitted with their FINAL indices (GPU)
+ *   4. sdfb200_shard_words/export flat uint32 payload in a caller-owned DEVICE buffer -> caller all-gathers (NCCL),
+ *                                 every rank's payload at q * strideWords
+ *   5. sdfb200_assemble           block copies into the complete arrays; the handle is then a normal SdfFunction
+ * The collectives themselves stay with the caller (torch.distributed / NCCL in sdflib_b200/sharded.py). */
 int sdfb200_build_octree_shard(const float* vertices, uint32_t numVertices, const uint32_t* indices,
                                uint32_t numIndices, const float* box6, uint32_t depth, uint32_t startDepth,
                                int terminationRule, float param0, float param1, int initAlgorithm,
                                uint32_t numThreads, uint32_t rank, uint32_t worldSize, sdfb200_sdf** out);
+int sdfb200_build_exact_shard(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                              const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
+                              uint32_t numThreads, uint32_t rank, uint32_t worldSize, sdfb200_sdf** out);
+int sdfb200_shard_sizes(const sdfb200_sdf* shard, uint32_t* outSizes, uint64_t capacity, uint64_t* outCount);
+int sdfb200_shard_finish(sdfb200_sdf* shard, const uint32_t* allSizes, uint64_t count);
 int sdfb200_shard_words(const sdfb200_sdf* shard, uint64_t* outWords);
 int sdfb200_shard_export(const sdfb200_sdf* shard, uint32_t* devicePtr, uint64_t capacityWords);
 int sdfb200_assemble(sdfb200_sdf* shard, const uint32_t* gatheredDevicePtr, const uint64_t* wordsPerRank,
-                     uint32_t worldSize);
+                     uint64_t strideWords, uint32_t worldSize);
 
 /* ---- persistence (.bin, cereal PortableBinary layout of the reference) ------------------------ */
 int sdfb200_save(const sdfb200_sdf* sdf, const char* path);

@@ -33,6 +33,7 @@ UNITS = [
     ("mesh_host.cpp", "mesh_host.o", ["-x", "cu"] + NO_FMA),
     ("bin_io.cpp", "bin_io.o", ["-x", "cu"]),
     ("capi.cpp", "capi.o", ["-x", "cu"]),
+    ("shard.cpp", "shard.o", ["-x", "cu"]),
     ("fixtures.cpp", "fixtures.o", ["-x", "cu"] + NO_FMA),
     ("octree_build.cu", "octree_build.o", NO_FMA),
     ("octree_query.cu", "octree_query_fast.o", []),

@@ -107,24 +107,33 @@ int sdfb200_build_octree(const float* vertices, uint32_t numVertices, const uint
                                       param0, param1, initAlgorithm, numThreads, 0, 1, out);
 }
 
-int sdfb200_build_exact(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
-                        const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
-                        uint32_t numThreads, sdfb200_sdf** out) {
+int sdfb200_build_exact_shard(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                              const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
+                              uint32_t numThreads, uint32_t rank, uint32_t worldSize, sdfb200_sdf** out) {
     return guarded([&] {
         if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
         *out = nullptr;
         HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
         checkBox(box6);
+        if (worldSize == 0 || rank >= worldSize) throw Error(SDFB200_ERR_INVALID, "rank/worldSize out of range");
         requireDevice();
         std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
-        buildExactOnDevice(*s, mesh, box6, maxDepth, startDepth, minTrianglesPerNode, numThreads);
+        buildExactOnDevice(*s, mesh, box6, maxDepth, startDepth, minTrianglesPerNode, numThreads, rank, worldSize);
         *out = s.release();
     });
+}
+
+int sdfb200_build_exact(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                        const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
+                        uint32_t numThreads, sdfb200_sdf** out) {
+    return sdfb200_build_exact_shard(vertices, numVertices, indices, numIndices, box6, maxDepth, startDepth, minTrianglesPerNode,
+                                     numThreads, 0, 1, out);
 }
 
 int sdfb200_save(const sdfb200_sdf* sdf, const char* path) {
     return guarded([&] {
         if (!sdf || !path) throw Error(SDFB200_ERR_INVALID, "null argument");
+        if (sdf->isShard) throw Error(SDFB200_ERR_INVALID, "handle is an unassembled shard (sdfb200_assemble not called yet)");
         saveBin(*sdf, path);
     });
 }
@@ -177,6 +186,7 @@ int sdfb200_get_build_stats(const sdfb200_sdf* s, sdfb200_build_stats* o) {
 int sdfb200_get_octree_data(const sdfb200_sdf* s, uint32_t* out, uint64_t capacityWords) {
     return guarded([&] {
         if (!s || !out) throw Error(SDFB200_ERR_INVALID, "null argument");
+        if (s->isShard) throw Error(SDFB200_ERR_INVALID, "handle is an unassembled shard (sdfb200_assemble not called yet)");
         if (capacityWords < s->octree.size()) throw Error(SDFB200_ERR_INVALID, "output buffer too small");
         std::memcpy(out, s->octree.data(), s->octree.size() * sizeof(uint32_t));
     });
@@ -204,6 +214,7 @@ int sdfb200_query(sdfb200_sdf* s, const float* xyz, uint64_t n, float* dist, flo
         if (!s || (n && (!xyz || !dist))) throw Error(SDFB200_ERR_INVALID, "null argument");
         if (n == 0) return;
         if (!s->dOctree.p) throw Error(SDFB200_ERR_CUDA, "structure is not resident on a CUDA device");
+        if (s->isShard) throw Error(SDFB200_ERR_INVALID, "handle is an unassembled shard (sdfb200_assemble not called yet)");
         SDFB_CUDA(cudaSetDevice(s->device));
         cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
         auto launch = [&](const float* dXyz, float* dDist, float* dGrad) {
@@ -225,17 +236,51 @@ int sdfb200_query(sdfb200_sdf* s, const float* xyz, uint64_t n, float* dist, flo
     });
 }
 
-int sdfb200_shard_words(const sdfb200_sdf*, uint64_t*) {
-    setLastError("sharded construction is not built yet");
-    return SDFB200_ERR_UNSUPPORTED;
+int sdfb200_shard_sizes(const sdfb200_sdf* s, uint32_t* outSizes, uint64_t capacity, uint64_t* outCount) {
+    return guarded([&] {
+        if (!s || !outCount) throw Error(SDFB200_ERR_INVALID, "null argument");
+        *outCount = s->shardSizes.size();
+        if (!outSizes) return;   // size query
+        if (capacity < s->shardSizes.size()) throw Error(SDFB200_ERR_INVALID, "output buffer too small");
+        std::memcpy(outSizes, s->shardSizes.data(), s->shardSizes.size() * sizeof(uint32_t));
+    });
 }
-int sdfb200_shard_export(const sdfb200_sdf*, uint32_t*, uint64_t) {
-    setLastError("sharded construction is not built yet");
-    return SDFB200_ERR_UNSUPPORTED;
+
+int sdfb200_shard_finish(sdfb200_sdf* s, const uint32_t* allSizes, uint64_t count) {
+    return guarded([&] {
+        if (!s || !allSizes) throw Error(SDFB200_ERR_INVALID, "null argument");
+        if (!s->build) throw Error(SDFB200_ERR_INVALID, "handle is not a shard in phase 1 (built with worldSize > 1)");
+        if (count != s->shardSizes.size()) throw Error(SDFB200_ERR_INVALID, "size vector length differs from sdfb200_shard_sizes");
+        for (uint64_t i = 0; i < count; i++)
+            if (s->shardSizes[i] && s->shardSizes[i] != allSizes[i])
+                throw Error(SDFB200_ERR_INVALID, "all-reduced sizes disagree with this rank's own roots (ownership overlap?)");
+        SDFB_CUDA(cudaSetDevice(s->device));
+        s->build->finish(*s, allSizes);
+    });
 }
-int sdfb200_assemble(sdfb200_sdf*, const uint32_t*, const uint64_t*, uint32_t) {
-    setLastError("sharded construction is not built yet");
-    return SDFB200_ERR_UNSUPPORTED;
+
+int sdfb200_shard_words(const sdfb200_sdf* s, uint64_t* outWords) {
+    return guarded([&] {
+        if (!s || !outWords) throw Error(SDFB200_ERR_INVALID, "null argument");
+        *outWords = shardPayloadWords(*s);
+    });
+}
+
+int sdfb200_shard_export(const sdfb200_sdf* s, uint32_t* devicePtr, uint64_t capacityWords) {
+    return guarded([&] {
+        if (!s || !devicePtr) throw Error(SDFB200_ERR_INVALID, "null argument");
+        SDFB_CUDA(cudaSetDevice(s->device));
+        shardExport(*s, devicePtr, capacityWords);
+    });
+}
+
+int sdfb200_assemble(sdfb200_sdf* s, const uint32_t* gatheredDevicePtr, const uint64_t* wordsPerRank, uint64_t strideWords,
+                     uint32_t worldSize) {
+    return guarded([&] {
+        if (!s || !gatheredDevicePtr || !wordsPerRank) throw Error(SDFB200_ERR_INVALID, "null argument");
+        SDFB_CUDA(cudaSetDevice(s->device));
+        shardAssemble(*s, gatheredDevicePtr, wordsPerRank, strideWords, worldSize);
+    });
 }
 
 int sdfb200_triangle_data(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices, float* out37) {

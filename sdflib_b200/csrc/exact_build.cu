@@ -573,15 +573,316 @@ struct Level {
     }
 };
 
+__global__ void zeroUnownedKernel(const uint8_t* owned, uint32_t* parentCnt, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !owned[i]) parentCnt[i] = 0u;
+}
+
+struct ExactBuildState : BuildState {
+    std::vector<std::unique_ptr<Level>> levels;
+    uint32_t maxDepth = 0, startDepth = 0, minTris = 0, bitEnc = 0, bits = 0;
+    DevBuf<uint32_t> scalars;   // [0] maxTrianglesInLeafs, [1] maxTrianglesEncodedInLeafs
+    uint32_t numStreams() const override { return 3; }
+
+    void buildLevels(sdfb200_sdf& out, const HostMesh& mesh, uint32_t numThreads, uint32_t rank, uint32_t world) {
+        sdfb200_build_stats& st = out.stats;
+        // ---- serial set-up of the reference, on the host ---------------------------------------------------
+        auto t0 = std::chrono::steady_clock::now();
+        out.tris = computeTriangleData(mesh);
+        const uint32_t nT = uint32_t(out.tris.size());
+        out.bitsPerIndex = uint32_t(int32_t(std::ceil(std::log2(float(nT)))));   // ExactOctreeSdfDepthFirst.h:61
+        bits = out.bitsPerIndex;
+        if (bits == 0 || bits > 31) throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf needs between 2 and 2^31 triangles");
+        std::vector<float4> frames(size_t(nT) * 5);
+        std::vector<uint32_t> all;
+        all.reserve(nT);
+        for (uint32_t t = 0; t < nT; t++) {
+            float tmp[20];
+            std::memcpy(tmp, &out.tris[t], 19 * sizeof(float));
+            tmp[19] = 0.0f;
+            std::memcpy(&frames[size_t(t) * 5], tmp, sizeof(tmp));
+            const f3 nrm = triNormal(out.tris[t]);
+            if (dot3(nrm, nrm) > 1e-3f) all.push_back(t);   // ExactOctreeSdfDepthFirst.h:106 (false for NaN)
+        }
+        st.triangle_data_ms = msSince(t0);
+        t0 = std::chrono::steady_clock::now();
+        DevBuf<f3> dVerts(mesh.nVerts);
+        DevBuf<uint32_t> dIdx(mesh.nIdx), dAll(all.size() + 8);
+        DevBuf<float4> dFrames(frames.size());
+        dVerts.upload(mesh.verts, mesh.nVerts);
+        dIdx.upload(mesh.idx, mesh.nIdx);
+        dFrames.upload(frames.data(), frames.size());
+        dAll.upload(all.data(), all.size());
+        SDFB_CUDA(cudaDeviceSynchronize());
+        st.upload_ms = msSince(t0);
+        const DeviceMesh dmesh{dVerts.p, dIdx.p, nullptr, nullptr, nT};
+
+        t0 = std::chrono::steady_clock::now();
+        const uint32_t d0 = std::min(startDepth, 1u);
+        const f3 boxMin = mk3(out.boxMin[0], out.boxMin[1], out.boxMin[2]);
+        const float boxSize = out.boxMax[0] - out.boxMin[0];
+        levels.resize(maxDepth + 1);
+        ScannerT<uint32_t, uint32_t> scan32;
+        ScannerT<uint32_t, uint64_t> scan64;
+        ScannerT<uint8_t, uint32_t> scanFlags;
+        scalars.alloc(2);
+        SDFB_CUDA(cudaMemset(scalars.p, 0, 8));
+        DevBuf<unsigned long long> best;
+        DevBuf<uint32_t> subdivide, chunks, childIdx, chunkOff, midInfo;
+        DevBuf<float> region;
+        DevBuf<uint8_t> dOwned;
+
+        auto runSample = [&](auto ptsTag, const Level& L, const uint32_t* list, const uint32_t* lo, const uint32_t* cnt,
+                             const uint32_t* chOff, uint32_t nChunks, uint32_t* outInfo) {
+            constexpr int kPts = decltype(ptsTag)::value;
+            const uint64_t nKeys = uint64_t(L.count) * kPts;
+            if (best.n < nKeys) best.alloc(nKeys);
+            fillU64<<<divUp(nKeys, 256), 256>>>(best.p, kNoKey, nKeys);
+            if (nChunks) sampleKernel<kPts><<<nChunks, kSampleThreads>>>(dFrames.p, L.centerHalf.p, list, lo, cnt, chOff, L.count, best.p);
+            resolveKernel<<<divUp(nKeys, 256), 256>>>(best.p, list, lo, kPts, outInfo, nKeys);
+            st.kernel_launches += 3;
+            SDFB_CUDA(cudaGetLastError());
+        };
+
+        {   // seeds at depth d0; corner info = nearest of ALL valid triangles (ExactOctreeSdfDepthFirst.h:113-150)
+            const float h0 = float(0.5f * boxSize * std::pow(0.5f, d0));
+            const f3 c0 = boxMin + mk3(h0, h0, h0);
+            const uint32_t per = 1u << d0;
+            std::vector<float4> ch;
+            std::vector<uint32_t> coord;
+            for (uint32_t k = 0; k < per; k++)
+                for (uint32_t j = 0; j < per; j++)
+                    for (uint32_t i = 0; i < per; i++) {
+                        const f3 c = c0 + (mk3(float(i), float(j), float(k)) * 2.0f) * h0;
+                        ch.push_back(make_float4(c.x, c.y, c.z, h0));
+                        coord.push_back(i | (j << 10) | (k << 20));
+                    }
+            levels[d0].reset(new Level());
+            Level& L = *levels[d0];
+            const uint32_t n = uint32_t(ch.size());
+            L.allocNodes(n, d0);
+            L.centerHalf.upload(ch.data(), n);
+            L.coord.upload(coord.data(), n);
+            std::vector<uint32_t> zero(n, 0u), cntAll(n, uint32_t(all.size())), chOff(n + 1);
+            const uint32_t perNode = divUp(all.size(), kChunk);
+            for (uint32_t i = 0; i <= n; i++) chOff[i] = i * perNode;
+            L.parent.upload(zero.data(), n);
+            L.parentLo.upload(zero.data(), n);
+            L.parentCnt.upload(cntAll.data(), n);
+            chunkOff.alloc(n + 1);
+            chunkOff.upload(chOff.data(), n + 1);
+            runSample(std::integral_constant<int, 8>(), L, dAll.p, L.parentLo.p, L.parentCnt.p, chunkOff.p, n * perNode, L.info.p);
+        }
+
+        for (uint32_t d = d0; d <= maxDepth; d++) {
+            Level& L = *levels[d];
+            const uint32_t* parentList = d == d0 ? dAll.p : levels[d - 1]->list.p;
+            if (d == startDepth) {
+                makePlan(out, L, numThreads, rank, world);
+                if (world > 1) {   // roots of other ranks: empty list -> terminal, nothing below them is built here
+                    dOwned.alloc(L.count);
+                    dOwned.upload(out.plan.owned.data(), L.count);
+                    zeroUnownedKernel<<<divUp(L.count, 256), 256>>>(dOwned.p, L.parentCnt.p, L.count);
+                }
+            }
+            if (L.count == 0) {
+                if (d < maxDepth) { levels[d + 1].reset(new Level()); levels[d + 1]->depth = d + 1; }
+                L.list.alloc(8);
+                continue;
+            }
+            // HOT LOOP A
+            L.numPairs = scan64.run(L.parentCnt.p, L.pairOff.p, L.count, true);
+            // list positions are 32-bit (ScannerT<uint8_t, uint32_t> would wrap silently): bound them by the pair count
+            if (L.numPairs >= (uint64_t(1) << 32)) throw Error(SDFB200_ERR_INVALID, "more than 2^32 (node, triangle) pairs on one octree level");
+            if (region.n < size_t(L.count) * 72) region.alloc(size_t(L.count) * 72);
+            regionKernel<<<divUp(L.count, 4), 256>>>(dFrames.p, L.view(), region.p);
+            L.flags.alloc(L.numPairs + 1);
+            L.pos.alloc(L.numPairs + 1);
+            if (L.numPairs) filterKernel<<<divUp(L.numPairs, 256), 256>>>(dmesh, L.view(), parentList, region.p, L.flags.p, L.numPairs);
+            SDFB_CUDA(cudaGetLastError());
+            L.listTotal = L.numPairs ? scanFlags.run(L.flags.p, L.pos.p, L.numPairs) : 0u;
+            L.list.alloc(size_t(L.listTotal) + 8);   // + 8: the TMA window of the sample kernel may read past the end
+            SDFB_CUDA(cudaMemsetAsync(L.list.p + L.listTotal, 0, 8 * sizeof(uint32_t)));
+            if (L.numPairs) compactKernel<<<divUp(L.numPairs, 256), 256>>>(L.view(), parentList, L.flags.p, L.pos.p, L.list.p, L.numPairs);
+            listRangeKernel<<<divUp(L.count, 256), 256>>>(L.pairOff.p, L.pos.p, L.numPairs, L.listTotal, L.listLo.p, L.listCnt.p, L.count);
+            st.kernel_launches += 10;
+            st.nodes_processed += L.count;
+            st.samples_evaluated += L.numPairs;   // Frank-Wolfe runs
+            // terminal rule
+            subdivide.alloc(L.count); chunks.alloc(L.count); childIdx.alloc(L.count); chunkOff.alloc(size_t(L.count) + 1);
+            decideKernel<<<divUp(L.count, 256), 256>>>(L.listCnt.p, L.count, d, startDepth, maxDepth, minTris, subdivide.p, chunks.p, scalars.p);
+            if (d == maxDepth) { SDFB_CUDA(cudaMemsetAsync(L.childOf.p, 0xFF, size_t(L.count) * 4)); break; }
+            const uint32_t nSub = scan32.run(subdivide.p, childIdx.p, L.count);
+            const uint32_t nChunks = scan32.run(chunks.p, chunkOff.p, L.count, true);
+            // HOT LOOP B
+            midInfo.alloc(size_t(L.count) * 19);
+            runSample(std::integral_constant<int, 19>(), L, L.list.p, L.listLo.p, L.listCnt.p, chunkOff.p, nChunks, midInfo.p);
+            st.leaves += uint64_t(L.listTotal);   // list entries kept at this depth (19 distance evaluations each where subdividing)
+            levels[d + 1].reset(new Level());
+            Level& N = *levels[d + 1];
+            N.allocNodes(nSub * 8, d + 1);
+            childrenKernel<<<divUp(L.count, 4), 256>>>(L.view(), L.coord.p, subdivide.p, childIdx.p, midInfo.p, L.childOf.p, N.centerHalf.p,
+                                                      N.info.p, N.coord.p, N.parent.p, N.parentLo.p, N.parentCnt.p);
+            st.kernel_launches += 8;
+            SDFB_CUDA(cudaGetLastError());
+            if (d + 1 < maxDepth) { L.flags.release(); L.pos.release(); }   // only the flags of levels maxDepth-1 and maxDepth feed the merge
+        }
+        SDFB_CUDA(cudaDeviceSynchronize());
+        st.levels_ms = msSince(t0);
+
+        // ---- post-order merge: levels maxDepth-1, then maxDepth-2 ------------------------------------------------
+        t0 = std::chrono::steady_clock::now();
+        DevBuf<uint8_t> keep;
+        DevBuf<uint32_t> mpos;
+        for (uint32_t d = maxDepth - 1; d + 1 > bitEnc; d--) {
+            Level& L = *levels[d];
+            Level& C = *levels[d + 1];
+            L.mergedLo.alloc(L.count); L.mergedCnt.alloc(L.count);
+            if (L.count == 0) { if (d == 0) break; continue; }
+            L.member.alloc(size_t(L.listTotal) + 1); keep.alloc(size_t(L.listTotal) + 1); mpos.alloc(size_t(L.listTotal) + 1);
+            if (L.listTotal) {
+                MergeChildView cv{C.pairOff.p, C.flags.p, C.pos.p, C.childOf.p, d + 1 == maxDepth ? nullptr : C.member.p};
+                memberKernel<<<divUp(L.listTotal, 256), 256>>>(L.listLo.p, L.childOf.p, L.count, L.listTotal, cv, L.member.p, keep.p);
+                L.mergedTotal = scanFlags.run(keep.p, mpos.p, L.listTotal);
+            }
+            L.mergedList.alloc(size_t(L.mergedTotal) + 1); L.mergedMember.alloc(size_t(L.mergedTotal) + 1);
+            if (L.listTotal) mergeCompactKernel<<<divUp(L.listTotal, 256), 256>>>(L.list.p, L.member.p, mpos.p, L.listTotal, L.mergedList.p, L.mergedMember.p);
+            mergedRangeKernel<<<divUp(L.count, 256), 256>>>(L.listLo.p, L.listCnt.p, mpos.p, L.listTotal, L.mergedTotal, L.mergedLo.p, L.mergedCnt.p, L.count);
+            st.kernel_launches += 6;
+            SDFB_CUDA(cudaGetLastError());
+            if (d == 0) break;
+        }
+
+        // ---- layout: subtree sizes bottom-up ------------------------------------------------------------------------
+        for (int d = int(maxDepth); d >= int(startDepth); d--) {
+            Level& L = *levels[size_t(d)];
+            L.allocLayout();
+            if (!L.count) continue;
+            LayoutView next = d < int(maxDepth) ? levels[size_t(d) + 1]->layout() : LayoutView{};
+            sizesKernel<<<divUp(L.count, 256), 256>>>(L.layout(), next, L.count, uint32_t(d), maxDepth, bitEnc, bits, scalars.p + 1);
+            st.kernel_launches++;
+        }
+        Level& R = *levels[startDepth];
+        const uint32_t G3 = out.plan.G3;
+        std::vector<uint32_t> rootNodes(G3), rootSets(G3), rootMasks(G3);
+        R.nodeCnt.download(rootNodes.data(), G3);
+        R.setWords.download(rootSets.data(), G3);
+        R.maskBytes.download(rootMasks.data(), G3);
+        SDFB_CUDA(cudaDeviceSynchronize());
+        out.shardSizes.assign(size_t(G3) * 3, 0u);
+        for (uint32_t r = 0; r < G3; r++) {
+            if (!out.plan.owned[r]) continue;
+            const size_t s = size_t(out.plan.rootSlot[r]) * 3;
+            out.shardSizes[s] = rootNodes[r];
+            out.shardSizes[s + 1] = rootSets[r];
+            out.shardSizes[s + 2] = rootMasks[r];
+        }
+        st.layout_ms = msSince(t0);
+    }
+
+    void makePlan(sdfb200_sdf& out, Level& R, uint32_t numThreads, uint32_t rank, uint32_t world) {
+        const uint32_t G = uint32_t(out.startGridSize), G3 = G * G * G;
+        if (R.count != G3) throw Error(SDFB200_ERR_INVALID, "internal: start level is not a full grid");
+        std::vector<float4> rootCH(G3);
+        std::vector<uint32_t> rootCoord(G3);
+        R.centerHalf.download(rootCH.data(), G3);
+        R.coord.download(rootCoord.data(), G3);
+        SDFB_CUDA(cudaDeviceSynchronize());
+        out.plan = makeRootPlan(rootCH.data(), rootCoord.data(), G, startDepth, out.boxMin, out.cellSize, numThreads, rank, world);
+    }
+
+    void finish(sdfb200_sdf& out, const uint32_t* allSizesBySlot) override {
+        sdfb200_build_stats& st = out.stats;
+        auto t0 = std::chrono::steady_clock::now();
+        const RootPlan& plan = out.plan;
+        const uint32_t G3 = plan.G3;
+        Level& R = *levels[startDepth];
+        out.streams.assign(3, ShardStream());
+        const uint32_t elem[3] = {8, 4, 1};
+        for (int k = 0; k < 3; k++) { out.streams[k].elemBytes = elem[k]; out.streams[k].rootBase.resize(G3); out.streams[k].rootSize.resize(G3); }
+        std::vector<uint32_t> nodeBase(G3), setBase(G3), maskBase(G3);
+        uint64_t run[3] = {G3, 0, 0};
+        for (uint32_t i = 0; i < G3; i++) {
+            const uint32_t r = plan.order[i];
+            for (int k = 0; k < 3; k++) {
+                out.streams[k].rootBase[r] = run[k];
+                out.streams[k].rootSize[r] = allSizesBySlot[size_t(plan.rootSlot[r]) * 3 + k];
+            }
+            nodeBase[r] = plan.owned[r] ? uint32_t(run[0]) : kNone;
+            setBase[r] = uint32_t(run[1]);
+            maskBase[r] = uint32_t(run[2]);
+            for (int k = 0; k < 3; k++) run[k] += out.streams[k].rootSize[r];
+        }
+        const uint64_t rn = run[0], rs = run[1], rm = run[2];
+        if (rn > uint64_t(kExactIndexMask) || rs > 0xFFFFFFFFull || rm > 0xFFFFFFFFull)
+            throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf exceeds the 32-bit index space of its arrays");
+        R.slot.upload(plan.rootSlot.data(), G3);
+        R.nodeBase.upload(nodeBase.data(), G3);
+        R.setBase.upload(setBase.data(), G3);
+        R.maskBase.upload(maskBase.data(), G3);
+        for (uint32_t d = startDepth; d < maxDepth; d++) {
+            Level& L = *levels[d];
+            Level& N = *levels[d + 1];
+            if (!L.count) continue;
+            offsetsKernel<<<divUp(L.count, 256), 256>>>(L.layout(), N.layout(), L.count);
+            st.kernel_launches++;
+        }
+        // ---- emit -----------------------------------------------------------------------------------------------------
+        out.dOctree.alloc(size_t(rn) * 2);
+        out.dSets.alloc(size_t(rs) + 1);
+        out.dMasks.alloc(size_t(rm) + 8);
+        out.streams[0].dBase = reinterpret_cast<uint8_t*>(out.dOctree.p);
+        out.streams[1].dBase = reinterpret_cast<uint8_t*>(out.dSets.p);
+        out.streams[2].dBase = reinterpret_cast<uint8_t*>(out.dMasks.p);
+        SDFB_CUDA(cudaMemsetAsync(out.dOctree.p, 0, size_t(rn) * 8));
+        SDFB_CUDA(cudaMemsetAsync(out.dSets.p, 0, (size_t(rs) + 1) * 4));
+        SDFB_CUDA(cudaMemsetAsync(out.dMasks.p, 0, size_t(rm) + 8));
+        for (uint32_t d = startDepth; d <= maxDepth; d++) {
+            Level& L = *levels[d];
+            if (!L.count) continue;
+            emitNodesKernel<<<divUp(L.count, 256), 256>>>(L.layout(), L.count, d, bitEnc, out.dOctree.p);
+            if (d <= bitEnc) {
+                emitSetsKernel<<<L.count, 128>>>(L.layout(), L.count, d, bitEnc, bits, L.list.p, L.listLo.p, L.listCnt.p, false, out.dSets.p);
+                if (d == bitEnc)
+                    emitSetsKernel<<<L.count, 128>>>(L.layout(), L.count, d, bitEnc, bits, L.mergedList.p, L.mergedLo.p, L.mergedCnt.p, true, out.dSets.p);
+            }
+            if (d >= bitEnc && d < maxDepth) emitMasksKernel<<<L.count, 128>>>(L.layout(), L.count, L.mergedLo.p, L.mergedMember.p, out.dMasks.p);
+            st.kernel_launches += 4;
+            SDFB_CUDA(cudaGetLastError());
+        }
+        scalars.download(out.shardScalars, 2);
+        SDFB_CUDA(cudaDeviceSynchronize());
+        st.layout_ms += msSince(t0);
+        levels.clear();   // release the builder's working set before the query-side pool is allocated
+        out.octree.resize(size_t(rn) * 2);
+        out.sets.resize(size_t(rs));
+        out.masks.resize(size_t(rm));
+        out.dTris.alloc(out.tris.size());
+        out.dTris.upload(out.tris.data(), out.tris.size());
+        if (plan.world == 1) {
+            out.maxTrisInLeafs = out.shardScalars[0];
+            out.maxTrisEncoded = out.shardScalars[1];
+            t0 = std::chrono::steady_clock::now();
+            out.dOctree.download(out.octree.data(), out.octree.size());
+            out.dSets.download(out.sets.data(), out.sets.size());
+            out.dMasks.download(out.masks.data(), out.masks.size());
+            SDFB_CUDA(cudaDeviceSynchronize());
+            st.download_ms = msSince(t0);
+            prepareExactQuery(out);
+            out.isShard = false;
+        }
+        SDFB_CUDA(cudaDeviceSynchronize());
+    }
+};
+
 }  // namespace
 
 void cubifyBox(sdfb200_sdf& s, const float* box6, uint32_t startDepth);   // octree_build.cu
 
 void buildExactOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
-                        uint32_t minTris, uint32_t numThreads) {
+                        uint32_t minTris, uint32_t numThreads, uint32_t rank, uint32_t world) {
     const auto tStart = std::chrono::steady_clock::now();
-    sdfb200_build_stats& st = out.stats;
-    st = sdfb200_build_stats{};
+    out.stats = sdfb200_build_stats{};
     if (maxDepth > 10) throw Error(SDFB200_ERR_INVALID, "octree depth > 10 is not supported (node coordinates are packed in 3x10 bits)");
     if (maxDepth < startDepth + 2)
         throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf needs maxDepth >= startDepth + 2 (the reference dereferences a null node otherwise)");
@@ -590,268 +891,16 @@ void buildExactOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box
     out.startDepth = startDepth;
     out.minTrisInLeafs = minTris;
     out.bitEncodingStartDepth = maxDepth - 2;
+    out.slotWords = 2;
     cubifyBox(out, box6, startDepth);
     SDFB_CUDA(cudaGetDevice(&out.device));
-    const uint32_t bitEnc = maxDepth - 2;
-
-    // ---- serial set-up of the reference, on the host ---------------------------------------------------
-    auto t0 = std::chrono::steady_clock::now();
-    out.tris = computeTriangleData(mesh);
-    const uint32_t nT = uint32_t(out.tris.size());
-    out.bitsPerIndex = uint32_t(int32_t(std::ceil(std::log2(float(nT)))));   // ExactOctreeSdfDepthFirst.h:61
-    const uint32_t bits = out.bitsPerIndex;
-    if (bits == 0 || bits > 31) throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf needs between 2 and 2^31 triangles");
-    std::vector<float4> frames(size_t(nT) * 5);
-    std::vector<uint32_t> all;
-    all.reserve(nT);
-    for (uint32_t t = 0; t < nT; t++) {
-        float tmp[20];
-        std::memcpy(tmp, &out.tris[t], 19 * sizeof(float));
-        tmp[19] = 0.0f;
-        std::memcpy(&frames[size_t(t) * 5], tmp, sizeof(tmp));
-        const f3 nrm = triNormal(out.tris[t]);
-        if (dot3(nrm, nrm) > 1e-3f) all.push_back(t);   // ExactOctreeSdfDepthFirst.h:106 (false for NaN)
-    }
-    st.triangle_data_ms = msSince(t0);
-    t0 = std::chrono::steady_clock::now();
-    DevBuf<f3> dVerts(mesh.nVerts);
-    DevBuf<uint32_t> dIdx(mesh.nIdx), dAll(all.size() + 8);
-    DevBuf<float4> dFrames(frames.size());
-    dVerts.upload(mesh.verts, mesh.nVerts);
-    dIdx.upload(mesh.idx, mesh.nIdx);
-    dFrames.upload(frames.data(), frames.size());
-    dAll.upload(all.data(), all.size());
-    SDFB_CUDA(cudaDeviceSynchronize());
-    st.upload_ms = msSince(t0);
-    const DeviceMesh dmesh{dVerts.p, dIdx.p, nullptr, nullptr, nT};
-
-    t0 = std::chrono::steady_clock::now();
-    const uint32_t d0 = std::min(startDepth, 1u);
-    const f3 boxMin = mk3(out.boxMin[0], out.boxMin[1], out.boxMin[2]);
-    const float boxSize = out.boxMax[0] - out.boxMin[0];
-    std::vector<std::unique_ptr<Level>> levels(maxDepth + 1);
-    ScannerT<uint32_t, uint32_t> scan32;
-    ScannerT<uint32_t, uint64_t> scan64;
-    ScannerT<uint8_t, uint32_t> scanFlags;
-    DevBuf<uint32_t> scalars(2);   // [0] maxTrianglesInLeafs, [1] maxTrianglesEncodedInLeafs
-    SDFB_CUDA(cudaMemset(scalars.p, 0, 8));
-    DevBuf<unsigned long long> best;
-    DevBuf<uint32_t> subdivide, chunks, childIdx, chunkOff, midInfo;
-    DevBuf<float> region;
-
-    auto runSample = [&](auto ptsTag, const Level& L, const uint32_t* list, const uint32_t* lo, const uint32_t* cnt,
-                         const uint32_t* chOff, uint32_t nChunks, uint32_t* outInfo) {
-        constexpr int kPts = decltype(ptsTag)::value;
-        const uint64_t nKeys = uint64_t(L.count) * kPts;
-        if (best.n < nKeys) best.alloc(nKeys);
-        fillU64<<<divUp(nKeys, 256), 256>>>(best.p, kNoKey, nKeys);
-        if (nChunks) sampleKernel<kPts><<<nChunks, kSampleThreads>>>(dFrames.p, L.centerHalf.p, list, lo, cnt, chOff, L.count, best.p);
-        resolveKernel<<<divUp(nKeys, 256), 256>>>(best.p, list, lo, kPts, outInfo, nKeys);
-        st.kernel_launches += 3;
-        SDFB_CUDA(cudaGetLastError());
-    };
-
-    {   // seeds at depth d0; corner info = nearest of ALL valid triangles (ExactOctreeSdfDepthFirst.h:113-150)
-        const float h0 = float(0.5f * boxSize * std::pow(0.5f, d0));
-        const f3 c0 = boxMin + mk3(h0, h0, h0);
-        const uint32_t per = 1u << d0;
-        std::vector<float4> ch;
-        std::vector<uint32_t> coord;
-        for (uint32_t k = 0; k < per; k++)
-            for (uint32_t j = 0; j < per; j++)
-                for (uint32_t i = 0; i < per; i++) {
-                    const f3 c = c0 + (mk3(float(i), float(j), float(k)) * 2.0f) * h0;
-                    ch.push_back(make_float4(c.x, c.y, c.z, h0));
-                    coord.push_back(i | (j << 10) | (k << 20));
-                }
-        levels[d0].reset(new Level());
-        Level& L = *levels[d0];
-        const uint32_t n = uint32_t(ch.size());
-        L.allocNodes(n, d0);
-        L.centerHalf.upload(ch.data(), n);
-        L.coord.upload(coord.data(), n);
-        std::vector<uint32_t> zero(n, 0u), cntAll(n, uint32_t(all.size())), chOff(n + 1);
-        const uint32_t perNode = divUp(all.size(), kChunk);
-        for (uint32_t i = 0; i <= n; i++) chOff[i] = i * perNode;
-        L.parent.upload(zero.data(), n);
-        L.parentLo.upload(zero.data(), n);
-        L.parentCnt.upload(cntAll.data(), n);
-        chunkOff.alloc(n + 1);
-        chunkOff.upload(chOff.data(), n + 1);
-        runSample(std::integral_constant<int, 8>(), L, dAll.p, L.parentLo.p, L.parentCnt.p, chunkOff.p, n * perNode, L.info.p);
-        st.samples_evaluated += uint64_t(n) * 8;
-    }
-
-    for (uint32_t d = d0; d <= maxDepth; d++) {
-        Level& L = *levels[d];
-        const uint32_t* parentList = d == d0 ? dAll.p : levels[d - 1]->list.p;
-        if (L.count == 0) {
-            if (d < maxDepth) { levels[d + 1].reset(new Level()); levels[d + 1]->depth = d + 1; }
-            L.list.alloc(8);
-            continue;
-        }
-        // HOT LOOP A
-        L.numPairs = scan64.run(L.parentCnt.p, L.pairOff.p, L.count, true);
-        // list positions are 32-bit (ScannerT<uint8_t, uint32_t> would wrap silently): bound them by the pair count
-        if (L.numPairs >= (uint64_t(1) << 32)) throw Error(SDFB200_ERR_INVALID, "more than 2^32 (node, triangle) pairs on one octree level");
-        if (region.n < size_t(L.count) * 72) region.alloc(size_t(L.count) * 72);
-        regionKernel<<<divUp(L.count, 4), 256>>>(dFrames.p, L.view(), region.p);
-        L.flags.alloc(L.numPairs + 1);
-        L.pos.alloc(L.numPairs + 1);
-        if (L.numPairs) filterKernel<<<divUp(L.numPairs, 256), 256>>>(dmesh, L.view(), parentList, region.p, L.flags.p, L.numPairs);
-        SDFB_CUDA(cudaGetLastError());
-        L.listTotal = L.numPairs ? scanFlags.run(L.flags.p, L.pos.p, L.numPairs) : 0u;
-        L.list.alloc(size_t(L.listTotal) + 8);   // + 8: the TMA window of the sample kernel may read past the end
-        SDFB_CUDA(cudaMemsetAsync(L.list.p + L.listTotal, 0, 8 * sizeof(uint32_t)));
-        if (L.numPairs) compactKernel<<<divUp(L.numPairs, 256), 256>>>(L.view(), parentList, L.flags.p, L.pos.p, L.list.p, L.numPairs);
-        listRangeKernel<<<divUp(L.count, 256), 256>>>(L.pairOff.p, L.pos.p, L.numPairs, L.listTotal, L.listLo.p, L.listCnt.p, L.count);
-        st.kernel_launches += 10;
-        st.nodes_processed += L.count;
-        st.samples_evaluated += L.numPairs;   // Frank-Wolfe runs
-        // terminal rule
-        subdivide.alloc(L.count); chunks.alloc(L.count); childIdx.alloc(L.count); chunkOff.alloc(size_t(L.count) + 1);
-        decideKernel<<<divUp(L.count, 256), 256>>>(L.listCnt.p, L.count, d, startDepth, maxDepth, minTris, subdivide.p, chunks.p, scalars.p);
-        if (d == maxDepth) { SDFB_CUDA(cudaMemsetAsync(L.childOf.p, 0xFF, size_t(L.count) * 4)); break; }
-        const uint32_t nSub = scan32.run(subdivide.p, childIdx.p, L.count);
-        const uint32_t nChunks = scan32.run(chunks.p, chunkOff.p, L.count, true);
-        // HOT LOOP B
-        midInfo.alloc(size_t(L.count) * 19);
-        runSample(std::integral_constant<int, 19>(), L, L.list.p, L.listLo.p, L.listCnt.p, chunkOff.p, nChunks, midInfo.p);
-        levels[d + 1].reset(new Level());
-        Level& N = *levels[d + 1];
-        N.allocNodes(nSub * 8, d + 1);
-        childrenKernel<<<divUp(L.count, 4), 256>>>(L.view(), L.coord.p, subdivide.p, childIdx.p, midInfo.p, L.childOf.p, N.centerHalf.p,
-                                                  N.info.p, N.coord.p, N.parent.p, N.parentLo.p, N.parentCnt.p);
-        st.kernel_launches += 8;
-        SDFB_CUDA(cudaGetLastError());
-        if (d + 1 < maxDepth) { L.flags.release(); L.pos.release(); }   // only the flags of levels maxDepth-1 and maxDepth feed the merge
-    }
-    SDFB_CUDA(cudaDeviceSynchronize());
-    st.levels_ms = msSince(t0);
-
-    // ---- post-order merge: levels maxDepth-1, then maxDepth-2 ------------------------------------------------
-    t0 = std::chrono::steady_clock::now();
-    DevBuf<uint8_t> keep;
-    DevBuf<uint32_t> mpos;
-    for (uint32_t d = maxDepth - 1; d + 1 > bitEnc; d--) {
-        Level& L = *levels[d];
-        Level& C = *levels[d + 1];
-        L.mergedLo.alloc(L.count); L.mergedCnt.alloc(L.count);
-        if (L.count == 0) continue;
-        L.member.alloc(size_t(L.listTotal) + 1); keep.alloc(size_t(L.listTotal) + 1); mpos.alloc(size_t(L.listTotal) + 1);
-        if (L.listTotal) {
-            MergeChildView cv{C.pairOff.p, C.flags.p, C.pos.p, C.childOf.p, d + 1 == maxDepth ? nullptr : C.member.p};
-            memberKernel<<<divUp(L.listTotal, 256), 256>>>(L.listLo.p, L.childOf.p, L.count, L.listTotal, cv, L.member.p, keep.p);
-            L.mergedTotal = scanFlags.run(keep.p, mpos.p, L.listTotal);
-        }
-        L.mergedList.alloc(size_t(L.mergedTotal) + 1); L.mergedMember.alloc(size_t(L.mergedTotal) + 1);
-        if (L.listTotal) mergeCompactKernel<<<divUp(L.listTotal, 256), 256>>>(L.list.p, L.member.p, mpos.p, L.listTotal, L.mergedList.p, L.mergedMember.p);
-        mergedRangeKernel<<<divUp(L.count, 256), 256>>>(L.listLo.p, L.listCnt.p, mpos.p, L.listTotal, L.mergedTotal, L.mergedLo.p, L.mergedCnt.p, L.count);
-        st.kernel_launches += 6;
-        SDFB_CUDA(cudaGetLastError());
-        if (d == 0) break;
-    }
-
-    // ---- layout: subtree sizes bottom-up ------------------------------------------------------------------------
-    for (int d = int(maxDepth); d >= int(startDepth); d--) {
-        Level& L = *levels[size_t(d)];
-        L.allocLayout();
-        if (!L.count) continue;
-        LayoutView next = d < int(maxDepth) ? levels[size_t(d) + 1]->layout() : LayoutView{};
-        sizesKernel<<<divUp(L.count, 256), 256>>>(L.layout(), next, L.count, uint32_t(d), maxDepth, bitEnc, bits, scalars.p + 1);
-        st.kernel_launches++;
-    }
-    Level& R = *levels[startDepth];
-    const uint32_t G = uint32_t(out.startGridSize), G3 = G * G * G;
-    if (R.count != G3) throw Error(SDFB200_ERR_INVALID, "internal: start level is not a full grid");
-    std::vector<float4> rootCH(G3);
-    std::vector<uint32_t> rootCoord(G3), rootNodes(G3), rootSets(G3), rootMasks(G3);
-    R.centerHalf.download(rootCH.data(), G3);
-    R.coord.download(rootCoord.data(), G3);
-    R.nodeCnt.download(rootNodes.data(), G3);
-    R.setWords.download(rootSets.data(), G3);
-    R.maskBytes.download(rootMasks.data(), G3);
-    SDFB_CUDA(cudaDeviceSynchronize());
-    std::vector<uint32_t> rootSlot(G3), order(G3), nodeBase(G3), setBase(G3), maskBase(G3);
-    std::vector<uint64_t> key(G3);
-    for (uint32_t r = 0; r < G3; r++) {
-        const f3 f = (mk3(rootCH[r].x, rootCH[r].y, rootCH[r].z) - boxMin) / out.cellSize;   // ExactOctreeSdfDepthFirst.h:505-506
-        const int x = int(std::floor(f.x)), y = int(std::floor(f.y)), z = int(std::floor(f.z));
-        rootSlot[r] = uint32_t(z * int(G * G) + y * int(G) + x);
-        if (numThreads >= 2) key[r] = rootSlot[r];   // per-voxel sub-octrees concatenated in start-grid order (:576-622)
-        else {                                       // one global stack: virtual levels popped 7-first (:497-511)
-            const uint32_t ix = rootCoord[r] & 1023u, iy = (rootCoord[r] >> 10) & 1023u, iz = rootCoord[r] >> 20;
-            uint64_t k = 0;
-            for (int b = int(startDepth) - 1; b >= 0; b--) {
-                const uint32_t c = ((ix >> b) & 1u) | (((iy >> b) & 1u) << 1) | (((iz >> b) & 1u) << 2);
-                k = (k << 3) | (7u - c);
-            }
-            key[r] = k;
-        }
-        order[r] = r;
-    }
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
-    uint64_t rn = G3, rs = 0, rm = 0;
-    for (uint32_t i = 0; i < G3; i++) {
-        const uint32_t r = order[i];
-        nodeBase[r] = uint32_t(rn); rn += rootNodes[r];
-        setBase[r] = uint32_t(rs);  rs += rootSets[r];
-        maskBase[r] = uint32_t(rm); rm += rootMasks[r];
-    }
-    if (rn > uint64_t(kExactIndexMask) || rs > 0xFFFFFFFFull || rm > 0xFFFFFFFFull)
-        throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf exceeds the 32-bit index space of its arrays");
-    R.slot.upload(rootSlot.data(), G3);
-    R.nodeBase.upload(nodeBase.data(), G3);
-    R.setBase.upload(setBase.data(), G3);
-    R.maskBase.upload(maskBase.data(), G3);
-    for (uint32_t d = startDepth; d < maxDepth; d++) {
-        Level& L = *levels[d];
-        Level& N = *levels[d + 1];
-        if (!L.count) continue;
-        offsetsKernel<<<divUp(L.count, 256), 256>>>(L.layout(), N.layout(), L.count);
-        st.kernel_launches++;
-    }
-    // ---- emit -----------------------------------------------------------------------------------------------------
-    out.dOctree.alloc(size_t(rn) * 2);
-    out.dSets.alloc(size_t(rs) + 1);
-    out.dMasks.alloc(size_t(rm) + 8);
-    SDFB_CUDA(cudaMemsetAsync(out.dOctree.p, 0, size_t(rn) * 8));
-    SDFB_CUDA(cudaMemsetAsync(out.dSets.p, 0, (size_t(rs) + 1) * 4));
-    SDFB_CUDA(cudaMemsetAsync(out.dMasks.p, 0, size_t(rm) + 8));
-    for (uint32_t d = startDepth; d <= maxDepth; d++) {
-        Level& L = *levels[d];
-        if (!L.count) continue;
-        emitNodesKernel<<<divUp(L.count, 256), 256>>>(L.layout(), L.count, d, bitEnc, out.dOctree.p);
-        if (d <= bitEnc) {
-            emitSetsKernel<<<L.count, 128>>>(L.layout(), L.count, d, bitEnc, bits, L.list.p, L.listLo.p, L.listCnt.p, false, out.dSets.p);
-            if (d == bitEnc)
-                emitSetsKernel<<<L.count, 128>>>(L.layout(), L.count, d, bitEnc, bits, L.mergedList.p, L.mergedLo.p, L.mergedCnt.p, true, out.dSets.p);
-        }
-        if (d >= bitEnc && d < maxDepth) emitMasksKernel<<<L.count, 128>>>(L.layout(), L.count, L.mergedLo.p, L.mergedMember.p, out.dMasks.p);
-        st.kernel_launches += 4;
-        SDFB_CUDA(cudaGetLastError());
-    }
-    uint32_t scalarOut[2];
-    scalars.download(scalarOut, 2);
-    SDFB_CUDA(cudaDeviceSynchronize());
-    out.maxTrisInLeafs = scalarOut[0];
-    out.maxTrisEncoded = scalarOut[1];
-    st.layout_ms = msSince(t0);
-
-    t0 = std::chrono::steady_clock::now();
-    out.octree.resize(size_t(rn) * 2);
-    out.sets.resize(size_t(rs));
-    out.masks.resize(size_t(rm));
-    out.dOctree.download(out.octree.data(), out.octree.size());
-    out.dSets.download(out.sets.data(), out.sets.size());
-    out.dMasks.download(out.masks.data(), out.masks.size());
-    out.dTris.alloc(out.tris.size());
-    out.dTris.upload(out.tris.data(), out.tris.size());
-    SDFB_CUDA(cudaDeviceSynchronize());
-    st.download_ms = msSince(t0);
-    levels.clear();   // release the builder's working set before the query-side pool is allocated
-    prepareExactQuery(out);
-    st.total_ms = msSince(tStart);
+    std::unique_ptr<ExactBuildState> state(new ExactBuildState());
+    state->maxDepth = maxDepth; state->startDepth = startDepth; state->minTris = minTris; state->bitEnc = maxDepth - 2;
+    out.isShard = true;
+    state->buildLevels(out, mesh, numThreads, rank, world);
+    if (world == 1) state->finish(out, out.shardSizes.data());
+    else out.build = std::move(state);
+    out.stats.total_ms = msSince(tStart);
 }
 
 }  // namespace sdfb200

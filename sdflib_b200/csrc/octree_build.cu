@@ -438,125 +438,20 @@ void cubifyBox(sdfb200_sdf& s, const float* box6, uint32_t startDepth) {   // Oc
     s.cellSize = maxSize / float(s.startGridSize);
 }
 
-void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
-                         int rule, float param0, float param1, uint32_t numThreads, uint32_t rank, uint32_t world) {
-    const auto tStart = std::chrono::steady_clock::now();
-    sdfb200_build_stats& st = out.stats;
-    st = sdfb200_build_stats{};
-    if (depth > 10) throw Error(SDFB200_ERR_INVALID, "octree depth > 10 is not supported (node coordinates are packed in 3x10 bits)");
-    if (startDepth > depth) throw Error(SDFB200_ERR_INVALID, "startDepth must not exceed depth");
-    if (rule == SDFB200_RULE_SIMPSONS) throw Error(SDFB200_ERR_UNSUPPORTED, "SIMPSONS_RULE is not built yet");
-    out.format = SDFB200_FORMAT_OCTREE;
-    out.maxDepth = depth;
-    cubifyBox(out, box6, startDepth);
-    SDFB_CUDA(cudaGetDevice(&out.device));
-    uploadHermite();
-
-    // serial set-up steps of the reference, on the host (see mesh_host.h)
-    auto t0 = std::chrono::steady_clock::now();
-    std::vector<TriData> tris = computeTriangleData(mesh);
-    st.triangle_data_ms = msSince(t0);
-    t0 = std::chrono::steady_clock::now();
-    std::vector<BvhNode> bvh = buildBvh(mesh);
-    st.bvh_ms = msSince(t0);
-    t0 = std::chrono::steady_clock::now();
-    MeshOnDevice dm;
-    uploadMesh(dm, mesh, tris, &bvh);
-    SDFB_CUDA(cudaDeviceSynchronize());
-    st.upload_ms = msSince(t0);
-    const DeviceMesh dmesh = dm.view();
-
-    t0 = std::chrono::steady_clock::now();
-    const uint32_t d0 = std::min(startDepth, 1u);
-    const f3 boxMin = mk3(out.boxMin[0], out.boxMin[1], out.boxMin[2]);
-    const float boxSize = out.boxMax[0] - out.boxMin[0];
-    std::vector<std::unique_ptr<Level>> levels(depth + 1);
-
-    {   // seeds at depth d0 (OctreeSdfDepthFirst.h:113-135); centres in the reference's float arithmetic
-        const float h0 = float(0.5f * boxSize * std::pow(0.5f, d0));
-        const f3 c0 = boxMin + mk3(h0, h0, h0);
-        const uint32_t per = 1u << d0;
-        std::vector<float4> ch;
-        std::vector<uint32_t> coord;
-        for (uint32_t k = 0; k < per; k++)
-            for (uint32_t j = 0; j < per; j++)
-                for (uint32_t i = 0; i < per; i++) {
-                    const f3 c = c0 + (mk3(float(i), float(j), float(k)) * 2.0f) * h0;
-                    ch.push_back(make_float4(c.x, c.y, c.z, h0));
-                    coord.push_back(i | (j << 10) | (k << 20));
-                }
-        levels[d0].reset(new Level());
-        Level& L = *levels[d0];
-        L.alloc(uint32_t(ch.size()));
-        L.centerHalf.upload(ch.data(), ch.size());
-        L.coord.upload(coord.data(), coord.size());
-        seedCornersKernel<<<divUp(L.count * 8, 64), 64>>>(dmesh, L.centerHalf.p, L.corners.p, L.count);
-        st.kernel_launches++;
-        st.samples_evaluated += L.count * 8;
-    }
-
-    // sharding: at the start depth keep only the voxels this rank owns (others are marked unowned later)
-    DevBuf<float4> mids;
-    DevBuf<uint32_t> flags, scan;
-    Scanner scanner;
-    for (uint32_t d = d0; d < depth; d++) {
-        Level& L = *levels[d];
-        if (L.count == 0) { levels[d + 1].reset(new Level()); continue; }
-        mids.alloc(size_t(L.count) * 19);
-        flags.alloc(L.count);
-        scan.alloc(L.count);
-        const uint32_t grid = divUp(L.count, kWarpsPerCta);
-        if (d >= startDepth)
-            levelSampleKernel<true><<<grid, kWarpsPerCta * 32>>>(dmesh, L.view(), mids.p, flags.p, rule, param0 * param0, param1);
-        else
-            levelSampleKernel<false><<<grid, kWarpsPerCta * 32>>>(dmesh, L.view(), mids.p, flags.p, rule, 0.0f, 0.0f);
-        const uint32_t nSubdivide = scanner.run(flags.p, scan.p, L.count);
-        st.kernel_launches += 4;
-        st.samples_evaluated += uint64_t(L.count) * 19;
-        levels[d + 1].reset(new Level());
-        Level& N = *levels[d + 1];
-        N.alloc(nSubdivide * 8);
-        emitChildrenKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), mids.p, flags.p, scan.p, L.childOf.p, N.centerHalf.p,
-                                                        N.corners.p, N.coord.p);
-        st.kernel_launches++;
-        st.nodes_processed += L.count;
-    }
-    SDFB_CUDA(cudaDeviceSynchronize());
-    st.levels_ms = msSince(t0);
-
-    // ---- layout --------------------------------------------------------------------------------
-    t0 = std::chrono::steady_clock::now();
-    {
-        Level& D = *levels[depth];
-        if (D.count) { leafSizesKernel<<<divUp(D.count, 256), 256>>>(D.words.p, D.childOf.p, D.count); st.kernel_launches++; }
-        st.nodes_processed += D.count;
-    }
-    for (int d = int(depth) - 1; d >= int(startDepth); d--) {
-        Level& L = *levels[size_t(d)];
-        if (!L.count) continue;
-        subtreeSizesKernel<<<divUp(L.count, 256), 256>>>(L.childOf.p, levels[size_t(d) + 1]->words.p, L.words.p, L.count);
-        st.kernel_launches++;
-    }
-    // roots = nodes of the start depth. Their order in the output follows the reference's drivers:
-    //   numThreads < 2 : one global stack, virtual levels popped 7-first (OctreeSdfDepthFirst.h:397-416)
-    //   numThreads >= 2: sub-octrees concatenated in start-grid index order (:471-503)
-    Level& R = *levels[startDepth];
-    const uint32_t G = uint32_t(out.startGridSize), G3 = G * G * G;
-    if (R.count != G3) throw Error(SDFB200_ERR_INVALID, "internal: start level is not a full grid");
-    std::vector<float4> rootCH(G3);
-    std::vector<uint32_t> rootCoord(G3), rootWords(G3);
-    R.centerHalf.download(rootCH.data(), G3);
-    R.coord.download(rootCoord.data(), G3);
-    R.words.download(rootWords.data(), G3);
-    SDFB_CUDA(cudaDeviceSynchronize());
-    std::vector<uint32_t> rootSlot(G3), order(G3), rootBlock(G3);
+RootPlan makeRootPlan(const float4* rootCH, const uint32_t* rootCoord, uint32_t G, uint32_t startDepth, const float* boxMin3,
+                      float cellSize, uint32_t numThreads, uint32_t rank, uint32_t world) {
+    RootPlan plan;
+    const uint32_t G3 = G * G * G;
+    plan.G3 = G3; plan.world = world; plan.rank = rank;
+    plan.rootSlot.resize(G3); plan.order.resize(G3); plan.owned.assign(G3, 0); plan.ownerOf.resize(G3);
+    const f3 boxMin = mk3(boxMin3[0], boxMin3[1], boxMin3[2]);
     std::vector<uint64_t> key(G3);
     for (uint32_t r = 0; r < G3; r++) {
-        const f3 f = (mk3(rootCH[r].x, rootCH[r].y, rootCH[r].z) - boxMin) / out.cellSize;   // :408-409
+        const f3 f = (mk3(rootCH[r].x, rootCH[r].y, rootCH[r].z) - boxMin) / cellSize;   // OctreeSdfDepthFirst.h:408-409
         const int x = int(std::floor(f.x)), y = int(std::floor(f.y)), z = int(std::floor(f.z));
-        rootSlot[r] = uint32_t(z * int(G * G) + y * int(G) + x);
-        if (numThreads >= 2) key[r] = rootSlot[r];
-        else {
+        plan.rootSlot[r] = uint32_t(z * int(G * G) + y * int(G) + x);
+        if (numThreads >= 2) key[r] = plan.rootSlot[r];   // sub-octrees concatenated in start-grid order (:471-503)
+        else {                                            // one global stack, virtual levels popped 7-first (:397-416)
             const uint32_t ix = rootCoord[r] & 1023u, iy = (rootCoord[r] >> 10) & 1023u, iz = rootCoord[r] >> 20;
             uint64_t k = 0;
             for (int b = int(startDepth) - 1; b >= 0; b--) {
@@ -565,70 +460,238 @@ void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* bo
             }
             key[r] = k;
         }
-        order[r] = r;
+        plan.order[r] = r;
     }
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
-    // ownership (sharded build): the i-th root in layout order belongs to rank i % world. Every rank
-    // computes the same global offsets, but only needs the sizes of its own roots here; unowned roots
-    // get kNoChild as block and are skipped by the emit pass. Global offsets need all sizes, which a
-    // shard obtains from its peers (see sdfb200_build_octree_shard); with world == 1 they are local.
-    out.shardVoxelWords.assign(G3, 0u);
-    uint64_t running = G3;
-    std::vector<uint8_t> owned(G3, 0);
+    std::sort(plan.order.begin(), plan.order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
     for (uint32_t i = 0; i < G3; i++) {
-        const uint32_t r = order[i];
-        owned[r] = (i % world) == rank;
-        rootBlock[r] = uint32_t(running);
-        running += rootWords[r];
-        out.shardVoxelWords[rootSlot[r]] = rootWords[r];
+        const uint32_t r = plan.order[i];
+        plan.ownerOf[r] = i % world;
+        plan.owned[r] = (i % world) == rank;
     }
-    if (running > uint64_t(kOctIndexMask)) throw Error(SDFB200_ERR_INVALID, "octree exceeds the 30-bit index space of OctreeNode");
-    const uint64_t totalWords = running;
-    if (world > 1) for (uint32_t r = 0; r < G3; r++) if (!owned[r]) rootBlock[r] = kNoChild;
-    R.slot.upload(rootSlot.data(), G3);
-    R.block.upload(rootBlock.data(), G3);
-    for (uint32_t d = startDepth; d < depth; d++) {
-        Level& L = *levels[d];
-        Level& N = *levels[d + 1];
-        if (!L.count || !N.count) continue;
-        childOffsetsKernel<<<divUp(L.count, 256), 256>>>(L.childOf.p, L.block.p, N.words.p, N.slot.p, N.block.p, L.count);
-        st.kernel_launches++;
+    return plan;
+}
+
+namespace {
+
+__global__ void maskUnownedKernel(const uint8_t* owned, uint32_t* subdivide, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !owned[i]) subdivide[i] = 0u;
+}
+
+struct OctreeBuildState : BuildState {
+    std::vector<std::unique_ptr<Level>> levels;
+    uint32_t depth = 0, startDepth = 0;
+    uint32_t numStreams() const override { return 1; }
+
+    // phase 1: candidate levels top-down (only the subtrees of the own roots below the start depth), subtree sizes
+    void buildLevels(sdfb200_sdf& out, const HostMesh& mesh, int rule, float param0, float param1, uint32_t numThreads,
+                     uint32_t rank, uint32_t world) {
+        sdfb200_build_stats& st = out.stats;
+        // serial set-up steps of the reference, on the host (see mesh_host.h)
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<TriData> tris = computeTriangleData(mesh);
+        st.triangle_data_ms = msSince(t0);
+        t0 = std::chrono::steady_clock::now();
+        std::vector<BvhNode> bvh = buildBvh(mesh);
+        st.bvh_ms = msSince(t0);
+        t0 = std::chrono::steady_clock::now();
+        MeshOnDevice dm;
+        uploadMesh(dm, mesh, tris, &bvh);
+        SDFB_CUDA(cudaDeviceSynchronize());
+        st.upload_ms = msSince(t0);
+        const DeviceMesh dmesh = dm.view();
+
+        t0 = std::chrono::steady_clock::now();
+        const uint32_t d0 = std::min(startDepth, 1u);
+        const f3 boxMin = mk3(out.boxMin[0], out.boxMin[1], out.boxMin[2]);
+        const float boxSize = out.boxMax[0] - out.boxMin[0];
+        levels.resize(depth + 1);
+        {   // seeds at depth d0 (OctreeSdfDepthFirst.h:113-135); centres in the reference's float arithmetic
+            const float h0 = float(0.5f * boxSize * std::pow(0.5f, d0));
+            const f3 c0 = boxMin + mk3(h0, h0, h0);
+            const uint32_t per = 1u << d0;
+            std::vector<float4> ch;
+            std::vector<uint32_t> coord;
+            for (uint32_t k = 0; k < per; k++)
+                for (uint32_t j = 0; j < per; j++)
+                    for (uint32_t i = 0; i < per; i++) {
+                        const f3 c = c0 + (mk3(float(i), float(j), float(k)) * 2.0f) * h0;
+                        ch.push_back(make_float4(c.x, c.y, c.z, h0));
+                        coord.push_back(i | (j << 10) | (k << 20));
+                    }
+            levels[d0].reset(new Level());
+            Level& L = *levels[d0];
+            L.alloc(uint32_t(ch.size()));
+            L.centerHalf.upload(ch.data(), ch.size());
+            L.coord.upload(coord.data(), coord.size());
+            seedCornersKernel<<<divUp(L.count * 8, 64), 64>>>(dmesh, L.centerHalf.p, L.corners.p, L.count);
+            st.kernel_launches++;
+            st.samples_evaluated += L.count * 8;
+        }
+        DevBuf<float4> mids;
+        DevBuf<uint32_t> flags, scan;
+        DevBuf<uint8_t> dOwned;
+        Scanner scanner;
+        for (uint32_t d = d0; d <= depth; d++) {
+            Level& L = *levels[d];
+            if (d == startDepth) makePlan(out, L, numThreads, rank, world);
+            if (d == depth) break;
+            if (L.count == 0) { levels[d + 1].reset(new Level()); continue; }
+            mids.alloc(size_t(L.count) * 19);
+            flags.alloc(L.count);
+            scan.alloc(L.count);
+            const uint32_t grid = divUp(L.count, kWarpsPerCta);
+            if (d >= startDepth)
+                levelSampleKernel<true><<<grid, kWarpsPerCta * 32>>>(dmesh, L.view(), mids.p, flags.p, rule, param0 * param0, param1);
+            else
+                levelSampleKernel<false><<<grid, kWarpsPerCta * 32>>>(dmesh, L.view(), mids.p, flags.p, rule, 0.0f, 0.0f);
+            if (d == startDepth && world > 1) {   // the roots of other ranks are not refined here
+                dOwned.alloc(L.count);
+                dOwned.upload(out.plan.owned.data(), L.count);
+                maskUnownedKernel<<<divUp(L.count, 256), 256>>>(dOwned.p, flags.p, L.count);
+            }
+            const uint32_t nSubdivide = scanner.run(flags.p, scan.p, L.count);
+            st.kernel_launches += 4;
+            st.samples_evaluated += uint64_t(L.count) * 19;
+            levels[d + 1].reset(new Level());
+            Level& N = *levels[d + 1];
+            N.alloc(nSubdivide * 8);
+            emitChildrenKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), mids.p, flags.p, scan.p, L.childOf.p, N.centerHalf.p,
+                                                            N.corners.p, N.coord.p);
+            st.kernel_launches++;
+            st.nodes_processed += L.count;
+        }
+        SDFB_CUDA(cudaDeviceSynchronize());
+        st.levels_ms = msSince(t0);
+
+        // subtree sizes, bottom-up
+        t0 = std::chrono::steady_clock::now();
+        {
+            Level& D = *levels[depth];
+            if (D.count) { leafSizesKernel<<<divUp(D.count, 256), 256>>>(D.words.p, D.childOf.p, D.count); st.kernel_launches++; }
+            st.nodes_processed += D.count;
+        }
+        for (int d = int(depth) - 1; d >= int(startDepth); d--) {
+            Level& L = *levels[size_t(d)];
+            if (!L.count) continue;
+            subtreeSizesKernel<<<divUp(L.count, 256), 256>>>(L.childOf.p, levels[size_t(d) + 1]->words.p, L.words.p, L.count);
+            st.kernel_launches++;
+        }
+        Level& R = *levels[startDepth];
+        const uint32_t G3 = out.plan.G3;
+        std::vector<uint32_t> rootWords(G3);
+        R.words.download(rootWords.data(), G3);
+        SDFB_CUDA(cudaDeviceSynchronize());
+        out.shardSizes.assign(G3, 0u);
+        for (uint32_t r = 0; r < G3; r++)
+            if (out.plan.owned[r]) out.shardSizes[out.plan.rootSlot[r]] = rootWords[r];
+        st.layout_ms = msSince(t0);
     }
-    out.dOctree.alloc(totalWords);
-    SDFB_CUDA(cudaMemsetAsync(out.dOctree.p, 0, totalWords * sizeof(uint32_t)));
-    DevBuf<uint32_t> scalars(2);
-    const uint32_t scalarInit[2] = {0u, 0xFFFFFFFFu};
-    scalars.upload(scalarInit, 2);
-    for (uint32_t d = startDepth; d <= depth; d++) {
-        Level& L = *levels[d];
-        if (!L.count) continue;
-        emitWordsKernel<<<divUp(L.count, kWarpsPerCta), kWarpsPerCta * 32>>>(L.view(), L.childOf.p, L.slot.p, L.block.p, out.dOctree.p, d,
-                                                                              scalars.p, scalars.p + 1);
-        st.kernel_launches++;
+
+    void makePlan(sdfb200_sdf& out, Level& R, uint32_t numThreads, uint32_t rank, uint32_t world) {
+        const uint32_t G = uint32_t(out.startGridSize), G3 = G * G * G;
+        if (R.count != G3) throw Error(SDFB200_ERR_INVALID, "internal: start level is not a full grid");
+        std::vector<float4> rootCH(G3);
+        std::vector<uint32_t> rootCoord(G3);
+        R.centerHalf.download(rootCH.data(), G3);
+        R.coord.download(rootCoord.data(), G3);
+        SDFB_CUDA(cudaDeviceSynchronize());
+        out.plan = makeRootPlan(rootCH.data(), rootCoord.data(), G, startDepth, out.boxMin, out.cellSize, numThreads, rank, world);
     }
-    uint32_t scalarOut[2];
-    scalars.download(scalarOut, 2);
-    SDFB_CUDA(cudaDeviceSynchronize());
-    st.layout_ms = msSince(t0);
-    {
-        float vr;
-        std::memcpy(&vr, &scalarOut[0], 4);
-        out.valueRange = vr;
-        const uint32_t o = scalarOut[1];
-        const uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
-        float mb;
-        std::memcpy(&mb, &bits, 4);
-        out.minBorderValue = (o == 0xFFFFFFFFu) ? INFINITY : mb;
+
+    // phase 2: global offsets, node words + leaf blocks of the own roots at their final positions
+    void finish(sdfb200_sdf& out, const uint32_t* allSizesBySlot) override {
+        sdfb200_build_stats& st = out.stats;
+        auto t0 = std::chrono::steady_clock::now();
+        const RootPlan& plan = out.plan;
+        const uint32_t G3 = plan.G3;
+        Level& R = *levels[startDepth];
+        std::vector<uint32_t> rootBlock(G3);
+        out.streams.assign(1, ShardStream());
+        ShardStream& S = out.streams[0];
+        S.elemBytes = 4; S.rootBase.resize(G3); S.rootSize.resize(G3);
+        uint64_t running = G3;
+        for (uint32_t i = 0; i < G3; i++) {
+            const uint32_t r = plan.order[i];
+            S.rootBase[r] = running;
+            S.rootSize[r] = allSizesBySlot[plan.rootSlot[r]];
+            rootBlock[r] = plan.owned[r] ? uint32_t(running) : kNoChild;
+            running += S.rootSize[r];
+        }
+        if (running > uint64_t(kOctIndexMask)) throw Error(SDFB200_ERR_INVALID, "octree exceeds the 30-bit index space of OctreeNode");
+        const uint64_t totalWords = running;
+        R.slot.upload(plan.rootSlot.data(), G3);
+        R.block.upload(rootBlock.data(), G3);
+        for (uint32_t d = startDepth; d < depth; d++) {
+            Level& L = *levels[d];
+            Level& N = *levels[d + 1];
+            if (!L.count || !N.count) continue;
+            childOffsetsKernel<<<divUp(L.count, 256), 256>>>(L.childOf.p, L.block.p, N.words.p, N.slot.p, N.block.p, L.count);
+            st.kernel_launches++;
+        }
+        out.dOctree.alloc(totalWords);
+        S.dBase = reinterpret_cast<uint8_t*>(out.dOctree.p);
+        SDFB_CUDA(cudaMemsetAsync(out.dOctree.p, 0, totalWords * sizeof(uint32_t)));
+        DevBuf<uint32_t> scalars(2);
+        const uint32_t scalarInit[2] = {0u, 0xFFFFFFFFu};
+        scalars.upload(scalarInit, 2);
+        for (uint32_t d = startDepth; d <= depth; d++) {
+            Level& L = *levels[d];
+            if (!L.count) continue;
+            emitWordsKernel<<<divUp(L.count, kWarpsPerCta), kWarpsPerCta * 32>>>(L.view(), L.childOf.p, L.slot.p, L.block.p, out.dOctree.p, d,
+                                                                                  scalars.p, scalars.p + 1);
+            st.kernel_launches++;
+        }
+        scalars.download(out.shardScalars, 2);
+        SDFB_CUDA(cudaDeviceSynchronize());
+        st.layout_ms += msSince(t0);
+        levels.clear();
+        if (plan.world == 1) {
+            finalizeOctreeScalars(out);
+            t0 = std::chrono::steady_clock::now();
+            out.octree.resize(totalWords);
+            out.dOctree.download(out.octree.data(), totalWords);
+            SDFB_CUDA(cudaDeviceSynchronize());
+            st.download_ms = msSince(t0);
+            out.isShard = false;
+        }
     }
-    t0 = std::chrono::steady_clock::now();
-    out.octree.resize(totalWords);
-    out.dOctree.download(out.octree.data(), totalWords);
-    SDFB_CUDA(cudaDeviceSynchronize());
-    st.download_ms = msSince(t0);
-    out.isShard = world > 1;
-    out.shardRank = rank;
-    out.shardWorld = world;
-    st.total_ms = msSince(tStart);
+};
+
+}  // namespace
+
+void finalizeOctreeScalars(sdfb200_sdf& s) {
+    float vr;
+    std::memcpy(&vr, &s.shardScalars[0], 4);
+    s.valueRange = vr;
+    const uint32_t o = s.shardScalars[1];
+    const uint32_t bits = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    float mb;
+    std::memcpy(&mb, &bits, 4);
+    s.minBorderValue = (o == 0xFFFFFFFFu) ? INFINITY : mb;
+}
+
+void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+                         int rule, float param0, float param1, uint32_t numThreads, uint32_t rank, uint32_t world) {
+    const auto tStart = std::chrono::steady_clock::now();
+    out.stats = sdfb200_build_stats{};
+    if (depth > 10) throw Error(SDFB200_ERR_INVALID, "octree depth > 10 is not supported (node coordinates are packed in 3x10 bits)");
+    if (startDepth > depth) throw Error(SDFB200_ERR_INVALID, "startDepth must not exceed depth");
+    if (rule == SDFB200_RULE_SIMPSONS) throw Error(SDFB200_ERR_UNSUPPORTED, "SIMPSONS_RULE is not built yet");
+    out.format = SDFB200_FORMAT_OCTREE;
+    out.maxDepth = depth;
+    out.slotWords = 1;
+    cubifyBox(out, box6, startDepth);
+    SDFB_CUDA(cudaGetDevice(&out.device));
+    uploadHermite();
+    std::unique_ptr<OctreeBuildState> state(new OctreeBuildState());
+    state->depth = depth;
+    state->startDepth = startDepth;
+    out.isShard = true;
+    state->buildLevels(out, mesh, rule, param0, param1, numThreads, rank, world);
+    if (world == 1) state->finish(out, out.shardSizes.data());
+    else out.build = std::move(state);
+    out.stats.total_ms = msSince(tStart);
 }
 
 void nearestTriangleOnDevice(const HostMesh& mesh, const float* xyz, uint64_t n, uint32_t* outTri) {

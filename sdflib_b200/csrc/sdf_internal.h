@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -70,6 +71,36 @@ struct MeshOnDevice {
     DeviceMesh view() const { return DeviceMesh{verts.p, idx.p, tris.p, bvh.p, numTriangles}; }
 };
 
+// ---- sharded construction: state shared by both builders ---------------------------------
+// Roots = nodes of the start depth. Their order in the output arrays follows the reference's drivers
+// (numThreads < 2: one global stack, virtual levels popped 7-first; numThreads >= 2: start-grid order);
+// root i of that order is built by rank i % world. Identical on every rank.
+struct RootPlan {
+    uint32_t G3 = 0, world = 1, rank = 0;
+    std::vector<uint32_t> rootSlot;   // by root index (position in the start-depth level): start-grid slot
+    std::vector<uint32_t> order;      // layout order -> root index
+    std::vector<uint8_t> owned;       // by root index: built by this rank
+    std::vector<uint32_t> ownerOf;    // by root index
+};
+RootPlan makeRootPlan(const float4* rootCenterHalf, const uint32_t* rootCoord, uint32_t G, uint32_t startDepth, const float* boxMin,
+                      float cellSize, uint32_t numThreads, uint32_t rank, uint32_t world);
+
+// One output array of a structure, as the shard exporter / assembler sees it.
+struct ShardStream {
+    uint8_t* dBase = nullptr;          // device array
+    uint32_t elemBytes = 4;
+    std::vector<uint64_t> rootBase;    // by root index: first element of the root's block
+    std::vector<uint32_t> rootSize;    // by root index: elements in the root's block (all ranks' roots)
+};
+
+// Builder state kept alive between the phases of a sharded build (levels stay on the device).
+struct BuildState {
+    virtual ~BuildState() {}
+    virtual uint32_t numStreams() const = 0;
+    // phase 2: global offsets from every root's sizes (numStreams() values per start-grid slot), emit own words
+    virtual void finish(sdfb200_sdf& out, const uint32_t* allSizesBySlot) = 0;
+};
+
 // octree node word encoding (reference: OctreeSdf::OctreeNode, include/SdfLib/OctreeSdf.h:39-98)
 constexpr uint32_t kLeafBit = 1u << 31;
 constexpr uint32_t kOctIndexMask = ~(3u << 30);
@@ -110,11 +141,14 @@ struct sdfb200_sdf {
     sdfb200::DevBuf<float> dPts, dDist, dGrad;
     float* hPinned = nullptr;
     size_t hPinnedFloats = 0;
-    // sharded build
-    bool isShard = false;
-    uint32_t shardRank = 0, shardWorld = 1;
-    sdfb200::DevBuf<uint32_t> dShardPayload;
-    std::vector<uint32_t> shardVoxelWords;   // per start voxel: subtree words (0 when not owned)
+    // sharded build: phase state, root plan, per-slot sizes of the own roots, streams for export / assembly
+    bool isShard = false;          // true until sdfb200_assemble completed the structure
+    std::unique_ptr<sdfb200::BuildState> build;
+    sdfb200::RootPlan plan;
+    std::vector<uint32_t> shardSizes;          // numStreams values per start-grid slot, 0 for roots of other ranks
+    std::vector<sdfb200::ShardStream> streams;
+    uint32_t slotWords = 1;                    // words of one start-slot record (OCTREE 1, EXACT 2)
+    uint32_t shardScalars[2] = {0, 0};         // OCTREE: valueRange bits / ordered minBorder; EXACT: max leaf / max encoded
     sdfb200_build_stats stats = {};
 
     ~sdfb200_sdf() { if (hPinned) cudaFreeHost(hPinned); }
@@ -123,8 +157,15 @@ struct sdfb200_sdf {
 namespace sdfb200 {
 
 // octree_build.cu
+// Builders: with world == 1 the structure is complete on return; with world > 1 only phase 1 (levels + sizes of
+// the own roots) has run and out.build holds the state for finish().
 void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
                          int rule, float param0, float param1, uint32_t numThreads, uint32_t rank, uint32_t world);
+void finalizeOctreeScalars(sdfb200_sdf& s);   // shardScalars -> valueRange / minBorderValue
+// shard.cpp
+uint64_t shardPayloadWords(const sdfb200_sdf& s);
+void shardExport(const sdfb200_sdf& s, uint32_t* dDst, uint64_t capacityWords);
+void shardAssemble(sdfb200_sdf& s, const uint32_t* dGathered, const uint64_t* wordsPerRank, uint64_t strideWords, uint32_t world);
 void nearestTriangleOnDevice(const HostMesh& mesh, const float* xyz, uint64_t n, uint32_t* outTri);
 void pointTriangleOnDevice(const float* tri37, const float* v123, const float* xyz, uint64_t n, int mode, float* outDist,
                            float* outGrad);
@@ -133,7 +174,7 @@ void launchOctreeQueryFast(const sdfb200_sdf& s, const float* dXyz, uint64_t n, 
 void launchOctreeQueryExact(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
 // exact_build.cu / exact_query.cu
 void buildExactOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
-                        uint32_t minTris, uint32_t numThreads);
+                        uint32_t minTris, uint32_t numThreads, uint32_t rank, uint32_t world);
 void prepareExactQuery(sdfb200_sdf& s);
 void launchExactQuery(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
 // bin_io.cpp
