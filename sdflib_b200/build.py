@@ -39,9 +39,8 @@ UNITS = [
     ("octree_query.cu", "octree_query_fast.o", []),
     ("octree_query.cu", "octree_query_exact.o", ["-DSDFB_QUERY_EXACT"] + NO_FMA),
 ]
-for optional in ("exact_build.cu", "exact_query.cu", "exact_stub.cu", "unity_abi.cpp"):
-    if os.path.exists(os.path.join(CSRC, optional)):
-        UNITS.append((optional, optional.rsplit(".", 1)[0] + ".o", (["-x", "cu"] if optional.endswith(".cpp") else []) + NO_FMA))
+UNITS += [("exact_build.cu", "exact_build.o", NO_FMA), ("exact_query.cu", "exact_query.o", NO_FMA)]
+UNITY_LIB = os.path.join(HERE, "libSdfLibUnity.so")   # the reference's Unity plugin exports on top of the C-ABI
 
 
 def _nvcc():
@@ -95,6 +94,14 @@ def build(force=False, verbose=True):
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link of libsdfb200.so failed")
+    unity_src = os.path.join(CSRC, "unity_abi.cpp")
+    if force or _stale(UNITY_LIB, [unity_src, LIB] + headers):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-std=c++17", "-O2", "-fPIC", "-shared", unity_src, "-o", UNITY_LIB, "-L" + HERE, "-lsdfb200", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link of libSdfLibUnity.so failed")
     return LIB
 
 
