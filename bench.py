@@ -16,6 +16,12 @@ A step = one pass of getDistance over the whole 16.7 M-point grid.
 The working set (201 MB points + 67 MB distances + 82.5 MB structure) exceeds the 126 MB L2, so successive
 steps cannot be served from cache ("inputs larger than L2").
 
+Besides the headline line the same JSON object carries the other half of BASELINE.json's metric ("octree build sec"):
+  build.octree_c2 / build.exact_c3 : wall-clock seconds of the OctreeSdf (C2) and ExactOctreeSdf (C3: depth 7, minTri 128)
+          constructors through the public API; with N > 1 the builds are SHARDED over start-depth voxels
+          (sdflib_b200.sharded: size all-reduce + one NCCL all-gather), seconds = max over ranks
+  exact_query : ExactOctreeSdf bulk getDistance over the same 256^3 grid, device-resident
+
 --impl reference times the UNMODIFIED reference (oracle/_ref/libsdfref.so: OctreeSdf built by its own
 OpenMP builder, getDistance driven from an `omp parallel for` over all host threads) on the same config.
 """
@@ -34,6 +40,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(mesh="M1 displaced icosphere, 327680 triangles (Armadillo-class, synthetic)", depth=8, start_depth=3,
                 threshold=1e-3, algorithm="NO_CONTINUITY", grid=256)
+EXACT = dict(depth=7, start_depth=3, min_triangles=128)   # BASELINE.json configs[2] ("C3"), same mesh
 METRIC = "sdf_queries_per_sec_256cubed_grid"
 UNIT = "queries/s"
 
@@ -46,6 +53,16 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture of this same command (profiles/query_kernel_traffic.json); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "query_kernel_traffic.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -108,6 +125,11 @@ def run_reference(args):
     v, i, box = build_inputs()
     sdf = ref.build_octree(v, i, box, WORKLOAD["depth"], WORKLOAD["start_depth"], WORKLOAD["threshold"], 1, max(cores, 2))
     build_s = sdf.build_seconds
+    exact_build_s = None
+    if not args.no_exact_reference:
+        ex = ref.build_exact(v, i, box, EXACT["depth"], EXACT["start_depth"], EXACT["min_triangles"], max(cores, 2))
+        exact_build_s = ex.build_seconds
+        ex.close()
     area = sdf.sample_area()
     # bounded sample of the workload: every 8th point of the 256^3 cell-centre grid (2.1 M queries) per step
     n = WORKLOAD["grid"]
@@ -127,6 +149,8 @@ def run_reference(args):
                              "sample": f"every 8th point of the 256^3 grid ({len(pts)} queries) x {args.steps} steps, omp parallel for over getDistance",
                              "build_s": build_s, "build_threads": max(cores, 2)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "build": {"octree_c2": {"seconds": build_s, "threads": max(cores, 2)},
+                      "exact_c3": {"seconds": exact_build_s, "threads": max(cores, 2), "config": EXACT}},
             "build_s": build_s}
     print(json.dumps(line))
 
@@ -149,15 +173,52 @@ def run_ours(args):
 
     v, i, box = build_inputs()
     mesh, bb = S.Mesh(v, i), S.BoundingBox(box[:3], box[3:])
-    t0 = time.perf_counter()
-    sdf = S.OctreeSdf(mesh, bb, WORKLOAD["depth"], WORKLOAD["start_depth"], WORKLOAD["threshold"], S.OctreeSdf.NO_CONTINUITY, 2)
-    build_first_s = time.perf_counter() - t0
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed_build(make):
+        """(object, seconds): wall clock around the constructor, barrier on both sides, max over ranks."""
+        sync_all()
+        t0 = time.perf_counter()
+        obj = make()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return obj, float(t.item())
+
+    if world > 1:
+        from sdflib_b200 import sharded
+        make_oct = lambda: sharded.build_octree_sharded(mesh, bb, WORKLOAD["depth"], WORKLOAD["start_depth"], WORKLOAD["threshold"], numThreads=2)
+        make_ex = lambda: sharded.build_exact_sharded(mesh, bb, EXACT["depth"], EXACT["start_depth"], EXACT["min_triangles"], numThreads=2)
+    else:
+        make_oct = lambda: S.OctreeSdf(mesh, bb, WORKLOAD["depth"], WORKLOAD["start_depth"], WORKLOAD["threshold"], S.OctreeSdf.NO_CONTINUITY, 2)
+        make_ex = lambda: S.ExactOctreeSdf(mesh, bb, EXACT["depth"], EXACT["start_depth"], EXACT["min_triangles"], 2)
+    sdf, build_first_s = timed_build(make_oct)
     sdf.close()
-    t0 = time.perf_counter()
-    sdf = S.OctreeSdf(mesh, bb, WORKLOAD["depth"], WORKLOAD["start_depth"], WORKLOAD["threshold"], S.OctreeSdf.NO_CONTINUITY, 2)
-    build_s = time.perf_counter() - t0
+    builds = []
+    for _ in range(3):
+        sdf, t = timed_build(make_oct)
+        builds.append(t)
+        if _ < 2:
+            sdf.close()
+    build_s = min(builds)
     stats = sdf.build_stats()
     info = sdf.info()
+    exact, _t = timed_build(make_ex)
+    exact.close()
+    ex_builds = []
+    for _ in range(3):
+        exact, t = timed_build(make_ex)
+        ex_builds.append(t)
+        if _ < 2:
+            exact.close()
+    exact_build_s = min(ex_builds)
+    exact_stats = exact.build_stats()
+    exact_info = exact.info()
     area = sdf.getSampleArea().as_array()
     n = WORKLOAD["grid"]
     host_pts = meshes.cell_centre_grid(area, n)
@@ -210,6 +271,25 @@ def run_ours(args):
     e2e_value = world * nq * e2e_steps / float(e2e_s.item())
     e2e_ok = bool(np.array_equal(np_out, out.cpu().numpy()))
 
+    # ExactOctreeSdf bulk queries on the same grid (device-resident), a handful of steps
+    ex_out = torch.empty(nq, dtype=torch.float32, device="cuda")
+    ex_steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        exact.getDistance(pts, out=ex_out)
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record(stream)
+    for _ in range(ex_steps):
+        exact.getDistance(pts, out=ex_out)
+    x1.record(stream)
+    barrier()
+    ex_ms = torch.tensor([x0.elapsed_time(x1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ex_ms, op=dist.ReduceOp.MAX)
+    ex_ms_step = float(ex_ms.item()) / ex_steps
+    # the exact field and the tri-cubic approximation of the same mesh must agree to the octree's error threshold
+    approx_vs_exact = float((out - ex_out).abs().max().item())
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         ms_step = ms_total / args.steps
@@ -223,11 +303,19 @@ def run_ours(args):
                            "parallelism": f"replicated structure, {world} independent query shards"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nq * 12), "d2h_bytes_per_step": int(nq * 4),
                         "steps": e2e_steps, "matches_device_run": e2e_ok},
-                "gpu_launches": args.steps,
+                "gpu_launches": args.steps,   # one octreeQueryKernel launch per timed step (value region)
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src, "kernel": "octreeQueryKernel<false>",
+                             "traffic": measured_traffic(), "peak_source": peak_src, "kernel": "octreeQueryKernel<false>",
                              "algorithmic_bytes_per_launch": int(algo_bytes)},
-                "build_s": build_s, "build_first_call_s": build_first_s, "build_stats_ms": stats,
+                "build": {"scaling": "strong (one mesh, start-depth voxels sharded over the ranks)" if world > 1 else "single GPU",
+                          "octree_c2": {"seconds": build_s, "first_call_seconds": build_first_s, "all_seconds": builds, "stats_ms_rank0": stats},
+                          "exact_c3": {"seconds": exact_build_s, "all_seconds": ex_builds, "config": EXACT, "stats_ms_rank0": exact_stats,
+                                       "nodes": int(exact_info.octree_words), "set_words": int(exact_info.triangle_sets_words),
+                                       "mask_bytes": int(exact_info.triangle_masks_bytes),
+                                       "max_triangles_in_leafs": int(exact_info.max_triangles_in_leafs)}},
+                "exact_query": {"value": world * nq / (ex_ms_step * 1e-3), "unit": UNIT, "ms_per_step": ex_ms_step, "steps": ex_steps,
+                                "max_abs_difference_to_octree_sdf": approx_vs_exact},
+                "build_s": build_s,
                 "clocks": clocks, "checksum": checksum}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sdf, area)
@@ -268,6 +356,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exact-reference", action="store_true", help="reference arm: skip the (tens of seconds) ExactOctreeSdf build")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     if a.impl == "reference":

@@ -1,0 +1,23 @@
+"""Small driver for ncu captures (one GPU): runs ONE build or ONE query pass of the bench workloads.
+    python scripts/profile_kernels.py exact_build | octree_build | exact_query | octree_query"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import sdflib_b200 as S
+from sdflib_b200 import meshes
+
+what = sys.argv[1]
+v, i = meshes.config_mesh("M1")
+box = meshes.bounding_box_with_margin(v)
+mesh, bb = S.Mesh(v, i), S.BoundingBox(box[:3], box[3:])
+if what.startswith("exact"):
+    sdf = S.ExactOctreeSdf(mesh, bb, 7, 3, 128, 2)
+else:
+    sdf = S.OctreeSdf(mesh, bb, 8, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 2)
+if what.endswith("query"):
+    pts = torch.from_numpy(meshes.cell_centre_grid(sdf.getSampleArea().as_array(), 256)).cuda()
+    out = torch.empty(len(pts), dtype=torch.float32, device="cuda")
+    for _ in range(3):
+        sdf.getDistance(pts, out=out)
+    torch.cuda.synchronize()
+print("done", what)

@@ -34,6 +34,7 @@ UNITS = [
     ("bin_io.cpp", "bin_io.o", ["-x", "cu"]),
     ("capi.cpp", "capi.o", ["-x", "cu"]),
     ("shard.cpp", "shard.o", ["-x", "cu"]),
+    ("host_mem.cpp", "host_mem.o", ["-x", "cu"]),
     ("fixtures.cpp", "fixtures.o", ["-x", "cu"] + NO_FMA),
     ("octree_build.cu", "octree_build.o", NO_FMA),
     ("octree_query.cu", "octree_query_fast.o", []),

@@ -25,7 +25,8 @@ template <class T> void putArray(std::ostream& os, const T* p, uint64_t n) {
     put(os, n);
     os.write(reinterpret_cast<const char*>(p), std::streamsize(n * sizeof(T)));
 }
-template <class T> void getArray(std::istream& is, std::vector<T>& v, uint64_t elemsPerCount = 1) {
+template <class V> void getArray(std::istream& is, V& v, uint64_t elemsPerCount = 1) {
+    using T = typename std::remove_reference<decltype(v[0])>::type;
     uint64_t n = 0;
     get(is, n);
     if (n > (uint64_t(1) << 36)) throw Error(SDFB200_ERR_IO, "implausible array size in .bin file");

@@ -39,6 +39,7 @@ void requireDevice() {
         throw Error(SDFB200_ERR_CUDA, "no CUDA device available (sdfb200 has no CPU fallback)");
     }
     SDFB_CUDA(cudaSetDevice(gDevice));
+    configureDevicePool(gDevice);
 }
 
 HostMesh checkedMesh(const float* v, uint32_t nv, const uint32_t* idx, uint32_t ni) {
@@ -150,7 +151,11 @@ int sdfb200_load(const char* path, sdfb200_sdf** out) {
     });
 }
 
-void sdfb200_free(sdfb200_sdf* sdf) { delete sdf; }
+void sdfb200_free(sdfb200_sdf* sdf) {
+    if (!sdf) return;
+    if (sdf->dOctree.p) { cudaSetDevice(sdf->device); cudaDeviceSynchronize(); }   // no kernel may still read the arrays
+    delete sdf;
+}
 
 int sdfb200_get_info(const sdfb200_sdf* s, sdfb200_info* o) {
     return guarded([&] {
@@ -225,9 +230,11 @@ int sdfb200_query(sdfb200_sdf* s, const float* xyz, uint64_t n, float* dist, flo
         };
         if (flags & SDFB200_QUERY_DEVICE_POINTERS) { launch(xyz, dist, grad); return; }
         // host pointers: H2D of the points, kernel, D2H of the results, all on `st`
-        if (s->dPts.n < 3 * n) s->dPts.alloc(3 * n);
-        if (s->dDist.n < n) s->dDist.alloc(n);
-        if (grad && s->dGrad.n < 3 * n) s->dGrad.alloc(3 * n);
+        bool grown = false;
+        if (s->dPts.n < 3 * n) { s->dPts.alloc(3 * n); grown = true; }
+        if (s->dDist.n < n) { s->dDist.alloc(n); grown = true; }
+        if (grad && s->dGrad.n < 3 * n) { s->dGrad.alloc(3 * n); grown = true; }
+        if (grown) SDFB_CUDA(cudaStreamSynchronize(cudaStream_t(0)));   // allocations are ordered on the default stream
         SDFB_CUDA(cudaMemcpyAsync(s->dPts.p, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
         launch(s->dPts.p, s->dDist.p, grad ? s->dGrad.p : nullptr);
         SDFB_CUDA(cudaMemcpyAsync(dist, s->dDist.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -287,7 +294,7 @@ int sdfb200_triangle_data(const float* vertices, uint32_t numVertices, const uin
     return guarded([&] {
         if (!out37) throw Error(SDFB200_ERR_INVALID, "null output");
         HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
-        std::vector<TriData> t = computeTriangleData(mesh);
+        TriVec t = computeTriangleData(mesh);
         std::memcpy(out37, t.data(), t.size() * sizeof(TriData));
     });
 }

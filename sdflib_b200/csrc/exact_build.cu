@@ -593,14 +593,17 @@ struct ExactBuildState : BuildState {
         out.bitsPerIndex = uint32_t(int32_t(std::ceil(std::log2(float(nT)))));   // ExactOctreeSdfDepthFirst.h:61
         bits = out.bitsPerIndex;
         if (bits == 0 || bits > 31) throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf needs between 2 and 2^31 triangles");
-        std::vector<float4> frames(size_t(nT) * 5);
+        RawVec<float4> frames(size_t(nT) * 5);
+#pragma omp parallel for schedule(static) num_threads(hostThreads())
+        for (int64_t t = 0; t < int64_t(nT); t++) {
+            float tmp[20];
+            std::memcpy(tmp, &out.tris[size_t(t)], 19 * sizeof(float));
+            tmp[19] = 0.0f;
+            std::memcpy(&frames[size_t(t) * 5], tmp, sizeof(tmp));
+        }
         std::vector<uint32_t> all;
         all.reserve(nT);
         for (uint32_t t = 0; t < nT; t++) {
-            float tmp[20];
-            std::memcpy(tmp, &out.tris[t], 19 * sizeof(float));
-            tmp[19] = 0.0f;
-            std::memcpy(&frames[size_t(t) * 5], tmp, sizeof(tmp));
             const f3 nrm = triNormal(out.tris[t]);
             if (dot3(nrm, nrm) > 1e-3f) all.push_back(t);   // ExactOctreeSdfDepthFirst.h:106 (false for NaN)
         }

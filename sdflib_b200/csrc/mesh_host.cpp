@@ -3,10 +3,26 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
+#include <omp.h>
+#include <parallel/algorithm>
 #include <utility>
 
 namespace sdfb200 {
+
+// Threads of the host-side set-up steps: SDFB200_HOST_THREADS when set (a launcher like torchrun pins
+// OMP_NUM_THREADS=1 for every rank, which would serialise the per-triangle loops), else OpenMP's own default.
+int hostThreads() {
+    static const int n = [] {
+        const char* e = std::getenv("SDFB200_HOST_THREADS");
+        const int v = e ? std::atoi(e) : 0;
+        return v > 0 ? v : omp_get_max_threads();
+    }();
+    return n;
+}
 
 namespace {
 
@@ -56,14 +72,22 @@ struct EdgeUse { uint64_t key; uint32_t corner; };   // key = min<<32 | max, cor
 
 }  // namespace
 
-std::vector<TriData> computeTriangleData(const HostMesh& mesh) {
+TriVec computeTriangleData(const HostMesh& mesh) {
     const uint32_t nT = mesh.numTriangles();
-    std::vector<TriData> tris(nT);
-    std::vector<f3> cornerContribution(size_t(nT) * 3);
-    std::vector<EdgeUse> uses(size_t(nT) * 3);
+    const bool timing = std::getenv("SDFB200_TIMING") != nullptr;
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[sdfb200] triangle data: %-18s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+        tick = now;
+    };
+    TriVec tris(nT);
+    RawVec<f3> cornerContribution(size_t(nT) * 3);
+    RawVec<EdgeUse> uses(size_t(nT) * 3);
 
     // Frames and per-corner angle * normal are pure per-triangle functions: parallel.
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(hostThreads())
     for (int64_t t = 0; t < int64_t(nT); t++) {
         const uint32_t* ix = mesh.idx + 3 * t;
         tris[size_t(t)] = makeTriData(mesh.verts[ix[0]], mesh.verts[ix[1]], mesh.verts[ix[2]]);
@@ -77,29 +101,48 @@ std::vector<TriData> computeTriangleData(const HostMesh& mesh) {
         }
     }
 
+    lap("frames");
     // Edge pairing. The reference walks the corners in order through an ordered map: an edge seen
     // while its key is stored pairs with the stored corner and both get n_t + n_t'; the key is then
     // erased, so occurrences pair up (1st,2nd), (3rd,4th), ... and an odd one stays open. Sorting the
     // uses by (edge, corner) reproduces exactly those pairs without the serial map.
-    std::sort(uses.begin(), uses.end(), [](const EdgeUse& x, const EdgeUse& y) {
+    // (key, corner) pairs are unique, so any correct sort gives the same sequence: use the multi-threaded one
+    __gnu_parallel::sort(uses.begin(), uses.end(), [](const EdgeUse& x, const EdgeUse& y) {
         return x.key != y.key ? x.key < y.key : x.corner < y.corner;
-    });
-    std::vector<EdgeUse> open;
-    for (size_t i = 0; i < uses.size();) {
-        size_t j = i;
-        while (j < uses.size() && uses[j].key == uses[i].key) j++;
-        size_t p = i;
-        for (; p + 1 < j; p += 2) {
-            const uint32_t first = uses[p].corner, second = uses[p + 1].corner;
-            const uint32_t t2 = first / 3, t = second / 3;
-            const f3 n = triNormal(tris[t]) + triNormal(tris[t2]);
-            st3(tris[t].edgesNormal[second % 3], matMul(tris[t].T, n));
-            st3(tris[t2].edgesNormal[first % 3], matMul(tris[t2].T, n));
-        }
-        if (p < j) open.push_back(uses[p]);
-        i = j;
+    }, __gnu_parallel::default_parallel_tag(hostThreads()));
+    lap("edge sort");
+    // Groups of equal keys are independent: cut the sorted array into chunks at group boundaries, one per thread;
+    // the open (unpaired) uses are concatenated in chunk order, i.e. still in key order.
+    const int nChunks = std::max(1, std::min(hostThreads(), int(uses.size() / 4096) + 1));
+    std::vector<size_t> cut;
+    cut.resize(size_t(nChunks) + 1);
+    for (int c = 0; c <= nChunks; c++) {
+        size_t at = uses.size() * size_t(c) / size_t(nChunks);
+        while (at > 0 && at < uses.size() && uses[at].key == uses[at - 1].key) at++;
+        cut[size_t(c)] = at;
     }
-
+    std::vector<std::vector<EdgeUse>> openOf;
+    openOf.resize(size_t(nChunks));
+#pragma omp parallel for schedule(static, 1) num_threads(nChunks)
+    for (int c = 0; c < nChunks; c++) {
+        for (size_t i = cut[size_t(c)]; i < cut[size_t(c) + 1];) {
+            size_t j = i;
+            while (j < uses.size() && uses[j].key == uses[i].key) j++;
+            size_t p = i;
+            for (; p + 1 < j; p += 2) {
+                const uint32_t first = uses[p].corner, second = uses[p + 1].corner;
+                const uint32_t t2 = first / 3, t = second / 3;
+                const f3 n = triNormal(tris[t]) + triNormal(tris[t2]);
+                st3(tris[t].edgesNormal[second % 3], matMul(tris[t].T, n));
+                st3(tris[t2].edgesNormal[first % 3], matMul(tris[t2].T, n));
+            }
+            if (p < j) openOf[size_t(c)].push_back(uses[p]);
+            i = j;
+        }
+    }
+    std::vector<EdgeUse> open;
+    for (const auto& o : openOf) open.insert(open.end(), o.begin(), o.end());
+    lap("edge pairing");
     // Angle-weighted vertex normals, accumulated in corner order (float addition order matters).
     std::vector<f3> vNormal(mesh.nVerts, mk3(0.f, 0.f, 0.f));
     for (size_t cix = 0; cix < size_t(nT) * 3; cix++) {
@@ -107,6 +150,7 @@ std::vector<TriData> computeTriangleData(const HostMesh& mesh) {
         vNormal[a] = vNormal[a] + cornerContribution[cix];
     }
 
+    lap("vertex normals");
     if (!open.empty()) {
         // Non-manifold repair (src/utils/TriangleUtils.cpp:292-420): vertices of open edges that lie
         // within 1e-5/extent of each other (found through two staggered 2048^3 hash grids) are merged
@@ -172,9 +216,10 @@ std::vector<TriData> computeTriangleData(const HostMesh& mesh) {
         for (uint32_t v : nm) vNormal[v] = vNormal[root(v)];
     }
 
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(hostThreads())
     for (int64_t i = 0; i < int64_t(mesh.nIdx); i++)
         st3(tris[size_t(i / 3)].verticesNormal[i % 3], matMul(tris[size_t(i / 3)].T, vNormal[mesh.idx[i]]));
+    lap("to triangle frame");
     return tris;
 }
 
@@ -191,8 +236,8 @@ inline double sq3(const double* a, const double* b) {
 }
 
 struct BvhBuilder {
-    std::vector<BuildTri>& bt;
-    std::vector<BvhNode>& nodes;
+    RawVec<BuildTri>& bt;
+    RawVec<BvhNode>& nodes;
 
     // sphere = where the bounding sphere of this subtree is stored (a child slot of the parent)
     void build(int32_t nodeId, double* sphereCenter, double* sphereRadius, int32_t begin, int32_t end) {
@@ -249,10 +294,10 @@ struct BvhBuilder {
 
 }  // namespace
 
-std::vector<BvhNode> buildBvh(const HostMesh& mesh) {
+RawVec<BvhNode> buildBvh(const HostMesh& mesh) {
     const uint32_t nT = mesh.numTriangles();
-    std::vector<BuildTri> bt(nT);
-#pragma omp parallel for schedule(static)
+    RawVec<BuildTri> bt(nT);
+#pragma omp parallel for schedule(static) num_threads(hostThreads())
     for (int64_t t = 0; t < int64_t(nT); t++) {
         bt[size_t(t)].id = int32_t(t);
         for (int k = 0; k < 3; k++) {
@@ -260,10 +305,10 @@ std::vector<BvhNode> buildBvh(const HostMesh& mesh) {
             bt[size_t(t)].v[k][0] = double(p.x); bt[size_t(t)].v[k][1] = double(p.y); bt[size_t(t)].v[k][2] = double(p.z);
         }
     }
-    std::vector<BvhNode> nodes(size_t(2) * nT - 1);
+    RawVec<BvhNode> nodes(size_t(2) * nT - 1);
     double rootCenter[3], rootRadius;
     BvhBuilder b{bt, nodes};
-#pragma omp parallel
+#pragma omp parallel num_threads(hostThreads())
 #pragma omp single
     b.build(0, rootCenter, &rootRadius, 0, int32_t(nT));
     return nodes;

@@ -5,6 +5,8 @@
 // shape depends on std::sort's (unstable) tie order. Everything per-node / per-query runs on the GPU.
 #pragma once
 #include <cstdint>
+#include <memory>
+#include <utility>
 #include <vector>
 #include "tri_math.cuh"
 
@@ -16,8 +18,20 @@ struct HostMesh {
     uint32_t numTriangles() const { return nIdx / 3; }
 };
 
+// std::vector without value-initialisation: the big per-triangle arrays are written in full by parallel loops, and
+// zero-filling tens of MB from one thread first (plus its page faults) cost more than the computation itself.
+template <class T> struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+    template <class U> void construct(U* p) noexcept { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+template <class T> using RawVec = std::vector<T, DefaultInitAllocator<T>>;
+using TriVec = RawVec<TriData>;
+
+int hostThreads();   // SDFB200_HOST_THREADS or the OpenMP default
+
 // reference: TriangleUtils::calculateMeshTriangleData, src/utils/TriangleUtils.cpp:7-428
-std::vector<TriData> computeTriangleData(const HostMesh& mesh);
+TriVec computeTriangleData(const HostMesh& mesh);
 
 // Device-friendly BVH node: both child spheres + child links, 80 bytes, 16-byte aligned.
 // left < 0 marks a leaf and `right` is then the triangle id
@@ -33,6 +47,6 @@ static_assert(sizeof(BvhNode) == 80, "BvhNode layout");
 // reference: tmd::TriangleMeshDistance::_build_tree, TriangleMeshDistance.h:421-490.
 // Node ids equal the reference's push order (pre-order: a subtree over n triangles owns 2n-1
 // consecutive ids), which lets independent subtrees be built by parallel host tasks.
-std::vector<BvhNode> buildBvh(const HostMesh& mesh);
+RawVec<BvhNode> buildBvh(const HostMesh& mesh);
 
 }  // namespace sdfb200

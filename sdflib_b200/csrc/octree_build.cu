@@ -415,7 +415,7 @@ void uploadHermite() {
     if (dev < 64) done[dev] = true;
 }
 
-void uploadMesh(MeshOnDevice& m, const HostMesh& mesh, const std::vector<TriData>& tris, const std::vector<BvhNode>* bvh) {
+void uploadMesh(MeshOnDevice& m, const HostMesh& mesh, const TriVec& tris, const RawVec<BvhNode>* bvh) {
     m.numTriangles = mesh.numTriangles();
     m.verts.alloc(mesh.nVerts); m.verts.upload(mesh.verts, mesh.nVerts);
     m.idx.alloc(mesh.nIdx); m.idx.upload(mesh.idx, mesh.nIdx);
@@ -489,10 +489,10 @@ struct OctreeBuildState : BuildState {
         sdfb200_build_stats& st = out.stats;
         // serial set-up steps of the reference, on the host (see mesh_host.h)
         auto t0 = std::chrono::steady_clock::now();
-        std::vector<TriData> tris = computeTriangleData(mesh);
+        TriVec tris = computeTriangleData(mesh);
         st.triangle_data_ms = msSince(t0);
         t0 = std::chrono::steady_clock::now();
-        std::vector<BvhNode> bvh = buildBvh(mesh);
+        RawVec<BvhNode> bvh = buildBvh(mesh);
         st.bvh_ms = msSince(t0);
         t0 = std::chrono::steady_clock::now();
         MeshOnDevice dm;
@@ -695,8 +695,8 @@ void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* bo
 }
 
 void nearestTriangleOnDevice(const HostMesh& mesh, const float* xyz, uint64_t n, uint32_t* outTri) {
-    std::vector<TriData> tris = computeTriangleData(mesh);
-    std::vector<BvhNode> bvh = buildBvh(mesh);
+    TriVec tris = computeTriangleData(mesh);
+    RawVec<BvhNode> bvh = buildBvh(mesh);
     MeshOnDevice dm;
     uploadMesh(dm, mesh, tris, &bvh);
     DevBuf<f3> pts(n);

@@ -39,18 +39,48 @@ template <class T> struct DevBuf {
     DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; return *this; }
     ~DevBuf() { release(); }
+    // stream-ordered allocator on the legacy default stream: recycled from the device pool (host_mem.cpp)
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) SDFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+        if (count) SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), cudaStream_t(0)));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) cudaFreeAsync(p, cudaStream_t(0)); p = nullptr; n = 0; }
     void upload(const T* src, size_t count, cudaStream_t s = 0) {
         if (count) SDFB_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
     }
     void download(T* dst, size_t count, cudaStream_t s = 0) const {
         if (count) SDFB_CUDA(cudaMemcpyAsync(dst, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
     }
+};
+
+// ---- host mirror of a structure array: uninitialised, pinned when a device is present (host_mem.cpp) ----
+void* hostBlockAlloc(size_t bytes, size_t* outCapacity, bool* outPinned);
+void hostBlockFree(void* p, size_t capacity, bool pinned);
+void configureDevicePool(int device);
+
+template <class T> struct HostArray {
+    T* p = nullptr;
+    size_t n = 0, capBytes = 0;
+    bool pinned = false;
+    HostArray() {}
+    HostArray(const HostArray&) = delete;
+    HostArray& operator=(const HostArray&) = delete;
+    ~HostArray() { hostBlockFree(p, capBytes, pinned); }
+    // contents are NOT preserved and NOT initialised
+    void resize(size_t count) {
+        if (count * sizeof(T) > capBytes || !p) {
+            hostBlockFree(p, capBytes, pinned);
+            p = nullptr;
+            p = static_cast<T*>(hostBlockAlloc(count * sizeof(T), &capBytes, &pinned));
+        }
+        n = count;
+    }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return n; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
 };
 
 // ---- mesh on the device --------------------------------------------------------------------------
@@ -123,10 +153,10 @@ struct sdfb200_sdf {
     uint32_t startDepth = 0, minTrisInLeafs = 0, maxTrisInLeafs = 0, maxTrisEncoded = 0, bitEncodingStartDepth = 0,
              bitsPerIndex = 0;
     // host mirrors (what the getters / .bin writer read)
-    std::vector<uint32_t> octree;   // OCTREE: words; EXACT: (childrenIndex, trianglesArrayIndex) pairs
-    std::vector<uint32_t> sets;
-    std::vector<uint8_t> masks;
-    std::vector<sdfb200::TriData> tris;
+    sdfb200::HostArray<uint32_t> octree;   // OCTREE: words; EXACT: (childrenIndex, trianglesArrayIndex) pairs
+    sdfb200::HostArray<uint32_t> sets;
+    sdfb200::HostArray<uint8_t> masks;
+    sdfb200::TriVec tris;
     // device copies (what the query kernels read)
     sdfb200::DevBuf<uint32_t> dOctree;
     sdfb200::DevBuf<uint32_t> dSets;
