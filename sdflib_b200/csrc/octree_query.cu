@@ -15,6 +15,12 @@
 // Kernel shape: one query per thread, 256-thread CTAs, grid sized by the batch. The descent is a
 // chain of dependent 4-byte gathers (L2-resident after the first touch: the whole structure of the
 // headline config is 82 MB < 126 MB L2); the leaf block is 64 consecutive floats.
+// What bounds it (profiles/r1_summary.md): not HBM but the L1/LSU data pipe — every query must bring its
+// own 64 coefficients (256 B) into registers, i.e. 64 x 128 B write-back wavefronts per warp; ncu shows
+// l1tex__data_pipe_lsu_wavefronts at 77 % of peak with DRAM at 15 %. A warp-cooperative variant (distinct
+// leaves staged once per warp in shared memory, evaluated from there) was measured and is slower
+// (0.36 ms vs 0.26 ms on the 256^3 grid): it removes the tag-stage replays but keeps the same
+// register-fill traffic and adds match/shuffle/shared-store work. It was dropped.
 #include "sdf_internal.h"
 
 namespace sdfb200 {

@@ -169,8 +169,8 @@ struct sdfb200_sdf {
     sdfb200::DevBuf<uint32_t> dLeafCnt, dLeafPool;
     // staging for host-pointer queries
     sdfb200::DevBuf<float> dPts, dDist, dGrad;
-    float* hPinned = nullptr;
-    size_t hPinnedFloats = 0;
+    cudaStream_t qStream[2] = {nullptr, nullptr};
+    cudaEvent_t qEvent = nullptr;
     // sharded build: phase state, root plan, per-slot sizes of the own roots, streams for export / assembly
     bool isShard = false;          // true until sdfb200_assemble completed the structure
     std::unique_ptr<sdfb200::BuildState> build;
@@ -181,7 +181,10 @@ struct sdfb200_sdf {
     uint32_t shardScalars[2] = {0, 0};         // OCTREE: valueRange bits / ordered minBorder; EXACT: max leaf / max encoded
     sdfb200_build_stats stats = {};
 
-    ~sdfb200_sdf() { if (hPinned) cudaFreeHost(hPinned); }
+    ~sdfb200_sdf() {
+        for (int k = 0; k < 2; k++) if (qStream[k]) cudaStreamDestroy(qStream[k]);
+        if (qEvent) cudaEventDestroy(qEvent);
+    }
 };
 
 namespace sdfb200 {
