@@ -639,10 +639,33 @@ float errorTrapezoid(const Coeffs& c, const std::array<PointValues, 19>& mid, bo
     return acc;
 }
 
-}  // namespace
+// OctreeSdfUtils.h:213-238 (Simpson): weight 4^(#centred axes)/216, the float constant w/216 is
+// formed first, then multiplied by the squared difference; terms summed left to right in sample order.
+float errorSimpson(const Coeffs& c, const std::array<PointValues, 19>& mid) {
+    float acc = 0.0f;
+    for (int s = 0; s < 19; s++) {
+        const V3 rel = kLattice.sampleRel[s];
+        const int zeros = (rel.x == 0.0f) + (rel.y == 0.0f) + (rel.z == 0.0f);
+        const float w = (zeros == 1 ? 4.0f : (zeros == 2 ? 16.0f : 64.0f)) / 216.0f;
+        const V3 f = V3{0.5f * rel.x + 0.5f, 0.5f * rel.y + 0.5f, 0.5f * rel.z + 0.5f};
+        const float d = mid[size_t(s)][0] - tricubicValue(c.data(), f);
+        const float term = w * (d * d);
+        acc = (s == 0) ? term : acc + term;
+    }
+    return acc;
+}
 
-// The Simpson rule needs the literal sample table of OctreeSdfUtils.h:213-238; it is restated in
-// oracle_simpson.inc only if that file exists (lower-priority §8 option) — see orc_error_estimate.
+// switch at OctreeSdfDepthFirst.h:194-212 / OctreeSdfBreadthFirstNoDelay.h:346-363
+float errorByRule(int rule, const Coeffs& c, const std::array<PointValues, 19>& mid, float decay) {
+    switch (rule) {
+        case 1: return errorTrapezoid(c, mid, false, 0.0f);
+        case 2: return errorSimpson(c, mid);
+        case 3: return errorTrapezoid(c, mid, true, decay);
+        default: return INFINITY;
+    }
+}
+
+}  // namespace
 
 namespace {
 
@@ -805,14 +828,8 @@ struct OctBuilder {
         if (n.depth >= startDepth) {
             Coeffs c;
             tricubicCoefficients(n.values, 2.0f * n.half, c);
-            float value;
-            switch (rule) {
-                case 1: value = errorTrapezoid(c, mid, false, 0.0f); break;
-                case 3: value = errorTrapezoid(c, mid, true, p1); break;
-                case 0: value = INFINITY; break;
-                default: value = INFINITY; break;   // SIMPSONS_RULE: not restated
-            }
-            terminal = value < p0 * p0;
+            const float value = errorByRule(rule, c, mid, p1);
+            terminal = value < p0 * p0;   // NONE: value = INFINITY (:206-208)
         }
         if (terminal) { emitLeaf(n, oct); return; }
         const float h = 0.5f * n.half;
@@ -894,6 +911,411 @@ struct OctBuilder {
             }
         }
         out.octree.swap(dst);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// a15: OctreeSdf breadth-first build with C1 continuity across T-junctions, InitAlgorithm::CONTINUITY
+// (src/sdf/OctreeSdfBreadthFirstNoDelay.h:84-1224; helpers src/sdf/OctreeSdfBreadthFirst.h:35-89).
+//
+// Vocabulary used below. A node tracks six "outer" neighbour links, one per non-empty proper axis
+// set n in 1..6 (bit0 x, bit1 y, bit2 z): the region reached by leaving the node's PARENT through
+// the faces the node touches (sign of each axis = the node's own child bit). A link is either
+//   * bit31 set: word index of a coarser LEAF covering that region,
+//   * bit30 set: outside the start grid,
+//   * else: index of an 8-word children block (its depth is linkDepth), or, right after creation,
+//     the word of the parent-sized neighbour.
+// The 18 face/edge neighbours of a node are probed through (link of the outward axes | own sibling
+// block) + child id (dir ^ c). Which of the 19 mid-point samples lie on the face/edge shared with a
+// neighbour is a fixed bit table (:139-176): bit (18 - s) for sample s, entry 4*(dir-1) + sign, where
+// sign packs "positive side?" of dir's axes, lowest axis in bit 0.
+// ------------------------------------------------------------------------------------------
+struct ContNode {
+    uint64_t path = 0;                 // childIndices: 3 bits per level, own child id in the low 3
+    uint32_t parentBlock = 0xFFFFFFFFu;
+    bool terminal = false, ignore = false;
+    uint8_t linkDepth[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t link[6] = {0, 0, 0, 0, 0, 0};
+    V3 center{0, 0, 0};
+    float half = 0;
+    std::array<PointValues, 8> values{};
+    Coeffs coeff{};
+    std::array<PointValues, 19> mid{};
+};
+
+struct ContBuilder {
+    OrcSdf& out;
+    MeshView mesh;
+    std::vector<TriData> tris;
+    std::unique_ptr<Bvh> bvh;
+    VertexCache cacheMain;   // `trianglesInfluence`: start nodes + fix-up pass (:193, :917)
+    VertexCache cacheIter;   // `threadTrianglesInfluence[0]`: copy taken after the start nodes (:253), Iter 1
+    uint32_t startDepth, maxDepth;
+    int rule; float p0, p1;
+
+    static constexpr uint32_t B31 = 1u << 31, B30 = 1u << 30, MARK = 1u << 30;
+    uint32_t faceMask[24];
+
+    static inline int axisSign(uint32_t dir, uint32_t sign, int axis) {   // +1 / -1 side of `axis` (in dir)
+        int bit = 0;
+        for (int a = 0; a < axis; a++) if (dir & (1u << a)) bit++;
+        return ((sign >> bit) & 1u) ? 1 : -1;
+    }
+    void buildMaskTable() {
+        for (uint32_t dir = 1; dir <= 6; dir++)
+            for (uint32_t sign = 0; sign < 4; sign++) {
+                uint32_t m = 0;
+                const int nAxes = int((dir & 1) + ((dir >> 1) & 1) + ((dir >> 2) & 1));
+                if (sign < (1u << nAxes))
+                    for (int s = 0; s < 19; s++) {
+                        const V3 r = kLattice.sampleRel[s];
+                        const float rr[3] = {r.x, r.y, r.z};
+                        bool on = true;
+                        for (int a = 0; a < 3; a++)
+                            if ((dir & (1u << a)) && rr[a] != float(axisSign(dir, sign, a))) on = false;
+                        if (on) m |= 1u << (18 - s);
+                    }
+                faceMask[4 * (dir - 1) + sign] = m;
+            }
+    }
+    // sign index of direction `dir` for a node with child id c: axes in `outward` go to the node's own
+    // side (bit of c), the others to the opposite side (:419-438)
+    static inline uint32_t signOf(uint32_t dir, uint32_t outward, uint32_t c) {
+        uint32_t sign = 0, bit = 0;
+        for (uint32_t a = 0; a < 3; a++)
+            if (dir & (1u << a)) {
+                const uint32_t pos = (outward & (1u << a)) ? ((c >> a) & 1u) : (((~c) >> a) & 1u);
+                sign |= pos << bit;
+                bit++;
+            }
+        return sign;
+    }
+
+    inline bool isLeaf(uint32_t w) const { return (out.octree[w] & B31) != 0; }
+    inline bool isMarked(uint32_t w) const { return (out.octree[w] & MARK) != 0; }
+    inline uint32_t childrenOf(uint32_t w) const { return out.octree[w] & OCT_INDEX_MASK; }
+    inline void setWord(uint32_t w, bool leaf, uint32_t index) { out.octree[w] = (index & OCT_INDEX_MASK) | (leaf ? B31 : 0u); }
+
+    void trueSample(VertexCache& cache, V3 p, PointValues& vals) {   // TrianglesInfluence.h:971-992
+        uint32_t slot, key[3], tri;
+        if (!cache.lookup(p, slot, key, tri)) { tri = bvh->nearest(p); cache.store(slot, key, tri); }
+        V3 g;
+        vals[0] = signedDistGradMesh(p, tris[tri], mesh.verts[mesh.idx[3 * tri]], mesh.verts[mesh.idx[3 * tri + 1]],
+                                     mesh.verts[mesh.idx[3 * tri + 2]], g);
+        vals[1] = g.x; vals[2] = g.y; vals[3] = g.z;
+        vals[4] = vals[5] = vals[6] = vals[7] = 0.0f;
+    }
+    static inline V3 sampleFrac(int s) { return 0.5f * kLattice.sampleRel[s] + 0.5f; }
+    // calculateVerticesInfo<19> with an interpolation mask (TrianglesInfluence.h:952-996)
+    void sampleMid(VertexCache& cache, ContNode& n, uint32_t interpolateMask) {
+        for (int s = 0; s < 19; s++) {
+            if (interpolateMask & (1u << (18 - s))) tricubicVertexValues(n.coeff.data(), sampleFrac(s), 2.0f * n.half, n.mid[size_t(s)]);
+            else trueSample(cache, n.center + kLattice.sampleRel[s] * n.half, n.mid[size_t(s)]);
+        }
+    }
+
+    void gridPos(V3 center, int pos[3]) const {   // :282, :389
+        V3 f = (center - out.box.mn) / out.cellSize;
+        pos[0] = int(std::floor(f.x)); pos[1] = int(std::floor(f.y)); pos[2] = int(std::floor(f.z));
+    }
+    inline bool inGrid(const int p[3]) const {
+        const int G = out.startGridSize;
+        return p[0] >= 0 && p[0] < G && p[1] >= 0 && p[1] < G && p[2] >= 0 && p[2] < G;
+    }
+    inline uint32_t gridSlot(const int p[3]) const {
+        const int G = out.startGridSize;
+        return uint32_t(p[2] * G * G + p[1] * G + p[0]);
+    }
+    uint32_t wordOf(const ContNode& n, uint32_t depth) const {
+        if (depth > startDepth) return n.parentBlock + uint32_t(n.path & 7u);
+        int pos[3];
+        gridPos(n.center, pos);
+        return gridSlot(pos);
+    }
+
+    // the 8 children of `n` (depth `depth`): inherited lattice values (:532-707) and neighbour links
+    // (getNeighboursVector / getNeighboursVectorInUniformGrid, OctreeSdfBreadthFirst.h:47-89)
+    void makeChildren(const ContNode& n, uint32_t depth, uint32_t childBlock, std::vector<ContNode>& dst,
+                      std::vector<uint32_t>* dstDepth) {
+        const float h = 0.5f * n.half;
+        const uint32_t c = uint32_t(n.path & 7u);
+        int pos[3] = {0, 0, 0};
+        if (depth == startDepth) gridPos(n.center, pos);
+        for (uint32_t o = 0; o < 8; o++) {
+            ContNode ch;
+            ch.parentBlock = childBlock;
+            ch.path = (n.path << 3) | o;
+            ch.center = n.center + cornerDir(o) * h;   // center + vec3(±h)
+            ch.half = h;
+            for (uint32_t k = 0; k < 8; k++) {
+                const int L = int((o & 1) + (k & 1)) + 3 * int(((o >> 1) & 1) + ((k >> 1) & 1)) + 9 * int((o >> 2) + (k >> 2));
+                ch.values[k] = (kLattice.cornerOfLattice[L] >= 0) ? n.values[size_t(kLattice.cornerOfLattice[L])]
+                                                                  : n.mid[size_t(kLattice.sampleOfLattice[L])];
+            }
+            if (depth == startDepth) {
+                for (uint32_t m = 1; m <= 6; m++) {
+                    int q[3];
+                    for (int a = 0; a < 3; a++) q[a] = pos[a] + ((m & (1u << a)) ? ((o & (1u << a)) ? 1 : -1) : 0);
+                    ch.link[m - 1] = inGrid(q) ? gridSlot(q) : B30;
+                    ch.linkDepth[m - 1] = uint8_t(depth);
+                }
+            } else {
+                for (uint32_t m = 1; m <= 6; m++) {
+                    const uint32_t same = (~(o ^ c)) & m;   // axes on which the child also leaves n's parent
+                    if (same != 0) {
+                        const uint32_t pl = n.link[same - 1];
+                        ch.link[m - 1] = pl + (m ^ c) * (1u - (pl >> 31));
+                        ch.linkDepth[m - 1] = n.linkDepth[same - 1];
+                    } else {
+                        ch.link[m - 1] = n.parentBlock + (m ^ c);
+                        ch.linkDepth[m - 1] = uint8_t(depth);
+                    }
+                }
+            }
+            dst.push_back(ch);
+            if (dstDepth) dstDepth->push_back(depth + 1);
+        }
+    }
+
+    void run() {
+        buildMaskTable();
+        std::vector<uint32_t>& oct = out.octree;
+        const float sqThr = p0 * p0;
+        const uint32_t d0 = std::min(startDepth, 1u);
+        const uint32_t G = uint32_t(out.startGridSize);
+        oct.assign(size_t(G) * G * G, 0u);
+        std::vector<std::vector<ContNode>> level(maxDepth + 2);
+        {
+            const float h0 = float(0.5f * out.box.size().x * std::pow(0.5f, d0));
+            const V3 c0 = out.box.mn + h0;
+            const uint32_t per = 1u << d0;
+            for (uint32_t k = 0; k < per; k++)
+                for (uint32_t j = 0; j < per; j++)
+                    for (uint32_t i = 0; i < per; i++) {
+                        ContNode n;
+                        n.center = c0 + v3(float(i), float(j), float(k)) * 2.0f * h0;
+                        n.half = h0;
+                        for (uint32_t c = 0; c < 8; c++) trueSample(cacheMain, n.center + cornerDir(c) * n.half, n.values[c]);
+                        level[d0].push_back(n);
+                    }
+        }
+        cacheIter = cacheMain;
+        std::vector<uint32_t> toSubdivide;
+        std::map<uint32_t, std::pair<uint32_t, uint32_t>> leaves;   // word -> (depth, index in level[depth])
+        float valueRange = 0.0f;   // the reference leaves mValueRange uninitialised on this path (OctreeSdf.h:251)
+
+        for (uint32_t depth = d0; depth <= maxDepth; depth++) {
+            // ---- Iter 1 (:258-369): advance links, fit, sample, decide ------------------------------
+            if (depth < maxDepth) {
+                for (size_t id = 0; id < level[depth].size(); id++) {
+                    ContNode& n = level[depth][id];
+                    if (n.ignore) continue;
+                    if (depth > startDepth) {
+                        for (uint32_t m = 1; m <= 6; m++) {
+                            uint32_t& l = n.link[m - 1];
+                            if (((l >> 30) & 1u) != 0) continue;
+                            if (isLeaf(l & ~B31)) { l |= B31; continue; }
+                            l = childrenOf(l & ~B31);
+                            n.linkDepth[m - 1]++;
+                            while (n.linkDepth[m - 1] < depth) {
+                                const uint32_t diff = depth - n.linkDepth[m - 1];
+                                const uint32_t cid = uint32_t((n.path >> (3 * diff)) & 7u);
+                                l += (m ^ cid);
+                                if (isLeaf(l & ~B31)) { l |= B31; break; }
+                                l = childrenOf(l & ~B31);
+                                n.linkDepth[m - 1]++;
+                            }
+                        }
+                    }
+                    if (depth >= startDepth) tricubicCoefficients(n.values, 2.0f * n.half, n.coeff);
+                    sampleMid(cacheIter, n, 0u);
+                    bool terminal = false;
+                    if (depth >= startDepth) terminal = errorByRule(rule, n.coeff, n.mid, p1) < sqThr;
+                    n.terminal = terminal;
+                    if (depth >= startDepth) setWord(wordOf(n, depth), terminal, 0xFFFFFFFFu);
+                }
+            }
+            // ---- Iter 2 (:372-734): serial; T-junction samples, children / leaf emission -------------
+            toSubdivide.clear();
+            for (size_t id = 0; id < level[depth].size(); id++) {
+                if (level[depth][id].ignore) continue;
+                const uint32_t word = depth >= startDepth ? wordOf(level[depth][id], depth) : 0xFFFFFFFFu;
+                if (!level[depth][id].terminal && depth < maxDepth) {
+                    ContNode& n = level[depth][id];
+                    const uint32_t c = uint32_t(n.path & 7u);
+                    uint32_t samplesMask = 0;
+                    uint32_t neighbourWord[24];
+                    for (int i = 0; i < 24; i++) neighbourWord[i] = 0xFFFFFFFFu;
+                    if (depth > startDepth) {
+                        for (uint32_t dir = 1; dir <= 6; dir++)
+                            for (uint32_t outward = 0; outward <= dir; outward++) {
+                                if ((outward & dir) != outward) continue;   // subsets of dir
+                                const uint32_t ptr = outward ? n.link[outward - 1] : n.parentBlock;
+                                const uint32_t entry = 4 * (dir - 1) + signOf(dir, outward, c);
+                                if (ptr >> 31) { neighbourWord[entry] = ptr & ~B31; samplesMask |= faceMask[entry]; }
+                                else if (!(ptr >> 30) && isLeaf(ptr + (dir ^ c))) {
+                                    neighbourWord[entry] = ptr + (dir ^ c);
+                                    samplesMask |= faceMask[entry];
+                                }
+                            }
+                    } else if (depth == startDepth) {
+                        int pos[3];
+                        gridPos(n.center, pos);
+                        for (uint32_t dir = 1; dir <= 6; dir++) {
+                            const uint32_t nAxes = (dir & 1) + ((dir >> 1) & 1) + ((dir >> 2) & 1);
+                            for (uint32_t sign = 0; sign < (1u << nAxes); sign++) {
+                                int q[3];
+                                for (int a = 0; a < 3; a++) q[a] = pos[a] + ((dir & (1u << a)) ? axisSign(dir, sign, a) : 0);
+                                if (inGrid(q) && isLeaf(gridSlot(q))) {
+                                    neighbourWord[4 * (dir - 1) + sign] = gridSlot(q);
+                                    samplesMask |= faceMask[4 * (dir - 1) + sign];
+                                }
+                            }
+                        }
+                    }
+                    uint32_t subdivisionMask = 0;
+                    for (int s = 0; s < 19; s++)
+                        if (samplesMask & (1u << (18 - s))) {
+                            const float inter = tricubicValue(n.coeff.data(), sampleFrac(s));
+                            const float d = n.mid[size_t(s)][0] - inter;
+                            if (d * d > sqThr) subdivisionMask |= samplesMask & (1u << (18 - s));
+                            else tricubicVertexValues(n.coeff.data(), sampleFrac(s), 2.0f * n.half, n.mid[size_t(s)]);
+                        }
+                    for (int i = 0; i < 24; i++)
+                        if ((subdivisionMask & faceMask[i]) && !(neighbourWord[i] >> 30)) toSubdivide.push_back(neighbourWord[i]);
+
+                    uint32_t childBlock = 0xFFFFFFFFu;
+                    if (depth >= startDepth) {
+                        childBlock = uint32_t(oct.size());
+                        setWord(word, false, childBlock);
+                        oct.resize(oct.size() + 8, ~(7u << 29));
+                    }
+                    const ContNode parent = n;   // level[depth + 1] may alias nothing, but keep a stable copy
+                    makeChildren(parent, depth, childBlock, level[depth + 1], nullptr);
+                } else {
+                    ContNode& n = level[depth][id];
+                    const uint32_t at = uint32_t(oct.size());
+                    setWord(word, true, at);
+                    oct.resize(oct.size() + 64);
+                    if (depth >= maxDepth) tricubicCoefficients(n.values, 2.0f * n.half, n.coeff);
+                    std::memcpy(&oct[at], n.coeff.data(), 64 * sizeof(float));
+                    for (int i = 0; i < 8; i++) valueRange = fmax_(valueRange, fabs_(n.values[size_t(i)][0]));
+                    leaves.insert(std::make_pair(word, std::make_pair(depth, uint32_t(id))));
+                }
+            }
+            // ---- fix-up (:741-1181): re-open queued coarser leaves ---------------------------------
+            for (size_t q = 0; q < toSubdivide.size(); q++) {
+                auto it = leaves.find(toSubdivide[q]);
+                if (it == leaves.end()) continue;   // the reference prints "Leaf data not found" and is undefined here
+                std::vector<ContNode> queue;
+                std::vector<uint32_t> queueDepth;
+                queue.push_back(level[it->second.first][it->second.second]);
+                queueDepth.push_back(it->second.first);
+                const uint32_t rootWord = wordOf(queue[0], queueDepth[0]);
+                if (!isLeaf(rootWord)) continue;
+                bool recycled = false;
+                const uint32_t oldCoefficients = childrenOf(rootWord);
+                bool first = true;
+                for (size_t qi = 0; qi < queue.size(); qi++) {
+                    ContNode n = queue[qi];
+                    const uint32_t nd = queueDepth[qi];
+                    const uint32_t c = uint32_t(n.path & 7u);
+                    const uint32_t word = wordOf(n, nd);
+                    uint32_t subdivided = 0;
+                    if (nd > startDepth) {
+                        for (uint32_t m = 1; m <= 6; m++) {
+                            uint32_t& l = n.link[m - 1];
+                            if (((l >> 30) & 1u) != 0) continue;
+                            const bool follow = !first || (l >> 31);
+                            if (follow && isLeaf(l & ~B31)) { l |= B31; continue; }
+                            if (follow) { l = childrenOf(l & ~B31); n.linkDepth[m - 1]++; }
+                            while (n.linkDepth[m - 1] < nd && n.linkDepth[m - 1] < depth) {
+                                const uint32_t diff = nd - n.linkDepth[m - 1];
+                                const uint32_t cid = uint32_t((n.path >> (3 * diff)) & 7u);
+                                l += (m ^ cid);
+                                if (isLeaf(l & ~B31)) { l |= B31; break; }
+                                l = childrenOf(l & ~B31);
+                                n.linkDepth[m - 1]++;
+                            }
+                            if (depth >= nd && !(l >> 31)) {
+                                const uint32_t nw = (l & ~B31) + (m ^ c);
+                                if (!(isLeaf(nw) || isMarked(nw))) subdivided |= faceMask[4 * (m - 1) + signOf(m, m, c)];
+                            }
+                        }
+                    }
+                    bool split = false;
+                    uint32_t interpolateMask = 0;
+                    if (depth >= nd) {
+                        if (nd > startDepth) {
+                            for (uint32_t dir = 1; dir <= 6; dir++)
+                                for (uint32_t outward = 0; outward < dir; outward++) {
+                                    if ((outward & dir) != outward) continue;   // proper subsets of dir
+                                    const uint32_t ptr = outward ? n.link[outward - 1] : n.parentBlock;
+                                    const bool closed = (ptr >> 31) || (ptr >> 30) || isLeaf(ptr + (dir ^ c)) || isMarked(ptr + (dir ^ c));
+                                    if (!closed) subdivided |= faceMask[4 * (dir - 1) + signOf(dir, outward, c)];
+                                }
+                        } else if (nd == startDepth) {
+                            int pos[3];
+                            gridPos(n.center, pos);
+                            for (uint32_t dir = 1; dir <= 6; dir++) {
+                                const uint32_t nAxes = (dir & 1) + ((dir >> 1) & 1) + ((dir >> 2) & 1);
+                                for (uint32_t sign = 0; sign < (1u << nAxes); sign++) {
+                                    int p[3];
+                                    for (int a = 0; a < 3; a++) p[a] = pos[a] + ((dir & (1u << a)) ? axisSign(dir, sign, a) : 0);
+                                    if (inGrid(p) && !(isLeaf(gridSlot(p)) || isMarked(gridSlot(p)))) subdivided |= faceMask[4 * (dir - 1) + sign];
+                                }
+                            }
+                        }
+                        interpolateMask = ~subdivided;
+                        split = interpolateMask != ~0u;
+                    }
+                    if (split) {
+                        const bool recycleMid = first && !n.ignore;
+                        if (!recycleMid) {
+                            tricubicCoefficients(n.values, 2.0f * n.half, n.coeff);
+                            sampleMid(cacheMain, n, interpolateMask);
+                        }
+                        for (int s = 0; s < 19; s++) {
+                            if ((interpolateMask & (1u << (18 - s))) == 0) {
+                                const float inter = tricubicValue(n.coeff.data(), sampleFrac(s));
+                                const float d = n.mid[size_t(s)][0] - inter;
+                                if (d * d < sqThr) tricubicVertexValues(n.coeff.data(), sampleFrac(s), 2.0f * n.half, n.mid[size_t(s)]);
+                            } else if (recycleMid) {
+                                tricubicVertexValues(n.coeff.data(), sampleFrac(s), 2.0f * n.half, n.mid[size_t(s)]);
+                            }
+                        }
+                        const uint32_t childBlock = uint32_t(oct.size());
+                        setWord(word, false, childBlock);
+                        oct[word] |= MARK;
+                        oct.resize(oct.size() + 8, B31);   // setValues(true, 0)
+                        makeChildren(n, nd, childBlock, queue, &queueDepth);
+                    } else {
+                        uint32_t at = uint32_t(oct.size());
+                        if (recycled) { setWord(word, true, at); oct.resize(oct.size() + 64); }
+                        else { at = oldCoefficients; setWord(word, true, at); recycled = true; }
+                        tricubicCoefficients(n.values, 2.0f * n.half, n.coeff);
+                        std::memcpy(&oct[at], n.coeff.data(), 64 * sizeof(float));
+                        n.terminal = true;
+                        n.ignore = true;
+                        level[nd].push_back(n);
+                        leaves.insert(std::make_pair(n.parentBlock + c, std::make_pair(nd, uint32_t(level[nd].size() - 1))));
+                    }
+                    first = false;
+                }
+            }
+        }
+        // final un-mark (:1191-1217): every word reachable from the start grid
+        {
+            std::vector<uint32_t> st;
+            for (uint32_t v = 0; v < G * G * G; v++) st.push_back(v);
+            while (!st.empty()) {
+                const uint32_t w = st.back();
+                st.pop_back();
+                oct[w] &= ~MARK;
+                if (!(oct[w] & B31)) for (uint32_t i = 0; i < 8; i++) st.push_back((oct[w] & OCT_INDEX_MASK) + i);
+            }
+        }
+        out.valueRange = valueRange;
     }
 };
 
@@ -1327,7 +1749,7 @@ float orc_error_estimate(const float* coeff64, const float* mid19x8, int rule, f
     std::memcpy(c.data(), coeff64, sizeof(c));
     std::array<PointValues, 19> mid;
     std::memcpy(mid.data(), mid19x8, sizeof(mid));
-    return errorTrapezoid(c, mid, rule == 3, decay);
+    return errorByRule(rule, c, mid, decay);
 }
 
 int orc_is_near_minimize(float half, const float* r8, const float* tri9, float thr, uint32_t* outIter) {
@@ -1356,12 +1778,20 @@ void orc_nearest_triangle(const float* verts, uint32_t nVerts, const uint32_t* i
 OrcSdf* orc_build_octree(const float* verts, uint32_t nVerts, const uint32_t* idx, uint32_t nIdx, const float* box6,
                          uint32_t depth, uint32_t startDepth, int rule, float param0, float param1, int algorithm,
                          uint32_t numThreads, int useCache) {
-    if (algorithm != 1) return nullptr;   // NO_CONTINUITY only (CONTINUITY / UNIFORM: see DESIGN.md, out of round-1 scope)
+    if (algorithm != 1 && algorithm != 2) return nullptr;   // UNIFORM ("for testing", OctreeSdf.h:286): not restated
     auto* s = new OrcSdf();
     s->format = 1;
     s->maxDepth = depth;
     cubify(*s, box6, startDepth);
     MeshView m{reinterpret_cast<const V3*>(verts), nVerts, idx, nIdx};
+    if (algorithm == 2) {
+        ContBuilder b{*s, m, meshTriangleData(m), nullptr, VertexCache(), VertexCache(), startDepth, depth, rule, param0, param1, {}};
+        b.bvh.reset(new Bvh(m));
+        b.cacheMain.init(s->box, depth, useCache != 0);
+        b.run();
+        computeMinBorder(*s);
+        return s;
+    }
     OctBuilder b{*s, m, meshTriangleData(m), nullptr, VertexCache(), startDepth, depth, rule, param0, param1};
     b.bvh.reset(new Bvh(m));
     b.cache.init(s->box, depth, useCache != 0);

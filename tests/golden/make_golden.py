@@ -104,10 +104,41 @@ def main():
     ed, eg2 = e.query(q2, True)
     np.savez_compressed(os.path.join(OUT, "small_structures.npz"), box=boxd, octree_bin=ob, exact_bin=eb, query_points=q2,
                         octree_distances=od, octree_gradients=og, exact_distances=ed, exact_gradients=eg2)
+    continuity()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def continuity():
+    """InitAlgorithm::CONTINUITY (src/sdf/OctreeSdfBreadthFirstNoDelay.h) + the Simpson / by-distance rules.
+    Own generator so that `make_golden.py continuity` adds this fixture without touching the others."""
+    rng = np.random.default_rng(3333)
+    v, i = ref.isosphere(2)
+    vd = displace(v)
+    box = box_of(vd)
+    out = {"box": box}
+    for name, rule, p1 in (("trapezoid", 1, 0.0), ("simpson", 2, 0.0), ("by_distance", 3, 0.1)):
+        a = ref.build_octree(vd, i, box, 5, 3, 1e-3, 2, 1, termination_rule=rule, param1=p1)
+        d = a.octree_data()
+        out[name + "_words"] = np.int64(d.size)
+        out[name + "_sha256"] = sha(d)
+        out[name + "_min_border_value"] = np.float32(a.header()["min_border_value"])
+        if rule == 1:
+            area = a.sample_area()
+            q = (area[:3] + rng.uniform(-0.05, 1.05, (512, 3)) * (area[3:] - area[:3])).astype(np.float32)
+            dist, grad = a.query(q, True)
+            out.update(query_points=q, distances=dist, gradients=grad, start_slots=d[:512])
+    vals = rng.standard_normal((8, 8)).astype(np.float32)
+    coeff = ref.tricubic_coefficients(vals, 0.41)     # all eight Hermite slots in use (mixed derivatives non-zero)
+    mid = rng.standard_normal((19, 8)).astype(np.float32)
+    out.update(corner_values=vals, node_size=np.float32(0.41), coefficients=coeff, mid_values=mid,
+               error=np.float32([ref.error_estimate(coeff, mid, r, 0.1) for r in (1, 2, 3)]))
+    np.savez_compressed(os.path.join(OUT, "continuity_small.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["continuity"]:
+        continuity()
+    else:
+        main()

@@ -164,7 +164,76 @@ def test_mt_layout_is_a_relayout(port):
     assert np.array_equal(canon(a), canon(b))
 
 
+def test_continuity_golden(port):
+    """InitAlgorithm::CONTINUITY and the three termination rules against reference-generated fixtures."""
+    g = golden("continuity_small.npz")
+    import hashlib
+    v, i = displaced_sphere(2)
+    c = port.tricubic_coefficients(g["corner_values"], float(g["node_size"]))
+    assert_bit_equal(c, g["coefficients"], "calculateCoefficients with mixed derivatives")
+    e = np.float32([port.error_estimate(c, g["mid_values"], r, 0.1) for r in (1, 2, 3)])
+    assert_bit_equal(e, g["error"], "trapezoid / Simpson / by-distance integrals")
+    for name, rule, p1 in (("trapezoid", 1, 0.0), ("simpson", 2, 0.0), ("by_distance", 3, 0.1)):
+        a = port.build_octree(v, i, g["box"], 5, 3, 1e-3, 2, 1, termination_rule=rule, param1=p1, use_cache=True)
+        d = a.octree_data()
+        assert d.size == int(g[name + "_words"])
+        assert hashlib.sha256(d.tobytes()).hexdigest() == str(g[name + "_sha256"]), name
+        assert_bit_equal(np.float32(a.header()["min_border_value"]), g[name + "_min_border_value"])
+        if rule == 1:
+            assert np.array_equal(d[:512], g["start_slots"])
+            dist, grad = a.query(g["query_points"], True)
+            assert_bit_equal(dist, g["distances"]); assert_bit_equal(grad, g["gradients"])
+
+
+def test_continuity_field_is_continuous_across_t_junctions(port):
+    """The property the algorithm exists for: across every face of the start grid the tri-cubic field is
+    continuous (value jump far below the termination threshold), which NO_CONTINUITY does not give."""
+    v, i = displaced_sphere(2)
+    from sdflib_b200 import meshes
+    box = meshes.bounding_box_with_margin(v)
+    jumps = {}
+    for alg in (1, 2):
+        a = port.build_octree(v, i, box, 5, 3, 1e-3, alg, 1, use_cache=False)
+        area = a.sample_area()
+        rng = np.random.default_rng(9)
+        n = 20000
+        uv = rng.uniform(0.02, 0.98, (n, 3))
+        plane = rng.integers(1, 32, n) / 32.0   # faces of depth-5 cells
+        axis = rng.integers(0, 3, n)
+        eps = 2e-6
+        lo, hi = uv.copy(), uv.copy()
+        lo[np.arange(n), axis] = plane - eps
+        hi[np.arange(n), axis] = plane + eps
+        size = area[3:] - area[:3]
+        dl = a.query((area[:3] + lo * size).astype(np.float32))
+        dh = a.query((area[:3] + hi * size).astype(np.float32))
+        jumps[alg] = float(np.abs(dl - dh).max())
+    assert jumps[2] < 2e-4, jumps
+    assert jumps[2] < 0.25 * jumps[1], jumps
+
+
 # ---- port vs the unmodified reference (only where oracle/_ref exists) -------------------------------
+@pytest.mark.parametrize("subdiv,depth,start,rule", [(2, 5, 3, 1), (2, 5, 2, 1), (3, 6, 3, 1), (2, 4, 0, 1), (3, 5, 3, 2), (3, 5, 3, 3)])
+def test_port_continuity_equals_reference(port, ref, subdiv, depth, start, rule, tmp_path):
+    v, i = displaced_sphere(subdiv)
+    from sdflib_b200 import meshes
+    box = meshes.bounding_box_with_margin(v)
+    a = ref.build_octree(v, i, box, depth, start, 1e-3, 2, 1, termination_rule=rule, param1=0.1)
+    b = port.build_octree(v, i, box, depth, start, 1e-3, 2, 1, termination_rule=rule, param1=0.1, use_cache=True)
+    assert np.array_equal(a.octree_data(), b.octree_data())
+    pa, pb = str(tmp_path / "a.bin"), str(tmp_path / "b.bin")
+    a.save(pa); b.save(pb)
+    ba, bb = bytearray(open(pa, "rb").read()), bytearray(open(pb, "rb").read())
+    # mValueRange is never initialised on the reference's CONTINUITY path (OctreeSdf.h:251 — max() accumulates
+    # onto heap garbage, OctreeSdfBreadthFirstNoDelay.h:728): bytes 37..40 of the file are excluded.
+    ba[37:41] = bb[37:41] = b"\0\0\0\0"
+    assert ba == bb
+    area = a.sample_area()
+    q = (area[:3] + np.random.default_rng(5).uniform(-0.1, 1.1, (20000, 3)) * (area[3:] - area[:3])).astype(np.float32)
+    (da, ga), (db, gb) = a.query(q, True), b.query(q, True)
+    assert_bit_equal(da, db); assert_bit_equal(ga, gb)
+
+
 @pytest.mark.parametrize("subdiv,depth,start,threads", [(2, 5, 3, 1), (3, 5, 2, 1), (3, 6, 3, 1)])
 def test_port_octree_equals_reference(port, ref, subdiv, depth, start, threads, tmp_path):
     v, i = displaced_sphere(subdiv)
