@@ -37,6 +37,7 @@ UNITS = [
     ("host_mem.cpp", "host_mem.o", ["-x", "cu"]),
     ("fixtures.cpp", "fixtures.o", ["-x", "cu"] + NO_FMA),
     ("octree_build.cu", "octree_build.o", NO_FMA),
+    ("octree_cont.cu", "octree_cont.o", NO_FMA),
     ("octree_query.cu", "octree_query_fast.o", []),
     ("octree_query.cu", "octree_query_exact.o", ["-DSDFB_QUERY_EXACT"] + NO_FMA),
 ]

@@ -91,13 +91,18 @@ int sdfb200_build_octree_shard(const float* vertices, uint32_t numVertices, cons
         HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
         checkBox(box6);
         if (worldSize == 0 || rank >= worldSize) throw Error(SDFB200_ERR_INVALID, "rank/worldSize out of range");
-        if (initAlgorithm != SDFB200_ALG_NO_CONTINUITY)
-            throw Error(SDFB200_ERR_UNSUPPORTED, "only InitAlgorithm::NO_CONTINUITY is built (CONTINUITY / UNIFORM: see DESIGN.md)");
+        if (initAlgorithm != SDFB200_ALG_NO_CONTINUITY && initAlgorithm != SDFB200_ALG_CONTINUITY)
+            throw Error(SDFB200_ERR_UNSUPPORTED, "InitAlgorithm::UNIFORM (the reference's testing variant) is not built: see DESIGN.md");
         if (terminationRule < SDFB200_RULE_NONE || terminationRule > SDFB200_RULE_BY_DISTANCE)
             throw Error(SDFB200_ERR_INVALID, "unknown termination rule");
+        if (initAlgorithm == SDFB200_ALG_CONTINUITY && worldSize > 1)
+            throw Error(SDFB200_ERR_UNSUPPORTED, "CONTINUITY builds are not sharded (neighbour probes cross start voxels): build on one device");
         requireDevice();
         std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
-        buildOctreeOnDevice(*s, mesh, box6, depth, startDepth, terminationRule, param0, param1, numThreads, rank, worldSize);
+        if (initAlgorithm == SDFB200_ALG_CONTINUITY)
+            buildOctreeContinuityOnDevice(*s, mesh, box6, depth, startDepth, terminationRule, param0, param1);
+        else
+            buildOctreeOnDevice(*s, mesh, box6, depth, startDepth, terminationRule, param0, param1, numThreads, rank, worldSize);
         *out = s.release();
     });
 }

@@ -195,6 +195,10 @@ namespace sdfb200 {
 void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
                          int rule, float param0, float param1, uint32_t numThreads, uint32_t rank, uint32_t world);
 void finalizeOctreeScalars(sdfb200_sdf& s);   // shardScalars -> valueRange / minBorderValue
+void cubifyBox(sdfb200_sdf& s, const float* box6, uint32_t startDepth);
+// octree_cont.cu: InitAlgorithm::CONTINUITY (single device; the structure is complete on return)
+void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+                                   int rule, float param0, float param1);
 // shard.cpp
 uint64_t shardPayloadWords(const sdfb200_sdf& s);
 void shardExport(const sdfb200_sdf& s, uint32_t* dDst, uint64_t capacityWords);

@@ -170,3 +170,88 @@ def test_full_size_properties(sdf):
     assert (d_exact - d_fast).abs().max().item() < 2e-6
     assert d_exact.min().item() < 0 < d_exact.max().item()
     assert abs(d_exact.abs().max().item()) <= a.info().value_range * 1.01
+
+
+# ---- InitAlgorithm::CONTINUITY (src/sdf/OctreeSdfBreadthFirstNoDelay.h) -----------------------------
+def build_continuity(sdf, port, v, i, depth, start, thr=1e-3, rule=1, params=None):
+    box = sdf.meshes.bounding_box_with_margin(v)
+    g = sdf.OctreeSdf(sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:]), depth, start, thr, sdf.OctreeSdf.CONTINUITY, 1,
+                      terminationRule=rule, terminationRuleParams=params)
+    p = port.build_octree(v, i, box, depth, start, thr if params is None else params[0], 2, 1, termination_rule=rule,
+                          param1=0.0 if params is None or len(params) < 2 else params[1], use_cache=False)
+    return g, p, box
+
+
+@pytest.mark.parametrize("subdiv,depth,start,thr", [(2, 5, 3, 1e-3), (2, 5, 2, 1e-3), (3, 6, 3, 1e-3), (4, 6, 3, 1e-3), (3, 6, 1, 2e-3),
+                                                    (2, 4, 0, 1e-3), (3, 7, 3, 3e-4), (2, 3, 3, 1e-3)])
+def test_continuity_build_bit_exact_vs_oracle(sdf, port, subdiv, depth, start, thr):
+    """Words (node words in the reference's breadth-first + fix-up ORDER, and every leaf coefficient), value range and
+    border minimum of the level-synchronous GPU build against the serial oracle."""
+    v, i = displaced_sphere(subdiv)
+    g, p, _ = build_continuity(sdf, port, v, i, depth, start, thr)
+    got, want = g.getOctreeData(), p.octree_data()
+    assert got.size == want.size
+    assert np.array_equal(got, want), f"{int((got != want).sum())} words differ, first at {int(np.nonzero(got != want)[0][0])}"
+    h, info = p.header(), g.info()
+    assert_bit_equal(np.float32([info.value_range, info.min_border_value]), np.float32([h["value_range"], h["min_border_value"]]))
+
+
+@pytest.mark.parametrize("rule,params", [(2, [1e-3]), (3, [1e-3, 0.05])])
+def test_continuity_termination_rules(sdf, port, rule, params):
+    v, i = displaced_sphere(3)
+    g, p, _ = build_continuity(sdf, port, v, i, 5, 3, rule=rule, params=params)
+    assert np.array_equal(g.getOctreeData(), p.octree_data())
+
+
+def test_simpson_rule_no_continuity(sdf, port):
+    v, i = displaced_sphere(3)
+    g, p, _ = build_both(sdf, port, v, i, 5, 2, rule=2, params=[1e-3])
+    assert np.array_equal(g.getOctreeData(), p.octree_data())
+
+
+def test_continuity_topology_equals_reference(sdf, ref):
+    """Against the reference itself (single thread, with its history-dependent vertex cache): identical node words —
+    i.e. identical topology AND identical array order through Iter 2 and the fix-up pass."""
+    v, i = displaced_sphere(3)
+    box = sdf.meshes.bounding_box_with_margin(v)
+    s = sdf.OctreeSdf(sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:]), 6, 3, 1e-3, sdf.OctreeSdf.CONTINUITY, 1)
+    r = ref.build_octree(v, i, box, 6, 3, 1e-3, 2, 1)
+    a, b = s.getOctreeData(), r.octree_data()
+    assert a.size == b.size
+    ta, _, _ = octree_topology(a, 8)
+    tb, _, _ = octree_topology(b, 8)
+    assert np.array_equal(ta, tb) and np.array_equal(a[ta], b[tb])
+    q = random_points(s.getSampleArea().as_array(), 200000, 1, spill=0.0)
+    d, dr = s.getDistance(q), r.query(q)
+    assert np.abs(d - dr).max() < 5e-4   # tie-broken nearest triangles propagate through the interpolated samples
+
+
+def test_continuity_golden_fixture(sdf):
+    g = golden("continuity_small.npz")
+    v, i = displaced_sphere(2)
+    s = sdf.OctreeSdf(sdf.Mesh(v, i), sdf.BoundingBox(g["box"][:3], g["box"][3:]), 5, 3, 1e-3, sdf.OctreeSdf.CONTINUITY, 1)
+    d = s.getOctreeData()
+    assert d.size == int(g["trapezoid_words"])
+    assert np.array_equal(d[:512], g["start_slots"])
+    dist = s.getDistance(g["query_points"], exact_order=True)
+    assert np.abs(dist - g["distances"]).max() < 5e-4
+
+
+def test_continuity_query_bit_exact_and_continuous(sdf, port):
+    v, i = displaced_sphere(3)
+    g, p, _ = build_continuity(sdf, port, v, i, 6, 3)
+    q = random_points(g.getSampleArea().as_array(), 200000, 4)
+    (d, gr), (od, og) = g.getDistance(q, gradient=True, exact_order=True), p.query(q, True)
+    assert_bit_equal(d, od, "distance"); assert_bit_equal(gr, og, "gradient")
+    # C0 across cell faces of every depth: the point of the algorithm
+    area = g.getSampleArea().as_array()
+    rng = np.random.default_rng(9)
+    n = 200000
+    uv = rng.uniform(0.02, 0.98, (n, 3))
+    plane, axis = rng.integers(1, 64, n) / 64.0, rng.integers(0, 3, n)
+    lo, hi = uv.copy(), uv.copy()
+    lo[np.arange(n), axis] = plane - 2e-6
+    hi[np.arange(n), axis] = plane + 2e-6
+    size = area[3:] - area[:3]
+    jump = np.abs(g.getDistance((area[:3] + lo * size).astype(np.float32)) - g.getDistance((area[:3] + hi * size).astype(np.float32)))
+    assert jump.max() < 2e-4, float(jump.max())
