@@ -130,6 +130,11 @@ def run_reference(args):
         ex = ref.build_exact(v, i, box, EXACT["depth"], EXACT["start_depth"], EXACT["min_triangles"], max(cores, 2))
         exact_build_s = ex.build_seconds
         ex.close()
+    cont_build_s = None
+    if not args.no_continuity_reference:
+        co = ref.build_octree(v, i, box, WORKLOAD["depth"], WORKLOAD["start_depth"], WORKLOAD["threshold"], 2, max(cores, 2))
+        cont_build_s = co.build_seconds
+        co.close()
     area = sdf.sample_area()
     # bounded sample of the workload: every 8th point of the 256^3 cell-centre grid (2.1 M queries) per step
     n = WORKLOAD["grid"]
@@ -150,6 +155,7 @@ def run_reference(args):
                              "build_s": build_s, "build_threads": max(cores, 2)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "build": {"octree_c2": {"seconds": build_s, "threads": max(cores, 2)},
+                      "octree_c2_continuity": {"seconds": cont_build_s, "threads": max(cores, 2)},
                       "exact_c3": {"seconds": exact_build_s, "threads": max(cores, 2), "config": EXACT}},
             "build_s": build_s}
     print(json.dumps(line))
@@ -208,6 +214,19 @@ def run_ours(args):
     build_s = min(builds)
     stats = sdf.build_stats()
     info = sdf.info()
+    cont = None
+    if world == 1:   # InitAlgorithm::CONTINUITY (the reference's CLI / Unity default), same mesh and depth; single device
+        make_cont = lambda: S.OctreeSdf(mesh, bb, WORKLOAD["depth"], WORKLOAD["start_depth"], WORKLOAD["threshold"], S.OctreeSdf.CONTINUITY, 2)
+        c, _t = timed_build(make_cont)
+        c.close()
+        cont_builds = []
+        for _ in range(3):
+            c, t = timed_build(make_cont)
+            cont_builds.append(t)
+            if _ == 2:
+                cont = {"seconds": min(cont_builds), "all_seconds": cont_builds, "stats_ms_rank0": c.build_stats(),
+                        "octree_words": int(c.info().octree_words)}
+            c.close()
     exact, _t = timed_build(make_ex)
     exact.close()
     ex_builds = []
@@ -309,6 +328,7 @@ def run_ours(args):
                              "algorithmic_bytes_per_launch": int(algo_bytes)},
                 "build": {"scaling": "strong (one mesh, start-depth voxels sharded over the ranks)" if world > 1 else "single GPU",
                           "octree_c2": {"seconds": build_s, "first_call_seconds": build_first_s, "all_seconds": builds, "stats_ms_rank0": stats},
+                          "octree_c2_continuity": cont,
                           "exact_c3": {"seconds": exact_build_s, "all_seconds": ex_builds, "config": EXACT, "stats_ms_rank0": exact_stats,
                                        "nodes": int(exact_info.octree_words), "set_words": int(exact_info.triangle_sets_words),
                                        "mask_bytes": int(exact_info.triangle_masks_bytes),
@@ -356,6 +376,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-continuity-reference", action="store_true", help="reference arm: skip the CONTINUITY OctreeSdf build")
     ap.add_argument("--no-exact-reference", action="store_true", help="reference arm: skip the (tens of seconds) ExactOctreeSdf build")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)

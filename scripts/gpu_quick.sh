@@ -8,7 +8,7 @@ python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_quick.json'))
 print('value %.2f Gq/s  e2e %.2f Gq/s  frac %.3f' % (d['value']/1e9, d['e2e']['value']/1e9, d['roofline']['frac']))
-for k in ('octree_c2','exact_c3'):
+for k in ('octree_c2','octree_c2_continuity','exact_c3'):
     b=d['build'][k]; print(k, b['seconds'], b['all_seconds'], {a:round(v,1) for a,v in b['stats_ms_rank0'].items() if a.endswith('_ms')})
 print('exact_query', d['exact_query'])
 PY

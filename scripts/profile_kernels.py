@@ -1,5 +1,5 @@
 """Small driver for ncu captures (one GPU): runs ONE build or ONE query pass of the bench workloads.
-    python scripts/profile_kernels.py exact_build | octree_build | exact_query | octree_query"""
+    python scripts/profile_kernels.py exact_build | octree_build | octree_cont | exact_query | octree_query"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -12,6 +12,8 @@ box = meshes.bounding_box_with_margin(v)
 mesh, bb = S.Mesh(v, i), S.BoundingBox(box[:3], box[3:])
 if what.startswith("exact"):
     sdf = S.ExactOctreeSdf(mesh, bb, 7, 3, 128, 2)
+elif what == "octree_cont":
+    sdf = S.OctreeSdf(mesh, bb, 8, 3, 1e-3, S.OctreeSdf.CONTINUITY, 2)
 else:
     sdf = S.OctreeSdf(mesh, bb, 8, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 2)
 if what.endswith("query"):

@@ -44,12 +44,6 @@ SdfFunctionHandle* createOctreeSdf(sdfb200_vec3* vertices, uint32_t numVertices,
     sdfb200_sdf* h = nullptr;
     int code = sdfb200_build_octree(&vertices->x, numVertices, indices, numIndices, box, maxOctreeDepth, startOctreeDepth,
                                     SDFB200_RULE_TRAPEZOIDAL, maxError, 0.0f, SDFB200_ALG_CONTINUITY, numThreads, &h);
-    if (code == SDFB200_ERR_UNSUPPORTED) {
-        // CONTINUITY is not built yet: say so and build the same octree without the continuity pass
-        std::fprintf(stderr, "[sdfb200] createOctreeSdf: InitAlgorithm::CONTINUITY is not available, building NO_CONTINUITY\n");
-        code = sdfb200_build_octree(&vertices->x, numVertices, indices, numIndices, box, maxOctreeDepth, startOctreeDepth,
-                                    SDFB200_RULE_TRAPEZOIDAL, maxError, 0.0f, SDFB200_ALG_NO_CONTINUITY, numThreads, &h);
-    }
     if (code != SDFB200_OK) {
         std::fprintf(stderr, "[sdfb200] createOctreeSdf: %s\n", sdfb200_last_error());
         return nullptr;

@@ -47,7 +47,7 @@ def test_argument_validation_returns_codes(sdf):
     flat = np.float32([0, 0, 0, 1, 0, 1])
     assert L.sdfb200_build_octree(_capi.ptr(v), len(v), _capi.ptr(i), i.size, _capi.ptr(flat), 5, 3, 1, C.c_float(1e-3), C.c_float(0), 1, 1, C.byref(h)) == _capi.ERR_INVALID
     # options of the reference API that are not built yet are reported, not silently changed
-    assert L.sdfb200_build_octree(_capi.ptr(v), len(v), _capi.ptr(i), i.size, _capi.ptr(box), 5, 3, 1, C.c_float(1e-3), C.c_float(0), 2, 1, C.byref(h)) == _capi.ERR_UNSUPPORTED
+    assert L.sdfb200_build_octree(_capi.ptr(v), len(v), _capi.ptr(i), i.size, _capi.ptr(box), 5, 3, 1, C.c_float(1e-3), C.c_float(0), 0, 1, C.byref(h)) == _capi.ERR_UNSUPPORTED   # UNIFORM
     assert h.value is None
 
 
