@@ -252,6 +252,8 @@ struct BvhBuilder {
             *sphereRadius = std::max(std::max(r0, r1), r2);
             node.left = -1;
             node.right = t.id;
+            node.pad[0] = 1;   // leaf
+            node.pad[1] = 0;
             return;
         }
         double top[3], bottom[3], c[3] = {0, 0, 0};
@@ -281,6 +283,7 @@ struct BvhBuilder {
         const int32_t mid = int32_t(0.5 * (begin + end));
         node.left = nodeId + 1;
         node.right = nodeId + 2 * (mid - begin);
+        node.pad[0] = node.pad[1] = 0;
         const int32_t l = node.left, r = node.right;
         double* lc = node.lc;
         double* lr = &node.lr;
@@ -311,6 +314,17 @@ RawVec<BvhNode> buildBvh(const HostMesh& mesh) {
 #pragma omp parallel num_threads(hostThreads())
 #pragma omp single
     b.build(0, rootCenter, &rootRadius, 0, int32_t(nT));
+    // Device traversal never loads a leaf node: links to leaves are replaced by ~triangleId (mesh_host.h).
+    const int64_t nNodes = int64_t(nodes.size());
+#pragma omp parallel for schedule(static) num_threads(hostThreads())
+    for (int64_t i = 0; i < nNodes; i++) {
+        BvhNode& nd = nodes[size_t(i)];
+        if (nd.pad[0]) continue;
+        const BvhNode& l = nodes[size_t(nd.left)];
+        const BvhNode& r = nodes[size_t(nd.right)];
+        if (l.pad[0]) nd.left = ~l.right;
+        if (r.pad[0]) nd.right = ~r.right;
+    }
     return nodes;
 }
 

@@ -33,9 +33,10 @@ int hostThreads();   // SDFB200_HOST_THREADS or the OpenMP default
 // reference: TriangleUtils::calculateMeshTriangleData, src/utils/TriangleUtils.cpp:7-428
 TriVec computeTriangleData(const HostMesh& mesh);
 
-// Device-friendly BVH node: both child spheres + child links, 80 bytes, 16-byte aligned.
-// left < 0 marks a leaf and `right` is then the triangle id
+// Device-friendly BVH node: both child spheres + child links, 80 bytes, 16-byte aligned
 // (reference: tmd::TriangleMeshDistance::Node, TriangleMeshDistance.h:96-109).
+// pad[0] != 0 marks a leaf node (`right` = triangle id). In inner nodes a link >= 0 is the index of an inner
+// child and a link < 0 is ~triangleId of a leaf child, so the traversal never has to load a leaf node.
 struct alignas(16) BvhNode {
     double lc[3], lr;
     double rc[3], rr;

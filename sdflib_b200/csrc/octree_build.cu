@@ -53,15 +53,15 @@ __global__ void seedCornersKernel(DeviceMesh mesh, const float4* centerHalf, flo
     corners[i] = samplePoint(mesh, p);
 }
 
-// One warp per candidate node of a level below maxDepth: 19 samples, fit, error integral, decision.
-template <bool kDecide>
+// One warp per candidate node of a level below maxDepth: fit, error integral, decision. The 19 samples were
+// taken by sampleLatticeKernel (one thread per sample, octree_device.cuh).
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-levelSampleKernel(DeviceMesh mesh, LevelView lv, float4* mids, uint32_t* subdivide, int rule, float sqThreshold, float decay) {
+levelDecideKernel(LevelView lv, const float4* mids, uint32_t* subdivide, int rule, float sqThreshold, float decay) {
     __shared__ HermiteTable tab;
     __shared__ float4 lattice[kWarpsPerCta][27];
     __shared__ float coeff[kWarpsPerCta][64];
     __shared__ float terms[kWarpsPerCta][19];
-    if (kDecide) {
+    {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&cHermite);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&tab);
         for (uint32_t i = threadIdx.x; i < sizeof(HermiteTable) / 4; i += blockDim.x) dst[i] = src[i];
@@ -72,16 +72,8 @@ levelSampleKernel(DeviceMesh mesh, LevelView lv, float4* mids, uint32_t* subdivi
     if (node >= lv.count) return;
     const float4 ch = lv.centerHalf[node];
     if (lane < 8) lattice[warp][2 * (lane & 1) + 6 * ((lane >> 1) & 1) + 18 * (lane >> 2)] = lv.corners[size_t(node) * 8 + lane];
-    if (lane < 19) {
-        const int L = cSampleLattice[lane];
-        const f3 rel = mk3(float(L % 3 - 1), float((L / 3) % 3 - 1), float(L / 9 - 1));
-        const f3 p = mk3(ch.x, ch.y, ch.z) + rel * ch.w;
-        const float4 v = samplePoint(mesh, p);
-        lattice[warp][L] = v;
-        mids[size_t(node) * 19 + lane] = v;
-    }
+    if (lane < 19) lattice[warp][cSampleLattice[lane]] = mids[size_t(node) * 19 + lane];
     __syncwarp();
-    if (!kDecide) { if (lane == 0) subdivide[node] = 1u; return; }
     const float nodeSize = 2.0f * ch.w;
     coeff[warp][tab.order[lane]] = hermiteRow(tab, tab.order[lane], lattice[warp], nodeSize);
     coeff[warp][tab.order[32 + lane]] = hermiteRow(tab, tab.order[32 + lane], lattice[warp], nodeSize);
@@ -108,6 +100,11 @@ levelSampleKernel(DeviceMesh mesh, LevelView lv, float4* mids, uint32_t* subdivi
         }
         subdivide[node] = (value < sqThreshold) ? 0u : 1u;
     }
+}
+
+__global__ void fillOnesKernel(uint32_t* p, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 1u;
 }
 
 // Children of the subdividing nodes: 8 records each, corner values inherited from the 27-point lattice
@@ -392,10 +389,12 @@ struct OctreeBuildState : BuildState {
             flags.alloc(L.count);
             scan.alloc(L.count);
             const uint32_t grid = divUp(L.count, kWarpsPerCta);
+            sampleLatticeKernel<<<divUp(uint64_t(L.count) * 19, 256), 256>>>(dmesh, L.centerHalf.p, L.count, mids.p, 1);
             if (d >= startDepth)
-                levelSampleKernel<true><<<grid, kWarpsPerCta * 32>>>(dmesh, L.view(), mids.p, flags.p, rule, param0 * param0, param1);
+                levelDecideKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), mids.p, flags.p, rule, param0 * param0, param1);
             else
-                levelSampleKernel<false><<<grid, kWarpsPerCta * 32>>>(dmesh, L.view(), mids.p, flags.p, rule, 0.0f, 0.0f);
+                fillOnesKernel<<<divUp(L.count, 256), 256>>>(flags.p, L.count);   // virtual levels always subdivide
+            st.kernel_launches++;
             if (d == startDepth && world > 1) {   // the roots of other ranks are not refined here
                 dOwned.alloc(L.count);
                 dOwned.upload(out.plan.owned.data(), L.count);

@@ -198,31 +198,25 @@ __global__ void contSeedKernel(DeviceMesh mesh, Grid g, LevelArrays lv, uint32_t
     if ((i & 7u) == 0) lv.word[i >> 3] = (depth == g.startDepth) ? startSlotOf(g, c) : kNone;
 }
 
-// Iter 1 (:258-369): 19 true samples, fit, error integral, provisional leaf bit. One warp per node.
-template <bool kDecide>
+// Iter 1 (:258-369): fit, error integral, provisional leaf bit. One warp per node; the 19 true samples were
+// taken by sampleLatticeKernel (one thread per sample).
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-contSampleKernel(DeviceMesh mesh, LevelArrays lv, float4* mids, float* coeffOut, uint32_t* oct, int rule, float sqThreshold, float decay) {
+contDecideKernel(LevelArrays lv, const float4* mids, float* coeffOut, uint32_t* oct, int rule, float sqThreshold, float decay) {
     __shared__ HermiteTable tab;
     __shared__ float4 lattice[kWarpsPerCta][27][2];
     __shared__ float coeff[kWarpsPerCta][64];
     __shared__ float terms[kWarpsPerCta][19];
-    if (kDecide) loadHermite(tab);
+    loadHermite(tab);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t node = blockIdx.x * kWarpsPerCta + warp;
     if (node >= lv.count) return;
     const float4 ch = lv.centerHalf[node];
     if (lane < 16) lattice[warp][cornerLattice(lane >> 1)][lane & 1] = lv.values[size_t(node) * 16 + lane];
     if (lane < 19) {
-        const int L = cSampleLattice[lane];
-        const f3 rel = mk3(float(L % 3 - 1), float((L / 3) % 3 - 1), float(L / 9 - 1));
-        const float4 v = samplePoint(mesh, mk3(ch.x, ch.y, ch.z) + rel * ch.w);
-        lattice[warp][L][0] = v;
-        lattice[warp][L][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        mids[size_t(node) * 38 + 2 * lane] = v;
-        mids[size_t(node) * 38 + 2 * lane + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        lattice[warp][cSampleLattice[lane]][0] = mids[size_t(node) * 38 + 2 * lane];
+        lattice[warp][cSampleLattice[lane]][1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
-    if (!kDecide) { if (lane == 0) lv.terminal[node] = 0; return; }
     const float nodeSize = 2.0f * ch.w;
     fitCoefficients(tab, lattice[warp], nodeSize, coeff[warp], lane);
     __syncwarp();
@@ -408,6 +402,7 @@ struct RoundArrays {
     float4* centerHalf;
     float4* values;         // 16 per node
     uint32_t* split;        // 0 / 1
+    uint32_t* nSamples;     // true samples the node needs (0 unless it splits)
     uint32_t* interpMask;
     uint32_t* size;
     uint32_t* word;
@@ -464,14 +459,32 @@ fixProbeKernel(Grid g, RoundArrays rd, uint32_t round, uint32_t currentDepth, co
     const uint32_t subdivided = __reduce_or_sync(0xffffffffu, mine);
     if (lane == 0) {
         rd.split[node] = subdivided ? 1u : 0u;
+        rd.nSamples[node] = uint32_t(__popc(subdivided & 0x7FFFFu));   // true samples: the points on faces shared with subdivided neighbours
         rd.interpMask[node] = ~subdivided;
         if (!subdivided) atomicMin(&firstLeaf[rd.rootIdx[node]], (static_cast<unsigned long long>(round) << 32) | node);
     }
 }
 
+// positions of the true samples of the splitting nodes, in (node, sample) order
+__global__ void fixSamplePointsKernel(RoundArrays rd, const uint32_t* sampleScan, float4* points) {
+    const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= rd.count || !rd.nSamples[node]) return;
+    const float4 ch = rd.centerHalf[node];
+    const uint32_t need = ~rd.interpMask[node] & 0x7FFFFu;
+    uint32_t at = sampleScan[node];
+    for (int s = 0; s < 19; s++)
+        if (need & (1u << (18 - s))) {
+            const int L = cSampleLattice[s];
+            const f3 rel = mk3(float(L % 3 - 1), float((L / 3) % 3 - 1), float(L / 9 - 1));
+            const f3 p = mk3(ch.x, ch.y, ch.z) + rel * ch.w;
+            points[at++] = make_float4(p.x, p.y, p.z, 0.f);
+        }
+}
+
 // values of a splitting fix-up node (:913-939) and its 8 children (:955-1142). One warp per node.
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-fixValuesKernel(DeviceMesh mesh, RoundArrays rd, RoundArrays next, const uint32_t* splitScan, float sqThreshold) {
+fixValuesKernel(RoundArrays rd, RoundArrays next, const uint32_t* splitScan, const uint32_t* sampleScan, const float4* samples,
+                float sqThreshold) {
     __shared__ HermiteTable tab;
     __shared__ float4 lattice[kWarpsPerCta][27][2];
     __shared__ float coeff[kWarpsPerCta][64];
@@ -492,8 +505,8 @@ fixValuesKernel(DeviceMesh mesh, RoundArrays rd, RoundArrays next, const uint32_
         float4 lo, hi = make_float4(0.f, 0.f, 0.f, 0.f);
         bool interpolate = (interpMask & (1u << (18 - lane))) != 0;
         if (!interpolate) {   // on a face shared with a subdivided neighbour: the true sample, unless the polynomial is close enough
-            const f3 rel = mk3(float(L % 3 - 1), float((L / 3) % 3 - 1), float(L / 9 - 1));
-            lo = samplePoint(mesh, mk3(ch.x, ch.y, ch.z) + rel * ch.w);
+            const uint32_t need = ~interpMask & 0x7FFFFu;
+            lo = samples[sampleScan[node] + __popc(need >> (19 - lane))];   // rank among the node's true samples (lane 0: shift by 19 = none)
             const float d = lo.x - polyValueExact(coeff[warp], x, y, z);
             interpolate = d * d < sqThreshold;
         }
@@ -655,17 +668,17 @@ struct NodeLevel {
 
 struct FixRound {
     uint32_t count = 0;
-    DevBuf<uint32_t> rootIdx, parent, coord, split, interpMask, size, word, block, sizeScan, splitScan;
+    DevBuf<uint32_t> rootIdx, parent, coord, split, nSamples, sampleScan, interpMask, size, word, block, sizeScan, splitScan;
     DevBuf<uint8_t> depth, childId;
     DevBuf<float4> centerHalf, values;
     uint32_t nSplit = 0;
     void alloc(uint32_t n) {
         count = n;
-        rootIdx.alloc(n); parent.alloc(n); coord.alloc(n); split.alloc(n); interpMask.alloc(n); size.alloc(n); word.alloc(n); block.alloc(n);
+        rootIdx.alloc(n); parent.alloc(n); coord.alloc(n); split.alloc(n); nSamples.alloc(n); sampleScan.alloc(n); interpMask.alloc(n); size.alloc(n); word.alloc(n); block.alloc(n);
         sizeScan.alloc(n); splitScan.alloc(n); depth.alloc(n); childId.alloc(n); centerHalf.alloc(n); values.alloc(size_t(n) * 16);
     }
     RoundArrays arrays() {
-        return RoundArrays{count, rootIdx.p, depth.p, childId.p, parent.p, coord.p, centerHalf.p, values.p, split.p, interpMask.p, size.p, word.p, block.p};
+        return RoundArrays{count, rootIdx.p, depth.p, childId.p, parent.p, coord.p, centerHalf.p, values.p, split.p, nSamples.p, interpMask.p, size.p, word.p, block.p};
     }
 };
 
@@ -799,7 +812,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         st.samples_evaluated += L.count * 8;
     }
 
-    DevBuf<float4> mids;
+    DevBuf<float4> mids, fixPoints, fixSamples;
     DevBuf<float> coeffs;
     DevBuf<uint32_t> sizes, sub, sizeScan, subScan, candCount32, candScan, candWords, candList, isRoot, rootPos;
     DevBuf<uint8_t> candCount;
@@ -815,13 +828,14 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         // ---- Iter 1
         if (!deepest) {
             mids.alloc(size_t(L.count) * 38);
+            sampleLatticeKernel<<<divUp(uint64_t(L.count) * 19, 256), 256>>>(dmesh, L.centerHalf.p, L.count, mids.p, 2);
             if (real) {
                 coeffs.alloc(size_t(L.count) * 64);
-                contSampleKernel<true><<<grid8, kWarpsPerCta * 32>>>(dmesh, L.arrays(), mids.p, coeffs.p, oc.oct.p, rule, sqThreshold, param1);
+                contDecideKernel<<<grid8, kWarpsPerCta * 32>>>(L.arrays(), mids.p, coeffs.p, oc.oct.p, rule, sqThreshold, param1);
             } else {
-                contSampleKernel<false><<<grid8, kWarpsPerCta * 32>>>(dmesh, L.arrays(), mids.p, nullptr, oc.oct.p, rule, 0.0f, 0.0f);
+                SDFB_CUDA(cudaMemsetAsync(L.terminal.p, 0, L.count));
             }
-            st.kernel_launches++;
+            st.kernel_launches += 2;
             st.samples_evaluated += uint64_t(L.count) * 19;
         }
         // ---- Iter 2: T-junction samples
@@ -879,8 +893,13 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
             rounds.emplace_back(new FixRound());
             FixRound& Nx = *rounds[r + 1];
             Nx.alloc(R.nSplit * 8);
-            fixValuesKernel<<<g8, kWarpsPerCta * 32>>>(dmesh, R.arrays(), Nx.arrays(), R.splitScan.p, sqThreshold);
-            st.kernel_launches++;
+            const uint32_t nTrue = scanner.run(R.nSamples.p, R.sampleScan.p, R.count);
+            fixPoints.alloc(std::max<uint32_t>(nTrue, 1)); fixSamples.alloc(std::max<uint32_t>(nTrue, 1));
+            fixSamplePointsKernel<<<divUp(R.count, 128), 128>>>(R.arrays(), R.sampleScan.p, fixPoints.p);
+            if (nTrue) samplePointsKernel<<<divUp(nTrue, 256), 256>>>(dmesh, fixPoints.p, nTrue, fixSamples.p);
+            fixValuesKernel<<<g8, kWarpsPerCta * 32>>>(R.arrays(), Nx.arrays(), R.splitScan.p, R.sampleScan.p, fixSamples.p, sqThreshold);
+            st.kernel_launches += 6;
+            st.samples_evaluated += nTrue;
             st.nodes_processed += R.count;
         }
         const uint32_t nRounds = uint32_t(rounds.size());

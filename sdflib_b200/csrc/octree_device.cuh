@@ -52,14 +52,77 @@ HermiteTable makeHermiteTable() {
 
 // ---- device helpers ------------------------------------------------------------------------------
 
-__device__ __forceinline__ d3 vertexD(const DeviceMesh& m, uint32_t v) {
-    const f3 p = m.verts[v];
-    return mkd(double(p.x), double(p.y), double(p.z));
+// Squared point-triangle distance in float64 (the vendored BVH's point_triangle_sq_unsigned, Eberly's
+// region method; TriangleMeshDistance.h:542-798). Same operations per region as eberlySqDist (tri_math.cuh),
+// restructured so that a warp whose lanes fall into different regions still shares the expensive part: the
+// region only selects a mode and one (numerator, denominator) pair, then ONE division and ONE quadratic form
+// are evaluated by all lanes together.
+__device__ __forceinline__ double eberlySqDistConverged(d3 p, d3 v0, d3 v1, d3 v2) {
+    const d3 diff = v0 - p, e0 = v1 - v0, e1 = v2 - v0;
+    const double a00 = ddot(e0, e0), a01 = ddot(e0, e1), a11 = ddot(e1, e1);
+    const double b0 = ddot(diff, e0), b1 = ddot(diff, e1), c = ddot(diff, diff);
+    const double det = fabs(a00 * a11 - a01 * a01);
+    const double s = a01 * b1 - a11 * b0;
+    const double t = a01 * b0 - a00 * b1;
+    enum { kC, kV1, kV2, kE0, kE1, kQ0, kQs, kQt };
+    int mode;
+    double num = 1.0, den = 1.0;
+    if (s + t <= det) {
+        if (s < 0) {
+            if (t < 0 && b0 < 0) mode = (-b0 >= a00) ? kV1 : kE0;
+            else mode = (b1 >= 0) ? kC : ((-b1 >= a11) ? kV2 : kE1);
+        } else if (t < 0) {
+            mode = (b0 >= 0) ? kC : ((-b0 >= a00) ? kV1 : kE0);
+        } else {
+            mode = kQ0;
+            den = det;
+        }
+    } else if (s < 0) {   // region 2
+        const double tmp0 = a01 + b0, tmp1 = a11 + b1;
+        if (tmp1 > tmp0) {
+            num = tmp1 - tmp0; den = a00 - 2 * a01 + a11;
+            if (num >= den) { mode = kV1; num = 1.0; den = 1.0; } else mode = kQs;
+        } else mode = (tmp1 <= 0) ? kV2 : ((b1 >= 0) ? kC : kE1);
+    } else if (t < 0) {   // region 6
+        const double tmp0 = a01 + b1, tmp1 = a00 + b0;
+        if (tmp1 > tmp0) {
+            num = tmp1 - tmp0; den = a00 - 2 * a01 + a11;
+            if (num >= den) { mode = kV2; num = 1.0; den = 1.0; } else mode = kQt;
+        } else mode = (tmp1 <= 0) ? kV1 : ((b0 >= 0) ? kC : kE0);
+    } else {              // region 1
+        num = a11 + b1 - a01 - b0;
+        if (num <= 0) { mode = kV2; num = 1.0; }
+        else {
+            den = a00 - 2 * a01 + a11;
+            if (num >= den) { mode = kV1; num = 1.0; den = 1.0; } else mode = kQs;
+        }
+    }
+    if (mode == kE0) { num = -b0; den = a00; }
+    if (mode == kE1) { num = -b1; den = a11; }
+    const double q = num / den;
+    double ss, tt;
+    if (mode == kQ0) { ss = s * q; tt = t * q; }
+    else if (mode == kQt) { tt = q; ss = 1 - tt; }
+    else { ss = q; tt = 1 - ss; }
+    const double quad = ss * (a00 * ss + a01 * tt + 2 * b0) + tt * (a01 * ss + a11 * tt + 2 * b1) + c;
+    double d2;
+    switch (mode) {
+        case kC: d2 = c; break;
+        case kV1: d2 = a00 + 2 * b0 + c; break;
+        case kV2: d2 = a11 + 2 * b1 + c; break;
+        case kE0: d2 = b0 * q + c; break;
+        case kE1: d2 = b1 * q + c; break;
+        default: d2 = quad; break;
+    }
+    return d2 < 0 ? 0 : d2;
 }
 
-// Nearest triangle id with the reference's traversal order: near child first, the far child is
-// re-tested against the running best when the near subtree is done, leaves replace the best only on
-// strict '<' against the re-squared running distance.
+// Nearest triangle id with the reference's traversal order (TriangleMeshDistance.h:492-540): near child
+// first, the far child is re-tested against the running best when the near subtree is done, leaves replace
+// the best only on strict '<' against the re-squared running distance.
+// "while-while" form: every lane first walks inner nodes until it holds a leaf (links < 0 are ~triangleId, so
+// no leaf node is ever loaded), then all lanes of the warp evaluate their leaf together. Per-lane semantics are
+// exactly those of the one-node-per-iteration loop; only the interleaving across lanes differs.
 __device__ uint32_t bvhNearest(const DeviceMesh& m, f3 pf) {
     const d3 p = mkd(double(pf.x), double(pf.y), double(pf.z));
     double best = DBL_MAX;
@@ -67,15 +130,11 @@ __device__ uint32_t bvhNearest(const DeviceMesh& m, f3 pf) {
     int stackNode[48];
     double stackDist[48];
     int sp = 0;
-    int cur = 0;
+    int cur = m.rootLink;
+    bool active = true;
     for (;;) {
-        const BvhNode nd = m.bvh[cur];
-        bool descend = false;
-        if (nd.left < 0) {
-            const uint32_t t = uint32_t(nd.right);
-            const double d2 = eberlySqDist(p, vertexD(m, m.idx[3 * t]), vertexD(m, m.idx[3 * t + 1]), vertexD(m, m.idx[3 * t + 2]));
-            if (d2 < best * best) { best = sqrt(d2); bestTri = nd.right; }
-        } else {
+        while (active && cur >= 0) {
+            const BvhNode nd = m.bvh[cur];
             const d3 dl3 = p - mkd(nd.lc[0], nd.lc[1], nd.lc[2]);
             const d3 dr3 = p - mkd(nd.rc[0], nd.rc[1], nd.rc[2]);
             const double dl = sqrt(ddot(dl3, dl3)) - nd.lr;
@@ -86,15 +145,29 @@ __device__ uint32_t bvhNearest(const DeviceMesh& m, f3 pf) {
             stackNode[sp] = second;
             stackDist[sp] = dSecond;
             sp++;
-            if (dFirst < best) { cur = first; descend = true; }
+            if (dFirst < best) cur = first;
+            else {
+                active = false;
+                while (sp > 0) {
+                    sp--;
+                    if (stackDist[sp] < best) { cur = stackNode[sp]; active = true; break; }
+                }
+            }
         }
-        if (descend) continue;
-        bool found = false;
-        while (sp > 0) {
-            sp--;
-            if (stackDist[sp] < best) { cur = stackNode[sp]; found = true; break; }
+        if (!active) break;
+        {
+            const int t = ~cur;
+            const float4 a = m.triVerts[3 * size_t(t)], b = m.triVerts[3 * size_t(t) + 1], c = m.triVerts[3 * size_t(t) + 2];
+            const double d2 = eberlySqDistConverged(p, mkd(double(a.x), double(a.y), double(a.z)), mkd(double(b.x), double(b.y), double(b.z)),
+                                                    mkd(double(c.x), double(c.y), double(c.z)));
+            if (d2 < best * best) { best = sqrt(d2); bestTri = t; }
+            active = false;
+            while (sp > 0) {
+                sp--;
+                if (stackDist[sp] < best) { cur = stackNode[sp]; active = true; break; }
+            }
         }
-        if (!found) break;
+        if (!active) break;
     }
     return uint32_t(bestTri);
 }
@@ -103,8 +176,38 @@ __device__ uint32_t bvhNearest(const DeviceMesh& m, f3 pf) {
 __device__ __forceinline__ float4 samplePoint(const DeviceMesh& m, f3 p) {
     const uint32_t t = bvhNearest(m, p);
     f3 g;
-    const float d = signedDistGradMesh(p, m.tris[t], m.verts[m.idx[3 * t]], m.verts[m.idx[3 * t + 1]], m.verts[m.idx[3 * t + 2]], g);
+    const float4 a = m.triVerts[3 * size_t(t)], b = m.triVerts[3 * size_t(t) + 1], c = m.triVerts[3 * size_t(t) + 2];
+    const float d = signedDistGradMesh(p, m.tris[t], mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), g);
     return make_float4(d, g.x, g.y, g.z);
+}
+
+// The 19 mid-point samples of every node of a level, one thread per (node, sample): all 32 lanes of a warp
+// traverse the BVH (a warp-per-node layout leaves 13 of 32 lanes idle during the dominant phase).
+// out[(node * 19 + s) * stride] = (d, gx, gy, gz); with stride 2 the mixed-derivative half is zeroed.
+__global__ void __launch_bounds__(256) sampleLatticeKernel(DeviceMesh mesh, const float4* centerHalf, uint32_t count, float4* out, int stride) {
+    const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= uint64_t(count) * 19) return;
+    const uint32_t node = uint32_t(t / 19), s = uint32_t(t % 19);
+    const float4 ch = centerHalf[node];
+    const int L = cSampleLattice[s];
+    const f3 rel = mk3(float(L % 3 - 1), float((L / 3) % 3 - 1), float(L / 9 - 1));
+    out[t * stride] = samplePoint(mesh, mk3(ch.x, ch.y, ch.z) + rel * ch.w);
+    if (stride == 2) out[t * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// explicit point list (fix-up pass of the CONTINUITY builder)
+__global__ void __launch_bounds__(256) samplePointsKernel(DeviceMesh mesh, const float4* points, uint32_t n, float4* out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float4 p = points[t];
+    out[t] = samplePoint(mesh, mk3(p.x, p.y, p.z));
+}
+
+__global__ void gatherTriVertsKernel(const f3* verts, const uint32_t* idx, uint32_t nTris, float4* triVerts) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTris * 3) return;
+    const f3 v = verts[idx[t]];
+    triVerts[t] = make_float4(v.x, v.y, v.z, 0.f);
 }
 
 // interpolateValue, scalar branch: acc = 0 + sum_n ((c_n * x^i) * y^j) * z^k, n ascending, left to right.
@@ -160,7 +263,12 @@ inline void uploadMesh(MeshOnDevice& m, const HostMesh& mesh, const TriVec& tris
     m.verts.alloc(mesh.nVerts); m.verts.upload(mesh.verts, mesh.nVerts);
     m.idx.alloc(mesh.nIdx); m.idx.upload(mesh.idx, mesh.nIdx);
     m.tris.alloc(tris.size()); m.tris.upload(tris.data(), tris.size());
-    if (bvh) { m.bvh.alloc(bvh->size()); m.bvh.upload(bvh->data(), bvh->size()); }
+    if (bvh) {
+        m.bvh.alloc(bvh->size()); m.bvh.upload(bvh->data(), bvh->size());
+        m.rootLink = (*bvh)[0].pad[0] ? ~(*bvh)[0].right : 0;   // single-triangle mesh: the root is a leaf
+        m.triVerts.alloc(size_t(m.numTriangles) * 3);
+        gatherTriVertsKernel<<<divUp(uint64_t(m.numTriangles) * 3, 256), 256>>>(m.verts.p, m.idx.p, m.numTriangles, m.triVerts.p);
+    }
 }
 
 // Weight of a mid-point in the error integral: trapezoid / by-distance 2^k/64 (OctreeSdfUtils.h:60-138),

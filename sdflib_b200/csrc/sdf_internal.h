@@ -90,6 +90,8 @@ struct DeviceMesh {
     const TriData* tris;
     const BvhNode* bvh;   // may be null (exact builder does not need it)
     uint32_t numTriangles;
+    const float4* triVerts;   // with bvh: the 3 vertices of every triangle, pre-gathered (one 48-byte record instead of 3 + 3 gathers)
+    int rootLink;             // with bvh: link of the root (0, or ~triangleId for a single-triangle mesh)
 };
 
 struct MeshOnDevice {
@@ -97,8 +99,10 @@ struct MeshOnDevice {
     DevBuf<uint32_t> idx;
     DevBuf<TriData> tris;
     DevBuf<BvhNode> bvh;
+    DevBuf<float4> triVerts;
     uint32_t numTriangles = 0;
-    DeviceMesh view() const { return DeviceMesh{verts.p, idx.p, tris.p, bvh.p, numTriangles}; }
+    int rootLink = 0;
+    DeviceMesh view() const { return DeviceMesh{verts.p, idx.p, tris.p, bvh.p, numTriangles, triVerts.p, rootLink}; }
 };
 
 // ---- sharded construction: state shared by both builders ---------------------------------
