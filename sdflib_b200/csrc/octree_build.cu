@@ -372,7 +372,7 @@ struct OctreeBuildState : BuildState {
             L.alloc(uint32_t(ch.size()));
             L.centerHalf.upload(ch.data(), ch.size());
             L.coord.upload(coord.data(), coord.size());
-            seedCornersKernel<<<divUp(L.count * 8, 64), 64>>>(dmesh, L.centerHalf.p, L.corners.p, L.count);
+            seedCornersKernel<<<divUp(L.count * 8, 64), 64, bvhStackBytes(dmesh, 64)>>>(dmesh, L.centerHalf.p, L.corners.p, L.count);
             st.kernel_launches++;
             st.samples_evaluated += L.count * 8;
         }
@@ -389,7 +389,7 @@ struct OctreeBuildState : BuildState {
             flags.alloc(L.count);
             scan.alloc(L.count);
             const uint32_t grid = divUp(L.count, kWarpsPerCta);
-            sampleLatticeKernel<<<divUp(uint64_t(L.count) * 19, 256), 256>>>(dmesh, L.centerHalf.p, L.count, mids.p, 1);
+            sampleLatticeKernel<<<divUp(uint64_t(L.count) * 19, kBvhThreads), kBvhThreads, bvhStackBytes(dmesh)>>>(dmesh, L.centerHalf.p, L.count, mids.p, 1);
             if (d >= startDepth)
                 levelDecideKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), mids.p, flags.p, rule, param0 * param0, param1);
             else
@@ -551,7 +551,7 @@ void nearestTriangleOnDevice(const HostMesh& mesh, const float* xyz, uint64_t n,
     DevBuf<f3> pts(n);
     DevBuf<uint32_t> out(n);
     pts.upload(reinterpret_cast<const f3*>(xyz), n);
-    if (n) nearestKernel<<<divUp(n, 128), 128>>>(dm.view(), pts.p, n, out.p);
+    if (n) nearestKernel<<<divUp(n, kBvhThreads), kBvhThreads, bvhStackBytes(dm.view())>>>(dm.view(), pts.p, n, out.p);
     out.download(outTri, n);
     SDFB_CUDA(cudaDeviceSynchronize());
 }

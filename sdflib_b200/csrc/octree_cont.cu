@@ -806,7 +806,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         L.alloc(uint32_t(ch.size()));
         L.centerHalf.upload(ch.data(), ch.size());
         L.coord.upload(coord.data(), coord.size());
-        contSeedKernel<<<divUp(L.count * 8, 64), 64>>>(dmesh, grid, L.arrays(), d0);
+        contSeedKernel<<<divUp(L.count * 8, 64), 64, bvhStackBytes(dmesh, 64)>>>(dmesh, grid, L.arrays(), d0);
         SDFB_CUDA(cudaStreamSynchronize(0));   // ch / coord are stack vectors
         st.kernel_launches++;
         st.samples_evaluated += L.count * 8;
@@ -828,7 +828,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         // ---- Iter 1
         if (!deepest) {
             mids.alloc(size_t(L.count) * 38);
-            sampleLatticeKernel<<<divUp(uint64_t(L.count) * 19, 256), 256>>>(dmesh, L.centerHalf.p, L.count, mids.p, 2);
+            sampleLatticeKernel<<<divUp(uint64_t(L.count) * 19, kBvhThreads), kBvhThreads, bvhStackBytes(dmesh)>>>(dmesh, L.centerHalf.p, L.count, mids.p, 2);
             if (real) {
                 coeffs.alloc(size_t(L.count) * 64);
                 contDecideKernel<<<grid8, kWarpsPerCta * 32>>>(L.arrays(), mids.p, coeffs.p, oc.oct.p, rule, sqThreshold, param1);
@@ -896,7 +896,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
             const uint32_t nTrue = scanner.run(R.nSamples.p, R.sampleScan.p, R.count);
             fixPoints.alloc(std::max<uint32_t>(nTrue, 1)); fixSamples.alloc(std::max<uint32_t>(nTrue, 1));
             fixSamplePointsKernel<<<divUp(R.count, 128), 128>>>(R.arrays(), R.sampleScan.p, fixPoints.p);
-            if (nTrue) samplePointsKernel<<<divUp(nTrue, 256), 256>>>(dmesh, fixPoints.p, nTrue, fixSamples.p);
+            if (nTrue) samplePointsKernel<<<divUp(nTrue, kBvhThreads), kBvhThreads, bvhStackBytes(dmesh)>>>(dmesh, fixPoints.p, nTrue, fixSamples.p);
             fixValuesKernel<<<g8, kWarpsPerCta * 32>>>(R.arrays(), Nx.arrays(), R.splitScan.p, R.sampleScan.p, fixSamples.p, sqThreshold);
             st.kernel_launches += 6;
             st.samples_evaluated += nTrue;

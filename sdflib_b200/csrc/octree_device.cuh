@@ -5,6 +5,7 @@
 #pragma once
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "device_utils.cuh"
 #include "sdf_internal.h"
@@ -119,57 +120,91 @@ __device__ __forceinline__ double eberlySqDistConverged(d3 p, d3 v0, d3 v1, d3 v
 
 // Nearest triangle id with the reference's traversal order (TriangleMeshDistance.h:492-540): near child
 // first, the far child is re-tested against the running best when the near subtree is done, leaves replace
-// the best only on strict '<' against the re-squared running distance.
-// "while-while" form: every lane first walks inner nodes until it holds a leaf (links < 0 are ~triangleId, so
-// no leaf node is ever loaded), then all lanes of the warp evaluate their leaf together. Per-lane semantics are
-// exactly those of the one-node-per-iteration loop; only the interleaving across lanes differs.
-__device__ uint32_t bvhNearest(const DeviceMesh& m, f3 pf) {
-    const d3 p = mkd(double(pf.x), double(pf.y), double(pf.z));
-    double best = DBL_MAX;
-    int bestTri = -1;
-    int stackNode[48];
-    double stackDist[48];
-    int sp = 0;
-    int cur = m.rootLink;
-    bool active = true;
-    for (;;) {
-        while (active && cur >= 0) {
-            const BvhNode nd = m.bvh[cur];
-            const d3 dl3 = p - mkd(nd.lc[0], nd.lc[1], nd.lc[2]);
-            const d3 dr3 = p - mkd(nd.rc[0], nd.rc[1], nd.rc[2]);
-            const double dl = sqrt(ddot(dl3, dl3)) - nd.lr;
-            const double dr = sqrt(ddot(dr3, dr3)) - nd.rr;
-            const bool leftFirst = dl < dr;
-            const int first = leftFirst ? nd.left : nd.right, second = leftFirst ? nd.right : nd.left;
-            const double dFirst = leftFirst ? dl : dr, dSecond = leftFirst ? dr : dl;
-            stackNode[sp] = second;
-            stackDist[sp] = dSecond;
-            sp++;
-            if (dFirst < best) cur = first;
-            else {
-                active = false;
-                while (sp > 0) {
-                    sp--;
-                    if (stackDist[sp] < best) { cur = stackNode[sp]; active = true; break; }
-                }
-            }
-        }
-        if (!active) break;
-        {
-            const int t = ~cur;
-            const float4 a = m.triVerts[3 * size_t(t)], b = m.triVerts[3 * size_t(t) + 1], c = m.triVerts[3 * size_t(t) + 2];
-            const double d2 = eberlySqDistConverged(p, mkd(double(a.x), double(a.y), double(a.z)), mkd(double(b.x), double(b.y), double(b.z)),
-                                                    mkd(double(c.x), double(c.y), double(c.z)));
-            if (d2 < best * best) { best = sqrt(d2); bestTri = t; }
-            active = false;
-            while (sp > 0) {
-                sp--;
-                if (stackDist[sp] < best) { cur = stackNode[sp]; active = true; break; }
-            }
-        }
-        if (!active) break;
+// the best only on strict '<' against the re-squared running distance. Links < 0 are ~triangleId, so no
+// leaf node is ever loaded. Per-lane semantics are identical in all variants below; they differ only in how
+// the lanes of a warp are kept together (measured on B200, see profiles/).
+// The traversal stack lives in SHARED memory, one column per thread: entry i of thread t is at [i * blockDim + t],
+// so a warp access is conflict-free whatever the per-lane stack pointers are. (In local memory the same accesses
+// were uncoalesced — 1.9 useful bytes per 32-byte sector — and made up 60 % of the L1 wavefronts of the sampling
+// kernel: profiles/r1_sample_lattice_*.) Depth = height of the median-split BVH, known on the host.
+struct BvhStack {
+    double* dist;   // [depth][blockDim]
+    int* node;      // [depth][blockDim]
+    int stride;
+};
+constexpr int kBvhThreads = 128;   // CTA size of every kernel that traverses the BVH
+inline size_t bvhStackBytes(const DeviceMesh& m, int threads = kBvhThreads) { return size_t(m.stackDepth) * threads * 12; }
+__device__ __forceinline__ BvhStack bvhStackOfThread(const DeviceMesh& m) {
+    extern __shared__ double bvhStackSmem[];
+    BvhStack st;
+    st.stride = int(blockDim.x);
+    st.dist = bvhStackSmem + threadIdx.x;
+    st.node = reinterpret_cast<int*>(bvhStackSmem + size_t(m.stackDepth) * blockDim.x) + threadIdx.x;
+    return st;
+}
+
+struct BvhCursor {
+    d3 p;
+    double best;
+    int bestTri, sp, cur;
+    bool active;
+};
+
+__device__ __forceinline__ void bvhPop(BvhCursor& c, const BvhStack& st) {
+    c.active = false;
+    while (c.sp > 0) {
+        c.sp--;
+        if (st.dist[c.sp * st.stride] < c.best) { c.cur = st.node[c.sp * st.stride]; c.active = true; break; }
     }
-    return uint32_t(bestTri);
+}
+
+__device__ __forceinline__ void bvhInnerStep(const DeviceMesh& m, BvhCursor& c, const BvhStack& st) {
+    const BvhNode nd = m.bvh[c.cur];
+    const d3 dl3 = c.p - mkd(nd.lc[0], nd.lc[1], nd.lc[2]);
+    const d3 dr3 = c.p - mkd(nd.rc[0], nd.rc[1], nd.rc[2]);
+    const double dl = sqrt(ddot(dl3, dl3)) - nd.lr;
+    const double dr = sqrt(ddot(dr3, dr3)) - nd.rr;
+    const bool leftFirst = dl < dr;
+    const int first = leftFirst ? nd.left : nd.right, second = leftFirst ? nd.right : nd.left;
+    const double dFirst = leftFirst ? dl : dr, dSecond = leftFirst ? dr : dl;
+    // the far child is re-tested against the running best when it is popped; the best only shrinks, so a far
+    // child that already fails now can never pass later and is not pushed at all
+    if (dSecond < c.best) {
+        st.node[c.sp * st.stride] = second;
+        st.dist[c.sp * st.stride] = dSecond;
+        c.sp++;
+    }
+    if (dFirst < c.best) c.cur = first;
+    else bvhPop(c, st);
+}
+
+__device__ __forceinline__ void bvhLeafStep(const DeviceMesh& m, BvhCursor& c, const BvhStack& st) {
+    const int t = ~c.cur;
+    const float4 a = m.triVerts[3 * size_t(t)], b = m.triVerts[3 * size_t(t) + 1], v = m.triVerts[3 * size_t(t) + 2];
+    const double d2 = eberlySqDistConverged(c.p, mkd(double(a.x), double(a.y), double(a.z)), mkd(double(b.x), double(b.y), double(b.z)),
+                                            mkd(double(v.x), double(v.y), double(v.z)));
+    if (d2 < c.best * c.best) { c.best = sqrt(d2); c.bestTri = t; }
+    bvhPop(c, st);
+}
+
+// One node per iteration and lane. Two warp-synchronous schedules were measured on the C2 build and dropped:
+// "while-while" (walk inner nodes until a leaf is held, then evaluate; 354 ms against 158 ms) and a ballot-driven
+// schedule where the whole warp does either an inner or a leaf step per iteration (213 ms): lanes are bound by
+// their own dependent-load chains, and waiting for the slowest lane costs more than the divergence.
+__device__ uint32_t bvhNearest(const DeviceMesh& m, f3 pf) {
+    const BvhStack st = bvhStackOfThread(m);
+    BvhCursor c;
+    c.p = mkd(double(pf.x), double(pf.y), double(pf.z));
+    c.best = DBL_MAX;
+    c.bestTri = -1;
+    c.sp = 0;
+    c.cur = m.rootLink;
+    c.active = true;
+    while (c.active) {
+        if (c.cur >= 0) bvhInnerStep(m, c, st);
+        else bvhLeafStep(m, c, st);
+    }
+    return uint32_t(c.bestTri);
 }
 
 // TriCubicInterpolation::calculatePointValues: (signed distance, unit gradient) of the nearest triangle
@@ -184,7 +219,7 @@ __device__ __forceinline__ float4 samplePoint(const DeviceMesh& m, f3 p) {
 // The 19 mid-point samples of every node of a level, one thread per (node, sample): all 32 lanes of a warp
 // traverse the BVH (a warp-per-node layout leaves 13 of 32 lanes idle during the dominant phase).
 // out[(node * 19 + s) * stride] = (d, gx, gy, gz); with stride 2 the mixed-derivative half is zeroed.
-__global__ void __launch_bounds__(256) sampleLatticeKernel(DeviceMesh mesh, const float4* centerHalf, uint32_t count, float4* out, int stride) {
+__global__ void __launch_bounds__(kBvhThreads) sampleLatticeKernel(DeviceMesh mesh, const float4* centerHalf, uint32_t count, float4* out, int stride) {
     const uint64_t t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= uint64_t(count) * 19) return;
     const uint32_t node = uint32_t(t / 19), s = uint32_t(t % 19);
@@ -196,7 +231,7 @@ __global__ void __launch_bounds__(256) sampleLatticeKernel(DeviceMesh mesh, cons
 }
 
 // explicit point list (fix-up pass of the CONTINUITY builder)
-__global__ void __launch_bounds__(256) samplePointsKernel(DeviceMesh mesh, const float4* points, uint32_t n, float4* out) {
+__global__ void __launch_bounds__(kBvhThreads) samplePointsKernel(DeviceMesh mesh, const float4* points, uint32_t n, float4* out) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const float4 p = points[t];
@@ -266,6 +301,10 @@ inline void uploadMesh(MeshOnDevice& m, const HostMesh& mesh, const TriVec& tris
     if (bvh) {
         m.bvh.alloc(bvh->size()); m.bvh.upload(bvh->data(), bvh->size());
         m.rootLink = (*bvh)[0].pad[0] ? ~(*bvh)[0].right : 0;   // single-triangle mesh: the root is a leaf
+        // height of the median-split tree (mesh_host.cpp: halves of floor / ceil size) = deepest possible stack, + 1 spare
+        uint32_t n = m.numTriangles, h = 0;
+        while (n > 1) { n = n - n / 2; h++; }
+        m.stackDepth = int(h) + 1;
         m.triVerts.alloc(size_t(m.numTriangles) * 3);
         gatherTriVertsKernel<<<divUp(uint64_t(m.numTriangles) * 3, 256), 256>>>(m.verts.p, m.idx.p, m.numTriangles, m.triVerts.p);
     }

@@ -92,6 +92,7 @@ struct DeviceMesh {
     uint32_t numTriangles;
     const float4* triVerts;   // with bvh: the 3 vertices of every triangle, pre-gathered (one 48-byte record instead of 3 + 3 gathers)
     int rootLink;             // with bvh: link of the root (0, or ~triangleId for a single-triangle mesh)
+    int stackDepth;           // with bvh: entries of the per-thread traversal stack (tree height + 1)
 };
 
 struct MeshOnDevice {
@@ -101,8 +102,8 @@ struct MeshOnDevice {
     DevBuf<BvhNode> bvh;
     DevBuf<float4> triVerts;
     uint32_t numTriangles = 0;
-    int rootLink = 0;
-    DeviceMesh view() const { return DeviceMesh{verts.p, idx.p, tris.p, bvh.p, numTriangles, triVerts.p, rootLink}; }
+    int rootLink = 0, stackDepth = 1;
+    DeviceMesh view() const { return DeviceMesh{verts.p, idx.p, tris.p, bvh.p, numTriangles, triVerts.p, rootLink, stackDepth}; }
 };
 
 // ---- sharded construction: state shared by both builders ---------------------------------
