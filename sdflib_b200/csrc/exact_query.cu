@@ -9,11 +9,11 @@
 // lands in a leaf, so it is done ONCE per leaf: prepareExactQuery() decodes the public arrays
 // (mOctreeData / mTrianglesSets / mTrianglesMasks — freshly built or loaded from a .bin) level by level
 // into a private pool of explicit per-leaf triangle lists with flat (node, entry) pair passes and scans.
-// The public arrays stay bit-identical to the reference; the query kernel walks the node array, then
-// streams its leaf's list: one query per thread, triangle frames fetched as 5 x 128-bit read-only loads
-// (neighbouring queries of a warp share the leaf, so the loads are warp-uniform broadcasts).
+// The public arrays stay bit-identical to the reference; the query kernel walks the node array per lane, then
+// the warp streams each query's leaf list cooperatively (frames fetched as 5 x 128-bit read-only loads).
 // Compiled with -fmad=false: distances are bit-identical to the CPU reference.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -202,24 +202,35 @@ __device__ __forceinline__ float boxDistance(const ExactQueryParams& q, f3 p) { 
     return sqrtf(dot3(ap, ap)) + gmin(gmax(a.x, gmax(a.y, a.z)), 0.0f);
 }
 
+// Warp-cooperative: each lane walks the node array for its own query, then the warp works through its 32
+// queries one leaf at a time with the LANES STRIDING OVER THE TRIANGLE LIST (two queries per pass when the next
+// one landed in the same leaf, so a frame is fetched once for both). Every lane runs the same trip count whatever
+// the list lengths of the other queries are. The first version of this kernel looped over the list per thread and
+// ran with 10 of 32 lanes active on the 256^3 grid (the 32 x-consecutive queries of a warp fall into 16 different
+// leaves): C3, 16.7 M queries, 9.97 ms grid / 19.5 ms random points against 8.6 / 14.0 ms here. The serial rule
+// "first strict minimum over ascending list positions" is kept exactly: per-lane strict '<' over ascending
+// positions, then redux.min over the distance bits (non-negative floats order like their bit patterns) and
+// redux.min over the positions of the lanes that hold that minimum.
 template <bool kGrad>
 __global__ void __launch_bounds__(256)
-exactQueryKernel(const uint32_t* __restrict__ nodes, const uint64_t* __restrict__ leafLo, const uint32_t* __restrict__ leafCnt,
-                 const uint32_t* __restrict__ pool, const float4* __restrict__ frames, const TriData* __restrict__ tris,
-                 const ExactQueryParams q, const float* __restrict__ xyz, uint64_t n, float* __restrict__ dist,
-                 float* __restrict__ grad) {
+exactQueryWarpKernel(const uint32_t* __restrict__ nodes, const uint64_t* __restrict__ leafLo, const uint32_t* __restrict__ leafCnt,
+                     const uint32_t* __restrict__ pool, const float4* __restrict__ frames, const TriData* __restrict__ tris,
+                     const ExactQueryParams q, const float* __restrict__ xyz, uint64_t n, float* __restrict__ dist,
+                     float* __restrict__ grad) {
+    constexpr unsigned kFull = 0xffffffffu;
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const f3 p = mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+    const int lane = threadIdx.x & 31;
+    const bool valid = i < n;
+    f3 p = mk3(0.0f, 0.0f, 0.0f);
+    if (valid) p = mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
     float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
     const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     const int ix = int(flx), iy = int(fly), iz = int(flz);
     fx -= flx; fy -= fly; fz -= flz;
-    f3 g = mk3(0.0f, 0.0f, 0.0f);
-    float d;
-    if (ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid) {
-        d = boxDistance(q, p) + q.outside;   // the reference leaves the caller's gradient untouched here (zero-initialised by us)
-    } else {
+    const bool inside = valid && !(ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid);
+    unsigned long long lo = 0;
+    uint32_t cnt = 0;
+    if (inside) {
         uint32_t idx = uint32_t((iz * q.grid + iy) * q.grid + ix);
         uint32_t w0 = __ldg(nodes + 2 * size_t(idx));
         while (!(w0 & kLeafBit)) {   // roundFloat of ExactOctreeSdf.cpp:33-36 is a strict '>'
@@ -229,17 +240,49 @@ exactQueryKernel(const uint32_t* __restrict__ nodes, const uint64_t* __restrict_
             fx = 2.0f * fx; fy = 2.0f * fy; fz = 2.0f * fz;
             fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
         }
-        const uint32_t* lst = pool + leafLo[idx];
-        const uint32_t cnt = leafCnt[idx];
-        float best = INFINITY;
-        uint32_t bestTri = 0;
-        for (uint32_t k = 0; k < cnt; k++) {
-            const uint32_t t = __ldg(lst + k);
-            const float sq = sqDistPointTriangle(p, loadFrame(frames, t));
-            if (sq < best) { best = sq; bestTri = t; }
-        }
-        d = kGrad ? signedDistGradSelf(p, tris[bestTri], g) : signedDistPointTriangle(p, tris[bestTri]);
+        lo = leafLo[idx];
+        cnt = leafCnt[idx];
     }
+    uint32_t myTri = 0;   // the serial loop's initial bestTri
+    unsigned todo = __ballot_sync(kFull, inside && cnt > 0);
+    while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const unsigned long long loJ = __shfl_sync(kFull, lo, j);
+        const uint32_t cntJ = __shfl_sync(kFull, cnt, j);
+        const f3 p1 = mk3(__shfl_sync(kFull, p.x, j), __shfl_sync(kFull, p.y, j), __shfl_sync(kFull, p.z, j));
+        int j2 = todo ? __ffs(todo) - 1 : 0;
+        const bool pair = todo && __shfl_sync(kFull, lo, j2) == loJ;   // lists of non-empty leaves start at distinct offsets
+        const f3 p2 = mk3(__shfl_sync(kFull, p.x, j2), __shfl_sync(kFull, p.y, j2), __shfl_sync(kFull, p.z, j2));
+        if (pair) todo &= todo - 1;
+        const uint32_t* lst = pool + loJ;
+        float best1 = INFINITY, best2 = INFINITY;
+        uint32_t k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+        for (uint32_t k = lane; k < cntJ; k += 32) {
+            const TriFrame f = loadFrame(frames, __ldg(lst + k));
+            const float sq1 = sqDistPointTriangle(p1, f);
+            if (sq1 < best1) { best1 = sq1; k1 = k; }
+            if (pair) {
+                const float sq2 = sqDistPointTriangle(p2, f);
+                if (sq2 < best2) { best2 = sq2; k2 = k; }
+            }
+        }
+        const uint32_t m1 = __reduce_min_sync(kFull, __float_as_uint(best1));
+        const uint32_t w1 = __reduce_min_sync(kFull, (__float_as_uint(best1) == m1) ? k1 : 0xFFFFFFFFu);
+        const uint32_t t1 = (w1 != 0xFFFFFFFFu) ? __ldg(lst + w1) : 0u;
+        if (lane == j) myTri = t1;
+        if (pair) {
+            const uint32_t m2 = __reduce_min_sync(kFull, __float_as_uint(best2));
+            const uint32_t w2 = __reduce_min_sync(kFull, (__float_as_uint(best2) == m2) ? k2 : 0xFFFFFFFFu);
+            const uint32_t t2 = (w2 != 0xFFFFFFFFu) ? __ldg(lst + w2) : 0u;
+            if (lane == j2) myTri = t2;
+        }
+    }
+    if (!valid) return;
+    f3 g = mk3(0.0f, 0.0f, 0.0f);
+    float d;
+    if (!inside) d = boxDistance(q, p) + q.outside;   // the reference leaves the caller's gradient untouched here (zero-initialised by us)
+    else d = kGrad ? signedDistGradSelf(p, tris[myTri], g) : signedDistPointTriangle(p, tris[myTri]);
     dist[i] = d;
     if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
 }
@@ -362,9 +405,9 @@ void launchExactQuery(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float
     q.outside = sqrtf(3.0f) * (s.boxMax[0] - s.boxMin[0]);   // ExactOctreeSdf.cpp:48
     const uint32_t grid = uint32_t((n + 255) / 256);
     if (dGrad)
-        exactQueryKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, dGrad);
+        exactQueryWarpKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, dGrad);
     else
-        exactQueryKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, nullptr);
+        exactQueryWarpKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, nullptr);
     SDFB_CUDA(cudaGetLastError());
 }
 
