@@ -115,4 +115,21 @@ template <class In, class Out> struct ScannerT {
 };
 using Scanner = ScannerT<uint32_t, uint32_t>;
 
+// 64-bit count of set flags: guards the 32-bit flag scans (their totals would wrap silently) once a pass has
+// more than 2^32 pairs.
+static __global__ void countFlagsKernel(const uint8_t* flags, uint64_t n, unsigned long long* total) {
+    unsigned long long c = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) c += flags[i];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+}
+inline uint64_t countFlags64(const uint8_t* flags, uint64_t n) {
+    DevBuf<unsigned long long> total(1);
+    SDFB_CUDA(cudaMemsetAsync(total.p, 0, 8));
+    countFlagsKernel<<<148 * 8, 256>>>(flags, n, total.p);
+    unsigned long long t = 0;
+    SDFB_CUDA(cudaMemcpy(&t, total.p, 8, cudaMemcpyDeviceToHost));
+    return t;
+}
+
 }  // namespace sdfb200

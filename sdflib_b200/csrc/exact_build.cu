@@ -695,14 +695,18 @@ struct ExactBuildState : BuildState {
             }
             // HOT LOOP A
             L.numPairs = scan64.run(L.parentCnt.p, L.pairOff.p, L.count, true);
-            // list positions are 32-bit (ScannerT<uint8_t, uint32_t> would wrap silently): bound them by the pair count
-            if (L.numPairs >= (uint64_t(1) << 32)) throw Error(SDFB200_ERR_INVALID, "more than 2^32 (node, triangle) pairs on one octree level");
+            // pair indices are 64-bit everywhere; list positions (kept pairs) are 32-bit and are checked after the filter
+            if (L.numPairs >= (uint64_t(1) << 38)) throw Error(SDFB200_ERR_INVALID, "more than 2^38 (node, triangle) pairs on one octree level");
             if (region.n < size_t(L.count) * 72) region.alloc(size_t(L.count) * 72);
             regionKernel<<<divUp(L.count, 4), 256>>>(dFrames.p, L.view(), region.p);
             L.flags.alloc(L.numPairs + 1);
             L.pos.alloc(L.numPairs + 1);
             if (L.numPairs) filterKernel<<<divUp(L.numPairs, 256), 256>>>(dmesh, L.view(), parentList, region.p, L.flags.p, L.numPairs);
             SDFB_CUDA(cudaGetLastError());
+            if (L.numPairs >= (uint64_t(1) << 32)) {   // the 32-bit scan below would wrap silently: count the kept pairs in 64 bits first
+                const uint64_t kept = countFlags64(L.flags.p, L.numPairs);
+                if (kept >= (1ull << 32)) throw Error(SDFB200_ERR_INVALID, "more than 2^32 triangle-list entries on one octree level");
+            }
             L.listTotal = L.numPairs ? scanFlags.run(L.flags.p, L.pos.p, L.numPairs) : 0u;
             L.list.alloc(size_t(L.listTotal) + 8);   // + 8: the TMA window of the sample kernel may read past the end
             SDFB_CUDA(cudaMemsetAsync(L.list.p + L.listTotal, 0, 8 * sizeof(uint32_t)));

@@ -344,11 +344,13 @@ void prepareExactQuery(sdfb200_sdf& s) {
             maskRangeCheckKernel<<<divUp(n, 256), 256>>>(pv, F.nodeIdx.p, F.parentCnt.p, n, F.inner.p, err.p);
             F.pairOff.alloc(size_t(n) + 1);
             const uint64_t numPairs = scan64.run(F.parentCnt.p, F.pairOff.p, n, true);
-            if (numPairs >= (uint64_t(1) << 32)) throw Error(SDFB200_ERR_IO, "mask chain of one level exceeds 2^32 entries");
+            if (numPairs >= (uint64_t(1) << 38)) throw Error(SDFB200_ERR_IO, "mask chain of one level exceeds 2^38 entries");
             F.flags.alloc(numPairs + 1); F.pos.alloc(numPairs + 1);
             uint32_t total = 0;
             if (numPairs) {
                 maskFlagsKernel<<<divUp(numPairs, 256), 256>>>(pv, F.nodeIdx.p, F.pairOff.p, n, numPairs, F.flags.p);
+                if (numPairs >= (uint64_t(1) << 32) && countFlags64(F.flags.p, numPairs) >= (uint64_t(1) << 32))
+                    throw Error(SDFB200_ERR_IO, "decoded triangle lists of one level exceed 2^32 entries");
                 total = scanFlags.run(F.flags.p, F.pos.p, numPairs);
             }
             F.dec.alloc(size_t(total) + 1);
