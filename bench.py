@@ -175,6 +175,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     S.lib().sdfb200_set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout; stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     v, i, box = build_inputs()

@@ -11,22 +11,26 @@ import sdflib_b200 as S
 from sdflib_b200 import meshes
 
 what = sys.argv[1]
+c5_depth = int(os.environ.get("C5_DEPTH", "9"))
+c5_thr = float(os.environ.get("C5_THRESHOLD", "1e-4"))
 t0 = time.perf_counter()
 v, i = meshes.config_mesh("M2" if what == "c4" else "M3")
 box = meshes.bounding_box_with_margin(v)
 mesh, bb = S.Mesh(v, i), S.BoundingBox(box[:3], box[3:])
 mesh_s = time.perf_counter() - t0
 out = {"config": what, "triangles": int(i.size // 3), "mesh_generation_s": round(mesh_s, 2)}
+if what == "c5":
+    out.update(depth=c5_depth, threshold=c5_thr)
 if len(sys.argv) > 2 and sys.argv[2] == "reference":
     from oracle.binding import ref
     cores = os.cpu_count()
-    r = ref.build_exact(v, i, box, 8, 3, 128, cores) if what == "c4" else ref.build_octree(v, i, box, 9, 3, 1e-4, 2, cores)
+    r = ref.build_exact(v, i, box, 8, 3, 128, cores) if what == "c4" else ref.build_octree(v, i, box, c5_depth, 3, c5_thr, 2, cores)
     out.update(reference_build_s=r.build_seconds, threads=cores)
     print(json.dumps(out)); sys.exit(0)
 
 def build():
     torch.cuda.synchronize(); t = time.perf_counter()
-    s = S.ExactOctreeSdf(mesh, bb, 8, 3, 128, 2) if what == "c4" else S.OctreeSdf(mesh, bb, 9, 3, 1e-4, S.OctreeSdf.CONTINUITY, 2)
+    s = S.ExactOctreeSdf(mesh, bb, 8, 3, 128, 2) if what == "c4" else S.OctreeSdf(mesh, bb, c5_depth, 3, c5_thr, S.OctreeSdf.CONTINUITY, 2)
     torch.cuda.synchronize()
     return s, time.perf_counter() - t
 

@@ -18,7 +18,7 @@ else:
     v, i = meshes.config_mesh(name)
 box = meshes.bounding_box_with_margin(v)
 mesh, bb = S.Mesh(v, i), S.BoundingBox(box[:3], box[3:])
-od, ed = (6, 6) if name == "s4" else (8, 7)
+od, ed = (6, 6) if name == "s4" else ((8, 8) if name == "M2" else (8, 7))   # M2: BASELINE config 4 (ExactOctreeSdf depth 8)
 for rep in range(2):
     torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
     o = sharded.build_octree_sharded(mesh, bb, od, 3, 1e-3, numThreads=2)
