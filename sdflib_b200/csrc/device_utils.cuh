@@ -115,6 +115,86 @@ template <class In, class Out> struct ScannerT {
 };
 using Scanner = ScannerT<uint32_t, uint32_t>;
 
+// ---- exclusive scan of 0/1 byte flags into 32-bit positions, 16 flags per thread ---------------------------
+// The generic scan above moves one element per thread; the flag passes of the ExactOctreeSdf builder run over up to
+// billions of (node, triangle) pairs, so this variant reads the flags as 128-bit words (popcount per word) and writes
+// the positions as four 128-bit stores per thread.
+constexpr int kFlagThreads = 256, kFlagsPerThread = 16, kFlagsPerBlock = kFlagThreads * kFlagsPerThread;
+
+static __device__ __forceinline__ uint4 loadFlags16(const uint8_t* in, uint64_t i, uint64_t n) {
+    if (i + 16 <= n) return *reinterpret_cast<const uint4*>(in + i);
+    uint32_t w[4] = {0, 0, 0, 0};
+    for (int k = 0; k < 16; k++)
+        if (i + k < n) w[k >> 2] |= uint32_t(in[i + k]) << (8 * (k & 3));
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+static __global__ void __launch_bounds__(kFlagThreads) flagBlockSums(const uint8_t* in, uint32_t* blockSums, uint64_t n) {
+    __shared__ uint32_t warpSums[32];
+    const uint64_t i = (uint64_t(blockIdx.x) * kFlagThreads + threadIdx.x) * kFlagsPerThread;
+    uint32_t v = 0;
+    if (i < n) { const uint4 f = loadFlags16(in, i, n); v = __popc(f.x) + __popc(f.y) + __popc(f.z) + __popc(f.w); }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t s = threadIdx.x < kFlagThreads / 32 ? warpSums[threadIdx.x] : 0u;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) blockSums[blockIdx.x] = s;
+    }
+}
+
+static __global__ void __launch_bounds__(kFlagThreads) flagFinalize(const uint8_t* in, const uint32_t* blockSums, uint32_t* out, uint64_t n) {
+    __shared__ uint32_t warpTotals[32];
+    const uint64_t i = (uint64_t(blockIdx.x) * kFlagThreads + threadIdx.x) * kFlagsPerThread;
+    uint4 f = make_uint4(0, 0, 0, 0);
+    if (i < n) f = loadFlags16(in, i, n);
+    const uint32_t mine = __popc(f.x) + __popc(f.y) + __popc(f.z) + __popc(f.w);
+    // in-block inclusive scan of the per-thread sums (8 warps)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warpTotals[warp] = inc;
+    __syncthreads();
+    uint32_t base = blockSums[blockIdx.x] + inc - mine;
+    for (int w = 0; w < warp; w++) base += warpTotals[w];
+    if (i >= n) return;
+    const uint32_t words[4] = {f.x, f.y, f.z, f.w};
+    uint32_t pos[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        pos[k] = base;
+        base += (words[k >> 2] >> (8 * (k & 3))) & 1u;
+    }
+    if (i + 16 <= n) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) reinterpret_cast<uint4*>(out + i)[q] = make_uint4(pos[4 * q], pos[4 * q + 1], pos[4 * q + 2], pos[4 * q + 3]);
+    } else {
+        for (int k = 0; k < 16; k++) if (i + k < n) out[i + k] = pos[k];
+    }
+}
+
+// Flags must be exactly 0 or 1. Returns the number of set flags (32-bit: callers with n >= 2^32 check countFlags64 first).
+struct FlagScanner {
+    DevBuf<uint32_t> blockSums, total;
+    uint32_t run(const uint8_t* in, uint32_t* out, uint64_t n, cudaStream_t st = 0) {
+        if (!total.p) total.alloc(1);
+        if (n == 0) return 0;
+        const uint32_t nBlocks = divUp(n, kFlagsPerBlock);
+        if (blockSums.n < nBlocks) blockSums.alloc(size_t(nBlocks) + 64);
+        flagBlockSums<<<nBlocks, kFlagThreads, 0, st>>>(in, blockSums.p, n);
+        scanOfBlockSums<uint32_t><<<1, kScanBlock, 0, st>>>(blockSums.p, nBlocks, total.p);
+        flagFinalize<<<nBlocks, kFlagThreads, 0, st>>>(in, blockSums.p, out, n);
+        uint32_t t = 0;
+        SDFB_CUDA(cudaMemcpyAsync(&t, total.p, sizeof(t), cudaMemcpyDeviceToHost, st));
+        SDFB_CUDA(cudaStreamSynchronize(st));
+        return t;
+    }
+};
+
 // 64-bit count of set flags: guards the 32-bit flag scans (their totals would wrap silently) once a pass has
 // more than 2^32 pairs.
 static __global__ void countFlagsKernel(const uint8_t* flags, uint64_t n, unsigned long long* total) {

@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -96,68 +97,108 @@ regionKernel(const float4* __restrict__ frames, LevelView lv, float* __restrict_
     if (c == 0) region[size_t(node) * 72 + 64 + i] = m;
 }
 
-// a9: Frank-Wolfe proximity test between the rounded box (8 corner spheres) and a triangle.
-__device__ __forceinline__ bool isNearMinimize(float half, const float* __restrict__ radius, f3 a, f3 b, f3 c, float thr) {
-    uint32_t iter = 0;
-    bool isNear = false;
-    const float sqThr = thr * thr;
-    f3 x = -a;
-    for (;;) {
-        const f3 g = normalize3(-x);
-        float best = dot3(mk3(-half, -half, -half), g) + radius[0];
-        uint32_t bi = 0;
-#pragma unroll
-        for (uint32_t i = 1; i < 8; i++) {
-            const float v = dot3(cornerDir(i) * half, g) + radius[i];
-            if (v > best) { best = v; bi = i; }
-        }
-        const f3 boxPoint = cornerDir(bi) * half + radius[bi] * g;
-        const f3 ng = -g;
-        const float d1 = dot3(a, ng), d2 = dot3(b, ng), d3v = dot3(c, ng);
-        const f3 triPoint = (d1 > d2) ? ((d1 > d3v) ? a : c) : ((d2 > d3v) ? b : c);
-        const f3 p = boxPoint - triPoint;
-        const float distToP = dot3(g, p - x);
-        const float distToO = dot3(g, -x);
-        const f3 dir = p - x;
-        const float d = dot3(dir, -x);
-        if (double(d) < 1.0e-5) return distToO <= distToP + thr;
-        x = x + dir * gmin(d / dot3(dir, dir), 1.0f);
-        isNear = dot3(x, x) < sqThr;
-        if (!(!isNear && distToO <= distToP + thr && ++iter < 15)) break;
-    }
-    return isNear || iter >= 15;
-}
+// ---- HOT LOOP A, part 2: Frank-Wolfe proximity test (a9, src/utils/GJK.cpp:830-866) of every (node, parent-list
+// entry) pair, with lane refilling. Trip counts range from 1 to 15, so with one pair per thread a warp runs at the
+// pace of its slowest pair (the first version of this kernel: 11.7 of 32 lanes active per instruction on the
+// deepest C3 level, 28 ms of the 64 ms build; this one: C3 levels 52.4 -> 39.1 ms, identical flags).
+// Here a warp owns a chunk of consecutive pairs and every lane keeps ONE Frank-Wolfe iteration per loop trip in
+// flight: a lane whose pair has finished takes the next unassigned pair of the chunk (ballot + prefix), so the
+// iteration body always runs with (almost) all lanes. Per-pair arithmetic is unchanged.
+constexpr uint32_t kFilterChunk = 1024;   // pairs per warp
 
-// ---- HOT LOOP A, part 2: one thread per (node, parent-list entry) pair ----------------------------------
 __global__ void __launch_bounds__(256)
-filterKernel(DeviceMesh mesh, LevelView lv, const uint32_t* __restrict__ parentList, const float* __restrict__ region,
-             uint8_t* __restrict__ flags, uint64_t numPairs) {
-    __shared__ uint32_t sNode;
-    const uint64_t p0 = uint64_t(blockIdx.x) * 256;
-    if (threadIdx.x == 0) sNode = lastLessEqual<uint64_t>(lv.pairOff, lv.count + 1, p0);
-    __syncthreads();
-    const uint64_t p = p0 + threadIdx.x;
-    if (p >= numPairs) return;
-    uint32_t node = sNode;
-    while (p >= lv.pairOff[node + 1]) node++;
-    const uint32_t j = uint32_t(p - lv.pairOff[node]);
-    const uint32_t t = parentList[lv.parentLo[node] + j];
-    const float4 ch = lv.centerHalf[node];
-    const f3 ctr = mk3(ch.x, ch.y, ch.z);
-    const f3 a = mesh.verts[mesh.idx[3 * size_t(t)]] - ctr, b = mesh.verts[mesh.idx[3 * size_t(t) + 1]] - ctr,
-             c = mesh.verts[mesh.idx[3 * size_t(t) + 2]] - ctr;
-    const f3 g = 0.3333333f * ((a + b) + c);
-    const uint32_t v = ((g.z > 0) ? 4u : 0u) + ((g.y > 0) ? 2u : 0u) + ((g.x > 0) ? 1u : 0u);
-    bool keep = lv.info[size_t(node) * 8 + v] == t;
-    if (!keep) {
-        float radius[8];
-        const float4 r0 = *reinterpret_cast<const float4*>(region + size_t(node) * 72 + v * 8);
-        const float4 r1 = *reinterpret_cast<const float4*>(region + size_t(node) * 72 + v * 8 + 4);
-        radius[0] = r0.x; radius[1] = r0.y; radius[2] = r0.z; radius[3] = r0.w;
-        radius[4] = r1.x; radius[5] = r1.y; radius[6] = r1.z; radius[7] = r1.w;
-        keep = isNearMinimize(ch.w, radius, a, b, c, region[size_t(node) * 72 + 64 + v]);
+filterRefillKernel(DeviceMesh mesh, LevelView lv, const uint32_t* __restrict__ parentList, const float* __restrict__ region,
+                   uint8_t* __restrict__ flags, uint64_t numPairs) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const uint64_t begin = (uint64_t(blockIdx.x) * 8 + (threadIdx.x >> 5)) * kFilterChunk;
+    if (begin >= numPairs) return;
+    const uint64_t end = begin + kFilterChunk < numPairs ? begin + kFilterChunk : numPairs;
+    uint32_t nodeCur = 0;
+    if (lane == 0) nodeCur = lastLessEqual<uint64_t>(lv.pairOff, lv.count + 1, begin);
+    nodeCur = __shfl_sync(kFull, nodeCur, 0);
+    uint64_t next = begin;
+    bool have = false;
+    uint64_t myPair = 0;
+    float half = 0.0f, thr = 0.0f, sqThr = 0.0f;
+    float r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0;
+    f3 a = mk3(0, 0, 0), b = a, c = a, x = a;
+    uint32_t iter = 0;
+    for (;;) {
+        const unsigned need = __ballot_sync(kFull, !have);
+        if (need && next < end) {
+            const uint32_t avail = uint32_t(end - next);
+            const uint32_t want = uint32_t(__popc(need));
+            const uint32_t take = want < avail ? want : avail;
+            const uint32_t rank = uint32_t(__popc(need & ((1u << lane) - 1u)));
+            uint32_t node = nodeCur;
+            if (!have && rank < take) {
+                myPair = next + rank;
+                while (myPair >= lv.pairOff[node + 1]) node++;
+                const uint32_t j = uint32_t(myPair - lv.pairOff[node]);
+                const uint32_t t = parentList[lv.parentLo[node] + j];
+                const float4 ch = lv.centerHalf[node];
+                const f3 ctr = mk3(ch.x, ch.y, ch.z);
+                a = mesh.verts[mesh.idx[3 * size_t(t)]] - ctr;
+                b = mesh.verts[mesh.idx[3 * size_t(t) + 1]] - ctr;
+                c = mesh.verts[mesh.idx[3 * size_t(t) + 2]] - ctr;
+                const f3 g = 0.3333333f * ((a + b) + c);
+                const uint32_t v = ((g.z > 0) ? 4u : 0u) + ((g.y > 0) ? 2u : 0u) + ((g.x > 0) ? 1u : 0u);
+                if (lv.info[size_t(node) * 8 + v] == t) flags[myPair] = 1;   // the corner's own nearest triangle is always kept
+                else {
+                    const float4 q0 = *reinterpret_cast<const float4*>(region + size_t(node) * 72 + v * 8);
+                    const float4 q1 = *reinterpret_cast<const float4*>(region + size_t(node) * 72 + v * 8 + 4);
+                    r0 = q0.x; r1 = q0.y; r2 = q0.z; r3 = q0.w; r4 = q1.x; r5 = q1.y; r6 = q1.z; r7 = q1.w;
+                    half = ch.w;
+                    thr = region[size_t(node) * 72 + 64 + v];
+                    sqThr = thr * thr;
+                    x = -a;
+                    iter = 0;
+                    have = true;
+                }
+            }
+            nodeCur = __reduce_max_sync(kFull, node);
+            next += take;
+        }
+        if (!__any_sync(kFull, have)) {
+            if (next >= end) break;
+            continue;
+        }
+        if (have) {   // one iteration of GJK::IsNearMinimize (src/utils/GJK.cpp:830-866)
+            const f3 g = normalize3(-x);
+            float best = dot3(mk3(-half, -half, -half), g) + r0;
+            uint32_t bi = 0;
+            float br = r0;
+#define SDFB_SUPPORT(i, r)                                            \
+            {                                                         \
+                const float v = dot3(cornerDir(i) * half, g) + (r);   \
+                if (v > best) { best = v; bi = (i); br = (r); }       \
+            }
+            SDFB_SUPPORT(1u, r1) SDFB_SUPPORT(2u, r2) SDFB_SUPPORT(3u, r3) SDFB_SUPPORT(4u, r4)
+            SDFB_SUPPORT(5u, r5) SDFB_SUPPORT(6u, r6) SDFB_SUPPORT(7u, r7)
+#undef SDFB_SUPPORT
+            const f3 boxPoint = cornerDir(bi) * half + br * g;
+            const f3 ng = -g;
+            const float d1 = dot3(a, ng), d2 = dot3(b, ng), d3v = dot3(c, ng);
+            const f3 triPoint = (d1 > d2) ? ((d1 > d3v) ? a : c) : ((d2 > d3v) ? b : c);
+            const f3 p = boxPoint - triPoint;
+            const float distToP = dot3(g, p - x);
+            const float distToO = dot3(g, -x);
+            const f3 dir = p - x;
+            const float d = dot3(dir, -x);
+            bool done, result;
+            if (double(d) < 1.0e-5) { done = true; result = distToO <= distToP + thr; }
+            else {
+                x = x + dir * gmin(d / dot3(dir, dir), 1.0f);
+                const bool isNear = dot3(x, x) < sqThr;
+                bool again = false;
+                if (!isNear && distToO <= distToP + thr) { iter++; again = iter < 15; }
+                done = !again;
+                result = isNear || iter >= 15;
+            }
+            if (done) { flags[myPair] = result ? 1 : 0; have = false; }
+        }
     }
-    flags[p] = keep ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -627,7 +668,7 @@ struct ExactBuildState : BuildState {
         levels.resize(maxDepth + 1);
         ScannerT<uint32_t, uint32_t> scan32;
         ScannerT<uint32_t, uint64_t> scan64;
-        ScannerT<uint8_t, uint32_t> scanFlags;
+        FlagScanner scanFlags;
         scalars.alloc(2);
         SDFB_CUDA(cudaMemset(scalars.p, 0, 8));
         DevBuf<unsigned long long> best;
@@ -701,7 +742,7 @@ struct ExactBuildState : BuildState {
             regionKernel<<<divUp(L.count, 4), 256>>>(dFrames.p, L.view(), region.p);
             L.flags.alloc(L.numPairs + 1);
             L.pos.alloc(L.numPairs + 1);
-            if (L.numPairs) filterKernel<<<divUp(L.numPairs, 256), 256>>>(dmesh, L.view(), parentList, region.p, L.flags.p, L.numPairs);
+            if (L.numPairs) filterRefillKernel<<<divUp(L.numPairs, 8 * kFilterChunk), 256>>>(dmesh, L.view(), parentList, region.p, L.flags.p, L.numPairs);
             SDFB_CUDA(cudaGetLastError());
             if (L.numPairs >= (uint64_t(1) << 32)) {   // the 32-bit scan below would wrap silently: count the kept pairs in 64 bits first
                 const uint64_t kept = countFlags64(L.flags.p, L.numPairs);

@@ -314,7 +314,7 @@ void prepareExactQuery(sdfb200_sdf& s) {
     };
     ScannerT<uint32_t, uint32_t> scan32;
     ScannerT<uint32_t, uint64_t> scan64;
-    ScannerT<uint8_t, uint32_t> scanFlags;
+    FlagScanner scanFlags;
     const uint64_t G3 = uint64_t(s.startGridSize) * s.startGridSize * s.startGridSize;
     std::vector<std::unique_ptr<Frontier>> fr;
     fr.emplace_back(new Frontier());
