@@ -232,7 +232,8 @@ TriVec computeTriangleData(const HostMesh& mesh) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-struct BuildTri { double v[3][3]; int32_t id; };
+struct BuildTri { double v[3][3]; };          // by triangle id, never moved
+struct SortKey { double key; int32_t id; };     // what std::sort actually moves (16 bytes instead of 80)
 
 inline double sq3(const double* a, const double* b) {
     const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
@@ -240,7 +241,9 @@ inline double sq3(const double* a, const double* b) {
 }
 
 struct BvhBuilder {
-    RawVec<BuildTri>& bt;
+    const RawVec<BuildTri>& tri;   // vertices in float64, by triangle id
+    RawVec<int32_t>& order;        // current triangle order; a node owns the range [begin, end)
+    RawVec<SortKey>& scratch;      // same ranges, disjoint between tasks
     RawVec<BvhNode>& nodes;
 
     // sphere = where the bounding sphere of this subtree is stored (a child slot of the parent)
@@ -248,42 +251,50 @@ struct BvhBuilder {
         const int32_t n = end - begin;
         BvhNode& node = nodes[size_t(nodeId)];
         if (n == 1) {
-            const BuildTri& t = bt[size_t(begin)];
+            const BuildTri& t = tri[size_t(order[size_t(begin)])];
             double c[3];
             for (int a = 0; a < 3; a++) c[a] = (t.v[0][a] + t.v[1][a] + t.v[2][a]) / 3.0;
             const double r0 = std::sqrt(sq3(t.v[0], c)), r1 = std::sqrt(sq3(t.v[1], c)), r2 = std::sqrt(sq3(t.v[2], c));
             for (int a = 0; a < 3; a++) sphereCenter[a] = c[a];
             *sphereRadius = std::max(std::max(r0, r1), r2);
             node.left = -1;
-            node.right = t.id;
+            node.right = order[size_t(begin)];
             node.pad[0] = 1;   // leaf
             node.pad[1] = 0;
             return;
         }
         double top[3], bottom[3], c[3] = {0, 0, 0};
         for (int a = 0; a < 3; a++) { top[a] = std::numeric_limits<double>::lowest(); bottom[a] = std::numeric_limits<double>::max(); }
-        for (int32_t i = begin; i < end; i++)
+        for (int32_t i = begin; i < end; i++) {   // the centre is a sequential float64 sum: its order is part of the result
+            const BuildTri& t = tri[size_t(order[size_t(i)])];
             for (int k = 0; k < 3; k++)
                 for (int a = 0; a < 3; a++) {
-                    const double p = bt[size_t(i)].v[k][a];
+                    const double p = t.v[k][a];
                     c[a] += p;
                     top[a] = std::max(top[a], p);
                     bottom[a] = std::min(bottom[a], p);
                 }
+        }
         const double count = double(3 * n);
         for (int a = 0; a < 3; a++) c[a] /= count;
         int dim = 0;
         for (int a = 1; a < 3; a++)
             if (top[a] - bottom[a] > top[dim] - bottom[dim]) dim = a;
         double r2 = 0.0;
-        for (int32_t i = begin; i < end; i++)
-            for (int k = 0; k < 3; k++) r2 = std::max(r2, sq3(c, bt[size_t(i)].v[k]));
+        for (int32_t i = begin; i < end; i++) {
+            const BuildTri& t = tri[size_t(order[size_t(i)])];
+            for (int k = 0; k < 3; k++) r2 = std::max(r2, sq3(c, t.v[k]));
+        }
         for (int a = 0; a < 3; a++) sphereCenter[a] = c[a];
         *sphereRadius = std::sqrt(r2);
-        // Same call as the reference: std::sort is not stable, and triangles sharing their first
-        // vertex tie on this key, so the library's comparison sequence is part of the result.
-        std::sort(bt.begin() + begin, bt.begin() + end,
-                  [dim](const BuildTri& x, const BuildTri& y) { return x.v[0][dim] < y.v[0][dim]; });
+        // Same call as the reference: std::sort is not stable, and triangles sharing their first vertex tie on this
+        // key, so the library's comparison sequence is part of the result. That sequence depends only on the
+        // comparison outcomes, not on the element type, so 16-byte (key, id) records give the same permutation as
+        // sorting the reference's 80-byte triangle records.
+        SortKey* keys = scratch.data() + begin;
+        for (int32_t i = 0; i < n; i++) { const int32_t id = order[size_t(begin + i)]; keys[i] = SortKey{tri[size_t(id)].v[0][dim], id}; }
+        std::sort(keys, keys + n, [](const SortKey& x, const SortKey& y) { return x.key < y.key; });
+        for (int32_t i = 0; i < n; i++) order[size_t(begin + i)] = keys[i].id;
         const int32_t mid = int32_t(0.5 * (begin + end));
         node.left = nodeId + 1;
         node.right = nodeId + 2 * (mid - begin);
@@ -291,7 +302,7 @@ struct BvhBuilder {
         const int32_t l = node.left, r = node.right;
         double* lc = node.lc;
         double* lr = &node.lr;
-        // the two halves are independent once sorted; nodes/bt are pre-sized, so tasks only touch
+        // the two halves are independent once sorted; all arrays are pre-sized, so tasks only touch
         // disjoint ranges. The enclosing parallel region's barrier joins them.
 #pragma omp task firstprivate(l, lc, lr, begin, mid) if (n > 8192)
         build(l, lc, lr, begin, mid);
@@ -304,9 +315,11 @@ struct BvhBuilder {
 RawVec<BvhNode> buildBvh(const HostMesh& mesh) {
     const uint32_t nT = mesh.numTriangles();
     RawVec<BuildTri> bt(nT);
+    RawVec<int32_t> order(nT);
+    RawVec<SortKey> scratch(nT);
 #pragma omp parallel for schedule(static) num_threads(hostThreads())
     for (int64_t t = 0; t < int64_t(nT); t++) {
-        bt[size_t(t)].id = int32_t(t);
+        order[size_t(t)] = int32_t(t);
         for (int k = 0; k < 3; k++) {
             const f3 p = mesh.verts[mesh.idx[3 * t + k]];
             bt[size_t(t)].v[k][0] = double(p.x); bt[size_t(t)].v[k][1] = double(p.y); bt[size_t(t)].v[k][2] = double(p.z);
@@ -314,7 +327,7 @@ RawVec<BvhNode> buildBvh(const HostMesh& mesh) {
     }
     RawVec<BvhNode> nodes(size_t(2) * nT - 1);
     double rootCenter[3], rootRadius;
-    BvhBuilder b{bt, nodes};
+    BvhBuilder b{bt, order, scratch, nodes};
 #pragma omp parallel num_threads(hostThreads())
 #pragma omp single
     b.build(0, rootCenter, &rootRadius, 0, int32_t(nT));

@@ -337,11 +337,9 @@ struct OctreeBuildState : BuildState {
         sdfb200_build_stats& st = out.stats;
         // serial set-up steps of the reference, on the host (see mesh_host.h)
         auto t0 = std::chrono::steady_clock::now();
-        TriVec tris = computeTriangleData(mesh);
-        st.triangle_data_ms = msSince(t0);
-        t0 = std::chrono::steady_clock::now();
-        RawVec<BvhNode> bvh = buildBvh(mesh);
-        st.bvh_ms = msSince(t0);
+        TriVec tris;
+        RawVec<BvhNode> bvh;
+        buildHostStructures(mesh, tris, bvh, st);
         t0 = std::chrono::steady_clock::now();
         MeshOnDevice dm;
         uploadMesh(dm, mesh, tris, &bvh);

@@ -753,11 +753,9 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
     }
 
     auto t0 = std::chrono::steady_clock::now();
-    TriVec tris = computeTriangleData(mesh);
-    st.triangle_data_ms = msSince(t0);
-    t0 = std::chrono::steady_clock::now();
-    RawVec<BvhNode> bvh = buildBvh(mesh);
-    st.bvh_ms = msSince(t0);
+    TriVec tris;
+    RawVec<BvhNode> bvh;
+    buildHostStructures(mesh, tris, bvh, st);
     t0 = std::chrono::steady_clock::now();
     MeshOnDevice dm;
     uploadMesh(dm, mesh, tris, &bvh);

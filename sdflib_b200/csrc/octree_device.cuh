@@ -6,6 +6,8 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
+#include <exception>
+#include <thread>
 
 #include "device_utils.cuh"
 #include "sdf_internal.h"
@@ -308,6 +310,22 @@ inline void uploadMesh(MeshOnDevice& m, const HostMesh& mesh, const TriVec& tris
         m.triVerts.alloc(size_t(m.numTriangles) * 3);
         gatherTriVertsKernel<<<divUp(uint64_t(m.numTriangles) * 3, 256), 256>>>(m.verts.p, m.idx.p, m.numTriangles, m.triVerts.p);
     }
+}
+
+// The two serial set-up steps of the reference constructors, side by side: the BVH build is dominated by the
+// (inherently sequential) std::sort calls of its top levels, which leaves cores free for the TriangleData loops.
+// triangle_data_ms = duration of that step, bvh_ms = the remaining wall time until the BVH is ready.
+inline void buildHostStructures(const HostMesh& mesh, TriVec& tris, RawVec<BvhNode>& bvh, sdfb200_build_stats& st) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::exception_ptr failure;
+    std::thread bvhThread([&] {
+        try { bvh = buildBvh(mesh); } catch (...) { failure = std::current_exception(); }
+    });
+    try { tris = computeTriangleData(mesh); } catch (...) { bvhThread.join(); throw; }
+    st.triangle_data_ms = msSince(t0);
+    bvhThread.join();
+    if (failure) std::rethrow_exception(failure);
+    st.bvh_ms = msSince(t0) - st.triangle_data_ms;
 }
 
 // Weight of a mid-point in the error integral: trapezoid / by-distance 2^k/64 (OctreeSdfUtils.h:60-138),
