@@ -27,6 +27,8 @@
 // (DESIGN.md "parity"): oracle(use_cache=0) is the bit-exact comparison.
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -769,7 +771,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
     const float sqThreshold = param0 * param0;
     GrowingOctree oc;
     oc.G3 = G3;
-    oc.reserve(uint64_t(G3) + 4096);
+    oc.reserve(std::max<uint64_t>(uint64_t(G3) + 4096, uint64_t(32) << 20));   // 128 MB up front: growth (alloc + copy of three arrays) is the slow path
     SDFB_CUDA(cudaMemsetAsync(oc.oct.p, 0, size_t(G3) * 4));
     uint64_t words = G3;   // append cursor of mOctreeData
 
@@ -810,6 +812,14 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         st.samples_evaluated += L.count * 8;
     }
 
+    static const bool timing = std::getenv("SDFB200_TIMING") != nullptr;
+    auto tPhase = std::chrono::steady_clock::now();
+    auto tick = [&](const char* what, uint32_t d) {
+        if (!timing) return;
+        cudaDeviceSynchronize();
+        std::fprintf(stderr, "[sdfb200] continuity depth %u %-10s %8.2f ms\n", d, what, msSince(tPhase));
+        tPhase = std::chrono::steady_clock::now();
+    };
     DevBuf<float4> mids, fixPoints, fixSamples;
     DevBuf<float> coeffs;
     DevBuf<uint32_t> sizes, sub, sizeScan, subScan, candCount32, candScan, candWords, candList, isRoot, rootPos;
@@ -825,10 +835,10 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         const uint32_t grid8 = divUp(L.count, kWarpsPerCta);
         // ---- Iter 1
         if (!deepest) {
-            mids.alloc(size_t(L.count) * 38);
+            mids.ensure(size_t(L.count) * 38);
             sampleLatticeKernel<<<divUp(uint64_t(L.count) * 19, kBvhThreads), kBvhThreads, bvhStackBytes(dmesh)>>>(dmesh, L.centerHalf.p, L.count, mids.p, 2);
             if (real) {
-                coeffs.alloc(size_t(L.count) * 64);
+                coeffs.ensure(size_t(L.count) * 64);
                 contDecideKernel<<<grid8, kWarpsPerCta * 32>>>(L.arrays(), mids.p, coeffs.p, oc.oct.p, rule, sqThreshold, param1);
             } else {
                 SDFB_CUDA(cudaMemsetAsync(L.terminal.p, 0, L.count));
@@ -836,22 +846,23 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
             st.kernel_launches += 2;
             st.samples_evaluated += uint64_t(L.count) * 19;
         }
+        tick("iter1", d);
         // ---- Iter 2: T-junction samples
         uint32_t nCand = 0;
         const bool junctions = real && !deepest;
         if (junctions) {
-            candCount.alloc(L.count);
-            candWords.alloc(size_t(L.count) * 18);
+            candCount.ensure(L.count);
+            candWords.ensure(size_t(L.count) * 18);
             contJunctionKernel<<<grid8, kWarpsPerCta * 32>>>(grid, L.arrays(), d, mids.p, coeffs.p, oc.oct.p, sqThreshold, candCount.p, candWords.p);
-            candCount32.alloc(L.count);
-            candScan.alloc(L.count);
+            candCount32.ensure(L.count);
+            candScan.ensure(L.count);
             widenCountsKernel<<<divUp(L.count, 256), 256>>>(candCount.p, candCount32.p, L.count);
             nCand = scanner.run(candCount32.p, candScan.p, L.count);
-            candList.alloc(std::max<uint32_t>(nCand, 1));
+            candList.ensure(std::max<uint32_t>(nCand, 1));
             st.kernel_launches += 5;
         }
         // ---- Iter 2: layout of the level, words, leaves, children
-        sizes.alloc(L.count); sub.alloc(L.count); sizeScan.alloc(L.count); subScan.alloc(L.count);
+        sizes.ensure(L.count); sub.ensure(L.count); sizeScan.ensure(L.count); subScan.ensure(L.count);
         contSizesKernel<<<divUp(L.count, 256), 256>>>(L.arrays(), real, deepest, sizes.p, sub.p);
         const uint32_t levelWords = scanner.run(sizes.p, sizeScan.p, L.count);
         const uint32_t nSub = scanner.run(sub.p, subScan.p, L.count);
@@ -864,11 +875,12 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         st.kernel_launches += 8;
         st.nodes_processed += L.count;
         words += levelWords;
+        tick("iter2", d);
         if (nCand == 0) continue;
 
         // ---- fix-up pass: re-open the queued leaves
         SDFB_CUDA(cudaMemcpyAsync(dStores.p, storeTable.data(), sizeof(StoreView) * 32, cudaMemcpyHostToDevice));
-        isRoot.alloc(nCand); rootPos.alloc(nCand);
+        isRoot.ensure(nCand); rootPos.ensure(nCand);
         fixClaimKernel<<<divUp(nCand, 256), 256>>>(candList.p, nCand, oc.oct.p, G3, oc.claim.p);
         fixRootFlagKernel<<<divUp(nCand, 256), 256>>>(candList.p, nCand, oc.oct.p, G3, oc.claim.p, isRoot.p);
         const uint32_t K = scanner.run(isRoot.p, rootPos.p, nCand);
@@ -892,7 +904,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
             FixRound& Nx = *rounds[r + 1];
             Nx.alloc(R.nSplit * 8);
             const uint32_t nTrue = scanner.run(R.nSamples.p, R.sampleScan.p, R.count);
-            fixPoints.alloc(std::max<uint32_t>(nTrue, 1)); fixSamples.alloc(std::max<uint32_t>(nTrue, 1));
+            fixPoints.ensure(std::max<uint32_t>(nTrue, 1)); fixSamples.ensure(std::max<uint32_t>(nTrue, 1));
             fixSamplePointsKernel<<<divUp(R.count, 128), 128>>>(R.arrays(), R.sampleScan.p, fixPoints.p);
             if (nTrue) samplePointsKernel<<<divUp(nTrue, kBvhThreads), kBvhThreads, bvhStackBytes(dmesh)>>>(dmesh, fixPoints.p, nTrue, fixSamples.p);
             fixValuesKernel<<<g8, kWarpsPerCta * 32>>>(R.arrays(), Nx.arrays(), R.splitScan.p, R.sampleScan.p, fixSamples.p, sqThreshold);
@@ -900,6 +912,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
             st.samples_evaluated += nTrue;
             st.nodes_processed += R.count;
         }
+        tick("fix rounds", d);
         const uint32_t nRounds = uint32_t(rounds.size());
         DevBuf<uint32_t> byRoot(size_t(K) * nRounds + 1), byRound(size_t(K) * nRounds + 1);
         SDFB_CUDA(cudaMemsetAsync(byRoot.p, 0, byRoot.n * 4));
@@ -934,6 +947,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         }
         storeTable[kPoolStoreBase + d] = P.store();
         words += fixWords;
+        tick("fix write", d);
         st.nodes_processed += rounds.back()->count;
     }
     // final un-mark (:1191-1217), border minimum over the leaves of the final tree

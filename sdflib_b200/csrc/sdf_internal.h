@@ -45,6 +45,12 @@ template <class T> struct DevBuf {
         n = count;
         if (count) SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), cudaStream_t(0)));
     }
+    // grow-only variant for temporaries reused across the levels of a build: contents are not preserved, `n` is the
+    // capacity. Re-allocating a slightly larger block every level makes the pool grow (slow) instead of recycling.
+    void ensure(size_t count) {
+        if (count <= n) return;
+        alloc(count + count / 2 + 256);
+    }
     void release() { if (p) cudaFreeAsync(p, cudaStream_t(0)); p = nullptr; n = 0; }
     void upload(const T* src, size_t count, cudaStream_t s = 0) {
         if (count) SDFB_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
