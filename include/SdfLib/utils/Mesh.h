@@ -1,11 +1,16 @@
 // sdflib::BoundingBox / sdflib::Mesh — drop-in mirror of include/SdfLib/utils/Mesh.h:16-106 of the reference for the
 // B200-native library. Header-only; needs <glm/glm.hpp> exactly like the reference's public headers do.
-// File loading through assimp (Mesh(std::string), Mesh.h:76-79) is out of scope: construct from arrays.
+// Mesh(std::string) (Mesh.h:76-79, assimp in the reference) reads Stanford PLY (ascii / binary_little_endian) and
+// Wavefront OBJ directly: vertex positions and faces only, polygons triangulated as fans (aiProcess_Triangulate).
 #ifndef SDFB200_SDFLIB_MESH_H
 #define SDFB200_SDFLIB_MESH_H
 
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
 #include <string>
 #include <vector>
 #include <glm/glm.hpp>
@@ -42,6 +47,20 @@ public:
         computeBoundingBox();
     }
 
+    // src/utils/Mesh.cpp:9-26. Throws std::runtime_error on unreadable / unsupported files (the reference logs and
+    // leaves an empty mesh, which its builders then dereference).
+    explicit Mesh(const std::string& filePath)
+    {
+        const size_t dot = filePath.find_last_of('.');
+        std::string ext = dot == std::string::npos ? "" : filePath.substr(dot + 1);
+        for (char& c : ext) c = char(std::tolower(static_cast<unsigned char>(c)));
+        if (ext == "ply") loadPly(filePath);
+        else if (ext == "obj") loadObj(filePath);
+        else throw std::runtime_error("Mesh: unsupported model format '" + ext + "' (ply and obj are read)");
+        if (mVertices.empty() || mIndices.empty()) throw std::runtime_error("Mesh: " + filePath + " holds no triangles");
+        computeBoundingBox();
+    }
+
     std::vector<glm::vec3>& getVertices() { return mVertices; }
     const std::vector<glm::vec3>& getVertices() const { return mVertices; }
     std::vector<uint32_t>& getIndices() { return mIndices; }
@@ -67,6 +86,124 @@ public:
     }
 
 private:
+    void addPolygon(const std::vector<uint32_t>& poly)
+    {
+        for (size_t k = 1; k + 1 < poly.size(); k++) { mIndices.push_back(poly[0]); mIndices.push_back(poly[k]); mIndices.push_back(poly[k + 1]); }
+    }
+
+    void loadObj(const std::string& path)
+    {
+        std::ifstream in(path);
+        if (!in) throw std::runtime_error("Mesh: cannot open " + path);
+        std::string line;
+        std::vector<uint32_t> poly;
+        while (std::getline(in, line))
+        {
+            std::istringstream ls(line);
+            std::string tag;
+            ls >> tag;
+            if (tag == "v") { glm::vec3 v(0.0f); ls >> v.x >> v.y >> v.z; mVertices.push_back(v); }
+            else if (tag == "f")
+            {
+                poly.clear();
+                std::string ref;
+                while (ls >> ref)
+                {
+                    const long i = std::strtol(ref.c_str(), nullptr, 10);   // "v", "v/vt", "v//vn", "v/vt/vn"
+                    if (i == 0) throw std::runtime_error("Mesh: malformed face in " + path);
+                    poly.push_back(uint32_t(i > 0 ? i - 1 : long(mVertices.size()) + i));
+                }
+                addPolygon(poly);
+            }
+        }
+        for (uint32_t i : mIndices) if (i >= mVertices.size()) throw std::runtime_error("Mesh: face index out of range in " + path);
+    }
+
+    struct PlyProperty { std::string type, countType, name; bool list; };
+    static size_t plySize(const std::string& t)
+    {
+        if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+        if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+        if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+        if (t == "double" || t == "float64") return 8;
+        throw std::runtime_error("Mesh: unknown PLY type " + t);
+    }
+    static double plyRead(std::istream& in, const std::string& t, bool ascii)
+    {
+        if (ascii) { double v = 0; in >> v; return v; }
+        char b[8] = {0};
+        in.read(b, std::streamsize(plySize(t)));
+        if (t == "char" || t == "int8") { int8_t v; std::memcpy(&v, b, 1); return v; }
+        if (t == "uchar" || t == "uint8") { uint8_t v; std::memcpy(&v, b, 1); return v; }
+        if (t == "short" || t == "int16") { int16_t v; std::memcpy(&v, b, 2); return v; }
+        if (t == "ushort" || t == "uint16") { uint16_t v; std::memcpy(&v, b, 2); return v; }
+        if (t == "int" || t == "int32") { int32_t v; std::memcpy(&v, b, 4); return v; }
+        if (t == "uint" || t == "uint32") { uint32_t v; std::memcpy(&v, b, 4); return v; }
+        if (t == "float" || t == "float32") { float v; std::memcpy(&v, b, 4); return v; }
+        double v; std::memcpy(&v, b, 8); return v;
+    }
+
+    void loadPly(const std::string& path)
+    {
+        std::ifstream in(path, std::ios::binary);
+        if (!in) throw std::runtime_error("Mesh: cannot open " + path);
+        std::string line;
+        std::getline(in, line);
+        if (line.substr(0, 3) != "ply") throw std::runtime_error("Mesh: " + path + " is not a PLY file");
+        bool ascii = true;
+        struct Element { std::string name; size_t count; std::vector<PlyProperty> props; };
+        std::vector<Element> elements;
+        while (std::getline(in, line))
+        {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            std::istringstream ls(line);
+            std::string tag;
+            ls >> tag;
+            if (tag == "format")
+            {
+                std::string f; ls >> f;
+                if (f == "ascii") ascii = true;
+                else if (f == "binary_little_endian") ascii = false;
+                else throw std::runtime_error("Mesh: PLY format " + f + " is not supported");
+            }
+            else if (tag == "element") { Element e; ls >> e.name >> e.count; elements.push_back(e); }
+            else if (tag == "property")
+            {
+                if (elements.empty()) throw std::runtime_error("Mesh: PLY property before any element");
+                PlyProperty p; p.list = false;
+                ls >> p.type;
+                if (p.type == "list") { p.list = true; ls >> p.countType >> p.type; }
+                ls >> p.name;
+                elements.back().props.push_back(p);
+            }
+            else if (tag == "end_header") break;
+        }
+        std::vector<uint32_t> poly;
+        for (const Element& e : elements)
+            for (size_t i = 0; i < e.count; i++)
+            {
+                glm::vec3 v(0.0f);
+                for (const PlyProperty& p : e.props)
+                {
+                    if (p.list)
+                    {
+                        const size_t n = size_t(plyRead(in, p.countType, ascii));
+                        poly.clear();
+                        for (size_t k = 0; k < n; k++) poly.push_back(uint32_t(plyRead(in, p.type, ascii)));
+                        if (e.name == "face" && (p.name == "vertex_indices" || p.name == "vertex_index")) addPolygon(poly);
+                    }
+                    else
+                    {
+                        const double x = plyRead(in, p.type, ascii);
+                        if (p.name == "x") v.x = float(x); else if (p.name == "y") v.y = float(x); else if (p.name == "z") v.z = float(x);
+                    }
+                }
+                if (e.name == "vertex") mVertices.push_back(v);
+                if (!in) throw std::runtime_error("Mesh: " + path + " ends early");
+            }
+        for (uint32_t i : mIndices) if (i >= mVertices.size()) throw std::runtime_error("Mesh: face index out of range in " + path);
+    }
+
     std::vector<glm::vec3> mVertices;
     std::vector<uint32_t> mIndices;
     BoundingBox mBBox;

@@ -182,6 +182,8 @@ inline mat3 inverse(const mat3& m) {
 
 struct mat4 {
     vec4 c[4];
+    mat4() {}
+    explicit mat4(float d) { for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) c[i][j] = (i == j) ? d : 0.0f; }
     vec4& operator[](int i) { return c[i]; }
     const vec4& operator[](int i) const { return c[i]; }
 };

@@ -1,0 +1,125 @@
+"""The reference's two command-line tools (src/tools/SdfExporter, src/tools/SdfError) rebuilt on the drop-in headers,
+and the PLY / OBJ reader that replaces assimp in sdflib::Mesh(std::string).
+
+CPU: the tools compile, parse the reference's flags, read meshes, and fail loudly without a GPU.
+GPU: SdfExporter's .bin files are byte-identical to the ones the Python binding writes for the same arguments;
+SdfError reports the tri-cubic octree's error against the exact octree below the build threshold's order."""
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, displaced_sphere
+
+BIN = os.path.join(ROOT, "tools", "bin")
+
+
+@pytest.fixture(scope="module")
+def tools(sdf):
+    r = subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tools")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return BIN
+
+
+def write_ply(path, v, i, binary):
+    with open(path, "wb") as f:
+        f.write(("ply\nformat %s 1.0\ncomment test\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                 "element face %d\nproperty list uchar int vertex_indices\nend_header\n"
+                 % ("binary_little_endian" if binary else "ascii", len(v), len(i) // 3)).encode())
+        if binary:
+            f.write(np.ascontiguousarray(v, np.float32).tobytes())
+            for t in range(len(i) // 3):
+                f.write(struct.pack("<B3i", 3, *[int(x) for x in i[3 * t:3 * t + 3]]))
+        else:
+            for p in v:
+                f.write(("%.9g %.9g %.9g\n" % tuple(p)).encode())
+            for t in range(len(i) // 3):
+                f.write(("3 %d %d %d\n" % tuple(i[3 * t:3 * t + 3])).encode())
+
+
+def write_obj(path, v, i):
+    with open(path, "w") as f:
+        for p in v:
+            f.write("v %.9g %.9g %.9g\n" % tuple(p))
+        for t in range(len(i) // 3):
+            a, b, c = (int(x) + 1 for x in i[3 * t:3 * t + 3])
+            f.write("f %d//%d %d//%d %d//%d\n" % (a, a, b, b, c, c))
+
+
+def test_tools_compile_and_check_their_arguments(tools, tmp_path):
+    r = subprocess.run([os.path.join(tools, "SdfExporter")], capture_output=True, text=True)
+    assert r.returncode == 1 and "No model_path specified" in r.stderr
+    r = subprocess.run([os.path.join(tools, "SdfExporter"), "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "--termination_threshold" in r.stderr and "--min_triangles_per_node" in r.stderr
+    r = subprocess.run([os.path.join(tools, "SdfExporter"), "model.ply", "out.bin", "--no_such_flag", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "could not be matched" in r.stderr
+    r = subprocess.run([os.path.join(tools, "SdfExporter"), str(tmp_path / "missing.ply"), str(tmp_path / "o.bin")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
+    r = subprocess.run([os.path.join(tools, "SdfError"), str(tmp_path / "a.bin"), str(tmp_path / "b.bin")], capture_output=True, text=True)
+    assert r.returncode == 1
+
+
+def test_exporter_reads_meshes_and_has_no_cpu_fallback(sdf, tools, tmp_path):
+    if sdf.device_count() > 0:
+        pytest.skip("GPU present: covered by the gpu test")
+    v, i = displaced_sphere(1)
+    for name, writer in (("a.ply", lambda p: write_ply(p, v, i, False)), ("b.ply", lambda p: write_ply(p, v, i, True)), ("c.obj", lambda p: write_obj(p, v, i))):
+        path = str(tmp_path / name)
+        writer(path)
+        r = subprocess.run([os.path.join(tools, "SdfExporter"), path, str(tmp_path / "o.bin"), "-d", "3"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CUDA device" in r.stderr, r.stderr   # the mesh was read; the build needs the GPU
+
+
+@pytest.mark.gpu
+def test_exporter_and_error_tool_on_gpu(sdf, tools, tmp_path):
+    v, i = displaced_sphere(3)
+    models = {"ascii.ply": lambda p: write_ply(p, v, i, False), "binary.ply": lambda p: write_ply(p, v, i, True), "mesh.obj": lambda p: write_obj(p, v, i)}
+    for name, writer in models.items():
+        writer(str(tmp_path / name))
+    box = sdf.meshes.bounding_box_with_margin(v)   # bbox + 20 % of the largest extent = the tool's default margin
+    mesh, bb = sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:])
+    # octree, the tool's defaults: depth 8 -> use 6 here, start depth 1, continuity, trapezoidal 1e-3
+    want = tmp_path / "want_octree.bin"
+    sdf.OctreeSdf(mesh, bb, 6, 1, 1e-3, sdf.OctreeSdf.CONTINUITY, 1).saveToFile(want)
+    for name in models:
+        out = tmp_path / (name + ".octree.bin")
+        r = subprocess.run([os.path.join(tools, "SdfExporter"), str(tmp_path / name), str(out), "-d", "6"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert "Computation time" in r.stdout
+        assert open(out, "rb").read() == open(want, "rb").read(), name
+    # every flag spelled out: no_continuity, by-distance rule, start depth 2, two "threads" (per-voxel layout)
+    out = tmp_path / "flags.bin"
+    r = subprocess.run([os.path.join(tools, "SdfExporter"), str(tmp_path / "binary.ply"), str(out), "--depth=5", "--start_depth", "2",
+                        "--algorithm", "no_continuity", "--termination_rule", "by_distance_rule", "--termination_threshold", "2e-3",
+                        "--termination_threshold_by_distance", "0.05", "--num_threads", "2", "--bb_margin", "20"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want2 = tmp_path / "want_flags.bin"
+    sdf.OctreeSdf(mesh, bb, 5, 2, 2e-3, sdf.OctreeSdf.NO_CONTINUITY, 2, terminationRule=sdf.OctreeSdf.BY_DISTANCE_RULE,
+                  terminationRuleParams=[2e-3, 0.05]).saveToFile(want2)
+    assert open(out, "rb").read() == open(want2, "rb").read()
+    # exact octree with the tool's defaults (depth 5, start depth 1, 32 triangles per node)
+    exact = tmp_path / "exact.bin"
+    r = subprocess.run([os.path.join(tools, "SdfExporter"), str(tmp_path / "mesh.obj"), str(exact), "--sdf_format", "exact_octree"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want3 = tmp_path / "want_exact.bin"
+    sdf.ExactOctreeSdf(mesh, bb, 5, 1, 32, 1).saveToFile(want3)
+    assert open(exact, "rb").read() == open(want3, "rb").read()
+    # SdfError: tri-cubic octree against the exact field, one million rand() samples
+    r = subprocess.run([os.path.join(tools, "SdfError"), str(tmp_path / "ascii.ply.octree.bin"), str(exact), "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rmse = float(re.search(r"RMSE: ([0-9.eE+-]+)", r.stdout).group(1))
+    mae = float(re.search(r"MAE: ([0-9.eE+-]+)", r.stdout).group(1))
+    mx = float(re.search(r"Max error: ([0-9.eE+-]+)", r.stdout).group(1))
+    assert "Sdf us per query" in r.stdout and "Exact Sdf us per query" in r.stdout
+    assert 0 < mae <= rmse < 2e-3 and mx < 5e-2, r.stdout
+    # normalisation path: model scaled into [-1, 1] before the margin is added
+    out = tmp_path / "normalized.bin"
+    r = subprocess.run([os.path.join(tools, "SdfExporter"), str(tmp_path / "binary.ply"), str(out), "-d", "4", "-n", "--algorithm", "no_continuity"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    loaded = sdf.SdfFunction.loadFromFile(out)
+    area = loaded.getSampleArea().as_array()
+    assert abs((area[3:] - area[:3]).max() - 2.8) < 1e-4   # 2 (normalised extent) + 2 x 20 % margin
