@@ -261,3 +261,33 @@ def test_continuity_query_bit_exact_and_continuous(sdf, port):
     # a sample that misses the threshold keeps its true value (the coarser neighbour is re-opened instead, down to maxDepth),
     # so single faces may still jump by about the threshold; on average the field is an order of magnitude smoother
     assert jump.max() <= 2e-3 and jump.mean() < 0.25 * jump_plain.mean(), (float(jump.max()), float(jump.mean()), float(jump_plain.mean()))
+
+
+def test_continuity_full_size_properties(sdf, ref):
+    """Config-2 mesh at full size (327 680 triangles, depth 8, 1e-3) with CONTINUITY: determinism, structural validity
+    (every word is a node word or part of exactly one leaf block, no mark bit left), same size as the reference's own
+    build, .bin round trip, and agreement with the ExactOctreeSdf field of the same mesh."""
+    import torch
+    v, i = sdf.meshes.config_mesh("M1")
+    box = sdf.meshes.bounding_box_with_margin(v)
+    mesh, bb = sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:])
+    a = sdf.OctreeSdf(mesh, bb, 8, 3, 1e-3, sdf.OctreeSdf.CONTINUITY, 1)
+    b = sdf.OctreeSdf(mesh, bb, 8, 3, 1e-3, sdf.OctreeSdf.CONTINUITY, 8)      # thread count does not change this layout
+    da = a.getOctreeData()
+    assert hashlib.sha256(da.tobytes()).hexdigest() == hashlib.sha256(b.getOctreeData().tobytes()).hexdigest()
+    topo, leaves, inner = octree_topology(da, 8)
+    assert topo.sum() + 64 * leaves == da.size and topo.sum() == 512 + 8 * inner
+    assert not (da[topo] & 0x40000000).any()                                   # final un-mark pass (:1191-1217)
+    leaf_blocks = da[topo][(da[topo] & 0x80000000) != 0] & 0x3FFFFFFF
+    assert len(np.unique(leaf_blocks)) == leaves and (leaf_blocks % 4 == 0).all()
+    r = ref.build_octree(v, i, box, 8, 3, 1e-3, 2, 16)
+    rb = r.octree_data()
+    assert rb.size == da.size
+    rt, rl, ri = octree_topology(rb, 8)
+    assert (rl, ri) == (leaves, inner) and np.array_equal(rt, topo) and np.array_equal(rb[rt], da[topo])
+    grid = torch.from_numpy(sdf.meshes.cell_centre_grid(a.getSampleArea().as_array(), 256)).cuda()
+    d = a.getDistance(grid, exact_order=True)
+    assert torch.isfinite(d).all() and d.min().item() < 0 < d.max().item()
+    exact = sdf.ExactOctreeSdf(mesh, bb, 7, 3, 128, 2)
+    assert (d - exact.getDistance(grid)).abs().max().item() < 1e-2             # tri-cubic field against the exact distance
+    assert (d - exact.getDistance(grid)).abs().mean().item() < 2e-4
