@@ -375,6 +375,7 @@ struct OctreeBuildState : BuildState {
             st.samples_evaluated += L.count * 8;
         }
         DevBuf<float4> mids;
+        LevelSampler levelSampler;
         DevBuf<uint32_t> flags, scan;
         DevBuf<uint8_t> dOwned;
         Scanner scanner;
@@ -387,7 +388,7 @@ struct OctreeBuildState : BuildState {
             flags.alloc(L.count);
             scan.alloc(L.count);
             const uint32_t grid = divUp(L.count, kWarpsPerCta);
-            sampleLatticeKernel<<<divUp(uint64_t(L.count) * 19, kBvhThreads), kBvhThreads, bvhStackBytes(dmesh)>>>(dmesh, L.centerHalf.p, L.count, mids.p, 1);
+            { const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 1); st.leaves += ran == 0xFFFFFFFFu ? uint64_t(L.count) * 19 : ran; }   // stats.leaves: BVH traversals run
             if (d >= startDepth)
                 levelDecideKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), mids.p, flags.p, rule, param0 * param0, param1);
             else

@@ -821,6 +821,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         tPhase = std::chrono::steady_clock::now();
     };
     DevBuf<float4> mids, fixPoints, fixSamples;
+    LevelSampler levelSampler;
     DevBuf<float> coeffs;
     DevBuf<uint32_t> sizes, sub, sizeScan, subScan, candCount32, candScan, candWords, candList, isRoot, rootPos;
     DevBuf<uint8_t> candCount;
@@ -836,7 +837,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         // ---- Iter 1
         if (!deepest) {
             mids.ensure(size_t(L.count) * 38);
-            sampleLatticeKernel<<<divUp(uint64_t(L.count) * 19, kBvhThreads), kBvhThreads, bvhStackBytes(dmesh)>>>(dmesh, L.centerHalf.p, L.count, mids.p, 2);
+            { const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 2); st.leaves += ran == 0xFFFFFFFFu ? uint64_t(L.count) * 19 : ran; }   // stats.leaves: BVH traversals run
             if (real) {
                 coeffs.ensure(size_t(L.count) * 64);
                 contDecideKernel<<<grid8, kWarpsPerCta * 32>>>(L.arrays(), mids.p, coeffs.p, oc.oct.p, rule, sqThreshold, param1);

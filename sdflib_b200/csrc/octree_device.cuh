@@ -232,6 +232,88 @@ __global__ void __launch_bounds__(kBvhThreads) sampleLatticeKernel(DeviceMesh me
     if (stride == 2) out[t * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// ---- sampling with exact de-duplication ---------------------------------------------------------------------
+// Neighbouring nodes share lattice points, and the nearest-triangle query is a pure function of the sample
+// position, so positions that are BIT-IDENTICAL need one traversal only. (The positions of one lattice point
+// computed from different nodes differ by an ulp about 40 % of the time, because each node's centre went through its
+// own chain of float additions; those stay separate queries, which keeps every value exactly what the node would
+// have computed on its own.) On a uniformly refined level 59 % of the 19 N samples are distinct.
+// Open-addressing table of sample indices: a slot holds the index t of its owner, whose position is recomputed from
+// the node arrays for the comparison, so no key has to be published next to the claim.
+__device__ __forceinline__ f3 latticeSamplePosition(const float4* __restrict__ centerHalf, uint32_t t) {
+    const float4 ch = centerHalf[t / 19u];
+    const int L = cSampleLattice[t % 19u];
+    const f3 rel = mk3(float(L % 3 - 1), float((L / 3) % 3 - 1), float(L / 9 - 1));
+    return mk3(ch.x, ch.y, ch.z) + rel * ch.w;
+}
+
+__global__ void dedupeInsertKernel(const float4* __restrict__ centerHalf, uint32_t nSamples, uint32_t* table, uint32_t mask, uint32_t* rep,
+                                   uint32_t* isOwner) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nSamples) return;
+    const f3 p = latticeSamplePosition(centerHalf, t);
+    const uint32_t bx = __float_as_uint(p.x), by = __float_as_uint(p.y), bz = __float_as_uint(p.z);
+    uint32_t h = bx * 0x9E3779B1u ^ by * 0x85EBCA77u ^ bz * 0xC2B2AE3Du;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
+    uint32_t slot = h & mask, owner;
+    for (;;) {
+        const uint32_t old = atomicCAS(&table[slot], 0xFFFFFFFFu, t);
+        if (old == 0xFFFFFFFFu) { owner = t; break; }
+        const f3 q = latticeSamplePosition(centerHalf, old);
+        if (__float_as_uint(q.x) == bx && __float_as_uint(q.y) == by && __float_as_uint(q.z) == bz) { owner = old; break; }
+        slot = (slot + 1) & mask;
+    }
+    rep[t] = owner;
+    isOwner[t] = owner == t ? 1u : 0u;
+}
+
+__global__ void dedupeOwnersKernel(const uint32_t* __restrict__ isOwner, const uint32_t* __restrict__ pos, uint32_t nSamples, uint32_t* owners) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nSamples && isOwner[t]) owners[pos[t]] = t;
+}
+
+__global__ void __launch_bounds__(kBvhThreads)
+sampleOwnersKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const uint32_t* __restrict__ owners, uint32_t nUnique, float4* results) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nUnique) return;
+    results[u] = samplePoint(mesh, latticeSamplePosition(centerHalf, owners[u]));
+}
+
+__global__ void dedupeScatterKernel(const uint32_t* __restrict__ rep, const uint32_t* __restrict__ pos, const float4* __restrict__ results,
+                                    uint32_t nSamples, float4* out, int stride) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nSamples) return;
+    out[size_t(t) * stride] = results[pos[rep[t]]];
+    if (stride == 2) out[size_t(t) * 2 + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// The 19 mid-point samples of every node of a level into out[(node * 19 + s) * stride]; returns the number of BVH
+// traversals actually run. Workspace buffers are grow-only and live as long as the builder.
+struct LevelSampler {
+    DevBuf<uint32_t> table, rep, isOwner, pos, owners;
+    DevBuf<float4> results;
+    Scanner scanner;
+    uint32_t run(const DeviceMesh& mesh, const float4* centerHalf, uint32_t count, float4* out, int stride) {
+        const uint64_t n64 = uint64_t(count) * 19;
+        if (n64 >= (uint64_t(1) << 31)) {   // beyond the 32-bit sample index of the table: plain path
+            sampleLatticeKernel<<<divUp(n64, kBvhThreads), kBvhThreads, bvhStackBytes(mesh)>>>(mesh, centerHalf, count, out, stride);
+            return 0xFFFFFFFFu;
+        }
+        const uint32_t n = uint32_t(n64);
+        uint32_t size = 1024;
+        while (size < 2 * n) size <<= 1;
+        table.ensure(size); rep.ensure(n); isOwner.ensure(n); pos.ensure(n);
+        SDFB_CUDA(cudaMemsetAsync(table.p, 0xFF, size_t(size) * 4));
+        dedupeInsertKernel<<<divUp(n, 256), 256>>>(centerHalf, n, table.p, size - 1, rep.p, isOwner.p);
+        const uint32_t nUnique = scanner.run(isOwner.p, pos.p, n);
+        owners.ensure(nUnique); results.ensure(nUnique);
+        dedupeOwnersKernel<<<divUp(n, 256), 256>>>(isOwner.p, pos.p, n, owners.p);
+        sampleOwnersKernel<<<divUp(nUnique, kBvhThreads), kBvhThreads, bvhStackBytes(mesh)>>>(mesh, centerHalf, owners.p, nUnique, results.p);
+        dedupeScatterKernel<<<divUp(n, 256), 256>>>(rep.p, pos.p, results.p, n, out, stride);
+        return nUnique;
+    }
+};
+
 // explicit point list (fix-up pass of the CONTINUITY builder)
 __global__ void __launch_bounds__(kBvhThreads) samplePointsKernel(DeviceMesh mesh, const float4* points, uint32_t n, float4* out) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
