@@ -287,6 +287,146 @@ exactQueryWarpKernel(const uint32_t* __restrict__ nodes, const uint64_t* __restr
     if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
 }
 
+// ---- large batches: queries binned by leaf ----------------------------------------------------------------------
+// The kernel above fetches an 80-byte frame per (query, triangle) pair and is bound by the L1 data pipe (65 % busy,
+// profiles/r1_summary.md). Queries that land in the same leaf scan the same list, but on a regular grid the 8 queries
+// of a finest leaf sit in 4 different warps. For large batches the queries are therefore counting-sorted by leaf
+// first (walk + histogram, exclusive scan, scatter — no host synchronisation), then every warp takes 64 consecutive
+// sorted queries and, per run of up to 8 queries of one leaf, strides the leaf's list ONCE: each lane loads its frame
+// into registers and evaluates it against all queries of the run. Per query the arithmetic and the tie rule (first
+// strict minimum over ascending list positions) are unchanged, so distances are bit-identical to the other kernel.
+// Measured on C3, 16.7 M queries (value / with gradient identical): 256^3 grid 8.60 -> 8.00 ms, uniform random points
+// (5 % outside the box) 10.9 -> 6.6 ms. The grid gains little: once the frame traffic is shared the kernel is bound
+// by the ~100 non-contracted float instructions of each point-triangle evaluation (-fmad=false for bit parity).
+constexpr uint32_t kBinSegment = 64;   // sorted queries per warp
+constexpr uint32_t kBinRun = 8;        // queries of one leaf evaluated per pass over its list
+
+template <bool kGrad>
+__global__ void __launch_bounds__(256)
+exactWalkKernel(const uint32_t* __restrict__ nodes, const ExactQueryParams q, const float* __restrict__ xyz, uint64_t n,
+                uint32_t* __restrict__ leafOf, uint32_t* __restrict__ leafQueries, float* __restrict__ dist, float* __restrict__ grad) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f3 p = mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+    float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const int ix = int(flx), iy = int(fly), iz = int(flz);
+    fx -= flx; fy -= fly; fz -= flz;
+    if (ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid) {
+        leafOf[i] = kNone;
+        dist[i] = boxDistance(q, p) + q.outside;
+        if (kGrad) { grad[3 * i] = 0.0f; grad[3 * i + 1] = 0.0f; grad[3 * i + 2] = 0.0f; }
+        return;
+    }
+    uint32_t idx = uint32_t((iz * q.grid + iy) * q.grid + ix);
+    uint32_t w0 = __ldg(nodes + 2 * size_t(idx));
+    while (!(w0 & kLeafBit)) {
+        const uint32_t child = ((fz > 0.5f) ? 4u : 0u) + ((fy > 0.5f) ? 2u : 0u) + ((fx > 0.5f) ? 1u : 0u);
+        idx = (w0 & kExactIndexMask) + child;
+        w0 = __ldg(nodes + 2 * size_t(idx));
+        fx = 2.0f * fx; fy = 2.0f * fy; fz = 2.0f * fz;
+        fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
+    }
+    leafOf[i] = idx;
+    atomicAdd(&leafQueries[idx], 1u);
+}
+
+// exclusive scan of the per-node query counts, no host round trip (three launches on the caller's stream)
+__global__ void binBlockSums(const uint32_t* in, uint32_t* blockSums, uint64_t n) {
+    __shared__ uint32_t warpSums[32];
+    const uint64_t i = uint64_t(blockIdx.x) * kScanBlock + threadIdx.x;
+    uint32_t v = i < n ? in[i] : 0u;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t t = warpSums[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) blockSums[blockIdx.x] = t;
+    }
+}
+
+__global__ void exactScatterKernel(const uint32_t* __restrict__ leafOf, uint64_t n, const uint32_t* __restrict__ start,
+                                   uint32_t* __restrict__ remaining, uint32_t* __restrict__ order) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t leaf = leafOf[i];
+    if (leaf == kNone) return;
+    order[start[leaf] + atomicSub(&remaining[leaf], 1u) - 1u] = uint32_t(i);
+}
+
+template <bool kGrad>
+__global__ void __launch_bounds__(256)
+exactBinnedKernel(const uint64_t* __restrict__ leafLo, const uint32_t* __restrict__ leafCnt, const uint32_t* __restrict__ pool,
+                  const float4* __restrict__ frames, const TriData* __restrict__ tris, const float* __restrict__ xyz,
+                  const uint32_t* __restrict__ leafOf, const uint32_t* __restrict__ order, const uint32_t* __restrict__ numSorted,
+                  float* __restrict__ dist, float* __restrict__ grad) {
+    constexpr unsigned kFull = 0xffffffffu;
+    __shared__ float sP[8][kBinSegment][3];
+    __shared__ uint32_t sLeaf[8][kBinSegment], sTri[8][kBinSegment];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t total = *numSorted;
+    const uint64_t seg0 = (uint64_t(blockIdx.x) * 8 + warp) * kBinSegment;
+    if (seg0 >= total) return;
+    const uint32_t m = uint32_t(total - seg0 < kBinSegment ? total - seg0 : kBinSegment);
+    uint32_t qi[2] = {0, 0};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t k = lane + 32 * h;
+        if (k < m) {
+            qi[h] = order[seg0 + k];
+            sP[warp][k][0] = __ldg(xyz + 3 * size_t(qi[h]));
+            sP[warp][k][1] = __ldg(xyz + 3 * size_t(qi[h]) + 1);
+            sP[warp][k][2] = __ldg(xyz + 3 * size_t(qi[h]) + 2);
+            sLeaf[warp][k] = leafOf[qi[h]];
+            sTri[warp][k] = 0u;   // the serial loop's initial bestTri (empty lists keep it)
+        }
+    }
+    __syncwarp();
+    uint32_t r = 0;
+    while (r < m) {
+        const uint32_t leaf = sLeaf[warp][r];
+        uint32_t e = r + 1;
+        while (e < m && e < r + kBinRun && sLeaf[warp][e] == leaf) e++;
+        const uint32_t len = e - r;
+        const uint32_t cnt = leafCnt[leaf];
+        const uint32_t* lst = pool + leafLo[leaf];
+        float best[kBinRun];
+        uint32_t bestK[kBinRun];
+#pragma unroll
+        for (uint32_t c = 0; c < kBinRun; c++) { best[c] = INFINITY; bestK[c] = 0xFFFFFFFFu; }
+        for (uint32_t k = lane; k < cnt; k += 32) {
+            const TriFrame f = loadFrame(frames, __ldg(lst + k));
+#pragma unroll
+            for (uint32_t c = 0; c < kBinRun; c++)
+                if (c < len) {
+                    const float sq = sqDistPointTriangle(mk3(sP[warp][r + c][0], sP[warp][r + c][1], sP[warp][r + c][2]), f);
+                    if (sq < best[c]) { best[c] = sq; bestK[c] = k; }
+                }
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < kBinRun; c++)
+            if (c < len) {
+                const uint32_t mn = __reduce_min_sync(kFull, __float_as_uint(best[c]));
+                const uint32_t w = __reduce_min_sync(kFull, (__float_as_uint(best[c]) == mn) ? bestK[c] : 0xFFFFFFFFu);
+                if (lane == 0 && w != 0xFFFFFFFFu) sTri[warp][r + c] = __ldg(lst + w);
+            }
+        r = e;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t k = lane + 32 * h;
+        if (k < m) {
+            const f3 p = mk3(sP[warp][k][0], sP[warp][k][1], sP[warp][k][2]);
+            f3 g = mk3(0.0f, 0.0f, 0.0f);
+            const float d = kGrad ? signedDistGradSelf(p, tris[sTri[warp][k]], g) : signedDistPointTriangle(p, tris[sTri[warp][k]]);
+            dist[qi[h]] = d;
+            if (kGrad) { grad[3 * size_t(qi[h])] = g.x; grad[3 * size_t(qi[h]) + 1] = g.y; grad[3 * size_t(qi[h]) + 2] = g.z; }
+        }
+    }
+}
+
 }  // namespace
 
 // Decode the public arrays into the private per-leaf pool (see the header comment). Throws ERR_IO when the
@@ -406,6 +546,32 @@ void launchExactQuery(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float
     q.grid = s.startGridSize;
     q.outside = sqrtf(3.0f) * (s.boxMax[0] - s.boxMin[0]);   // ExactOctreeSdf.cpp:48
     const uint32_t grid = uint32_t((n + 255) / 256);
+    const uint64_t numNodes = s.dLeafCnt.n;
+    if (n >= (uint64_t(1) << 15) && n < (uint64_t(1) << 32)) {   // binned path: two uint32 per query + three per node of scratch, stream-ordered
+        uint32_t *leafOf = nullptr, *order = nullptr, *counts = nullptr, *start = nullptr, *blockSums = nullptr, *total = nullptr;
+        const uint32_t nBlocks = divUp(numNodes + 1, kScanBlock);
+        SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&leafOf), n * 4, st));
+        SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&order), n * 4, st));
+        SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&counts), (numNodes + 1) * 4, st));
+        SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&start), (numNodes + 1) * 4, st));
+        SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&blockSums), (size_t(nBlocks) + 1) * 4, st));
+        total = blockSums + nBlocks;
+        SDFB_CUDA(cudaMemsetAsync(counts, 0, (numNodes + 1) * 4, st));
+        if (dGrad) exactWalkKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, leafOf, counts, dDist, dGrad);
+        else exactWalkKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, leafOf, counts, dDist, nullptr);
+        binBlockSums<<<nBlocks, kScanBlock, 0, st>>>(counts, blockSums, numNodes + 1);
+        scanOfBlockSums<uint32_t><<<1, kScanBlock, 0, st>>>(blockSums, nBlocks, total);
+        scanFinalize<uint32_t, uint32_t><<<nBlocks, kScanBlock, 0, st>>>(counts, blockSums, start, numNodes + 1, total, false);
+        exactScatterKernel<<<grid, 256, 0, st>>>(leafOf, n, start, counts, order);
+        const uint32_t segGrid = divUp(n, 8 * kBinSegment);
+        if (dGrad)
+            exactBinnedKernel<true><<<segGrid, 256, 0, st>>>(s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, dXyz, leafOf, order, total, dDist, dGrad);
+        else
+            exactBinnedKernel<false><<<segGrid, 256, 0, st>>>(s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, dXyz, leafOf, order, total, dDist, nullptr);
+        SDFB_CUDA(cudaGetLastError());
+        cudaFreeAsync(leafOf, st); cudaFreeAsync(order, st); cudaFreeAsync(counts, st); cudaFreeAsync(start, st); cudaFreeAsync(blockSums, st);
+        return;
+    }
     if (dGrad)
         exactQueryWarpKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, dGrad);
     else
