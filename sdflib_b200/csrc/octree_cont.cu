@@ -964,11 +964,16 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
     t0 = std::chrono::steady_clock::now();
     levels.clear(); pools.clear();
     // keep exactly `words` entries on the device for the query kernels
+    auto finishStep = [&](const char* what) { if (timing) std::fprintf(stderr, "[sdfb200] continuity finish %-14s %8.2f ms\n", what, msSince(t0)); };
+    finishStep("free levels");
     out.dOctree.alloc(words);
     SDFB_CUDA(cudaMemcpyAsync(out.dOctree.p, oc.oct.p, words * 4, cudaMemcpyDeviceToDevice));
+    finishStep("device copy");
     out.octree.resize(words);
+    finishStep("host block");
     out.dOctree.download(out.octree.data(), words);
     SDFB_CUDA(cudaDeviceSynchronize());
+    finishStep("download");
     st.download_ms = msSince(t0);
     out.isShard = false;
     out.plan = RootPlan();

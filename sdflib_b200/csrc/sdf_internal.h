@@ -29,21 +29,27 @@ void setLastError(const std::string& msg);
     } while (0)
 
 // ---- device buffer -----------------------------------------------------------------------------
+// Device blocks: rounded to a size class and recycled through per-class free lists. Every kernel that touches a
+// DevBuf runs on the legacy default stream (or is synchronised before the buffer is released), so handing a freed
+// block to the next allocation is ordered by the stream itself.
+void* deviceBlockAlloc(size_t bytes, size_t* outCapacity);
+void deviceBlockFree(void* p, size_t capacity);
+
 template <class T> struct DevBuf {
     T* p = nullptr;
-    size_t n = 0;
+    size_t n = 0, capBytes = 0;
     DevBuf() {}
     explicit DevBuf(size_t count) { alloc(count); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; return *this; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), capBytes(o.capBytes) { o.p = nullptr; o.n = 0; o.capBytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; capBytes = o.capBytes; o.p = nullptr; o.n = 0; o.capBytes = 0; return *this; }
     ~DevBuf() { release(); }
-    // stream-ordered allocator on the legacy default stream: recycled from the device pool (host_mem.cpp)
+    // device blocks come from a process-wide size-class cache on top of the stream-ordered allocator (host_mem.cpp)
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), cudaStream_t(0)));
+        if (count) p = static_cast<T*>(deviceBlockAlloc(count * sizeof(T), &capBytes));
     }
     // grow-only variant for temporaries reused across the levels of a build: contents are not preserved, `n` is the
     // capacity. Re-allocating a slightly larger block every level makes the pool grow (slow) instead of recycling.
@@ -51,7 +57,7 @@ template <class T> struct DevBuf {
         if (count <= n) return;
         alloc(count + count / 2 + 256);
     }
-    void release() { if (p) cudaFreeAsync(p, cudaStream_t(0)); p = nullptr; n = 0; }
+    void release() { if (p) deviceBlockFree(p, capBytes); p = nullptr; n = 0; capBytes = 0; }
     void upload(const T* src, size_t count, cudaStream_t s = 0) {
         if (count) SDFB_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, s));
     }
