@@ -84,3 +84,16 @@ def octree_topology(words, start_grid):
             topo[c:c + 8] = True
             stack.extend(range(c, c + 8))
     return topo, leaves, inner
+
+
+def edge_case_meshes():
+    """Small meshes off the beaten path: a closed tetrahedron, a single (open) triangle, two disjoint spheres."""
+    from sdflib_b200 import meshes
+    tet_v = np.float32([[-0.5, -0.5, 0.0], [0.5, -0.5, 0.0], [0.0, 0.5, 0.0], [0.1, 0.0, 0.7]])
+    tet_i = np.uint32([0, 1, 2, 1, 0, 3, 2, 1, 3, 0, 2, 3])
+    tri_v = np.float32([[-0.5, -0.4, 0.1], [0.6, -0.5, 0.0], [0.05, 0.5, -0.1]])
+    tri_i = np.uint32([0, 1, 2])
+    sv, si = meshes.isosphere(1)
+    two_v = np.concatenate([sv * np.float32(0.4) + np.float32([-0.6, 0, 0]), sv * np.float32(0.3) + np.float32([0.7, 0.1, 0])]).astype(np.float32)
+    two_i = np.concatenate([si, si + len(sv)]).astype(np.uint32)
+    return {"tetrahedron": (tet_v, tet_i), "single_triangle": (tri_v, tri_i), "two_spheres": (two_v, two_i)}

@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import assert_bit_equal, golden, displaced_sphere, octree_topology
+from conftest import assert_bit_equal, golden, displaced_sphere, octree_topology, edge_case_meshes
 
 pytestmark = pytest.mark.gpu
 
@@ -293,3 +293,24 @@ def test_continuity_full_size_properties(sdf, ref):
     exact = sdf.ExactOctreeSdf(mesh, bb, 7, 3, 128, 2)
     err = (d - exact.getDistance(grid)).abs()                                  # tri-cubic field against the exact distance
     assert err.max().item() < 2e-2 and err.mean().item() < 1e-3, (err.max().item(), err.mean().item())
+
+
+@pytest.mark.parametrize("name", ["tetrahedron", "single_triangle", "two_spheres"])
+def test_edge_case_meshes_bit_exact(sdf, port, name):
+    """Open / tiny / disconnected inputs (single-triangle mesh: the BVH root is a leaf), depth == start depth, start depth 0."""
+    v, i = edge_case_meshes()[name]
+    box = sdf.meshes.bounding_box_with_margin(v)
+    mesh, bb = sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:])
+    for alg in (sdf.OctreeSdf.NO_CONTINUITY, sdf.OctreeSdf.CONTINUITY):
+        for depth, start in ((4, 2), (3, 3), (4, 0)):
+            g = sdf.OctreeSdf(mesh, bb, depth, start, 1e-3, alg, 1)
+            p = port.build_octree(v, i, box, depth, start, 1e-3, alg, 1, use_cache=False)
+            assert np.array_equal(g.getOctreeData(), p.octree_data()), (name, alg, depth, start)
+    if name == "single_triangle":   # 0 bits per index in the reference's encoding: refused
+        with pytest.raises(sdf.SdfB200Error):
+            sdf.ExactOctreeSdf(mesh, bb, 4, 1, 4, 1)
+        return
+    e, pe = sdf.ExactOctreeSdf(mesh, bb, 4, 1, 4, 1), port.build_exact(v, i, box, 4, 1, 4, 1, use_cache=False)
+    assert np.array_equal(e.getOctreeData().reshape(-1), pe.octree_data())
+    q = random_points(e.getSampleArea().as_array(), 40000, 21)
+    assert_bit_equal(e.getDistance(q), pe.query(q))

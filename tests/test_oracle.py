@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import assert_bit_equal, golden, displaced_sphere, octree_topology
+from conftest import assert_bit_equal, golden, displaced_sphere, octree_topology, edge_case_meshes
 
 
 # ---- port vs golden vectors (works without the reference) -----------------------------------------
@@ -286,3 +286,22 @@ def test_port_kernels_equal_reference(port, ref):
         tri = rng.uniform(-1, 1, 9).astype(np.float32)
         thr = float(rng.uniform(0, 0.5))
         assert ref.is_near_minimize(half, r, tri, thr) == port.is_near_minimize(half, r, tri, thr)
+
+
+@pytest.mark.parametrize("name", ["tetrahedron", "single_triangle", "two_spheres"])
+def test_port_equals_reference_on_edge_case_meshes(port, ref, name):
+    """Open / tiny / disconnected inputs, start depth equal to the depth, start depth 0 — all three builders."""
+    from sdflib_b200 import meshes
+    v, i = edge_case_meshes()[name]
+    box = meshes.bounding_box_with_margin(v)
+    for alg in (1, 2):
+        for depth, start in ((4, 2), (3, 3), (4, 0)):
+            a = ref.build_octree(v, i, box, depth, start, 1e-3, alg, 1).octree_data()
+            b = port.build_octree(v, i, box, depth, start, 1e-3, alg, 1, use_cache=True).octree_data()
+            assert np.array_equal(a, b), (name, alg, depth, start)
+    if name == "single_triangle":
+        return   # ExactOctreeSdf packs indices in ceil(log2(#triangles)) = 0 bits for one triangle: undefined in the reference
+    a, b = ref.build_exact(v, i, box, 4, 1, 4, 1), port.build_exact(v, i, box, 4, 1, 4, 1, use_cache=True)
+    assert np.array_equal(a.octree_data(), b.octree_data())
+    q = (box[:3] + np.random.default_rng(3).uniform(0, 1, (2000, 3)) * (box[3:] - box[:3])).astype(np.float32)
+    assert_bit_equal(a.query(q), b.query(q))
