@@ -110,6 +110,19 @@ int sdfb200_build_octree_shard(const float* vertices, uint32_t numVertices, cons
                                uint32_t numIndices, const float* box6, uint32_t depth, uint32_t startDepth,
                                int terminationRule, float param0, float param1, int initAlgorithm,
                                uint32_t numThreads, uint32_t rank, uint32_t worldSize, sdfb200_sdf** out);
+/* InitAlgorithm::CONTINUITY over several ranks (second row). Its neighbour probes cross start-voxel
+ * boundaries, so the octree logic is REPLICATED on every rank (deterministic, a few percent of the build) and the
+ * nearest-triangle sampling — 94 % of the kernel time — is what the ranks share: per depth every rank traverses the BVH
+ * for its slice of the level's distinct sample positions and the slices are all-gathered (16 bytes per sample).
+ * The collective stays with the caller: `allgather` must gather `bytesPerRank` bytes from every rank's dSend into dRecv
+ * in rank order (device pointers owned by the library, stream-ordered on the legacy default stream or complete on
+ * return) and return 0. Every rank returns the complete, identical structure (no assemble step). */
+typedef int (*sdfb200_allgather_fn)(void* user, const void* dSend, void* dRecv, uint64_t bytesPerRank);
+int sdfb200_build_octree_collective(const float* vertices, uint32_t numVertices, const uint32_t* indices,
+                                    uint32_t numIndices, const float* box6, uint32_t depth, uint32_t startDepth,
+                                    int terminationRule, float param0, float param1, int initAlgorithm,
+                                    uint32_t numThreads, uint32_t rank, uint32_t worldSize,
+                                    sdfb200_allgather_fn allgather, void* user, sdfb200_sdf** out);
 int sdfb200_build_exact_shard(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
                               const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
                               uint32_t numThreads, uint32_t rank, uint32_t worldSize, sdfb200_sdf** out);

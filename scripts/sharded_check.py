@@ -26,7 +26,16 @@ for rep in range(2):
     t0 = time.perf_counter()
     e = sharded.build_exact_sharded(mesh, bb, ed, 3, 128 if name != "s4" else 32, numThreads=2)
     torch.cuda.synchronize(); dist.barrier(); t_ex = time.perf_counter() - t0
+# InitAlgorithm::CONTINUITY: replicated logic, BVH sampling sliced over the ranks and all-gathered per depth
+for rep in range(2):
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    c = sharded.build_octree_sharded(mesh, bb, od, 3, 1e-3, initAlgorithm=S.OctreeSdf.CONTINUITY)
+    torch.cuda.synchronize(); dist.barrier(); t_cont = time.perf_counter() - t0
+    cont_stats = c.build_stats()
 if rank == 0:
+    t0 = time.perf_counter(); c1 = S.OctreeSdf(mesh, bb, od, 3, 1e-3, S.OctreeSdf.CONTINUITY, 2); t_c1 = time.perf_counter() - t0
+    assert np.array_equal(c.getOctreeData(), c1.getOctreeData())
+    print(f"collective CONTINUITY ok world={world} {t_cont:.3f}s (single {t_c1:.3f}s) levels {cont_stats['levels_ms']:.1f} ms (single {c1.build_stats()['levels_ms']:.1f} ms)", flush=True)
     t0 = time.perf_counter(); o1 = S.OctreeSdf(mesh, bb, od, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 2); t_o1 = time.perf_counter() - t0
     t0 = time.perf_counter(); e1 = S.ExactOctreeSdf(mesh, bb, ed, 3, 128 if name != "s4" else 32, 2); t_e1 = time.perf_counter() - t0
     assert np.array_equal(o.getOctreeData(), o1.getOctreeData())

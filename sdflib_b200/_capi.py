@@ -39,12 +39,15 @@ class BuildStats(C.Structure):
 
 # every symbol include/sdfb200.h declares (tests check that the library exports all of them)
 SYMBOLS = ["sdfb200_last_error", "sdfb200_version", "sdfb200_device_count", "sdfb200_set_device", "sdfb200_build_octree",
-           "sdfb200_build_exact", "sdfb200_build_octree_shard", "sdfb200_build_exact_shard", "sdfb200_shard_sizes",
+           "sdfb200_build_exact", "sdfb200_build_octree_shard", "sdfb200_build_octree_collective", "sdfb200_build_exact_shard", "sdfb200_shard_sizes",
            "sdfb200_shard_finish", "sdfb200_shard_words", "sdfb200_shard_export",
            "sdfb200_assemble", "sdfb200_save", "sdfb200_load", "sdfb200_free", "sdfb200_get_info",
            "sdfb200_get_build_stats", "sdfb200_get_octree_data", "sdfb200_get_exact_arrays", "sdfb200_get_device_octree",
            "sdfb200_query", "sdfb200_triangle_data", "sdfb200_nearest_triangle", "sdfb200_point_triangle",
            "sdfb200_make_isosphere"]
+
+# int (*sdfb200_allgather_fn)(void* user, const void* dSend, void* dRecv, uint64_t bytesPerRank)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
 
 _lib = None
 

@@ -96,13 +96,38 @@ int sdfb200_build_octree_shard(const float* vertices, uint32_t numVertices, cons
         if (terminationRule < SDFB200_RULE_NONE || terminationRule > SDFB200_RULE_BY_DISTANCE)
             throw Error(SDFB200_ERR_INVALID, "unknown termination rule");
         if (initAlgorithm == SDFB200_ALG_CONTINUITY && worldSize > 1)
-            throw Error(SDFB200_ERR_UNSUPPORTED, "CONTINUITY builds are not sharded (neighbour probes cross start voxels): build on one device");
+            throw Error(SDFB200_ERR_UNSUPPORTED, "CONTINUITY does not shard by start voxels (its neighbour probes cross them): use sdfb200_build_octree_collective");
         requireDevice();
         std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
         if (initAlgorithm == SDFB200_ALG_CONTINUITY)
             buildOctreeContinuityOnDevice(*s, mesh, box6, depth, startDepth, terminationRule, param0, param1);
         else
             buildOctreeOnDevice(*s, mesh, box6, depth, startDepth, terminationRule, param0, param1, numThreads, rank, worldSize);
+        *out = s.release();
+    });
+}
+
+int sdfb200_build_octree_collective(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                                    const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule, float param0,
+                                    float param1, int initAlgorithm, uint32_t numThreads, uint32_t rank, uint32_t worldSize,
+                                    sdfb200_allgather_fn allgather, void* user, sdfb200_sdf** out) {
+    (void)numThreads;   // the CONTINUITY layout does not depend on it
+    return guarded([&] {
+        if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
+        *out = nullptr;
+        HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
+        checkBox(box6);
+        if (worldSize == 0 || rank >= worldSize) throw Error(SDFB200_ERR_INVALID, "rank/worldSize out of range");
+        if (initAlgorithm != SDFB200_ALG_CONTINUITY)
+            throw Error(SDFB200_ERR_INVALID, "sdfb200_build_octree_collective builds InitAlgorithm::CONTINUITY (NO_CONTINUITY shards by start voxels: sdfb200_build_octree_shard)");
+        if (terminationRule < SDFB200_RULE_NONE || terminationRule > SDFB200_RULE_BY_DISTANCE)
+            throw Error(SDFB200_ERR_INVALID, "unknown termination rule");
+        if (worldSize > 1 && !allgather) throw Error(SDFB200_ERR_INVALID, "worldSize > 1 needs an allgather hook");
+        requireDevice();
+        std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
+        SampleExchange ex;
+        ex.rank = rank; ex.world = worldSize; ex.allgather = allgather; ex.user = user;
+        buildOctreeContinuityOnDevice(*s, mesh, box6, depth, startDepth, terminationRule, param0, param1, ex);
         *out = s.release();
     });
 }

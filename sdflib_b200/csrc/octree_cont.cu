@@ -718,7 +718,7 @@ struct GrowingOctree {
 }  // namespace
 
 void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
-                                   int rule, float param0, float param1) {
+                                   int rule, float param0, float param1, const SampleExchange& exchange) {
     const auto tStart = std::chrono::steady_clock::now();
     out.stats = sdfb200_build_stats{};
     sdfb200_build_stats& st = out.stats;
@@ -820,8 +820,11 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         std::fprintf(stderr, "[sdfb200] continuity depth %u %-10s %8.2f ms\n", d, what, msSince(tPhase));
         tPhase = std::chrono::steady_clock::now();
     };
-    DevBuf<float4> mids, fixPoints, fixSamples;
+    DevBuf<float4> mids, fixPoints;
     LevelSampler levelSampler;
+    levelSampler.exchange = exchange;
+    LevelSampler fixSampler;   // own result buffers: the fix-up samples of a round are read while the level's are still live
+    fixSampler.exchange = exchange;
     DevBuf<float> coeffs;
     DevBuf<uint32_t> sizes, sub, sizeScan, subScan, candCount32, candScan, candWords, candList, isRoot, rootPos;
     DevBuf<uint8_t> candCount;
@@ -905,10 +908,10 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
             FixRound& Nx = *rounds[r + 1];
             Nx.alloc(R.nSplit * 8);
             const uint32_t nTrue = scanner.run(R.nSamples.p, R.sampleScan.p, R.count);
-            fixPoints.ensure(std::max<uint32_t>(nTrue, 1)); fixSamples.ensure(std::max<uint32_t>(nTrue, 1));
+            fixPoints.ensure(std::max<uint32_t>(nTrue, 1));
             fixSamplePointsKernel<<<divUp(R.count, 128), 128>>>(R.arrays(), R.sampleScan.p, fixPoints.p);
-            if (nTrue) samplePointsKernel<<<divUp(nTrue, kBvhThreads), kBvhThreads, bvhStackBytes(dmesh)>>>(dmesh, fixPoints.p, nTrue, fixSamples.p);
-            fixValuesKernel<<<g8, kWarpsPerCta * 32>>>(R.arrays(), Nx.arrays(), R.splitScan.p, R.sampleScan.p, fixSamples.p, sqThreshold);
+            const float4* fixSamples = fixSampler.runPoints(dmesh, fixPoints.p, nTrue);
+            fixValuesKernel<<<g8, kWarpsPerCta * 32>>>(R.arrays(), Nx.arrays(), R.splitScan.p, R.sampleScan.p, fixSamples, sqThreshold);
             st.kernel_launches += 6;
             st.samples_evaluated += nTrue;
             st.nodes_processed += R.count;

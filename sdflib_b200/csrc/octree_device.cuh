@@ -5,6 +5,7 @@
 #pragma once
 #include <cfloat>
 #include <cmath>
+#include <algorithm>
 #include <cstdlib>
 #include <exception>
 #include <thread>
@@ -247,22 +248,31 @@ __device__ __forceinline__ f3 latticeSamplePosition(const float4* __restrict__ c
     return mk3(ch.x, ch.y, ch.z) + rel * ch.w;
 }
 
-__global__ void dedupeInsertKernel(const float4* __restrict__ centerHalf, uint32_t nSamples, uint32_t* table, uint32_t mask, uint32_t* rep,
-                                   uint32_t* isOwner) {
+__global__ void dedupeInsertKernel(const float4* __restrict__ centerHalf, uint32_t nSamples, uint32_t* table, uint32_t mask, uint32_t* slotOf) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nSamples) return;
     const f3 p = latticeSamplePosition(centerHalf, t);
     const uint32_t bx = __float_as_uint(p.x), by = __float_as_uint(p.y), bz = __float_as_uint(p.z);
     uint32_t h = bx * 0x9E3779B1u ^ by * 0x85EBCA77u ^ bz * 0xC2B2AE3Du;
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12;
-    uint32_t slot = h & mask, owner;
+    uint32_t slot = h & mask;
     for (;;) {
         const uint32_t old = atomicCAS(&table[slot], 0xFFFFFFFFu, t);
-        if (old == 0xFFFFFFFFu) { owner = t; break; }
-        const f3 q = latticeSamplePosition(centerHalf, old);
-        if (__float_as_uint(q.x) == bx && __float_as_uint(q.y) == by && __float_as_uint(q.z) == bz) { owner = old; break; }
+        if (old == 0xFFFFFFFFu) break;
+        const f3 q = latticeSamplePosition(centerHalf, old);   // any member of the slot's group has the group's position
+        if (__float_as_uint(q.x) == bx && __float_as_uint(q.y) == by && __float_as_uint(q.z) == bz) {
+            atomicMin(&table[slot], t);   // the owner is the LOWEST sample index: identical on every rank of a collective build
+            break;
+        }
         slot = (slot + 1) & mask;
     }
+    slotOf[t] = slot;
+}
+
+__global__ void dedupeResolveKernel(const uint32_t* __restrict__ table, uint32_t nSamples, uint32_t* rep /* in: slot, out: owner */, uint32_t* isOwner) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nSamples) return;
+    const uint32_t owner = table[rep[t]];
     rep[t] = owner;
     isOwner[t] = owner == t ? 1u : 0u;
 }
@@ -273,10 +283,11 @@ __global__ void dedupeOwnersKernel(const uint32_t* __restrict__ isOwner, const u
 }
 
 __global__ void __launch_bounds__(kBvhThreads)
-sampleOwnersKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const uint32_t* __restrict__ owners, uint32_t nUnique, float4* results) {
+sampleOwnersKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const uint32_t* __restrict__ owners, uint32_t first, uint32_t count,
+                   float4* results) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= nUnique) return;
-    results[u] = samplePoint(mesh, latticeSamplePosition(centerHalf, owners[u]));
+    if (u >= count) return;
+    results[u] = samplePoint(mesh, latticeSamplePosition(centerHalf, owners[first + u]));
 }
 
 __global__ void dedupeScatterKernel(const uint32_t* __restrict__ rep, const uint32_t* __restrict__ pos, const float4* __restrict__ results,
@@ -291,11 +302,33 @@ __global__ void dedupeScatterKernel(const uint32_t* __restrict__ rep, const uint
 // traversals actually run. Workspace buffers are grow-only and live as long as the builder.
 struct LevelSampler {
     DevBuf<uint32_t> table, rep, isOwner, pos, owners;
-    DevBuf<float4> results;
+    DevBuf<float4> results, slice;
     Scanner scanner;
+    SampleExchange exchange;   // world > 1: every rank traverses the BVH for its slice of the distinct positions only
+
+    // results[0 .. n) for n work items, item u computed by launch(first, count, dst) -> dst[0 .. count) = items first ..
+    template <class Launch> const float4* shared(uint32_t n, Launch launch) {
+        if (exchange.world <= 1) {
+            results.ensure(std::max<uint32_t>(n, 1));
+            if (n) launch(0u, n, results.p);
+            return results.p;
+        }
+        const uint32_t per = (n + exchange.world - 1) / exchange.world;   // equal blocks, the tail of the last ones is padding
+        results.ensure(size_t(std::max<uint32_t>(per, 1)) * exchange.world);
+        slice.ensure(std::max<uint32_t>(per, 1));
+        if (per == 0) return results.p;
+        const uint32_t first = std::min<uint64_t>(uint64_t(exchange.rank) * per, n), count = std::min<uint32_t>(per, n - first);
+        SDFB_CUDA(cudaMemsetAsync(slice.p, 0, size_t(per) * sizeof(float4)));
+        if (count) launch(first, count, slice.p);
+        if (exchange.allgather(exchange.user, slice.p, results.p, uint64_t(per) * sizeof(float4)) != 0)
+            throw Error(SDFB200_ERR_CUDA, "the all-gather hook of the collective build failed");
+        return results.p;   // item u sits at block u / per, offset u % per = index u
+    }
+
     uint32_t run(const DeviceMesh& mesh, const float4* centerHalf, uint32_t count, float4* out, int stride) {
         const uint64_t n64 = uint64_t(count) * 19;
         if (n64 >= (uint64_t(1) << 31)) {   // beyond the 32-bit sample index of the table: plain path
+            if (exchange.world > 1) throw Error(SDFB200_ERR_INVALID, "more than 2^31 samples on one level of a collective build");
             sampleLatticeKernel<<<divUp(n64, kBvhThreads), kBvhThreads, bvhStackBytes(mesh)>>>(mesh, centerHalf, count, out, stride);
             return 0xFFFFFFFFu;
         }
@@ -304,22 +337,35 @@ struct LevelSampler {
         while (size < 2 * n) size <<= 1;
         table.ensure(size); rep.ensure(n); isOwner.ensure(n); pos.ensure(n);
         SDFB_CUDA(cudaMemsetAsync(table.p, 0xFF, size_t(size) * 4));
-        dedupeInsertKernel<<<divUp(n, 256), 256>>>(centerHalf, n, table.p, size - 1, rep.p, isOwner.p);
+        dedupeInsertKernel<<<divUp(n, 256), 256>>>(centerHalf, n, table.p, size - 1, rep.p);
+        dedupeResolveKernel<<<divUp(n, 256), 256>>>(table.p, n, rep.p, isOwner.p);
         const uint32_t nUnique = scanner.run(isOwner.p, pos.p, n);
-        owners.ensure(nUnique); results.ensure(nUnique);
+        owners.ensure(nUnique);
         dedupeOwnersKernel<<<divUp(n, 256), 256>>>(isOwner.p, pos.p, n, owners.p);
-        sampleOwnersKernel<<<divUp(nUnique, kBvhThreads), kBvhThreads, bvhStackBytes(mesh)>>>(mesh, centerHalf, owners.p, nUnique, results.p);
-        dedupeScatterKernel<<<divUp(n, 256), 256>>>(rep.p, pos.p, results.p, n, out, stride);
+        const uint32_t* ownersPtr = owners.p;
+        const float4* res = shared(nUnique, [&](uint32_t first, uint32_t cnt, float4* dst) {
+            sampleOwnersKernel<<<divUp(cnt, kBvhThreads), kBvhThreads, bvhStackBytes(mesh)>>>(mesh, centerHalf, ownersPtr, first, cnt, dst);
+        });
+        dedupeScatterKernel<<<divUp(n, 256), 256>>>(rep.p, pos.p, res, n, out, stride);
         return nUnique;
     }
+
+    // explicit point list (fix-up pass of the CONTINUITY builder)
+    const float4* runPoints(const DeviceMesh& mesh, const float4* points, uint32_t n);
 };
 
 // explicit point list (fix-up pass of the CONTINUITY builder)
-__global__ void __launch_bounds__(kBvhThreads) samplePointsKernel(DeviceMesh mesh, const float4* points, uint32_t n, float4* out) {
+__global__ void __launch_bounds__(kBvhThreads) samplePointsKernel(DeviceMesh mesh, const float4* points, uint32_t first, uint32_t n, float4* out) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    const float4 p = points[t];
+    const float4 p = points[first + t];
     out[t] = samplePoint(mesh, mk3(p.x, p.y, p.z));
+}
+
+inline const float4* LevelSampler::runPoints(const DeviceMesh& mesh, const float4* points, uint32_t n) {
+    return shared(n, [&](uint32_t first, uint32_t cnt, float4* dst) {
+        samplePointsKernel<<<divUp(cnt, kBvhThreads), kBvhThreads, bvhStackBytes(mesh)>>>(mesh, points, first, cnt, dst);
+    });
 }
 
 __global__ void gatherTriVertsKernel(const f3* verts, const uint32_t* idx, uint32_t nTris, float4* triVerts) {

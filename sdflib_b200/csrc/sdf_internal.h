@@ -214,8 +214,14 @@ void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* bo
 void finalizeOctreeScalars(sdfb200_sdf& s);   // shardScalars -> valueRange / minBorderValue
 void cubifyBox(sdfb200_sdf& s, const float* box6, uint32_t startDepth);
 // octree_cont.cu: InitAlgorithm::CONTINUITY (single device; the structure is complete on return)
+// With world > 1 the BVH sampling of every level is sliced over the ranks and all-gathered through `allgather`.
+struct SampleExchange {
+    uint32_t rank = 0, world = 1;
+    sdfb200_allgather_fn allgather = nullptr;
+    void* user = nullptr;
+};
 void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
-                                   int rule, float param0, float param1);
+                                   int rule, float param0, float param1, const SampleExchange& exchange = SampleExchange());
 // shard.cpp
 uint64_t shardPayloadWords(const sdfb200_sdf& s);
 void shardExport(const sdfb200_sdf& s, uint32_t* dDst, uint64_t capacityWords);

@@ -94,12 +94,59 @@ def _mesh_args(mesh, box):
             _capi.ptr(_capi.f32(box.as_array())))
 
 
+class _DevicePointer:
+    """A library-owned device range as a CUDA array-interface object (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, pointer, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(pointer), False), "version": 2}
+
+
+def torch_allgather_hook(group=None, device=None):
+    """sdfb200_allgather_fn over torch.distributed (NCCL on the device pointers; gloo through host copies)."""
+    import torch
+    import torch.distributed as dist
+
+    def hook(_user, d_send, d_recv, nbytes):
+        try:
+            world = dist.get_world_size(group)
+            send = torch.as_tensor(_DevicePointer(d_send, nbytes), device=device)
+            recv = torch.as_tensor(_DevicePointer(d_recv, nbytes * world), device=device)
+            if dist.get_backend(group) == "nccl":
+                dist.all_gather_into_tensor(recv, send, group=group)
+            else:   # host-staged collective (tests)
+                parts = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(world)]
+                dist.all_gather(parts, send.cpu(), group=group)
+                recv.copy_(torch.cat(parts).to(recv.device))
+            return 0
+        except Exception as e:   # never let an exception cross the C boundary
+            import sys
+            print(f"[sdflib_b200] all-gather hook failed: {e}", file=sys.stderr)
+            return 1
+
+    return _capi.ALLGATHER_FN(hook)
+
+
+def build_octree_collective(mesh, box, depth, startDepth, params, terminationRule, rank, world, hook):
+    """InitAlgorithm::CONTINUITY over `world` ranks: replicated octree logic, BVH sampling sliced over the ranks and
+    all-gathered per depth through `hook` (an _capi.ALLGATHER_FN). Returns the complete OctreeSdf on every rank."""
+    h = C.c_void_p()
+    _capi.check(_capi.lib().sdfb200_build_octree_collective(
+        *_mesh_args(mesh, box), C.c_uint32(depth), C.c_uint32(startDepth), C.c_int(terminationRule), C.c_float(params[0]),
+        C.c_float(params[1]), C.c_int(OctreeSdf.CONTINUITY), C.c_uint32(1), C.c_uint32(rank), C.c_uint32(world), hook, None, C.byref(h)))
+    return Shard(h.value).into(OctreeSdf)
+
+
 def build_octree_sharded(mesh, box, depth, startDepth, maxError=1e-3, initAlgorithm=OctreeSdf.NO_CONTINUITY, numThreads=2,
                          terminationRule=OctreeSdf.TRAPEZOIDAL_RULE, terminationRuleParams=None, group=None):
     """OctreeSdf(...) built cooperatively by all ranks of `group`; every rank returns the complete structure."""
     import torch.distributed as dist
     params = list(terminationRuleParams) if terminationRuleParams is not None else [maxError]
     params += [0.0] * (2 - len(params))
+    if initAlgorithm == OctreeSdf.CONTINUITY:
+        import torch
+        hook = torch_allgather_hook(group, torch.device("cuda", torch.cuda.current_device()))
+        return build_octree_collective(mesh, box, depth, startDepth, params, terminationRule, dist.get_rank(group),
+                                       dist.get_world_size(group), hook)
     h = C.c_void_p()
     _capi.check(_capi.lib().sdfb200_build_octree_shard(
         *_mesh_args(mesh, box), C.c_uint32(depth), C.c_uint32(startDepth), C.c_int(terminationRule), C.c_float(params[0]),

@@ -115,3 +115,75 @@ def test_nccl_multi_process(sdf):
                         "--master-port", "29611", os.path.join(ROOT, "scripts", "sharded_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "sharded ok" in r.stdout
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_continuity_collective_build_equals_single_rank(sdf, world):
+    """InitAlgorithm::CONTINUITY over several ranks, played on ONE GPU: `world` threads build concurrently and the
+    all-gather hook exchanges the sample slices through a barrier in this process. Every rank must return exactly the
+    single-rank structure (replicated logic + deterministic owners of the de-duplicated samples)."""
+    import threading
+    import torch
+    from sdflib_b200 import sharded, _capi
+    v, i = displaced_sphere(3)
+    box = sdf.meshes.bounding_box_with_margin(v)
+    mesh, bb = sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:])
+    single = sdf.OctreeSdf(mesh, bb, 6, 2, 1e-3, sdf.OctreeSdf.CONTINUITY, 1).getOctreeData()
+    barrier = threading.Barrier(world)
+    staging = {}
+    calls = [0] * world
+
+    def make_hook(rank):
+        def hook(_user, d_send, d_recv, nbytes):
+            try:
+                send = torch.as_tensor(sharded._DevicePointer(d_send, nbytes), device="cuda")
+                recv = torch.as_tensor(sharded._DevicePointer(d_recv, nbytes * world), device="cuda")
+                staging[rank] = send.clone()
+                torch.cuda.synchronize()
+                barrier.wait()
+                recv.copy_(torch.cat([staging[r] for r in range(world)]))
+                torch.cuda.synchronize()
+                barrier.wait()          # nobody overwrites its staging slot before everybody has read it
+                calls[rank] += 1
+                return 0
+            except Exception as e:      # pragma: no cover
+                print("hook failed:", e)
+                barrier.abort()
+                return 1
+        return _capi.ALLGATHER_FN(hook)
+
+    results, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            results[rank] = sharded.build_octree_collective(mesh, bb, 6, 2, [1e-3, 0.0], sdf.OctreeSdf.TRAPEZOIDAL_RULE, rank, world,
+                                                            make_hook(rank)).getOctreeData()
+        except Exception as e:
+            errors.append(e)
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    assert not errors, errors
+    assert calls[0] > 4 and len(set(calls)) == 1       # one exchange per sampled level + per fix-up round, same on every rank
+    for r in range(world):
+        assert results[r].size == single.size and np.array_equal(results[r], single), f"rank {r} differs"
+
+
+def test_collective_entry_checks_arguments(sdf):
+    from sdflib_b200 import sharded, _capi
+    v, i = displaced_sphere(1)
+    box = sdf.meshes.bounding_box_with_margin(v)
+    mesh, bb = sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:])
+    h = C.c_void_p()
+    args = (*sharded._mesh_args(mesh, bb), C.c_uint32(4), C.c_uint32(2), C.c_int(1), C.c_float(1e-3), C.c_float(0))
+    L = _capi.lib()
+    # NO_CONTINUITY is not a collective build; more than one rank needs a hook; CONTINUITY refuses the voxel-sharded entry
+    assert L.sdfb200_build_octree_collective(*args, C.c_int(1), C.c_uint32(1), C.c_uint32(0), C.c_uint32(2), None, None, C.byref(h)) == _capi.ERR_INVALID
+    assert L.sdfb200_build_octree_collective(*args, C.c_int(2), C.c_uint32(1), C.c_uint32(0), C.c_uint32(2), None, None, C.byref(h)) == _capi.ERR_INVALID
+    assert L.sdfb200_build_octree_shard(*args, C.c_int(2), C.c_uint32(1), C.c_uint32(0), C.c_uint32(2), C.byref(h)) == _capi.ERR_UNSUPPORTED
+    # one rank needs no hook and equals the plain constructor
+    assert L.sdfb200_build_octree_collective(*args, C.c_int(2), C.c_uint32(1), C.c_uint32(0), C.c_uint32(1), None, None, C.byref(h)) == _capi.OK
+    one = sharded.Shard(h.value).into(sdf.OctreeSdf)
+    assert np.array_equal(one.getOctreeData(), sdf.OctreeSdf(mesh, bb, 4, 2, 1e-3, sdf.OctreeSdf.CONTINUITY, 1).getOctreeData())
