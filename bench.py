@@ -17,9 +17,10 @@ The working set (201 MB points + 67 MB distances + 82.5 MB structure) exceeds th
 steps cannot be served from cache ("inputs larger than L2").
 
 Besides the headline line the same JSON object carries the other half of BASELINE.json's metric ("octree build sec"):
-  build.octree_c2 / build.exact_c3 : wall-clock seconds of the OctreeSdf (C2) and ExactOctreeSdf (C3: depth 7, minTri 128)
-          constructors through the public API; with N > 1 the builds are SHARDED over start-depth voxels
-          (sdflib_b200.sharded: size all-reduce + one NCCL all-gather), seconds = max over ranks
+  build.octree_c2 / build.octree_c2_continuity / build.exact_c3 : wall-clock seconds of the OctreeSdf (C2, NO_CONTINUITY and
+          CONTINUITY) and ExactOctreeSdf (C3: depth 7, minTri 128) constructors through the public API; with N > 1 the
+          builds are cooperative (sdflib_b200.sharded: start-depth voxels sharded + one NCCL all-gather of the payload;
+          CONTINUITY: sampling sliced over the ranks + one all-gather per depth), seconds = max over ranks
   exact_query : ExactOctreeSdf bulk getDistance over the same 256^3 grid, device-resident
 
 --impl reference times the UNMODIFIED reference (oracle/_ref/libsdfref.so: OctreeSdf built by its own
@@ -217,8 +218,12 @@ def run_ours(args):
     stats = sdf.build_stats()
     info = sdf.info()
     cont = None
-    if world == 1:   # InitAlgorithm::CONTINUITY (the reference's CLI / Unity default), same mesh and depth; single device
-        make_cont = lambda: S.OctreeSdf(mesh, bb, WORKLOAD["depth"], WORKLOAD["start_depth"], WORKLOAD["threshold"], S.OctreeSdf.CONTINUITY, 2)
+    if True:   # InitAlgorithm::CONTINUITY (the reference's CLI / Unity default), same mesh and depth
+        if world > 1:   # replicated logic, BVH sampling sliced over the ranks, one all-gather per depth
+            make_cont = lambda: sharded.build_octree_sharded(mesh, bb, WORKLOAD["depth"], WORKLOAD["start_depth"], WORKLOAD["threshold"],
+                                                             initAlgorithm=S.OctreeSdf.CONTINUITY)
+        else:
+            make_cont = lambda: S.OctreeSdf(mesh, bb, WORKLOAD["depth"], WORKLOAD["start_depth"], WORKLOAD["threshold"], S.OctreeSdf.CONTINUITY, 2)
         c, _t = timed_build(make_cont)
         c.close()
         cont_builds = []
