@@ -7,8 +7,6 @@
 #include <cmath>
 #include <algorithm>
 #include <cstdlib>
-#include <exception>
-#include <thread>
 
 #include "device_utils.cuh"
 #include "sdf_internal.h"
@@ -440,20 +438,16 @@ inline void uploadMesh(MeshOnDevice& m, const HostMesh& mesh, const TriVec& tris
     }
 }
 
-// The two serial set-up steps of the reference constructors, side by side: the BVH build is dominated by the
-// (inherently sequential) std::sort calls of its top levels, which leaves cores free for the TriangleData loops.
-// triangle_data_ms = duration of that step, bvh_ms = the remaining wall time until the BVH is ready.
+// The two serial set-up steps of the reference constructors. (Running them side by side — the BVH build's top-level
+// std::sort calls are sequential — was measured: no gain on one rank, 62 ms instead of 16 ms for TriangleData with two
+// ranks sharing the cores, because the idle threads of the BVH task team spin. They run one after the other.)
 inline void buildHostStructures(const HostMesh& mesh, TriVec& tris, RawVec<BvhNode>& bvh, sdfb200_build_stats& st) {
-    const auto t0 = std::chrono::steady_clock::now();
-    std::exception_ptr failure;
-    std::thread bvhThread([&] {
-        try { bvh = buildBvh(mesh); } catch (...) { failure = std::current_exception(); }
-    });
-    try { tris = computeTriangleData(mesh); } catch (...) { bvhThread.join(); throw; }
+    auto t0 = std::chrono::steady_clock::now();
+    tris = computeTriangleData(mesh);
     st.triangle_data_ms = msSince(t0);
-    bvhThread.join();
-    if (failure) std::rethrow_exception(failure);
-    st.bvh_ms = msSince(t0) - st.triangle_data_ms;
+    t0 = std::chrono::steady_clock::now();
+    bvh = buildBvh(mesh);
+    st.bvh_ms = msSince(t0);
 }
 
 // Weight of a mid-point in the error integral: trapezoid / by-distance 2^k/64 (OctreeSdfUtils.h:60-138),
