@@ -111,9 +111,14 @@ TriVec computeTriangleData(const HostMesh& mesh) {
     // erased, so occurrences pair up (1st,2nd), (3rd,4th), ... and an odd one stays open. Sorting the
     // uses by (edge, corner) reproduces exactly those pairs without the serial map.
     // (key, corner) pairs are unique, so any correct sort gives the same sequence: use the multi-threaded one
+    // libstdc++'s parallel mode goes sequential when omp_get_max_threads() == 1, whatever the tag asks for (torchrun
+    // exports OMP_NUM_THREADS=1 to every rank): raise this thread's nthreads-var for the call and put it back.
+    const int callerThreads = omp_get_max_threads();
+    omp_set_num_threads(hostThreads());
     __gnu_parallel::sort(uses.begin(), uses.end(), [](const EdgeUse& x, const EdgeUse& y) {
         return x.key != y.key ? x.key < y.key : x.corner < y.corner;
     }, __gnu_parallel::default_parallel_tag(hostThreads()));
+    omp_set_num_threads(callerThreads);
     lap("edge sort");
     // Groups of equal keys are independent: cut the sorted array into chunks at group boundaries, one per thread;
     // the open (unpaired) uses are concatenated in chunk order, i.e. still in key order.
