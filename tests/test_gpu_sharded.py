@@ -140,10 +140,10 @@ def test_continuity_collective_build_equals_single_rank(sdf, world):
                 recv = torch.as_tensor(sharded._DevicePointer(d_recv, nbytes * world), device="cuda")
                 staging[rank] = send.clone()
                 torch.cuda.synchronize()
-                barrier.wait()
+                barrier.wait(timeout=120)
                 recv.copy_(torch.cat([staging[r] for r in range(world)]))
                 torch.cuda.synchronize()
-                barrier.wait()          # nobody overwrites its staging slot before everybody has read it
+                barrier.wait(timeout=120)   # nobody overwrites its staging slot before everybody has read it
                 calls[rank] += 1
                 return 0
             except Exception as e:      # pragma: no cover
@@ -164,7 +164,8 @@ def test_continuity_collective_build_equals_single_rank(sdf, world):
 
     threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
     for t in threads: t.start()
-    for t in threads: t.join()
+    for t in threads: t.join(timeout=300)
+    assert not any(t.is_alive() for t in threads), "a rank is stuck in the collective build"
     assert not errors, errors
     assert calls[0] > 4 and len(set(calls)) == 1       # one exchange per sampled level + per fix-up round, same on every rank
     for r in range(world):
