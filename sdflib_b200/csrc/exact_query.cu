@@ -93,52 +93,54 @@ unpackSetsKernel(PublicView pv, const uint32_t* nodeIdx, const uint64_t* lo, con
     }
 }
 
-// frontier below bitEnc: a node's list = its parent's decoded list filtered by the node's bit mask
-__global__ void maskRangeCheckKernel(PublicView pv, const uint32_t* nodeIdx, const uint32_t* parentCnt, uint32_t n, uint32_t* inner,
-                                     uint32_t* err) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// frontier below bitEnc: a node's list = its parent's decoded list filtered by the node's bit mask (MSB first,
+// ExactOctreeSdf.cpp:105-131). One warp per node, twice: count the set bits, then (after the scan of the counts)
+// copy the selected parent entries in order. No per-pair arrays: on the Dragon-class structure a level has more than
+// 2^32 (node, parent entry) pairs.
+__global__ void __launch_bounds__(256)
+maskCountKernel(PublicView pv, const uint32_t* __restrict__ nodeIdx, const uint32_t* __restrict__ parentCnt, uint32_t n, uint32_t* cnt,
+                uint32_t* inner, uint32_t* leafCnt, uint32_t* err) {
+    const uint32_t i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (i >= n) return;
     const uint32_t w0 = pv.nodes[2 * size_t(nodeIdx[i])], w1 = pv.nodes[2 * size_t(nodeIdx[i]) + 1];
-    if (uint64_t(w1) + (parentCnt[i] + 7u) / 8u > pv.numMasks) atomicOr(err, kErrMaskRange);
-    inner[i] = (w0 & kLeafBit) ? 0u : 1u;
+    const uint32_t pc = parentCnt[i], bytes = (pc + 7u) / 8u;
+    uint32_t c = 0;
+    if (uint64_t(w1) + bytes > pv.numMasks) { if (lane == 0) atomicOr(err, kErrMaskRange); }
+    else
+        for (uint32_t b = lane; b < bytes; b += 32) {
+            uint32_t byte = pv.masks[uint64_t(w1) + b];
+            if (b == bytes - 1 && (pc & 7u)) byte &= 0xFF00u >> (pc & 7u);   // bits beyond the parent's count are padding
+            c += __popc(byte);
+        }
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0) {
+        const bool leaf = (w0 & kLeafBit) != 0;
+        cnt[i] = c;
+        inner[i] = leaf ? 0u : 1u;
+        leafCnt[i] = leaf ? c : 0u;
+    }
 }
+
 __global__ void __launch_bounds__(256)
-maskFlagsKernel(PublicView pv, const uint32_t* nodeIdx, const uint64_t* pairOff, uint32_t n, uint64_t numPairs, uint8_t* flags) {
-    __shared__ uint32_t sNode;
-    const uint64_t p0 = uint64_t(blockIdx.x) * 256;
-    if (threadIdx.x == 0) sNode = lastLessEqual<uint64_t>(pairOff, n + 1, p0);
-    __syncthreads();
-    const uint64_t p = p0 + threadIdx.x;
-    if (p >= numPairs) return;
-    uint32_t node = sNode;
-    while (p >= pairOff[node + 1]) node++;
-    const uint32_t j = uint32_t(p - pairOff[node]);
-    const uint64_t at = uint64_t(pv.nodes[2 * size_t(nodeIdx[node]) + 1]) + (j >> 3);
-    const uint32_t byte = at < pv.numMasks ? pv.masks[at] : 0u;
-    flags[p] = (byte & (0x80u >> (j & 7u))) ? 1 : 0;
-}
-__global__ void __launch_bounds__(256)
-maskCompactKernel(const uint64_t* pairOff, const uint64_t* parentLo, uint32_t n, uint64_t numPairs, const uint8_t* flags,
-                  const uint32_t* pos, const uint32_t* parentDec, uint32_t* dec) {
-    __shared__ uint32_t sNode;
-    const uint64_t p0 = uint64_t(blockIdx.x) * 256;
-    if (threadIdx.x == 0) sNode = lastLessEqual<uint64_t>(pairOff, n + 1, p0);
-    __syncthreads();
-    const uint64_t p = p0 + threadIdx.x;
-    if (p >= numPairs || !flags[p]) return;
-    uint32_t node = sNode;
-    while (p >= pairOff[node + 1]) node++;
-    dec[pos[p]] = parentDec[parentLo[node] + (p - pairOff[node])];
-}
-__global__ void maskRangesKernel(const uint64_t* pairOff, const uint32_t* pos, uint64_t numPairs, uint32_t total, const uint32_t* inner,
-                                 uint64_t* lo, uint32_t* cnt, uint32_t* leafCnt, uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+maskSelectKernel(PublicView pv, const uint32_t* __restrict__ nodeIdx, const uint64_t* __restrict__ parentLo, const uint32_t* __restrict__ parentCnt,
+                 const uint64_t* __restrict__ lo, uint32_t n, const uint32_t* __restrict__ parentDec, uint32_t* __restrict__ dec) {
+    const uint32_t i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (i >= n) return;
-    const uint64_t a = pairOff[i], b = pairOff[i + 1];
-    const uint32_t l = a < numPairs ? pos[a] : total, h = b < numPairs ? pos[b] : total;
-    lo[i] = l;
-    cnt[i] = h - l;
-    leafCnt[i] = inner[i] ? 0u : h - l;
+    const uint32_t w1 = pv.nodes[2 * size_t(nodeIdx[i]) + 1];
+    const uint32_t pc = parentCnt[i];
+    if (uint64_t(w1) + (pc + 7u) / 8u > pv.numMasks) return;   // reported by maskCountKernel
+    const uint32_t* src = parentDec + parentLo[i];
+    uint32_t* dst = dec + lo[i];
+    uint32_t written = 0;
+    for (uint32_t j0 = 0; j0 < pc; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool keep = j < pc && (pv.masks[uint64_t(w1) + (j >> 3)] & (0x80u >> (j & 7u)));
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        if (keep) dst[written + __popc(ballot & ((1u << lane) - 1u))] = src[j];
+        written += __popc(ballot);
+    }
 }
 
 __global__ void nextFrontierKernel(PublicView pv, const uint32_t* nodeIdx, const uint32_t* inner, const uint32_t* childSlot,
@@ -216,8 +218,9 @@ __global__ void __launch_bounds__(256)
 exactQueryWarpKernel(const uint32_t* __restrict__ nodes, const uint64_t* __restrict__ leafLo, const uint32_t* __restrict__ leafCnt,
                      const uint32_t* __restrict__ pool, const float4* __restrict__ frames, const TriData* __restrict__ tris,
                      const ExactQueryParams q, const float* __restrict__ xyz, uint64_t n, float* __restrict__ dist,
-                     float* __restrict__ grad) {
+                     float* __restrict__ grad, const uint32_t* __restrict__ runIfZero) {
     constexpr unsigned kFull = 0xffffffffu;
+    if (runIfZero && *runIfZero != 0u) return;   // large batches: the binned kernel was chosen on the device
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool valid = i < n;
@@ -346,6 +349,19 @@ __global__ void binBlockSums(const uint32_t* in, uint32_t* blockSums, uint64_t n
     }
 }
 
+// Binning pays when leaves hold several queries each (a frame is then loaded once per run of up to 8 queries). With
+// one query per leaf — e.g. a 256^3 grid over a depth-8 structure — it is pure overhead (C4: 30.7 ms against 26.9 ms),
+// so the choice is made on the device from the histogram: bins iff queries >= 2 x non-empty leaves.
+__global__ void countNonEmptyKernel(const uint32_t* __restrict__ counts, uint64_t n, uint32_t* nonEmpty) {
+    uint32_t c = 0;
+    for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) c += counts[i] ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(nonEmpty, c);
+}
+__global__ void chooseBinsKernel(const uint32_t* nonEmpty, const uint32_t* numSorted, uint32_t* useBins) {
+    *useBins = (*numSorted >= 2u * *nonEmpty && *nonEmpty > 0u) ? 1u : 0u;
+}
+
 __global__ void exactScatterKernel(const uint32_t* __restrict__ leafOf, uint64_t n, const uint32_t* __restrict__ start,
                                    uint32_t* __restrict__ remaining, uint32_t* __restrict__ order) {
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -360,11 +376,12 @@ __global__ void __launch_bounds__(256)
 exactBinnedKernel(const uint64_t* __restrict__ leafLo, const uint32_t* __restrict__ leafCnt, const uint32_t* __restrict__ pool,
                   const float4* __restrict__ frames, const TriData* __restrict__ tris, const float* __restrict__ xyz,
                   const uint32_t* __restrict__ leafOf, const uint32_t* __restrict__ order, const uint32_t* __restrict__ numSorted,
-                  float* __restrict__ dist, float* __restrict__ grad) {
+                  const uint32_t* __restrict__ useBins, float* __restrict__ dist, float* __restrict__ grad) {
     constexpr unsigned kFull = 0xffffffffu;
     __shared__ float sP[8][kBinSegment][3];
     __shared__ uint32_t sLeaf[8][kBinSegment], sTri[8][kBinSegment];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (*useBins == 0u) return;   // too few queries per leaf to share anything: the warp kernel runs instead
     const uint32_t total = *numSorted;
     const uint64_t seg0 = (uint64_t(blockIdx.x) * 8 + warp) * kBinSegment;
     if (seg0 >= total) return;
@@ -481,22 +498,11 @@ void prepareExactQuery(sdfb200_sdf& s) {
             unpackSetsKernel<<<n, 128>>>(pv, F.nodeIdx.p, F.lo.p, F.cnt.p, F.dec.p, err.p);
         } else {
             Frontier& P = *fr[fr.size() - 2];
-            maskRangeCheckKernel<<<divUp(n, 256), 256>>>(pv, F.nodeIdx.p, F.parentCnt.p, n, F.inner.p, err.p);
-            F.pairOff.alloc(size_t(n) + 1);
-            const uint64_t numPairs = scan64.run(F.parentCnt.p, F.pairOff.p, n, true);
-            if (numPairs >= (uint64_t(1) << 38)) throw Error(SDFB200_ERR_IO, "mask chain of one level exceeds 2^38 entries");
-            F.flags.alloc(numPairs + 1); F.pos.alloc(numPairs + 1);
-            uint32_t total = 0;
-            if (numPairs) {
-                maskFlagsKernel<<<divUp(numPairs, 256), 256>>>(pv, F.nodeIdx.p, F.pairOff.p, n, numPairs, F.flags.p);
-                if (numPairs >= (uint64_t(1) << 32) && countFlags64(F.flags.p, numPairs) >= (uint64_t(1) << 32))
-                    throw Error(SDFB200_ERR_IO, "decoded triangle lists of one level exceed 2^32 entries");
-                total = scanFlags.run(F.flags.p, F.pos.p, numPairs);
-            }
-            F.dec.alloc(size_t(total) + 1);
-            if (numPairs) maskCompactKernel<<<divUp(numPairs, 256), 256>>>(F.pairOff.p, F.parentLo.p, n, numPairs, F.flags.p, F.pos.p, P.dec.p, F.dec.p);
-            maskRangesKernel<<<divUp(n, 256), 256>>>(F.pairOff.p, F.pos.p, numPairs, total, F.inner.p, F.lo.p, F.cnt.p, F.leafCnt.p, n);
-            F.flags.release(); F.pos.release();
+            maskCountKernel<<<divUp(n, 8), 256>>>(pv, F.nodeIdx.p, F.parentCnt.p, n, F.cnt.p, F.inner.p, F.leafCnt.p, err.p);
+            const uint64_t total = scan64.run(F.cnt.p, F.lo.p, n, true);
+            if (total >= (uint64_t(1) << 32)) throw Error(SDFB200_ERR_IO, "decoded triangle lists of one level exceed 2^32 entries");
+            F.dec.alloc(total + 1);
+            maskSelectKernel<<<divUp(n, 8), 256>>>(pv, F.nodeIdx.p, F.parentLo.p, F.parentCnt.p, F.lo.p, n, P.dec.p, F.dec.p);
         }
         SDFB_CUDA(cudaGetLastError());
         // leaves -> this level's pool segment
@@ -554,28 +560,35 @@ void launchExactQuery(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float
         SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&order), n * 4, st));
         SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&counts), (numNodes + 1) * 4, st));
         SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&start), (numNodes + 1) * 4, st));
-        SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&blockSums), (size_t(nBlocks) + 1) * 4, st));
+        SDFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&blockSums), (size_t(nBlocks) + 3) * 4, st));
         total = blockSums + nBlocks;
+        uint32_t *nonEmpty = total + 1, *useBins = total + 2;
         SDFB_CUDA(cudaMemsetAsync(counts, 0, (numNodes + 1) * 4, st));
+        SDFB_CUDA(cudaMemsetAsync(nonEmpty, 0, 4, st));
         if (dGrad) exactWalkKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, leafOf, counts, dDist, dGrad);
         else exactWalkKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, leafOf, counts, dDist, nullptr);
+        countNonEmptyKernel<<<148 * 4, 256, 0, st>>>(counts, numNodes, nonEmpty);
         binBlockSums<<<nBlocks, kScanBlock, 0, st>>>(counts, blockSums, numNodes + 1);
         scanOfBlockSums<uint32_t><<<1, kScanBlock, 0, st>>>(blockSums, nBlocks, total);
         scanFinalize<uint32_t, uint32_t><<<nBlocks, kScanBlock, 0, st>>>(counts, blockSums, start, numNodes + 1, total, false);
+        chooseBinsKernel<<<1, 1, 0, st>>>(nonEmpty, total, useBins);
         exactScatterKernel<<<grid, 256, 0, st>>>(leafOf, n, start, counts, order);
         const uint32_t segGrid = divUp(n, 8 * kBinSegment);
-        if (dGrad)
-            exactBinnedKernel<true><<<segGrid, 256, 0, st>>>(s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, dXyz, leafOf, order, total, dDist, dGrad);
-        else
-            exactBinnedKernel<false><<<segGrid, 256, 0, st>>>(s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, dXyz, leafOf, order, total, dDist, nullptr);
+        if (dGrad) {
+            exactBinnedKernel<true><<<segGrid, 256, 0, st>>>(s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, dXyz, leafOf, order, total, useBins, dDist, dGrad);
+            exactQueryWarpKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, dGrad, useBins);
+        } else {
+            exactBinnedKernel<false><<<segGrid, 256, 0, st>>>(s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, dXyz, leafOf, order, total, useBins, dDist, nullptr);
+            exactQueryWarpKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, nullptr, useBins);
+        }
         SDFB_CUDA(cudaGetLastError());
         cudaFreeAsync(leafOf, st); cudaFreeAsync(order, st); cudaFreeAsync(counts, st); cudaFreeAsync(start, st); cudaFreeAsync(blockSums, st);
         return;
     }
     if (dGrad)
-        exactQueryWarpKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, dGrad);
+        exactQueryWarpKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, dGrad, nullptr);
     else
-        exactQueryWarpKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, nullptr);
+        exactQueryWarpKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, nullptr, nullptr);
     SDFB_CUDA(cudaGetLastError());
 }
 
