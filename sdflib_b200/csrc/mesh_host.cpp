@@ -1,6 +1,7 @@
 #include "mesh_host.h"
 
 #include <algorithm>
+#include <thread>
 #include <cmath>
 #include <limits>
 #include <chrono>
@@ -248,8 +249,9 @@ inline double sq3(const double* a, const double* b) {
 struct BvhBuilder {
     const RawVec<BuildTri>& tri;   // vertices in float64, by triangle id
     RawVec<int32_t>& order;        // current triangle order; a node owns the range [begin, end)
-    RawVec<SortKey>& scratch;      // same ranges, disjoint between tasks
+    RawVec<SortKey>& scratch;      // same ranges, disjoint between threads
     RawVec<BvhNode>& nodes;
+    int forkLevels;                // levels below this node that still fork a thread for the left half
 
     // sphere = where the bounding sphere of this subtree is stored (a child slot of the parent)
     void build(int32_t nodeId, double* sphereCenter, double* sphereRadius, int32_t begin, int32_t end) {
@@ -307,11 +309,19 @@ struct BvhBuilder {
         const int32_t l = node.left, r = node.right;
         double* lc = node.lc;
         double* lr = &node.lr;
-        // the two halves are independent once sorted; all arrays are pre-sized, so tasks only touch
-        // disjoint ranges. The enclosing parallel region's barrier joins them.
-#pragma omp task firstprivate(l, lc, lr, begin, mid) if (n > 8192)
-        build(l, lc, lr, begin, mid);
-        build(r, node.rc, &node.rr, mid, end);
+        // The two halves are independent once sorted and all arrays are pre-sized, so they only touch disjoint ranges.
+        // Plain threads down to `forkLevels` levels (about 2 x hostThreads leaves of the fork tree), not an OpenMP
+        // task team: a team's idle threads SPIN while the master runs the sequential top-level sorts, which starves
+        // whatever else the host is doing (TriangleData of the same constructor, the other ranks of a multi-GPU job).
+        if (forkLevels > 0 && n > 8192) {
+            std::thread left([=] { BvhBuilder sub{tri, order, scratch, nodes, forkLevels - 1}; sub.build(l, lc, lr, begin, mid); });
+            BvhBuilder sub{tri, order, scratch, nodes, forkLevels - 1};
+            sub.build(r, node.rc, &node.rr, mid, end);
+            left.join();
+        } else {
+            build(l, lc, lr, begin, mid);
+            build(r, node.rc, &node.rr, mid, end);
+        }
     }
 };
 
@@ -332,9 +342,9 @@ RawVec<BvhNode> buildBvh(const HostMesh& mesh) {
     }
     RawVec<BvhNode> nodes(size_t(2) * nT - 1);
     double rootCenter[3], rootRadius;
-    BvhBuilder b{bt, order, scratch, nodes};
-#pragma omp parallel num_threads(hostThreads())
-#pragma omp single
+    int forkLevels = 1;
+    while ((1 << forkLevels) < 2 * hostThreads()) forkLevels++;
+    BvhBuilder b{bt, order, scratch, nodes, forkLevels};
     b.build(0, rootCenter, &rootRadius, 0, int32_t(nT));
     // Device traversal never loads a leaf node: links to leaves are replaced by ~triangleId (mesh_host.h).
     const int64_t nNodes = int64_t(nodes.size());

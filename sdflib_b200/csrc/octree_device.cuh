@@ -438,9 +438,9 @@ inline void uploadMesh(MeshOnDevice& m, const HostMesh& mesh, const TriVec& tris
     }
 }
 
-// The two serial set-up steps of the reference constructors. (Running them side by side — the BVH build's top-level
-// std::sort calls are sequential — was measured: no gain on one rank, 62 ms instead of 16 ms for TriangleData with two
-// ranks sharing the cores, because the idle threads of the BVH task team spin. They run one after the other.)
+// The two serial set-up steps of the reference constructors. Running them side by side was measured twice (OpenMP
+// task team and plain threads in the BVH builder): TriangleData saturates every host core, so the BVH thread only
+// gets going once it is done — no gain; they run one after the other.
 inline void buildHostStructures(const HostMesh& mesh, TriVec& tris, RawVec<BvhNode>& bvh, sdfb200_build_stats& st) {
     auto t0 = std::chrono::steady_clock::now();
     tris = computeTriangleData(mesh);
