@@ -15,6 +15,32 @@
 
 using namespace sdflib;
 
+// The reference's sample stream: three rand() draws per point (x, y, z in that order), mapped into the sample area
+// shrunk by 1e-5 (main.cpp:44-57).
+static std::vector<glm::vec3> drawSamples(const BoundingBox& area, size_t count)
+{
+    const glm::vec3 middle = area.getCenter();
+    const glm::vec3 extent = area.getSize() - glm::vec3(1e-5);
+    std::vector<glm::vec3> points(count);
+    for (glm::vec3& p : points)
+    {
+        const float u = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
+        const float v = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
+        const float w = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
+        p = middle + (glm::vec3(u, v, w) - 0.5f) * extent;
+    }
+    return points;
+}
+
+// one bulk call instead of the reference's per-point loop; returns microseconds per query
+static float timedQuery(const SdfFunction& f, const std::vector<glm::vec3>& points, std::vector<float>& out)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    f.getDistances(points.data(), points.size(), out.data());
+    const float seconds = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
+    return seconds * 1.0e6f / static_cast<float>(points.size());
+}
+
 int main(int argc, char** argv)
 {
     if (argc < 3 || std::string(argv[1]) == "-h" || std::string(argv[1]) == "--help")
@@ -29,44 +55,31 @@ int main(int argc, char** argv)
         if (!sdf || !exactSdf) { std::cerr << "[error] Cannot load the models: " << sdfb200_last_error() << std::endl; return 1; }
         std::cout << "[info] Models Loaded" << std::endl;
 
-        const uint32_t numSamples = 1000000u * (argc > 3 ? uint32_t(std::strtoul(argv[3], nullptr, 10)) : 1u);
-        std::vector<glm::vec3> samples(numSamples);
-        const glm::vec3 center = sdf->getSampleArea().getCenter();
-        const glm::vec3 size = sdf->getSampleArea().getSize() - glm::vec3(1e-5);
-        auto getRandomSample = [&]() -> glm::vec3
-        {
-            // one rand() per component, in x, y, z order (the reference's braced initialiser is sequenced left to right)
-            const float x = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
-            const float y = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
-            const float z = static_cast<float>(rand()) / static_cast<float>(RAND_MAX);
-            return center + (glm::vec3(x, y, z) - 0.5f) * size;
-        };
-        std::generate(samples.begin(), samples.end(), getRandomSample);
+        const uint32_t millions = argc > 3 ? uint32_t(std::strtoul(argv[3], nullptr, 10)) : 1u;
+        const size_t count = size_t(1000000) * millions;
+        const BoundingBox area = sdf->getSampleArea();
+        const std::vector<glm::vec3> points = drawSamples(area, count);
 
-        std::vector<float> sdfDist(numSamples), exactSdfDist(numSamples);
-        auto t0 = std::chrono::steady_clock::now();
-        sdf->getDistances(samples.data(), numSamples, sdfDist.data());
-        float seconds = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
-        std::cout << "[info] Sdf us per query: " << seconds * 1.0e6f / static_cast<float>(numSamples) << std::endl;
-        t0 = std::chrono::steady_clock::now();
-        exactSdf->getDistances(samples.data(), numSamples, exactSdfDist.data());
-        seconds = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
-        std::cout << "[info] Exact Sdf us per query: " << seconds * 1.0e6f / static_cast<float>(numSamples) << std::endl;
+        std::vector<float> approx(count), exact(count);
+        const float usApprox = timedQuery(*sdf, points, approx);
+        std::cout << "[info] Sdf us per query: " << usApprox << std::endl;
+        const float usExact = timedQuery(*exactSdf, points, exact);
+        std::cout << "[info] Exact Sdf us per query: " << usExact << std::endl;
 
-        double rmseError = 0.0, maeError = 0.0;
-        float maxError = 0.0f;
-        for (uint32_t s = 0; s < numSamples; s++)
+        // sums in double, differences in float, like the reference's report (main.cpp:76-93)
+        double sumSq = 0.0, sumAbs = 0.0;
+        float worst = 0.0f;
+        for (size_t k = 0; k < count; k++)
         {
-            const float d = sdfDist[s] - exactSdfDist[s];
-            rmseError += static_cast<double>(d * d);
-            maeError += static_cast<double>(glm::abs(d));
-            maxError = glm::max(maxError, glm::abs(d));
+            const float diff = approx[k] - exact[k];
+            const float mag = glm::abs(diff);
+            sumSq += static_cast<double>(diff * diff);
+            sumAbs += static_cast<double>(mag);
+            worst = glm::max(worst, mag);
         }
-        rmseError = std::sqrt(rmseError / static_cast<double>(numSamples));
-        maeError = maeError / static_cast<double>(numSamples);
-        std::cout << "[info] RMSE: " << rmseError << std::endl;
-        std::cout << "[info] MAE: " << maeError << std::endl;
-        std::cout << "[info] Max error: " << maxError << std::endl;
+        std::cout << "[info] RMSE: " << std::sqrt(sumSq / static_cast<double>(count)) << std::endl;
+        std::cout << "[info] MAE: " << sumAbs / static_cast<double>(count) << std::endl;
+        std::cout << "[info] Max error: " << worst << std::endl;
     }
     catch (const std::exception& e)
     {
