@@ -97,6 +97,11 @@ void trimDeviceCache(int device) {   // gDevMutex held
 }
 }  // namespace
 
+// Stream that new device memory is ordered on when a request misses the cache (and that overflowing blocks are
+// returned on). Thread-local: a builder that runs a pass on a side stream sets it for the duration of that pass.
+static thread_local cudaStream_t tBlockStream = nullptr;
+void setDeviceBlockStream(cudaStream_t s) { tBlockStream = s; }
+
 void* deviceBlockAlloc(size_t bytes, size_t* outCapacity) {
     const size_t cap = roundDeviceBlock(bytes);
     *outCapacity = cap;
@@ -113,7 +118,7 @@ void* deviceBlockAlloc(size_t bytes, size_t* outCapacity) {
         }
     }
     void* p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, cap, cudaStream_t(0));
+    cudaError_t e = cudaMallocAsync(&p, cap, tBlockStream);
     if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back and try once more
         cudaGetLastError();
         {
@@ -121,7 +126,7 @@ void* deviceBlockAlloc(size_t bytes, size_t* outCapacity) {
             trimDeviceCache(device);
         }
         cudaStreamSynchronize(cudaStream_t(0));
-        e = cudaMallocAsync(&p, cap, cudaStream_t(0));
+        e = cudaMallocAsync(&p, cap, tBlockStream);
     }
     if (e != cudaSuccess) throw Error(SDFB200_ERR_CUDA, std::string("cudaMallocAsync(") + std::to_string(cap) + " bytes): " + cudaGetErrorString(e));
     return p;
@@ -140,7 +145,7 @@ void deviceBlockFree(void* p, size_t capacity) {
             return;
         }
     }
-    cudaFreeAsync(p, cudaStream_t(0));
+    cudaFreeAsync(p, tBlockStream);
 }
 
 void configureDevicePool(int device) {

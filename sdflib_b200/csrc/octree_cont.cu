@@ -698,7 +698,9 @@ struct LeafPool {
 struct GrowingOctree {
     DevBuf<uint32_t> oct, leafRef, claim;
     uint64_t capacity = 0, G3 = 0;
-    void reserve(uint64_t words) {
+    // `st`: the stream whose work uses the arrays at this point. On a side stream the old blocks may only go back to
+    // the block cache (where the legacy-stream code would pick them up) once the copies have completed.
+    void reserve(uint64_t words, cudaStream_t st = nullptr) {
         if (words <= capacity) return;
         if (words > uint64_t(kOctIndexMask)) throw Error(SDFB200_ERR_INVALID, "octree exceeds the 30-bit index space of OctreeNode");
         uint64_t cap = std::max<uint64_t>(capacity * 2, words + (words >> 2) + 4096);
@@ -706,10 +708,11 @@ struct GrowingOctree {
         DevBuf<uint32_t> o(cap), r((cap - G3) / 8 + 2), c((cap - G3) / 8 + 2);
         const uint64_t oldSide = capacity ? (capacity - G3) / 8 + 2 : 0;
         if (capacity) {
-            SDFB_CUDA(cudaMemcpyAsync(o.p, oct.p, capacity * 4, cudaMemcpyDeviceToDevice));
-            SDFB_CUDA(cudaMemcpyAsync(r.p, leafRef.p, oldSide * 4, cudaMemcpyDeviceToDevice));
+            SDFB_CUDA(cudaMemcpyAsync(o.p, oct.p, capacity * 4, cudaMemcpyDeviceToDevice, st));
+            SDFB_CUDA(cudaMemcpyAsync(r.p, leafRef.p, oldSide * 4, cudaMemcpyDeviceToDevice, st));
         }
-        fillKernel<<<divUp(c.n, 256), 256>>>(c.p, kNone, c.n);   // the claim table is clean between passes
+        fillKernel<<<divUp(c.n, 256), 256, 0, st>>>(c.p, kNone, c.n);   // the claim table is clean between passes
+        if (st) SDFB_CUDA(cudaStreamSynchronize(st));
         oct = std::move(o); leafRef = std::move(r); claim = std::move(c);
         capacity = cap;
     }
@@ -829,18 +832,118 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
     DevBuf<uint32_t> sizes, sub, sizeScan, subScan, candCount32, candScan, candWords, candList, isRoot, rootPos;
     DevBuf<uint8_t> candCount;
     Scanner scanner;
+    // ---- fix-up pass of depth d: re-open the queued leaves (:741-1181). On one rank it is deferred until the Iter-1
+    // sampling of depth d + 1 has been launched and then runs on a side stream underneath it: its rounds are small,
+    // latency-bound launches (a far-field BVH traversal chain is ~1.8 ms) that would otherwise leave the GPU idle, and
+    // depth d + 1 needs its results only for the decision / junction kernels, which are issued after this returns.
+    cudaStream_t fs = nullptr;
+    Scanner fixScanner;
+    auto runFixup = [&](uint32_t d, uint32_t nCand) {
+        setDeviceBlockStream(fs);
+        fixSampler.stream = fs;
+        {
+            SDFB_CUDA(cudaMemcpyAsync(dStores.p, storeTable.data(), sizeof(StoreView) * 32, cudaMemcpyHostToDevice, fs));
+            isRoot.ensure(nCand); rootPos.ensure(nCand);
+            fixClaimKernel<<<divUp(nCand, 256), 256, 0, fs>>>(candList.p, nCand, oc.oct.p, G3, oc.claim.p);
+            fixRootFlagKernel<<<divUp(nCand, 256), 256, 0, fs>>>(candList.p, nCand, oc.oct.p, G3, oc.claim.p, isRoot.p);
+            const uint32_t K = fixScanner.run(isRoot.p, rootPos.p, nCand, false, fs);
+            std::vector<std::unique_ptr<FixRound>> rounds;
+            rounds.emplace_back(new FixRound());
+            rounds[0]->alloc(K);
+            DevBuf<uint32_t> oldCoef(K);
+            DevBuf<unsigned long long> firstLeaf(K);
+            SDFB_CUDA(cudaMemsetAsync(firstLeaf.p, 0xFF, size_t(K) * 8, fs));
+            fixRootInitKernel<<<divUp(uint64_t(nCand) * 16, 256), 256, 0, fs>>>(candList.p, isRoot.p, rootPos.p, nCand, oc.oct.p, G3, oc.claim.p, oc.leafRef.p,
+                                                                          dStores.p, rounds[0]->arrays(), oldCoef.p);
+            st.kernel_launches += 6;
+            for (uint32_t r = 0;; r++) {
+                FixRound& R = *rounds[r];
+                const uint32_t g8 = divUp(R.count, kWarpsPerCta);
+                fixProbeKernel<<<g8, kWarpsPerCta * 32, 0, fs>>>(grid, R.arrays(), r, d, oc.oct.p, firstLeaf.p);
+                R.nSplit = fixScanner.run(R.split.p, R.splitScan.p, R.count, false, fs);
+                st.kernel_launches += 4;
+                if (R.nSplit == 0) break;
+                rounds.emplace_back(new FixRound());
+                FixRound& Nx = *rounds[r + 1];
+                Nx.alloc(R.nSplit * 8);
+                const uint32_t nTrue = fixScanner.run(R.nSamples.p, R.sampleScan.p, R.count, false, fs);
+                fixPoints.ensure(std::max<uint32_t>(nTrue, 1));
+                fixSamplePointsKernel<<<divUp(R.count, 128), 128, 0, fs>>>(R.arrays(), R.sampleScan.p, fixPoints.p);
+                const float4* fixSamples = fixSampler.runPoints(dmesh, fixPoints.p, nTrue);
+                fixValuesKernel<<<g8, kWarpsPerCta * 32, 0, fs>>>(R.arrays(), Nx.arrays(), R.splitScan.p, R.sampleScan.p, fixSamples, sqThreshold);
+                st.kernel_launches += 6;
+                st.samples_evaluated += nTrue;
+                st.nodes_processed += R.count;
+            }
+            tick("fix rounds", d);
+            const uint32_t nRounds = uint32_t(rounds.size());
+            DevBuf<uint32_t> byRoot(size_t(K) * nRounds + 1), byRound(size_t(K) * nRounds + 1);
+            SDFB_CUDA(cudaMemsetAsync(byRoot.p, 0, byRoot.n * 4, fs));
+            SDFB_CUDA(cudaMemsetAsync(byRound.p, 0, byRound.n * 4, fs));
+            uint32_t nLeaves = 0, nSplits = 0;
+            for (uint32_t r = 0; r < nRounds; r++) {
+                FixRound& R = *rounds[r];
+                fixSizeKernel<<<divUp(R.count, 256), 256, 0, fs>>>(R.arrays(), r, nRounds, K, firstLeaf.p, byRoot.p, byRound.p);
+                fixScanner.run(R.size.p, R.sizeScan.p, R.count, false, fs);
+                nLeaves += R.count - R.nSplit;
+                nSplits += R.nSplit;
+                st.kernel_launches += 4;
+            }
+            const uint32_t fixWords = fixScanner.run(byRoot.p, byRoot.p, size_t(K) * nRounds, false, fs);
+            fixScanner.run(byRound.p, byRound.p, size_t(K) * nRounds, false, fs);
+            oc.reserve(words + fixWords, fs);
+            pools.emplace_back(new LeafPool());
+            LeafPool& P = *pools.back();
+            P.alloc(nLeaves);
+            if (nLeaves > kRefIndexMask) throw Error(SDFB200_ERR_INVALID, "more than 2^27 leaves in one fix-up pass");
+            splitWordLists.emplace_back(new DevBuf<uint32_t>(std::max<uint32_t>(nSplits, 1)));
+            splitWordCounts.push_back(nSplits);
+            uint32_t poolBase = 0, splitBase = 0;
+            for (uint32_t r = 0; r < nRounds; r++) {
+                FixRound& R = *rounds[r];
+                fixWriteKernel<<<divUp(R.count, kWarpsPerCta), kWarpsPerCta * 32, 0, fs>>>(
+                    R.arrays(), r ? rounds[r - 1]->block.p : nullptr, r, nRounds, K, R.sizeScan.p, R.splitScan.p, byRoot.p, byRound.p, oldCoef.p,
+                    uint32_t(words), G3, oc.oct.p, oc.leafRef.p, P.arrays(), poolBase, kPoolStoreBase + d, splitWordLists.back()->p + splitBase);
+                poolBase += R.count - R.nSplit;
+                splitBase += R.nSplit;
+                st.kernel_launches++;
+            }
+            storeTable[kPoolStoreBase + d] = P.store();
+            words += fixWords;
+            tick("fix write", d);
+            st.nodes_processed += rounds.back()->count;
+            if (fs) SDFB_CUDA(cudaStreamSynchronize(fs));   // the blocks of this pass go back to the cache only when its work is done
+        }
+        setDeviceBlockStream(nullptr);
+    };
+    static const bool overlapOff = std::getenv("SDFB200_CONT_NO_OVERLAP") != nullptr;   // A/B switch (profiles/)
+    const bool overlap = exchange.world <= 1 && !timing && !overlapOff;
+    cudaEvent_t emitted = nullptr;
+    struct StreamGuard {   // the side stream and its event live as long as this build
+        cudaStream_t& s; cudaEvent_t& e;
+        ~StreamGuard() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } if (e) cudaEventDestroy(e); setDeviceBlockStream(nullptr); }
+    } streamGuard{fs, emitted};
+    if (overlap) {
+        SDFB_CUDA(cudaStreamCreateWithFlags(&fs, cudaStreamNonBlocking));
+        SDFB_CUDA(cudaEventCreateWithFlags(&emitted, cudaEventDisableTiming));
+    }
+    uint32_t pendingDepth = 0, pendingCand = 0;
     for (uint32_t d = d0; d <= depth; d++) {
         NodeLevel& L = *levels[d];
         const bool real = d >= startDepth, deepest = d == depth;
         if (L.count > kRefIndexMask) throw Error(SDFB200_ERR_INVALID, "more than 2^27 nodes in one level");
         levels[d + 1].reset(new NodeLevel());
-        if (L.count == 0) continue;
+        if (L.count == 0) {
+            if (pendingCand) { runFixup(pendingDepth, pendingCand); pendingCand = 0; }
+            continue;
+        }
         storeTable[d] = L.store(d);
         const uint32_t grid8 = divUp(L.count, kWarpsPerCta);
         // ---- Iter 1
         if (!deepest) {
             mids.ensure(size_t(L.count) * 38);
             { const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 2); st.leaves += ran == 0xFFFFFFFFu ? uint64_t(L.count) * 19 : ran; }   // stats.leaves: BVH traversals run
+            if (pendingCand) { runFixup(pendingDepth, pendingCand); pendingCand = 0; }   // the previous depth's fix-up, under this sampling
             if (real) {
                 coeffs.ensure(size_t(L.count) * 64);
                 contDecideKernel<<<grid8, kWarpsPerCta * 32>>>(L.arrays(), mids.p, coeffs.p, oc.oct.p, rule, sqThreshold, param1);
@@ -850,6 +953,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
             st.kernel_launches += 2;
             st.samples_evaluated += uint64_t(L.count) * 19;
         }
+        if (pendingCand) { runFixup(pendingDepth, pendingCand); pendingCand = 0; }   // deepest level: nothing to hide it under
         tick("iter1", d);
         // ---- Iter 2: T-junction samples
         uint32_t nCand = 0;
@@ -882,78 +986,15 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         tick("iter2", d);
         if (nCand == 0) continue;
 
-        // ---- fix-up pass: re-open the queued leaves
-        SDFB_CUDA(cudaMemcpyAsync(dStores.p, storeTable.data(), sizeof(StoreView) * 32, cudaMemcpyHostToDevice));
-        isRoot.ensure(nCand); rootPos.ensure(nCand);
-        fixClaimKernel<<<divUp(nCand, 256), 256>>>(candList.p, nCand, oc.oct.p, G3, oc.claim.p);
-        fixRootFlagKernel<<<divUp(nCand, 256), 256>>>(candList.p, nCand, oc.oct.p, G3, oc.claim.p, isRoot.p);
-        const uint32_t K = scanner.run(isRoot.p, rootPos.p, nCand);
-        std::vector<std::unique_ptr<FixRound>> rounds;
-        rounds.emplace_back(new FixRound());
-        rounds[0]->alloc(K);
-        DevBuf<uint32_t> oldCoef(K);
-        DevBuf<unsigned long long> firstLeaf(K);
-        SDFB_CUDA(cudaMemsetAsync(firstLeaf.p, 0xFF, size_t(K) * 8));
-        fixRootInitKernel<<<divUp(uint64_t(nCand) * 16, 256), 256>>>(candList.p, isRoot.p, rootPos.p, nCand, oc.oct.p, G3, oc.claim.p, oc.leafRef.p,
-                                                                      dStores.p, rounds[0]->arrays(), oldCoef.p);
-        st.kernel_launches += 6;
-        for (uint32_t r = 0;; r++) {
-            FixRound& R = *rounds[r];
-            const uint32_t g8 = divUp(R.count, kWarpsPerCta);
-            fixProbeKernel<<<g8, kWarpsPerCta * 32>>>(grid, R.arrays(), r, d, oc.oct.p, firstLeaf.p);
-            R.nSplit = scanner.run(R.split.p, R.splitScan.p, R.count);
-            st.kernel_launches += 4;
-            if (R.nSplit == 0) break;
-            rounds.emplace_back(new FixRound());
-            FixRound& Nx = *rounds[r + 1];
-            Nx.alloc(R.nSplit * 8);
-            const uint32_t nTrue = scanner.run(R.nSamples.p, R.sampleScan.p, R.count);
-            fixPoints.ensure(std::max<uint32_t>(nTrue, 1));
-            fixSamplePointsKernel<<<divUp(R.count, 128), 128>>>(R.arrays(), R.sampleScan.p, fixPoints.p);
-            const float4* fixSamples = fixSampler.runPoints(dmesh, fixPoints.p, nTrue);
-            fixValuesKernel<<<g8, kWarpsPerCta * 32>>>(R.arrays(), Nx.arrays(), R.splitScan.p, R.sampleScan.p, fixSamples, sqThreshold);
-            st.kernel_launches += 6;
-            st.samples_evaluated += nTrue;
-            st.nodes_processed += R.count;
-        }
-        tick("fix rounds", d);
-        const uint32_t nRounds = uint32_t(rounds.size());
-        DevBuf<uint32_t> byRoot(size_t(K) * nRounds + 1), byRound(size_t(K) * nRounds + 1);
-        SDFB_CUDA(cudaMemsetAsync(byRoot.p, 0, byRoot.n * 4));
-        SDFB_CUDA(cudaMemsetAsync(byRound.p, 0, byRound.n * 4));
-        uint32_t nLeaves = 0, nSplits = 0;
-        for (uint32_t r = 0; r < nRounds; r++) {
-            FixRound& R = *rounds[r];
-            fixSizeKernel<<<divUp(R.count, 256), 256>>>(R.arrays(), r, nRounds, K, firstLeaf.p, byRoot.p, byRound.p);
-            scanner.run(R.size.p, R.sizeScan.p, R.count);
-            nLeaves += R.count - R.nSplit;
-            nSplits += R.nSplit;
-            st.kernel_launches += 4;
-        }
-        const uint32_t fixWords = scanner.run(byRoot.p, byRoot.p, size_t(K) * nRounds);
-        scanner.run(byRound.p, byRound.p, size_t(K) * nRounds);
-        oc.reserve(words + fixWords);
-        pools.emplace_back(new LeafPool());
-        LeafPool& P = *pools.back();
-        P.alloc(nLeaves);
-        if (nLeaves > kRefIndexMask) throw Error(SDFB200_ERR_INVALID, "more than 2^27 leaves in one fix-up pass");
-        splitWordLists.emplace_back(new DevBuf<uint32_t>(std::max<uint32_t>(nSplits, 1)));
-        splitWordCounts.push_back(nSplits);
-        uint32_t poolBase = 0, splitBase = 0;
-        for (uint32_t r = 0; r < nRounds; r++) {
-            FixRound& R = *rounds[r];
-            fixWriteKernel<<<divUp(R.count, kWarpsPerCta), kWarpsPerCta * 32>>>(
-                R.arrays(), r ? rounds[r - 1]->block.p : nullptr, r, nRounds, K, R.sizeScan.p, R.splitScan.p, byRoot.p, byRound.p, oldCoef.p,
-                uint32_t(words), G3, oc.oct.p, oc.leafRef.p, P.arrays(), poolBase, kPoolStoreBase + d, splitWordLists.back()->p + splitBase);
-            poolBase += R.count - R.nSplit;
-            splitBase += R.nSplit;
-            st.kernel_launches++;
-        }
-        storeTable[kPoolStoreBase + d] = P.store();
-        words += fixWords;
-        tick("fix write", d);
-        st.nodes_processed += rounds.back()->count;
+        if (nCand == 0) continue;
+        if (overlap && !deepest) {   // run it under the next depth's sampling
+            SDFB_CUDA(cudaEventRecord(emitted, cudaStream_t(0)));
+            SDFB_CUDA(cudaStreamWaitEvent(fs, emitted, 0));
+            pendingDepth = d;
+            pendingCand = nCand;
+        } else runFixup(d, nCand);
     }
+    if (pendingCand) runFixup(pendingDepth, pendingCand);
     // final un-mark (:1191-1217), border minimum over the leaves of the final tree
     for (size_t i = 0; i < splitWordLists.size(); i++)
         if (splitWordCounts[i]) unmarkKernel<<<divUp(splitWordCounts[i], 256), 256>>>(splitWordLists[i]->p, splitWordCounts[i], oc.oct.p);

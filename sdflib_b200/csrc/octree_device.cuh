@@ -304,6 +304,7 @@ struct LevelSampler {
     DevBuf<float4> results, slice;
     Scanner scanner;
     SampleExchange exchange;   // world > 1: every rank traverses the BVH for its slice of the distinct positions only
+    cudaStream_t stream = nullptr;   // where this sampler's launches go (legacy default stream unless a pass runs on a side stream)
 
     // results[0 .. n) for n work items, item u computed by launch(first, count, dst) -> dst[0 .. count) = items first ..
     template <class Launch> const float4* shared(uint32_t n, Launch launch) {
@@ -317,7 +318,7 @@ struct LevelSampler {
         slice.ensure(std::max<uint32_t>(per, 1));
         if (per == 0) return results.p;
         const uint32_t first = std::min<uint64_t>(uint64_t(exchange.rank) * per, n), count = std::min<uint32_t>(per, n - first);
-        SDFB_CUDA(cudaMemsetAsync(slice.p, 0, size_t(per) * sizeof(float4)));
+        SDFB_CUDA(cudaMemsetAsync(slice.p, 0, size_t(per) * sizeof(float4), stream));
         if (count) launch(first, count, slice.p);
         if (exchange.allgather(exchange.user, slice.p, results.p, uint64_t(per) * sizeof(float4)) != 0)
             throw Error(SDFB200_ERR_CUDA, "the all-gather hook of the collective build failed");
@@ -328,24 +329,24 @@ struct LevelSampler {
         const uint64_t n64 = uint64_t(count) * 19;
         if (n64 >= (uint64_t(1) << 31)) {   // beyond the 32-bit sample index of the table: plain path
             if (exchange.world > 1) throw Error(SDFB200_ERR_INVALID, "more than 2^31 samples on one level of a collective build");
-            sampleLatticeKernel<<<divUp(n64, kBvhThreads), kBvhThreads, bvhStackBytes(mesh)>>>(mesh, centerHalf, count, out, stride);
+            sampleLatticeKernel<<<divUp(n64, kBvhThreads), kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, count, out, stride);
             return 0xFFFFFFFFu;
         }
         const uint32_t n = uint32_t(n64);
         uint32_t size = 1024;
         while (size < 2 * n) size <<= 1;
         table.ensure(size); rep.ensure(n); isOwner.ensure(n); pos.ensure(n);
-        SDFB_CUDA(cudaMemsetAsync(table.p, 0xFF, size_t(size) * 4));
-        dedupeInsertKernel<<<divUp(n, 256), 256>>>(centerHalf, n, table.p, size - 1, rep.p);
-        dedupeResolveKernel<<<divUp(n, 256), 256>>>(table.p, n, rep.p, isOwner.p);
-        const uint32_t nUnique = scanner.run(isOwner.p, pos.p, n);
+        SDFB_CUDA(cudaMemsetAsync(table.p, 0xFF, size_t(size) * 4, stream));
+        dedupeInsertKernel<<<divUp(n, 256), 256, 0, stream>>>(centerHalf, n, table.p, size - 1, rep.p);
+        dedupeResolveKernel<<<divUp(n, 256), 256, 0, stream>>>(table.p, n, rep.p, isOwner.p);
+        const uint32_t nUnique = scanner.run(isOwner.p, pos.p, n, false, stream);
         owners.ensure(nUnique);
-        dedupeOwnersKernel<<<divUp(n, 256), 256>>>(isOwner.p, pos.p, n, owners.p);
+        dedupeOwnersKernel<<<divUp(n, 256), 256, 0, stream>>>(isOwner.p, pos.p, n, owners.p);
         const uint32_t* ownersPtr = owners.p;
         const float4* res = shared(nUnique, [&](uint32_t first, uint32_t cnt, float4* dst) {
-            sampleOwnersKernel<<<divUp(cnt, kBvhThreads), kBvhThreads, bvhStackBytes(mesh)>>>(mesh, centerHalf, ownersPtr, first, cnt, dst);
+            sampleOwnersKernel<<<divUp(cnt, kBvhThreads), kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst);
         });
-        dedupeScatterKernel<<<divUp(n, 256), 256>>>(rep.p, pos.p, res, n, out, stride);
+        dedupeScatterKernel<<<divUp(n, 256), 256, 0, stream>>>(rep.p, pos.p, res, n, out, stride);
         return nUnique;
     }
 
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(kBvhThreads) samplePointsKernel(DeviceMesh mes
 
 inline const float4* LevelSampler::runPoints(const DeviceMesh& mesh, const float4* points, uint32_t n) {
     return shared(n, [&](uint32_t first, uint32_t cnt, float4* dst) {
-        samplePointsKernel<<<divUp(cnt, kBvhThreads), kBvhThreads, bvhStackBytes(mesh)>>>(mesh, points, first, cnt, dst);
+        samplePointsKernel<<<divUp(cnt, kBvhThreads), kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, points, first, cnt, dst);
     });
 }
 

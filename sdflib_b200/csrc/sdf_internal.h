@@ -34,6 +34,7 @@ void setLastError(const std::string& msg);
 // block to the next allocation is ordered by the stream itself.
 void* deviceBlockAlloc(size_t bytes, size_t* outCapacity);
 void deviceBlockFree(void* p, size_t capacity);
+void setDeviceBlockStream(cudaStream_t s);   // thread-local: stream that cache misses / overflows are ordered on (default: legacy stream)
 
 template <class T> struct DevBuf {
     T* p = nullptr;
