@@ -82,7 +82,11 @@ typedef struct sdfb200_build_stats {
 const char* sdfb200_last_error(void);
 int sdfb200_version(void);
 int sdfb200_device_count(void);        /* 0 when no CUDA device is visible */
-int sdfb200_set_device(int device);    /* device used by subsequent build/load calls of this thread */
+int sdfb200_set_device(int device);
+/* The library recycles device blocks (size-class free lists over the stream-ordered allocator) and pinned host blocks
+ * between calls so that repeated builds do not pay for allocation. This returns everything that is cached and not in
+ * use by a live handle to the driver (device side: after a device synchronisation). */
+int sdfb200_release_cached_memory(void);    /* device used by subsequent build/load calls of this thread */
 
 /* ---- construction (hot path 1) ----------------------------------------------------------------
  * vertices: numVertices * 3 floats; indices: numIndices uint32 (3 per triangle); box6 = min xyz, max xyz.

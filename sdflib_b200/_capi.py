@@ -38,7 +38,7 @@ class BuildStats(C.Structure):
 
 
 # every symbol include/sdfb200.h declares (tests check that the library exports all of them)
-SYMBOLS = ["sdfb200_last_error", "sdfb200_version", "sdfb200_device_count", "sdfb200_set_device", "sdfb200_build_octree",
+SYMBOLS = ["sdfb200_last_error", "sdfb200_version", "sdfb200_device_count", "sdfb200_set_device", "sdfb200_release_cached_memory", "sdfb200_build_octree",
            "sdfb200_build_exact", "sdfb200_build_octree_shard", "sdfb200_build_octree_collective", "sdfb200_build_exact_shard", "sdfb200_shard_sizes",
            "sdfb200_shard_finish", "sdfb200_shard_words", "sdfb200_shard_export",
            "sdfb200_assemble", "sdfb200_save", "sdfb200_load", "sdfb200_free", "sdfb200_get_info",

@@ -81,6 +81,10 @@ int sdfb200_set_device(int device) {
     });
 }
 
+int sdfb200_release_cached_memory(void) {
+    return guarded([&] { releaseCachedMemory(); });
+}
+
 int sdfb200_build_octree_shard(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
                                const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule, float param0,
                                float param1, int initAlgorithm, uint32_t numThreads, uint32_t rank, uint32_t worldSize,

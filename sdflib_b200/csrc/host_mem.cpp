@@ -148,6 +148,35 @@ void deviceBlockFree(void* p, size_t capacity) {
     cudaFreeAsync(p, tBlockStream);
 }
 
+void releaseCachedMemory() {
+    int nDev = 0;
+    if (cudaGetDeviceCount(&nDev) != cudaSuccess) { cudaGetLastError(); nDev = 0; }
+    int current = 0;
+    if (nDev) cudaGetDevice(&current);
+    {
+        std::lock_guard<std::mutex> lock(gDevMutex);
+        for (auto& kv : gFreeDevice) {
+            if (kv.second.empty()) continue;
+            cudaSetDevice(kv.first.first);
+            cudaDeviceSynchronize();
+            for (void* p : kv.second) { cudaFreeAsync(p, cudaStream_t(0)); gDevCachedBytes -= kv.first.second; }
+            kv.second.clear();
+        }
+    }
+    for (int d = 0; d < nDev; d++) {
+        cudaMemPool_t pool;
+        cudaSetDevice(d);
+        if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, 0); }
+    }
+    if (nDev) cudaSetDevice(current);
+    cudaGetLastError();
+    std::lock_guard<std::mutex> lock(gMutex);
+    for (auto& kv : gFreePinned) {
+        for (void* p : kv.second) { cudaFreeHost(p); gCachedBytes -= kv.first; }
+        kv.second.clear();
+    }
+}
+
 void configureDevicePool(int device) {
     static std::mutex m;
     static bool done[64] = {};

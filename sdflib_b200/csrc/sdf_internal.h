@@ -71,6 +71,7 @@ template <class T> struct DevBuf {
 void* hostBlockAlloc(size_t bytes, size_t* outCapacity, bool* outPinned);
 void hostBlockFree(void* p, size_t capacity, bool pinned);
 void configureDevicePool(int device);
+void releaseCachedMemory();
 
 template <class T> struct HostArray {
     T* p = nullptr;

@@ -118,3 +118,9 @@ def test_fixture_meshes(sdf, port):
     assert i.size // 3 == 320
     g = sdf.meshes.cell_centre_grid(np.float32([0, 0, 0, 1, 1, 1]), 4)
     assert g.shape == (64, 3) and np.allclose(g[1] - g[0], [0.25, 0, 0]) and np.allclose(g[0], 0.125)
+
+
+def test_release_cached_memory_is_callable_without_a_device(sdf):
+    """Trims the device-block and pinned-block caches; a no-op (and still OK) on a box without a GPU."""
+    from sdflib_b200 import _capi
+    assert _capi.lib().sdfb200_release_cached_memory() == _capi.OK
