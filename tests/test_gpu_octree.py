@@ -314,3 +314,21 @@ def test_edge_case_meshes_bit_exact(sdf, port, name):
     assert np.array_equal(e.getOctreeData().reshape(-1), pe.octree_data())
     q = random_points(e.getSampleArea().as_array(), 40000, 21)
     assert_bit_equal(e.getDistance(q), pe.query(q))
+
+
+def test_release_cached_memory_between_builds(sdf):
+    """The block caches can be emptied at any time between calls; the next build re-allocates and gives the same result."""
+    from sdflib_b200 import _capi
+    v, i = displaced_sphere(3)
+    box = sdf.meshes.bounding_box_with_margin(v)
+    mesh, bb = sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:])
+    a = sdf.OctreeSdf(mesh, bb, 6, 3, 1e-3, sdf.OctreeSdf.CONTINUITY, 1)
+    first = a.getOctreeData()
+    keep = sdf.ExactOctreeSdf(mesh, bb, 5, 2, 16, 1)          # stays alive across the trim
+    q = random_points(keep.getSampleArea().as_array(), 50000, 31)
+    before = keep.getDistance(q)
+    a.close()
+    assert _capi.lib().sdfb200_release_cached_memory() == _capi.OK
+    b = sdf.OctreeSdf(mesh, bb, 6, 3, 1e-3, sdf.OctreeSdf.CONTINUITY, 1)
+    assert np.array_equal(first, b.getOctreeData())
+    assert_bit_equal(before, keep.getDistance(q))
