@@ -6,6 +6,7 @@
 
 #include <array>
 #include <optional>
+#include <utility>
 #include <vector>
 
 #include "SdfFunction.h"
@@ -78,7 +79,35 @@ public:
     BoundingBox getSampleArea() const override { return mBox; }
     uint32_t getOctreeMaxDepth() const { return mInfo.max_depth; }
     const std::vector<OctreeNode>& getOctreeData() const { return mOctreeData; }
+    std::vector<OctreeNode>& getOctreeData() { return mOctreeData; }   // host mirror; the device copy is what queries read
     SdfFunction::SdfFormat getFormat() const override { return SdfFunction::SdfFormat::OCTREE; }
+
+    // Volume fraction of the (unit) octree covered by the leaves of every depth (src/sdf/OctreeSdf.cpp:232-277):
+    // #leaves(depth) * 8^-depth. Walks the host mirror with an explicit stack.
+    void getDepthDensity(std::vector<float>& depthsDensity)
+    {
+        depthsDensity.assign(size_t(mInfo.max_depth) + 1, 0.0f);
+        std::vector<uint32_t> leavesPerDepth(depthsDensity.size(), 0u);
+        uint32_t startDepth = 0;
+        while ((1 << startDepth) < mInfo.start_grid_size) startDepth++;
+        const size_t startSlots = size_t(mInfo.start_grid_size) * mInfo.start_grid_size * mInfo.start_grid_size;
+        std::vector<std::pair<uint32_t, uint32_t>> open;   // (word, depth)
+        for (size_t slot = 0; slot < startSlots; slot++) open.emplace_back(uint32_t(slot), startDepth);
+        while (!open.empty())
+        {
+            const std::pair<uint32_t, uint32_t> at = open.back();
+            open.pop_back();
+            const OctreeNode& node = mOctreeData[at.first];
+            if (node.isLeaf()) { if (at.second < leavesPerDepth.size()) leavesPerDepth[at.second]++; }
+            else for (uint32_t c = 0; c < 8; c++) open.emplace_back(node.getChildrenIndex() + c, at.second + 1);
+        }
+        float cellVolume = 1.0f;
+        for (size_t d = 0; d < depthsDensity.size(); d++)
+        {
+            depthsDensity[d] = cellVolume * static_cast<float>(leavesPerDepth[d]);
+            cellVolume *= 0.125f;
+        }
+    }
 
 private:
     friend class SdfFunction;

@@ -61,6 +61,13 @@ int main(int argc, char** argv) {
             if (exactSdf.getDistance(pts[q], g) != dEx[q] || std::memcmp(&g, &gEx[q], 12) != 0) return 8;
         }
 
+        // getDepthDensity (OctreeSdf.cpp:232-277): the leaves tile the unit cube, so the densities sum to exactly 1
+        std::vector<float> density;
+        octreeSdf.getDepthDensity(density);
+        double covered = 0.0;
+        for (float d : density) covered += d;
+        if (density.size() != octreeSdf.getOctreeMaxDepth() + 1 || covered < 0.999999 || covered > 1.000001) return 10;
+
         FILE* f = fopen(argv[1], "wb");
         if (!f) return 9;
         put(f, verts); put(f, idx);
