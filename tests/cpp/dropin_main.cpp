@@ -61,6 +61,11 @@ int main(int argc, char** argv) {
             if (exactSdf.getDistance(pts[q], g) != dEx[q] || std::memcmp(&g, &gEx[q], 12) != 0) return 8;
         }
 
+        // TriangleUtils::calculateMeshTriangleData through the drop-in header equals what ExactOctreeSdf keeps
+        const std::vector<TriangleUtils::TriangleData> td = TriangleUtils::calculateMeshTriangleData(mesh);
+        if (td.size() != exactSdf.getTrianglesData().size() ||
+            std::memcmp(td.data(), exactSdf.getTrianglesData().data(), td.size() * sizeof(TriangleUtils::TriangleData)) != 0) return 11;
+
         // getDepthDensity (OctreeSdf.cpp:232-277): the leaves tile the unit cube, so the densities sum to exactly 1
         std::vector<float> density;
         octreeSdf.getDepthDensity(density);
