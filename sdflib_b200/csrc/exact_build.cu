@@ -39,8 +39,8 @@ namespace sdfb200 {
 namespace {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kChunk = 1024;          // list entries per CTA of the sample kernel
-constexpr int kSampleThreads = 256;
+constexpr int kChunk = 512;           // list entries per CTA of the sample kernel
+constexpr int kSampleThreads = 128;
 constexpr uint64_t kNoKey = ~uint64_t(0);
 
 __constant__ int cMidLattice[19] = {1, 3, 4, 5, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 19, 21, 22, 23, 25};
