@@ -127,7 +127,10 @@ __device__ __forceinline__ double eberlySqDistConverged(d3 p, d3 v0, d3 v1, d3 v
 // The traversal stack lives in SHARED memory, one column per thread: entry i of thread t is at [i * blockDim + t],
 // so a warp access is conflict-free whatever the per-lane stack pointers are. (In local memory the same accesses
 // were uncoalesced — 1.9 useful bytes per 32-byte sector — and made up 60 % of the L1 wavefronts of the sampling
-// kernel: profiles/r1_sample_lattice_*.) Depth = height of the median-split BVH, known on the host.
+// kernel: profiles/r1_sample_lattice_*.) Depth = height of the median-split BVH, known on the host. The full height
+// costs occupancy (20 entries x 12 B x 128 threads on the C2 mesh = 28 resident warps per SM), but keeping only 8
+// entries in shared memory and spilling the rest to a local array was measured slower (C2 levels 112.5 against 83 ms):
+// the dynamically indexed spill arrays put the whole cursor back into local memory.
 struct BvhStack {
     double* dist;   // [depth][blockDim]
     int* node;      // [depth][blockDim]
