@@ -123,3 +123,76 @@ def test_exporter_and_error_tool_on_gpu(sdf, tools, tmp_path):
     loaded = sdf.SdfFunction.loadFromFile(out)
     area = loaded.getSampleArea().as_array()
     assert abs((area[3:] - area[:3]).max() - 2.8) < 1e-4   # 2 (normalised extent) + 2 x 20 % margin
+
+
+# ---- sdflib::Mesh(path): the PLY / OBJ reader on its own (host only) ---------------------------------------------
+@pytest.fixture(scope="module")
+def mesh_reader(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("reader") / "mesh_reader")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle", "shim"),
+                        os.path.join(ROOT, "tests", "cpp", "mesh_reader_main.cpp"), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return exe
+
+
+def read_back(exe, path):
+    r = subprocess.run([exe, path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split("\n")
+    nv, ni = (int(x) for x in lines[0].split())
+    v = np.array([[float(x) for x in l.split()] for l in lines[1:1 + nv]], np.float32).reshape(nv, 3)
+    i = np.array([int(l) for l in lines[1 + nv:1 + nv + ni]], np.uint32)
+    box = np.array([float(x) for x in lines[1 + nv + ni].split()], np.float32)
+    return v, i, box
+
+
+def test_mesh_reader_round_trips_ply_and_obj(mesh_reader, tmp_path):
+    v, i = displaced_sphere(2)
+    for name, writer in (("a.ply", lambda p: write_ply(p, v, i, False)), ("b.ply", lambda p: write_ply(p, v, i, True)),
+                         ("c.obj", lambda p: write_obj(p, v, i))):
+        path = str(tmp_path / name)
+        writer(path)
+        rv, ri, box = read_back(mesh_reader, path)
+        assert np.array_equal(rv.view(np.uint32), v.view(np.uint32)), name      # %.9g round-trips float32 exactly
+        assert np.array_equal(ri, i), name
+        assert np.array_equal(box, np.concatenate([v.min(0), v.max(0)])), name
+
+
+def test_mesh_reader_polygons_extra_properties_and_relative_indices(mesh_reader, tmp_path):
+    quad = np.float32([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 0.5, 1]])
+    # binary PLY: double coordinates, extra vertex properties (normals, colour), a face property before the index list,
+    # a quad and a triangle -> fan triangulation 0 1 2, 0 2 3, 0 1 4
+    path = str(tmp_path / "rich.ply")
+    with open(path, "wb") as f:
+        f.write(b"ply\nformat binary_little_endian 1.0\nelement vertex 5\nproperty double x\nproperty double y\nproperty double z\n"
+                b"property float nx\nproperty uchar red\nelement face 2\nproperty uchar flags\nproperty list uchar uint vertex_index\n"
+                b"element edge 1\nproperty int vertex1\nproperty int vertex2\nend_header\n")
+        for p in quad:
+            f.write(struct.pack("<3dfB", float(p[0]), float(p[1]), float(p[2]), 0.5, 7))
+        f.write(struct.pack("<BB4I", 1, 4, 0, 1, 2, 3))
+        f.write(struct.pack("<BB3I", 0, 3, 0, 1, 4))
+        f.write(struct.pack("<2i", 0, 1))
+    rv, ri, _ = read_back(mesh_reader, path)
+    assert np.array_equal(rv, quad) and ri.tolist() == [0, 1, 2, 0, 2, 3, 0, 1, 4]
+    # OBJ: comments, texture / normal references, a quad, negative (relative) indices
+    path = str(tmp_path / "rich.obj")
+    with open(path, "w") as f:
+        f.write("# comment\nvn 0 0 1\nvt 0 0\n")
+        for p in quad:
+            f.write("v %g %g %g\n" % tuple(p))
+        f.write("f 1/1/1 2/1/1 3/1/1 4/1/1\nf -5//1 -4//1 -1//1\n")
+    rv, ri, _ = read_back(mesh_reader, path)
+    assert np.array_equal(rv, quad) and ri.tolist() == [0, 1, 2, 0, 2, 3, 0, 1, 4]
+
+
+def test_mesh_reader_rejects_bad_files(mesh_reader, tmp_path):
+    cases = {"empty.obj": "", "bad.ply": "not a ply\n", "big.ply": "ply\nformat binary_big_endian 1.0\nend_header\n",
+             "range.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n", "model.stl": "solid\n"}
+    for name, text in cases.items():
+        path = str(tmp_path / name)
+        open(path, "w").write(text)
+        r = subprocess.run([mesh_reader, path], capture_output=True, text=True)
+        assert r.returncode == 1 and "Mesh:" in r.stderr, (name, r.stderr)
+    r = subprocess.run([mesh_reader, str(tmp_path / "missing.ply")], capture_output=True, text=True)
+    assert r.returncode == 1 and "cannot open" in r.stderr
