@@ -2,7 +2,7 @@
  *
  * Plain sequential C++ written from the behaviour of the reference (file:line cited at every
  * function in oracle.cpp). It is pinned against oracle/_ref/libsdfref.so — the unmodified
- * reference compiled here — by tests/test_oracle_vs_ref.py (bit-exact on every entry point),
+ * reference compiled here — by tests/test_oracle.py (bit-exact on every entry point),
  * and against the committed fixtures under tests/golden/ where the reference is not present.
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference legs may load it.
  */
