@@ -102,15 +102,20 @@ class _DevicePointer:
 
 
 def torch_allgather_hook(group=None, device=None):
-    """sdfb200_allgather_fn over torch.distributed (NCCL on the device pointers; gloo through host copies)."""
+    """sdfb200_allgather_fn over torch.distributed: NCCL directly on the device pointers; gloo through host copies.
+    device=None means the two pointers are HOST memory (how the hook's choreography is tested without a GPU)."""
     import torch
     import torch.distributed as dist
 
     def hook(_user, d_send, d_recv, nbytes):
         try:
             world = dist.get_world_size(group)
-            send = torch.as_tensor(_DevicePointer(d_send, nbytes), device=device)
-            recv = torch.as_tensor(_DevicePointer(d_recv, nbytes * world), device=device)
+            if device is None:
+                send = torch.frombuffer((C.c_ubyte * nbytes).from_address(d_send), dtype=torch.uint8)
+                recv = torch.frombuffer((C.c_ubyte * (nbytes * world)).from_address(d_recv), dtype=torch.uint8)
+            else:
+                send = torch.as_tensor(_DevicePointer(d_send, nbytes), device=device)
+                recv = torch.as_tensor(_DevicePointer(d_recv, nbytes * world), device=device)
             if dist.get_backend(group) == "nccl":
                 dist.all_gather_into_tensor(recv, send, group=group)
             else:   # host-staged collective (tests)

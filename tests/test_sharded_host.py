@@ -100,3 +100,42 @@ def test_exchange_reassembles_the_structure_under_gloo(port, world):
         p.join(120)
         assert p.exitcode == 0
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+# ---- the all-gather hook of the collective CONTINUITY build (sdfb200_allgather_fn) under gloo --------------------------
+def _hook_worker(rank, world, port_no, ret):
+    import ctypes as C
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from sdflib_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hook = sharded.torch_allgather_hook(device=None)      # host pointers: the C side of the protocol, without a GPU
+        ok = True
+        for per in (1, 16, 4096):                              # bytes per rank of three "levels"
+            send = np.full(per, rank + 1, np.uint8)
+            send[0] = per % 251
+            recv = np.zeros(per * world, np.uint8)
+            rc = hook(None, send.ctypes.data, recv.ctypes.data, per)
+            want = np.concatenate([np.concatenate([[per % 251], np.full(per - 1, r + 1)]) for r in range(world)]).astype(np.uint8)
+            ok = ok and rc == 0 and np.array_equal(recv, want)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_allgather_hook_gathers_in_rank_order_under_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port_no = 31500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_hook_worker, args=(r, world, port_no, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert dict(ret) == {r: True for r in range(world)}
