@@ -330,8 +330,8 @@ struct LevelSampler {
 
     uint32_t run(const DeviceMesh& mesh, const float4* centerHalf, uint32_t count, float4* out, int stride) {
         const uint64_t n64 = uint64_t(count) * 19;
-        if (n64 >= (uint64_t(1) << 31)) {   // beyond the 32-bit sample index of the table: plain path
-            if (exchange.world > 1) throw Error(SDFB200_ERR_INVALID, "more than 2^31 samples on one level of a collective build");
+        if (n64 >= (uint64_t(1) << 30)) {   // the table (2 n slots, 32-bit sample indices) would pass 2^31 slots: plain path
+            if (exchange.world > 1) throw Error(SDFB200_ERR_INVALID, "more than 2^30 samples on one level of a collective build");
             sampleLatticeKernel<<<divUp(n64, kBvhThreads), kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, count, out, stride);
             return 0xFFFFFFFFu;
         }
