@@ -1,6 +1,8 @@
 #include "mesh_host.h"
+#include "host_sort.h"
 
 #include <algorithm>
+#include <atomic>
 #include <thread>
 #include <cmath>
 #include <limits>
@@ -92,7 +94,7 @@ TriVec computeTriangleData(const HostMesh& mesh) {
     RawVec<EdgeUse> uses(size_t(nT) * 3);
 
     // Frames and per-corner angle * normal are pure per-triangle functions: parallel.
-#pragma omp parallel for schedule(static) num_threads(hostThreads())
+#pragma omp parallel for schedule(static) num_threads(hostThreads()) if (nT > 8192)
     for (int64_t t = 0; t < int64_t(nT); t++) {
         const uint32_t* ix = mesh.idx + 3 * t;
         tris[size_t(t)] = makeTriData(mesh.verts[ix[0]], mesh.verts[ix[1]], mesh.verts[ix[2]]);
@@ -133,7 +135,7 @@ TriVec computeTriangleData(const HostMesh& mesh) {
     }
     std::vector<std::vector<EdgeUse>> openOf;
     openOf.resize(size_t(nChunks));
-#pragma omp parallel for schedule(static, 1) num_threads(nChunks)
+#pragma omp parallel for schedule(static, 1) num_threads(nChunks) if (nChunks > 1)
     for (int c = 0; c < nChunks; c++) {
         for (size_t i = cut[size_t(c)]; i < cut[size_t(c) + 1];) {
             size_t j = i;
@@ -226,7 +228,7 @@ TriVec computeTriangleData(const HostMesh& mesh) {
         for (uint32_t v : nm) vNormal[v] = vNormal[root(v)];
     }
 
-#pragma omp parallel for schedule(static) num_threads(hostThreads())
+#pragma omp parallel for schedule(static) num_threads(hostThreads()) if (nT > 8192)
     for (int64_t i = 0; i < int64_t(mesh.nIdx); i++)
         st3(tris[size_t(i / 3)].verticesNormal[i % 3], matMul(tris[size_t(i / 3)].T, vNormal[mesh.idx[i]]));
     lap("to triangle frame");
@@ -287,10 +289,24 @@ struct BvhBuilder {
         int dim = 0;
         for (int a = 1; a < 3; a++)
             if (top[a] - bottom[a] > top[dim] - bottom[dim]) dim = a;
-        double r2 = 0.0;
-        for (int32_t i = begin; i < end; i++) {
-            const BuildTri& t = tri[size_t(order[size_t(i)])];
-            for (int k = 0; k < 3; k++) r2 = std::max(r2, sq3(c, t.v[k]));
+        // Threads this node may use: the whole team at the root, half of it per child, ... (the halves run side by side).
+        const int team = std::max(1, (1 << forkLevels) / 2);
+        SortKey* keys = scratch.data() + begin;
+        double r2 = 0.0;   // a maximum: any evaluation order gives the same value
+        {
+            std::vector<double> part(size_t(team), 0.0);
+            std::atomic<int> slot{0};
+            forChunks(n, team, [&](int32_t lo, int32_t hi) {
+                double m = 0.0;
+                for (int32_t i = lo; i < hi; i++) {
+                    const int32_t id = order[size_t(begin + i)];
+                    const BuildTri& t = tri[size_t(id)];
+                    for (int k = 0; k < 3; k++) m = std::max(m, sq3(c, t.v[k]));
+                    keys[i] = SortKey{t.v[0][dim], id};
+                }
+                part[size_t(slot.fetch_add(1))] = m;
+            });
+            for (double m : part) r2 = std::max(r2, m);
         }
         for (int a = 0; a < 3; a++) sphereCenter[a] = c[a];
         *sphereRadius = std::sqrt(r2);
@@ -298,9 +314,7 @@ struct BvhBuilder {
         // key, so the library's comparison sequence is part of the result. That sequence depends only on the
         // comparison outcomes, not on the element type, so 16-byte (key, id) records give the same permutation as
         // sorting the reference's 80-byte triangle records.
-        SortKey* keys = scratch.data() + begin;
-        for (int32_t i = 0; i < n; i++) { const int32_t id = order[size_t(begin + i)]; keys[i] = SortKey{tri[size_t(id)].v[0][dim], id}; }
-        std::sort(keys, keys + n, [](const SortKey& x, const SortKey& y) { return x.key < y.key; });
+        sortLikeStd(keys, keys + n, [](const SortKey& x, const SortKey& y) { return x.key < y.key; }, team);
         for (int32_t i = 0; i < n; i++) order[size_t(begin + i)] = keys[i].id;
         const int32_t mid = int32_t(0.5 * (begin + end));
         node.left = nodeId + 1;
@@ -313,11 +327,12 @@ struct BvhBuilder {
         // Plain threads down to `forkLevels` levels (about 2 x hostThreads leaves of the fork tree), not an OpenMP
         // task team: a team's idle threads SPIN while the master runs the sequential top-level sorts, which starves
         // whatever else the host is doing (TriangleData of the same constructor, the other ranks of a multi-GPU job).
-        if (forkLevels > 0 && n > 8192) {
-            std::thread left([=] { BvhBuilder sub{tri, order, scratch, nodes, forkLevels - 1}; sub.build(l, lc, lr, begin, mid); });
+        std::vector<std::thread> fork;
+        if (forkLevels > 0 && n > 8192 &&
+            tryFork(fork, [=] { BvhBuilder sub{tri, order, scratch, nodes, forkLevels - 1}; sub.build(l, lc, lr, begin, mid); })) {
             BvhBuilder sub{tri, order, scratch, nodes, forkLevels - 1};
             sub.build(r, node.rc, &node.rr, mid, end);
-            left.join();
+            fork[0].join();
         } else {
             build(l, lc, lr, begin, mid);
             build(r, node.rc, &node.rr, mid, end);
@@ -332,14 +347,15 @@ RawVec<BvhNode> buildBvh(const HostMesh& mesh) {
     RawVec<BuildTri> bt(nT);
     RawVec<int32_t> order(nT);
     RawVec<SortKey> scratch(nT);
-#pragma omp parallel for schedule(static) num_threads(hostThreads())
-    for (int64_t t = 0; t < int64_t(nT); t++) {
-        order[size_t(t)] = int32_t(t);
-        for (int k = 0; k < 3; k++) {
-            const f3 p = mesh.verts[mesh.idx[3 * t + k]];
-            bt[size_t(t)].v[k][0] = double(p.x); bt[size_t(t)].v[k][1] = double(p.y); bt[size_t(t)].v[k][2] = double(p.z);
+    forChunks(int32_t(nT), hostThreads(), [&](int32_t lo, int32_t hi) {
+        for (int32_t t = lo; t < hi; t++) {
+            order[size_t(t)] = t;
+            for (int k = 0; k < 3; k++) {
+                const f3 p = mesh.verts[mesh.idx[3 * size_t(t) + size_t(k)]];
+                bt[size_t(t)].v[k][0] = double(p.x); bt[size_t(t)].v[k][1] = double(p.y); bt[size_t(t)].v[k][2] = double(p.z);
+            }
         }
-    }
+    });
     RawVec<BvhNode> nodes(size_t(2) * nT - 1);
     double rootCenter[3], rootRadius;
     int forkLevels = 1;
@@ -347,16 +363,16 @@ RawVec<BvhNode> buildBvh(const HostMesh& mesh) {
     BvhBuilder b{bt, order, scratch, nodes, forkLevels};
     b.build(0, rootCenter, &rootRadius, 0, int32_t(nT));
     // Device traversal never loads a leaf node: links to leaves are replaced by ~triangleId (mesh_host.h).
-    const int64_t nNodes = int64_t(nodes.size());
-#pragma omp parallel for schedule(static) num_threads(hostThreads())
-    for (int64_t i = 0; i < nNodes; i++) {
-        BvhNode& nd = nodes[size_t(i)];
-        if (nd.pad[0]) continue;
-        const BvhNode& l = nodes[size_t(nd.left)];
-        const BvhNode& r = nodes[size_t(nd.right)];
-        if (l.pad[0]) nd.left = ~l.right;
-        if (r.pad[0]) nd.right = ~r.right;
-    }
+    forChunks(int32_t(nodes.size()), hostThreads(), [&](int32_t lo, int32_t hi) {
+        for (int32_t i = lo; i < hi; i++) {
+            BvhNode& nd = nodes[size_t(i)];
+            if (nd.pad[0]) continue;
+            const BvhNode& l = nodes[size_t(nd.left)];
+            const BvhNode& r = nodes[size_t(nd.right)];
+            if (l.pad[0]) nd.left = ~l.right;
+            if (r.pad[0]) nd.right = ~r.right;
+        }
+    });
     return nodes;
 }
 

@@ -124,3 +124,25 @@ def test_release_cached_memory_is_callable_without_a_device(sdf):
     """Trims the device-block and pinned-block caches; a no-op (and still OK) on a box without a GPU."""
     from sdflib_b200 import _capi
     assert _capi.lib().sdfb200_release_cached_memory() == _capi.OK
+
+
+def test_bvh_builder_equals_serial_reference_order(sdf, tmp_path):
+    """The product BVH (16-byte sort proxies, std::sort's recursion split across threads) against a serial restatement
+    of tmd's _build_tree that moves 80-byte records with one std::sort per node: every node identical, for meshes full
+    of sort-key ties (plain isospheres) and in generic position, at several thread counts."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "bvh_host_main")
+    lib_dir = os.path.join(ROOT, "sdflib_b200")
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
+    cmd = [nvcc] + ccbin + ["-x", "cu", "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-I" + os.path.join(ROOT, "include"),
+                            "-I" + os.path.join(lib_dir, "csrc"), os.path.join(ROOT, "tests", "cpp", "bvh_host_main.cpp"), "-o", exe,
+                            "-L" + lib_dir, "-lsdfb200", "-Xlinker", "-rpath," + lib_dir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe, "sort"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), (r.stdout, r.stderr)
+    for subdivisions, displace, threads in ((2, 0, 4), (6, 0, 1), (6, 0, 8), (7, 0, 16), (7, 1, 3), (7, 1, 16)):
+        r = subprocess.run([exe, str(subdivisions), str(displace), str(threads)], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.startswith("ok "), (subdivisions, displace, threads, r.stdout, r.stderr)
