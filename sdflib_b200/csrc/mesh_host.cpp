@@ -344,6 +344,14 @@ struct BvhBuilder {
 
 RawVec<BvhNode> buildBvh(const HostMesh& mesh) {
     const uint32_t nT = mesh.numTriangles();
+    const bool timing = std::getenv("SDFB200_TIMING") != nullptr;
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[sdfb200] bvh: %-27s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+        tick = now;
+    };
     RawVec<BuildTri> bt(nT);
     RawVec<int32_t> order(nT);
     RawVec<SortKey> scratch(nT);
@@ -356,12 +364,14 @@ RawVec<BvhNode> buildBvh(const HostMesh& mesh) {
             }
         }
     });
+    lap("float64 records");
     RawVec<BvhNode> nodes(size_t(2) * nT - 1);
     double rootCenter[3], rootRadius;
     int forkLevels = 1;
     while ((1 << forkLevels) < 2 * hostThreads()) forkLevels++;
     BvhBuilder b{bt, order, scratch, nodes, forkLevels};
     b.build(0, rootCenter, &rootRadius, 0, int32_t(nT));
+    lap("tree");
     // Device traversal never loads a leaf node: links to leaves are replaced by ~triangleId (mesh_host.h).
     forChunks(int32_t(nodes.size()), hostThreads(), [&](int32_t lo, int32_t hi) {
         for (int32_t i = lo; i < hi; i++) {
@@ -373,6 +383,7 @@ RawVec<BvhNode> buildBvh(const HostMesh& mesh) {
             if (r.pad[0]) nd.right = ~r.right;
         }
     });
+    lap("leaf links");
     return nodes;
 }
 
