@@ -2,6 +2,7 @@
 // staging. No compute happens here; every entry point that needs the GPU fails with SDFB200_ERR_CUDA
 // when no device is present — there is no CPU fallback.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -257,6 +258,11 @@ int sdfb200_query(sdfb200_sdf* s, const float* xyz, uint64_t n, float* dist, flo
         if (s->isShard) throw Error(SDFB200_ERR_INVALID, "handle is an unassembled shard (sdfb200_assemble not called yet)");
         SDFB_CUDA(cudaSetDevice(s->device));
         cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
+        if (s->format == SDFB200_FORMAT_OCTREE) {   // EXPERIMENTAL dense leaf index, off unless the switch is set (octree_query.cu)
+            const char* sw = std::getenv("SDFB200_QUERY_INDEX");
+            s->useLeafIndex = sw && sw[0] == '1';
+            if (s->useLeafIndex) std::call_once(s->leafIndexOnce, [&] { buildLeafIndex(*s, st); });
+        }
         auto launchOn = [&](const float* dXyz, uint64_t count, float* dDist, float* dGrad, cudaStream_t on) {
             if (s->format == SDFB200_FORMAT_OCTREE) {
                 if (flags & SDFB200_QUERY_EXACT_ORDER) launchOctreeQueryExact(*s, dXyz, count, dDist, dGrad, on);

@@ -21,6 +21,8 @@
 // leaves staged once per warp in shared memory, evaluated from there) was measured and is slower
 // (0.36 ms vs 0.26 ms on the 256^3 grid): it removes the tag-stage replays but keeps the same
 // register-fill traffic and adds match/shuffle/shared-store work. It was dropped.
+#include <algorithm>
+
 #include "sdf_internal.h"
 
 namespace sdfb200 {
@@ -181,7 +183,110 @@ octreeQueryKernel(const uint32_t* __restrict__ oct, const QueryParams q, const f
     if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
 }
 
+// ---- EXPERIMENTAL (off unless SDFB200_QUERY_INDEX=1; not yet measured on a GPU) -------------------
+// Dense leaf index: one word per cell of the grid at depth startDepth + L holding the leaf that contains the cell,
+//   bit 31 set : leaf;  bits 27-30 = steps below the start grid at which it was reached, bits 0-26 = (block - G^3) / 8
+//   bit 31 clear: the cell is still an inner node at that depth; bits 0-26 = (children block - G^3) / 8
+// (every block of the array is 8 or 64 words long and starts after the G^3 start words, so block - G^3 is a multiple
+// of 8). A query then replaces its chain of dependent node gathers — about 32 of the 112 L1 wavefronts a warp of the
+// 256^3 workload issues — by ONE load, which is coalesced for grid-ordered queries (32 consecutive cells = 128 bytes).
+constexpr uint32_t kIndexLeaf = 1u << 31;
+constexpr uint32_t kIndexBlockMask = (1u << 27) - 1u;
+
+__global__ void __launch_bounds__(256)
+leafIndexKernel(const uint32_t* __restrict__ oct, int grid, int levels, uint32_t* __restrict__ index, uint32_t* __restrict__ bad) {
+    const uint32_t N = uint32_t(grid) << levels;
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= uint64_t(N) * N * N) return;
+    const uint32_t cx = uint32_t(i % N), cy = uint32_t((i / N) % N), cz = uint32_t(i / (uint64_t(N) * N));
+    const uint32_t G3 = uint32_t(grid) * uint32_t(grid) * uint32_t(grid);
+    uint32_t node = __ldg(oct + ((cz >> levels) * uint32_t(grid) + (cy >> levels)) * uint32_t(grid) + (cx >> levels));
+    int k = 0;
+    while (!(node & kLeafBit) && k < levels) {
+        const int sh = levels - 1 - k;
+        const uint32_t child = ((cx >> sh) & 1u) | (((cy >> sh) & 1u) << 1) | (((cz >> sh) & 1u) << 2);
+        node = __ldg(oct + (node & kOctIndexMask) + child);
+        k++;
+    }
+    const uint32_t block = node & kOctIndexMask;
+    if (block < G3 || ((block - G3) & 7u)) { atomicOr(bad, 1u); return; }
+    index[i] = ((block - G3) >> 3) | ((node & kLeafBit) ? (kIndexLeaf | (uint32_t(k) << 27)) : 0u);
+}
+
+template <bool kGrad, bool kVec>
+__global__ void __launch_bounds__(256)
+octreeQueryIndexedKernel(const uint32_t* __restrict__ oct, const uint32_t* __restrict__ index, int levels, const QueryParams q,
+                         const float* __restrict__ xyz, uint64_t n, float* __restrict__ dist, float* __restrict__ grad) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f3 p = mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+    float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const int ix = int(flx), iy = int(fly), iz = int(flz);
+    fx -= flx; fy -= fly; fz -= flz;
+    f3 g = mk3(0.0f, 0.0f, 0.0f);
+    float d;
+    if (ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid) {
+        d = (kGrad ? boxDistanceGrad(q, p, g) : boxDistance(q, p)) + q.minBorder;
+    } else {
+        // same path bits as octreeQueryKernel; the first `levels` of them select the index cell
+        constexpr int kPathBits = 16;
+        const uint32_t bx = uint32_t(fx * float(1 << kPathBits)), by = uint32_t(fy * float(1 << kPathBits)),
+                       bz = uint32_t(fz * float(1 << kPathBits));
+        const uint32_t N = uint32_t(q.grid) << levels;
+        const uint32_t cx = (uint32_t(ix) << levels) | (bx >> (kPathBits - levels)), cy = (uint32_t(iy) << levels) | (by >> (kPathBits - levels)),
+                       cz = (uint32_t(iz) << levels) | (bz >> (kPathBits - levels));
+        const uint32_t e = __ldg(index + (uint64_t(cz) * N + cy) * N + cx);
+        const uint32_t G3 = uint32_t(q.grid) * uint32_t(q.grid) * uint32_t(q.grid);
+        uint32_t block = ((e & kIndexBlockMask) << 3) + G3;
+        int k;
+        if (e & kIndexLeaf) k = int((e >> 27) & 15u);
+        else {
+            k = levels;
+            for (;;) {   // trees deeper than the index: finish the descent from the cell's node
+                const int sh = kPathBits - 1 - k;
+                const uint32_t child = ((bx >> sh) & 1u) | (((by >> sh) & 1u) << 1) | (((bz >> sh) & 1u) << 2);
+                const uint32_t node = __ldg(oct + block + child);
+                k++;
+                block = node & kOctIndexMask;
+                if (node & kLeafBit) break;
+            }
+        }
+        const float scale = float(1u << k);
+        fx *= scale; fy *= scale; fz *= scale;
+        fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
+        d = evalLeaf<kGrad, kVec>(reinterpret_cast<const float*>(oct + block), fx, fy, fz, g);
+    }
+    dist[i] = d;
+    if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
+}
+
 }  // namespace
+
+#ifndef SDFB_QUERY_EXACT
+// Builds s.dLeafIndex (EXPERIMENTAL, see leafIndexKernel). levels = as deep as the tree goes, capped so that the index
+// stays within 2^27 cells (512 MB); leaves s.leafIndexLevels = -1 when the array does not have the 8-word block
+// structure the packing relies on (a hand-made .bin), in which case the plain kernel keeps being used.
+void buildLeafIndex(sdfb200_sdf& s, cudaStream_t st) {
+    int startDepth = 0;
+    while ((1 << startDepth) < s.startGridSize) startDepth++;
+    int levels = std::max(0, int(s.maxDepth) - startDepth);
+    while (levels > 0 && 3 * (startDepth + levels) > 27) levels--;
+    s.leafIndexLevels = -1;
+    if ((1 << startDepth) != s.startGridSize || 3 * startDepth > 27) return;
+    const uint64_t cells = uint64_t(1) << (3 * (startDepth + levels));
+    s.dLeafIndex.alloc(cells + 1);
+    uint32_t* bad = s.dLeafIndex.p + cells;
+    SDFB_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st));
+    leafIndexKernel<<<uint32_t((cells + 255) / 256), 256, 0, st>>>(s.dOctree.p, s.startGridSize, levels, s.dLeafIndex.p, bad);
+    SDFB_CUDA(cudaGetLastError());
+    uint32_t hostBad = 1;
+    SDFB_CUDA(cudaMemcpyAsync(&hostBad, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SDFB_CUDA(cudaStreamSynchronize(st));
+    if (hostBad) { s.dLeafIndex.release(); return; }
+    s.leafIndexLevels = levels;
+}
+#endif
 
 #ifdef SDFB_QUERY_EXACT
 void launchOctreeQueryExact(
@@ -200,6 +305,19 @@ void launchOctreeQueryFast(
     // leaf blocks are 16-byte aligned iff the start grid has a multiple of 4 slots (all blocks are 8 or 64 words)
     const bool vec = (uint64_t(s.startGridSize) * s.startGridSize * s.startGridSize) % 4 == 0 && s.leafBlocksAligned;
     if (s.maxDepth > 16) throw Error(SDFB200_ERR_INVALID, "octree deeper than 16 levels");
+    if (s.useLeafIndex && s.leafIndexLevels >= 0) {   // EXPERIMENTAL, set by sdfb200_query under SDFB200_QUERY_INDEX=1
+        const uint32_t* ix = s.dLeafIndex.p;
+        const int lv = s.leafIndexLevels;
+        if (dGrad) {
+            if (vec) octreeQueryIndexedKernel<true, true><<<grid, 256, 0, st>>>(s.dOctree.p, ix, lv, q, dXyz, n, dDist, dGrad);
+            else octreeQueryIndexedKernel<true, false><<<grid, 256, 0, st>>>(s.dOctree.p, ix, lv, q, dXyz, n, dDist, dGrad);
+        } else {
+            if (vec) octreeQueryIndexedKernel<false, true><<<grid, 256, 0, st>>>(s.dOctree.p, ix, lv, q, dXyz, n, dDist, nullptr);
+            else octreeQueryIndexedKernel<false, false><<<grid, 256, 0, st>>>(s.dOctree.p, ix, lv, q, dXyz, n, dDist, nullptr);
+        }
+        SDFB_CUDA(cudaGetLastError());
+        return;
+    }
     if (dGrad) {
         if (vec) octreeQueryKernel<true, true><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, dGrad);
         else octreeQueryKernel<true, false><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, dGrad);

@@ -1,9 +1,11 @@
 // Internal definitions shared by the translation units of libsdfb200.so (not part of the C-ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -186,6 +188,11 @@ struct sdfb200_sdf {
     sdfb200::DevBuf<float4> dFrames;
     sdfb200::DevBuf<uint64_t> dLeafLo;
     sdfb200::DevBuf<uint32_t> dLeafCnt, dLeafPool;
+    // EXPERIMENTAL dense leaf index of an OCTREE (octree_query.cu, SDFB200_QUERY_INDEX=1): built once on first use
+    sdfb200::DevBuf<uint32_t> dLeafIndex;
+    int leafIndexLevels = -1;        // levels below the start grid the index resolves; -1 = no index
+    std::atomic<bool> useLeafIndex{false};   // what the next launch does (sdfb200_query re-reads the switch on every call)
+    std::once_flag leafIndexOnce;
     // staging for host-pointer queries
     sdfb200::DevBuf<float> dPts, dDist, dGrad;
     cudaStream_t qStream[2] = {nullptr, nullptr};
@@ -233,6 +240,7 @@ void pointTriangleOnDevice(const float* tri37, const float* v123, const float* x
                            float* outGrad);
 // octree_query.cu (two objects: fast = FMA Horner, exact = reference operation order)
 void launchOctreeQueryFast(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
+void buildLeafIndex(sdfb200_sdf& s, cudaStream_t st);
 void launchOctreeQueryExact(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
 // exact_build.cu / exact_query.cu
 void buildExactOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
