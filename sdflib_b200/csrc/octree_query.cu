@@ -276,6 +276,7 @@ void buildLeafIndex(sdfb200_sdf& s, cudaStream_t st) {
     if ((1 << startDepth) != s.startGridSize || 3 * startDepth > 27) return;
     const uint64_t cells = uint64_t(1) << (3 * (startDepth + levels));
     s.dLeafIndex.alloc(cells + 1);
+    SDFB_CUDA(cudaStreamSynchronize(cudaStream_t(0)));   // allocations are ordered on the default stream, the kernel runs on `st`
     uint32_t* bad = s.dLeafIndex.p + cells;
     SDFB_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st));
     leafIndexKernel<<<uint32_t((cells + 255) / 256), 256, 0, st>>>(s.dOctree.p, s.startGridSize, levels, s.dLeafIndex.p, bad);
