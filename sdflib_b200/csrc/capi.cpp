@@ -262,6 +262,8 @@ int sdfb200_query(sdfb200_sdf* s, const float* xyz, uint64_t n, float* dist, flo
             const char* sw = std::getenv("SDFB200_QUERY_INDEX");
             s->useLeafIndex = sw && sw[0] == '1';
             if (s->useLeafIndex) std::call_once(s->leafIndexOnce, [&] { buildLeafIndex(*s, st); });
+            const char* coop = std::getenv("SDFB200_QUERY_COOP");
+            s->useCoopQuery = coop && coop[0] == '1';
         }
         auto launchOn = [&](const float* dXyz, uint64_t count, float* dDist, float* dGrad, cudaStream_t on) {
             if (s->format == SDFB200_FORMAT_OCTREE) {

@@ -16,8 +16,9 @@
 // chain of dependent 4-byte gathers (L2-resident after the first touch: the whole structure of the
 // headline config is 82 MB < 126 MB L2); the leaf block is 64 consecutive floats.
 // What bounds it (profiles/r1_summary.md): not HBM but the L1/LSU data pipe — every query must bring its
-// own 64 coefficients (256 B) into registers, i.e. 64 x 128 B write-back wavefronts per warp; ncu shows
-// l1tex__data_pipe_lsu_wavefronts at 77 % of peak with DRAM at 15 %. A warp-cooperative variant (distinct
+// own 64 coefficients (256 B) into registers: each of the 16 vector loads costs one wavefront per distinct leaf
+// among the warp's lanes (6.2 on the 256^3 workload, tests/model_query_wavefronts.py: ~99 of ~115 wavefronts per
+// warp); ncu shows l1tex__data_pipe_lsu_wavefronts at 77 % of peak with DRAM at 15 %. A warp-cooperative variant (distinct
 // leaves staged once per warp in shared memory, evaluated from there) was measured and is slower
 // (0.36 ms vs 0.26 ms on the 256^3 grid): it removes the tag-stage replays but keeps the same
 // register-fill traffic and adds match/shuffle/shared-store work. It was dropped.
@@ -261,6 +262,118 @@ octreeQueryIndexedKernel(const uint32_t* __restrict__ oct, const uint32_t* __res
     if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
 }
 
+#ifndef SDFB_QUERY_EXACT
+// ---- EXPERIMENTAL (off unless SDFB200_QUERY_COOP=1; not yet measured on a GPU) --------------------
+// Quad-cooperative evaluation. In octreeQueryKernel 88 % of the L1 wavefronts are the coefficient fill: a warp issues
+// 16 x 128-bit loads and each costs one wavefront per DISTINCT leaf among its lanes (6.2 on average for the 256^3
+// workload: 99 of ~115 wavefronts per warp), every wavefront delivering only 16 useful bytes per lane. Here the four
+// lanes of an aligned quad share the work of one (leaf, y, z) class at a time: lane r loads the 4 vectors
+// c[0..3][j = r][k = 0..3] (the quad reads 64 contiguous bytes per step), forms its part of
+//     A_i(y, z) = sum_jk c_ijk y^j z^k,   i = 0..3,
+// the parts are summed with two butterfly shuffles (every lane gets the same bits: float addition commutes), and each
+// member evaluates the cubic in its own x. Grid-ordered queries put 4-8 neighbours of a row into the same class, so
+// most quads finish in one round (1.31 rounds per warp on the 256^3 workload: ~25 load wavefronts + ~16 shuffles
+// instead of 99); unrelated points cost one round per lane and still use the full width of every wavefront.
+// Same leaf and same final fractions as octreeQueryKernel; only the summation order of the polynomial differs, and it
+// does not depend on where in the batch a query sits.
+template <bool kGrad>
+__global__ void __launch_bounds__(256)
+octreeQueryCoopKernel(const uint32_t* __restrict__ oct, const QueryParams q, const float* __restrict__ xyz, uint64_t n,
+                      float* __restrict__ dist, float* __restrict__ grad) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool valid = i < n;   // no early exit: the shuffles below need the whole warp
+    const f3 p = valid ? mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2)) : mk3(0.0f, 0.0f, 0.0f);
+    float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const int ix = int(flx), iy = int(fly), iz = int(flz);
+    fx -= flx; fy -= fly; fz -= flz;
+    f3 g = mk3(0.0f, 0.0f, 0.0f);
+    float d = 0.0f;
+    uint32_t block = 0;
+    const bool inside = valid && !(ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid);
+    if (valid && !inside) d = (kGrad ? boxDistanceGrad(q, p, g) : boxDistance(q, p)) + q.minBorder;
+    if (inside) {
+        constexpr int kPathBits = 16;
+        const uint32_t bx = uint32_t(fx * float(1 << kPathBits)), by = uint32_t(fy * float(1 << kPathBits)),
+                       bz = uint32_t(fz * float(1 << kPathBits));
+        uint32_t node = __ldg(oct + (iz * q.grid + iy) * q.grid + ix);
+        int k = 0;
+        while (!(node & kLeafBit)) {
+            const int sh = kPathBits - 1 - k;
+            const uint32_t child = ((bx >> sh) & 1u) | (((by >> sh) & 1u) << 1) | (((bz >> sh) & 1u) << 2);
+            node = __ldg(oct + (node & kOctIndexMask) + child);
+            k++;
+        }
+        const float scale = float(1u << k);
+        fx *= scale; fy *= scale; fz *= scale;
+        fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
+        block = node & kOctIndexMask;
+    }
+    bool pending = inside;
+    const unsigned quadBase = lane & ~3u, r = lane & 3u;
+    const unsigned quadMask = 0xFu << quadBase;
+    for (;;) {
+        const unsigned pend = __ballot_sync(kFull, pending);
+        if (pend == 0) break;                                   // warp-uniform
+        const unsigned mine = pend & quadMask;
+        const int leader = mine ? __ffs(int(mine)) - 1 : int(quadBase);   // a finished quad idles through the shuffles
+        const uint32_t lb = __shfl_sync(kFull, block, leader);
+        const float ly = __shfl_sync(kFull, fy, leader), lz = __shfl_sync(kFull, fz, leader);
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;       // this lane's part of A_i
+        float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f, y3 = 0.0f;       // ... of dA_i/dy
+        float z0 = 0.0f, z1 = 0.0f, z2 = 0.0f, z3 = 0.0f;       // ... of dA_i/dz
+        if (mine) {
+            const float4* c = reinterpret_cast<const float4*>(oct + lb) + r;   // vector m = r + 4 k holds c[0..3][j = r][k]
+            const float4 c0 = __ldg(c), c1 = __ldg(c + 4), c2 = __ldg(c + 8), c3 = __ldg(c + 12);
+            const float yy = ly * ly;
+            const float yr = r == 0 ? 1.0f : (r == 1 ? ly : (r == 2 ? yy : yy * ly));           // y^r
+            // Horner in z over k = 3..0, for each i
+            a0 = yr * fmaf(fmaf(fmaf(c3.x, lz, c2.x), lz, c1.x), lz, c0.x);
+            a1 = yr * fmaf(fmaf(fmaf(c3.y, lz, c2.y), lz, c1.y), lz, c0.y);
+            a2 = yr * fmaf(fmaf(fmaf(c3.z, lz, c2.z), lz, c1.z), lz, c0.z);
+            a3 = yr * fmaf(fmaf(fmaf(c3.w, lz, c2.w), lz, c1.w), lz, c0.w);
+            if (kGrad) {
+                const float dyr = r == 0 ? 0.0f : (r == 1 ? 1.0f : (r == 2 ? 2.0f * ly : 3.0f * yy));   // d y^r / dy
+                const float h0 = fmaf(fmaf(fmaf(c3.x, lz, c2.x), lz, c1.x), lz, c0.x), h1 = fmaf(fmaf(fmaf(c3.y, lz, c2.y), lz, c1.y), lz, c0.y);
+                const float h2 = fmaf(fmaf(fmaf(c3.z, lz, c2.z), lz, c1.z), lz, c0.z), h3 = fmaf(fmaf(fmaf(c3.w, lz, c2.w), lz, c1.w), lz, c0.w);
+                y0 = dyr * h0; y1 = dyr * h1; y2 = dyr * h2; y3 = dyr * h3;
+                z0 = yr * fmaf(fmaf(3.0f * c3.x, lz, 2.0f * c2.x), lz, c1.x);
+                z1 = yr * fmaf(fmaf(3.0f * c3.y, lz, 2.0f * c2.y), lz, c1.y);
+                z2 = yr * fmaf(fmaf(3.0f * c3.z, lz, 2.0f * c2.z), lz, c1.z);
+                z3 = yr * fmaf(fmaf(3.0f * c3.w, lz, 2.0f * c2.w), lz, c1.w);
+            }
+        }
+#pragma unroll
+        for (int m = 1; m <= 2; m <<= 1) {                     // butterfly over the quad: all four lanes end with the same sums
+            a0 += __shfl_xor_sync(kFull, a0, m); a1 += __shfl_xor_sync(kFull, a1, m);
+            a2 += __shfl_xor_sync(kFull, a2, m); a3 += __shfl_xor_sync(kFull, a3, m);
+            if (kGrad) {
+                y0 += __shfl_xor_sync(kFull, y0, m); y1 += __shfl_xor_sync(kFull, y1, m);
+                y2 += __shfl_xor_sync(kFull, y2, m); y3 += __shfl_xor_sync(kFull, y3, m);
+                z0 += __shfl_xor_sync(kFull, z0, m); z1 += __shfl_xor_sync(kFull, z1, m);
+                z2 += __shfl_xor_sync(kFull, z2, m); z3 += __shfl_xor_sync(kFull, z3, m);
+            }
+        }
+        if (pending && block == lb && __float_as_uint(fy) == __float_as_uint(ly) && __float_as_uint(fz) == __float_as_uint(lz)) {
+            d = fmaf(fmaf(fmaf(a3, fx, a2), fx, a1), fx, a0);
+            if (kGrad) {
+                const float gx = fmaf(fmaf(3.0f * a3, fx, 2.0f * a2), fx, a1);
+                const float gy = fmaf(fmaf(fmaf(y3, fx, y2), fx, y1), fx, y0);
+                const float gz = fmaf(fmaf(fmaf(z3, fx, z2), fx, z1), fx, z0);
+                g = normalize3(mk3(gx, gy, gz));
+            }
+            pending = false;   // the leader always matches itself bit for bit, so every round retires at least one lane per quad
+        }
+    }
+    if (valid) {
+        dist[i] = d;
+        if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
+    }
+}
+#endif
+
 }  // namespace
 
 #ifndef SDFB_QUERY_EXACT
@@ -306,6 +419,14 @@ void launchOctreeQueryFast(
     // leaf blocks are 16-byte aligned iff the start grid has a multiple of 4 slots (all blocks are 8 or 64 words)
     const bool vec = (uint64_t(s.startGridSize) * s.startGridSize * s.startGridSize) % 4 == 0 && s.leafBlocksAligned;
     if (s.maxDepth > 16) throw Error(SDFB200_ERR_INVALID, "octree deeper than 16 levels");
+#ifndef SDFB_QUERY_EXACT
+    if (s.useCoopQuery && vec) {   // EXPERIMENTAL, set by sdfb200_query under SDFB200_QUERY_COOP=1
+        if (dGrad) octreeQueryCoopKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, dGrad);
+        else octreeQueryCoopKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, nullptr);
+        SDFB_CUDA(cudaGetLastError());
+        return;
+    }
+#endif
     if (s.useLeafIndex && s.leafIndexLevels >= 0) {   // EXPERIMENTAL, set by sdfb200_query under SDFB200_QUERY_INDEX=1
         const uint32_t* ix = s.dLeafIndex.p;
         const int lv = s.leafIndexLevels;

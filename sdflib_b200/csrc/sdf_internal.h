@@ -193,6 +193,7 @@ struct sdfb200_sdf {
     int leafIndexLevels = -1;        // levels below the start grid the index resolves; -1 = no index
     std::atomic<bool> useLeafIndex{false};   // what the next launch does (sdfb200_query re-reads the switch on every call)
     std::once_flag leafIndexOnce;
+    std::atomic<bool> useCoopQuery{false};   // EXPERIMENTAL quad-cooperative FMA kernel (SDFB200_QUERY_COOP=1), same protocol
     // staging for host-pointer queries
     sdfb200::DevBuf<float> dPts, dDist, dGrad;
     cudaStream_t qStream[2] = {nullptr, nullptr};

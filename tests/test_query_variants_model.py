@@ -1,4 +1,5 @@
-"""Host model of the EXPERIMENTAL dense leaf index of octree_query.cu (leafIndexKernel / octreeQueryIndexedKernel).
+"""Host models of the EXPERIMENTAL query variants of octree_query.cu: the dense leaf index (leafIndexKernel /
+octreeQueryIndexedKernel) and the quad-cooperative evaluation (octreeQueryCoopKernel, last test).
 
 The CUDA code cannot run here; what can be checked on the CPU is the arithmetic it transcribes: the entry packing
 ((block - G^3) / 8, steps, leaf flag), the cell chosen from the start cell and the leading path bits, and the finish of
@@ -84,3 +85,40 @@ def test_indexed_descent_reaches_the_same_leaf(port, depth, start, levels):
         assert got == want
         depths.add(want[1])
     assert len(depths) >= 2                        # leaves above, at and below the index depth were all visited
+
+
+def test_quad_cooperative_evaluation_is_the_same_polynomial(port):
+    """octreeQueryCoopKernel: lane r of a quad takes the vectors m = r + 4 k (coefficients c[0..3][j = r][k]), forms
+    y^r * Horner_z, the quad adds its four parts with a butterfly, members finish with the cubic in x (and the three
+    derivative forms). Same float32 operations here (without fusing); must agree with the reference's evaluation order
+    (oracle) within the FMA kernel's tolerance, and all four lanes must hold identical sums."""
+    f32 = np.float32
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        c = (rng.standard_normal(64) * rng.choice([1e-3, 1.0, 30.0])).astype(f32)
+        x, y, z = (f32(t) for t in rng.random(3))
+        if trial < 8:
+            x, y, z = f32(trial & 1), f32((trial >> 1) & 1), f32((trial >> 2) & 1)      # corners, incl. frac = 0
+        vec = c.reshape(16, 4)                                                        # vector m = j + 4 k, components i
+        parts = np.zeros((4, 12), f32)
+        for r in range(4):
+            c0, c1, c2, c3 = vec[r], vec[r + 4], vec[r + 8], vec[r + 12]
+            yr = [f32(1), y, f32(y * y), f32(f32(y * y) * y)][r]
+            dyr = [f32(0), f32(1), f32(f32(2) * y), f32(f32(3) * f32(y * y))][r]
+            h = ((c3 * z + c2) * z + c1) * z + c0
+            dh = (f32(3) * c3 * z + f32(2) * c2) * z + c1
+            parts[r, 0:4], parts[r, 4:8], parts[r, 8:12] = yr * h, dyr * h, yr * dh
+        lanes = parts.copy()
+        for m in (1, 2):                                                              # butterfly: lane l += lane l ^ m
+            lanes = (lanes + lanes[[l ^ m for l in range(4)]]).astype(f32)
+        assert (lanes.view(np.uint32) == lanes[0].view(np.uint32)).all()              # identical bits on all four lanes
+        a, ay, az = lanes[0, 0:4], lanes[0, 4:8], lanes[0, 8:12]
+        value = ((a[3] * x + a[2]) * x + a[1]) * x + a[0]
+        gx = (f32(3) * a[3] * x + f32(2) * a[2]) * x + a[1]
+        gy = ((ay[3] * x + ay[2]) * x + ay[1]) * x + ay[0]
+        gz = ((az[3] * x + az[2]) * x + az[1]) * x + az[0]
+        g = np.array([gx, gy, gz], np.float64)
+        want_v, want_g, _ = port.tricubic_eval(c, np.array([[x, y, z]], f32))
+        scale = float(np.abs(c).sum())
+        assert abs(float(value) - float(want_v[0])) <= 2e-6 * scale
+        np.testing.assert_allclose(g, want_g[0].astype(np.float64), atol=6e-6 * scale)   # raw (un-normalised) gradient
