@@ -116,6 +116,15 @@ class Backend:
                                     C.c_uint64(len(pts)), _p(out))
         return out
 
+    def nearest_triangle_visits(self, verts, idx, pts):
+        """Port only: nearest triangle plus (inner nodes, leaves) visited per query — traversal models in tests/."""
+        verts, idx, pts = _f(verts), _u(idx), _f(pts)
+        out = np.empty(len(pts), np.uint32)
+        visits = np.empty((len(pts), 2), np.uint32)
+        self.fn("nearest_triangle_visits")(_p(verts), C.c_uint32(len(verts)), _p(idx), C.c_uint32(idx.size), _p(pts),
+                                           C.c_uint64(len(pts)), _p(out), _p(visits))
+        return out, visits
+
     # ---- structures -----------------------------------------------------------------------
     def build_octree(self, verts, idx, box6, depth, start_depth, threshold=1e-3, algorithm=1, num_threads=1,
                      termination_rule=1, param1=0.0, use_cache=True):

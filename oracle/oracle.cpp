@@ -512,7 +512,9 @@ struct Bvh {
     }
 
     // :492-540 — near child first, strict '<', the running best is sqrt'ed and re-squared.
+    mutable uint32_t* visitCount = nullptr;   // optional counters {inner nodes, leaves} of the current query (traversal models in tests/)
     void query(const BvhNode& nd, D3 p, double& best, int& bestTri) const {
+        if (visitCount) visitCount[nd.l == -1 ? 1 : 0]++;
         if (nd.l == -1) {
             const auto& tr = tris[size_t(nd.r)];
             const double d2 = eberlySqDist(p, verts[size_t(tr[0])], verts[size_t(tr[1])], verts[size_t(tr[2])]);
@@ -1773,6 +1775,20 @@ void orc_nearest_triangle(const float* verts, uint32_t nVerts, const uint32_t* i
     MeshView m{reinterpret_cast<const V3*>(verts), nVerts, idx, nIdx};
     Bvh bvh(m);
     for (uint64_t i = 0; i < n; i++) outTri[i] = bvh.nearest(v3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+}
+
+// Same queries, plus how many inner nodes and leaves each traversal visited (2 counters per point): input of the
+// warp-occupancy model of the device sampler, tests/model_bvh_traversal.py.
+void orc_nearest_triangle_visits(const float* verts, uint32_t nVerts, const uint32_t* idx, uint32_t nIdx, const float* pts,
+                                 uint64_t n, uint32_t* outTri, uint32_t* outVisits2) {
+    MeshView m{reinterpret_cast<const V3*>(verts), nVerts, idx, nIdx};
+    Bvh bvh(m);
+    for (uint64_t i = 0; i < n; i++) {
+        outVisits2[2 * i] = outVisits2[2 * i + 1] = 0;
+        bvh.visitCount = outVisits2 + 2 * i;
+        outTri[i] = bvh.nearest(v3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+    }
+    bvh.visitCount = nullptr;
 }
 
 OrcSdf* orc_build_octree(const float* verts, uint32_t nVerts, const uint32_t* idx, uint32_t nIdx, const float* box6,

@@ -35,6 +35,9 @@ uint32_t orc_filter_triangles(const float* verts, uint32_t nVerts, const uint32_
 void orc_nearest_triangle(const float* verts, uint32_t nVerts, const uint32_t* idx, uint32_t nIdx, const float* pts,
                           uint64_t n, uint32_t* outTri);
 
+void orc_nearest_triangle_visits(const float* verts, uint32_t nVerts, const uint32_t* idx, uint32_t nIdx, const float* pts,
+                                 uint64_t n, uint32_t* outTri, uint32_t* outVisits2);
+
 /* whole structures. useCache=1 emulates the reference's 32^3 direct-mapped vertex cache
  * (TrianglesInfluence.h:934-991) — required for bit-identity with the reference's single-thread
  * build; useCache=0 is the history-free variant the level-synchronous GPU build is compared with.

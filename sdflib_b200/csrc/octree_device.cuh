@@ -292,6 +292,75 @@ sampleOwnersKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const
     results[u] = samplePoint(mesh, latticeSamplePosition(centerHalf, owners[first + u]));
 }
 
+// ---- EXPERIMENTAL (off unless SDFB200_SAMPLE_REFILL=1; not yet measured on a GPU) ----------------
+// Lane-refill schedule for the same traversals. With one sample per thread a lane whose traversal ends waits for the
+// longest one of its warp: on the C2 levels the lanes are busy 62-68 % of the warp's trips (tests/model_bvh_traversal.py;
+// ~650 node visits per sample, spread widely). Here a lane that runs out of work takes the next unassigned sample of
+// the launch (one atomicAdd per refill event, ballot + prefix inside the warp) and the warp leaves when the counter is
+// exhausted and every lane has finished. The per-sample arithmetic is untouched — each traversal is still one lane's
+// private loop — so the results are bit-identical; the nearest triangle is parked in results[u].x and turned into
+// (distance, gradient) by a dense second kernel instead of inside the divergent loop.
+__global__ void __launch_bounds__(kBvhThreads)
+sampleOwnersRefillKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const uint32_t* __restrict__ owners, uint32_t first,
+                         uint32_t count, float4* results, uint32_t* counter) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const BvhStack st = bvhStackOfThread(mesh);
+    const unsigned lane = threadIdx.x & 31u;
+    BvhCursor c;
+    c.active = false;
+    c.bestTri = -1; c.best = DBL_MAX; c.sp = 0; c.cur = mesh.rootLink; c.p = mkd(0.0, 0.0, 0.0);
+    uint32_t item = 0xFFFFFFFFu;   // sample this lane is traversing for
+    bool drained = false;          // warp-uniform: the counter has passed `count`
+    for (;;) {
+        const unsigned idle = __ballot_sync(kFull, !c.active);
+        if (idle) {
+            if (!c.active && item != 0xFFFFFFFFu) {
+                results[item] = make_float4(__int_as_float(c.bestTri), 0.f, 0.f, 0.f);
+                item = 0xFFFFFFFFu;
+            }
+            if (!drained) {
+                const int leader = __ffs(int(idle)) - 1;
+                uint32_t base = 0;
+                if (int(lane) == leader) base = atomicAdd(counter, uint32_t(__popc(idle)));
+                base = __shfl_sync(kFull, base, leader);
+                if (!c.active) {
+                    const uint32_t mine = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
+                    if (mine < count) {
+                        item = mine;
+                        const f3 pf = latticeSamplePosition(centerHalf, owners[first + mine]);
+                        c.p = mkd(double(pf.x), double(pf.y), double(pf.z));
+                        c.best = DBL_MAX; c.bestTri = -1; c.sp = 0; c.cur = mesh.rootLink;
+                        c.active = true;
+                    }
+                }
+                drained = base + uint32_t(__popc(idle)) >= count;
+            }
+            if (drained && __ballot_sync(kFull, c.active) == 0) break;
+        }
+        if (c.active) {
+            if (c.cur >= 0) bvhInnerStep(mesh, c, st);
+            else bvhLeafStep(mesh, c, st);
+        }
+    }
+}
+
+__global__ void finishOwnersKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const uint32_t* __restrict__ owners, uint32_t first,
+                                   uint32_t count, float4* results) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= count) return;
+    const uint32_t t = uint32_t(__float_as_int(results[u].x));
+    const f3 p = latticeSamplePosition(centerHalf, owners[first + u]);
+    f3 g;
+    const float4 a = mesh.triVerts[3 * size_t(t)], b = mesh.triVerts[3 * size_t(t) + 1], c = mesh.triVerts[3 * size_t(t) + 2];
+    const float d = signedDistGradMesh(p, mesh.tris[t], mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), g);
+    results[u] = make_float4(d, g.x, g.y, g.z);
+}
+
+inline bool sampleRefillEnabled() {
+    static const bool on = [] { const char* e = std::getenv("SDFB200_SAMPLE_REFILL"); return e && e[0] == '1'; }();
+    return on;
+}
+
 __global__ void dedupeScatterKernel(const uint32_t* __restrict__ rep, const uint32_t* __restrict__ pos, const float4* __restrict__ results,
                                     uint32_t nSamples, float4* out, int stride) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -305,6 +374,7 @@ __global__ void dedupeScatterKernel(const uint32_t* __restrict__ rep, const uint
 struct LevelSampler {
     DevBuf<uint32_t> table, rep, isOwner, pos, owners;
     DevBuf<float4> results, slice;
+    DevBuf<uint32_t> refillCounter;   // EXPERIMENTAL lane-refill schedule: next unassigned sample of the launch
     Scanner scanner;
     SampleExchange exchange;   // world > 1: every rank traverses the BVH for its slice of the distinct positions only
     cudaStream_t stream = nullptr;   // where this sampler's launches go (legacy default stream unless a pass runs on a side stream)
@@ -347,6 +417,14 @@ struct LevelSampler {
         dedupeOwnersKernel<<<divUp(n, 256), 256, 0, stream>>>(isOwner.p, pos.p, n, owners.p);
         const uint32_t* ownersPtr = owners.p;
         const float4* res = shared(nUnique, [&](uint32_t first, uint32_t cnt, float4* dst) {
+            if (sampleRefillEnabled()) {   // EXPERIMENTAL, see sampleOwnersRefillKernel
+                refillCounter.ensure(1);
+                SDFB_CUDA(cudaMemsetAsync(refillCounter.p, 0, sizeof(uint32_t), stream));
+                const uint32_t blocks = std::min<uint32_t>(divUp(cnt, kBvhThreads), 148u * 8u);
+                sampleOwnersRefillKernel<<<blocks, kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst, refillCounter.p);
+                finishOwnersKernel<<<divUp(cnt, 256), 256, 0, stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst);
+                return;
+            }
             sampleOwnersKernel<<<divUp(cnt, kBvhThreads), kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst);
         });
         dedupeScatterKernel<<<divUp(n, 256), 256, 0, stream>>>(rep.p, pos.p, res, n, out, stride);
