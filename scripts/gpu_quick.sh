@@ -1,8 +1,10 @@
 #!/bin/bash
 # Quick GPU pass: parity tests + bench (ours only).
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/gpu_tests.log
-cat gpurun_out/gpu_tests.log
+if [ -z "$SKIP_TESTS" ]; then
+  timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/gpu_tests.log
+  cat gpurun_out/gpu_tests.log
+fi
 SDFB200_TIMING=1 timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err
 python - <<'PY'
 import json
