@@ -1,0 +1,353 @@
+// The kernels of the bulk OctreeSdf query (octree_query.cu is the translation unit: see its header for the design).
+// Kept in a header so that tests/cpp/simt_query_main.cpp can run the very same source on the CPU under a lock-step
+// warp emulation (32 host threads per warp, collectives = barrier exchanges): the experimental kernels below were
+// written when no GPU was at hand, and that emulation checks their control flow — rounds, leaders, class membership,
+// index packing — against the plain kernel before a GPU minute is spent on them.
+// Include inside namespace sdfb200, inside an anonymous namespace.
+#pragma once
+
+
+struct QueryParams {
+    float minx, miny, minz;
+    float maxx, maxy, maxz;
+    float cell;
+    int grid;
+    float minBorder;
+};
+
+__device__ __forceinline__ float boxDistance(const QueryParams& q, f3 p) {   // Mesh.h:42-46
+    const f3 size = mk3(q.maxx - q.minx, q.maxy - q.miny, q.maxz - q.minz);
+    const f3 center = mk3(q.minx, q.miny, q.minz) + 0.5f * size;
+    const f3 d = p - center;
+    const f3 h = 0.5f * size;
+    const f3 a = mk3(gabs(d.x) - h.x, gabs(d.y) - h.y, gabs(d.z) - h.z);
+    const f3 ap = mk3(gmax(a.x, 0.0f), gmax(a.y, 0.0f), gmax(a.z, 0.0f));
+    return sqrtf(dot3(ap, ap)) + gmin(gmax(a.x, gmax(a.y, a.z)), 0.0f);
+}
+
+// Mesh.h:48-63. Kept bug-compatible: it measures |p| - size (not centred on the box) and leaves the
+// components it does not write untouched (the caller's gradient is zero-initialised here).
+__device__ __forceinline__ float boxDistanceGrad(const QueryParams& q, f3 p, f3& g) {
+    const float s[3] = {q.maxx - q.minx, q.maxy - q.miny, q.maxz - q.minz};
+    const float pp[3] = {p.x, p.y, p.z};
+    float a[3], gg[3] = {g.x, g.y, g.z};
+    for (int i = 0; i < 3; i++) a[i] = gabs(pp[i]) - s[i];
+    const int k = a[0] > a[1] ? 0 : 1;
+    const int l = a[2] > a[k] ? 2 : k;
+    if (a[l] < 0) gg[l] = pp[l] / gabs(pp[l]);
+    else {
+        float b[3];
+        for (int i = 0; i < 3; i++) b[i] = gmax(a[i], 0.0f);
+        const float tx = b[0] * b[0], ty = b[1] * b[1], tz = b[2] * b[2];
+        const float c = sqrtf(tx + ty + tz);
+        for (int i = 0; i < 3; i++) gg[i] = a[i] > 0 ? b[i] / c * pp[i] / gabs(pp[i]) : 0.0f;
+    }
+    g = mk3(gg[0], gg[1], gg[2]);
+    return boxDistance(q, p);
+}
+
+#ifdef SDFB_QUERY_EXACT
+__device__ __forceinline__ float monomialExact(float c, int i, int j, int k, float x, float y, float z) {
+    float t = c;
+    for (int a = 0; a < i; a++) t *= x;
+    for (int a = 0; a < j; a++) t *= y;
+    for (int a = 0; a < k; a++) t *= z;
+    return t;
+}
+__device__ __forceinline__ float polyValue(const float* c, float x, float y, float z) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int n = 0; n < 64; n++) acc += monomialExact(c[n], n & 3, (n >> 2) & 3, n >> 4, x, y, z);
+    return acc;
+}
+// interpolateGradient (InterpolationMethods.h:442-455): per component, terms in ascending n, the
+// integer factor multiplies the coefficient first, no leading zero.
+template <int AX> __device__ __forceinline__ float polyDerivative(const float* c, float x, float y, float z) {
+    float acc = 0.0f;
+    bool first = true;
+#pragma unroll
+    for (int n = 0; n < 64; n++) {
+        const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
+        const int p = AX == 0 ? i : (AX == 1 ? j : k);
+        if (p == 0) continue;
+        const float t = monomialExact(float(p) * c[n], i - (AX == 0), j - (AX == 1), k - (AX == 2), x, y, z);
+        acc = first ? t : acc + t;
+        first = false;
+    }
+    return acc;
+}
+template <bool kGrad, bool kVec> __device__ __forceinline__ float evalLeaf(const float* c, float x, float y, float z, f3& g) {
+    if (kGrad) g = normalize3(mk3(polyDerivative<0>(c, x, y, z), polyDerivative<1>(c, x, y, z), polyDerivative<2>(c, x, y, z)));
+    return polyValue(c, x, y, z);
+}
+#else
+// Horner in x, then y, then z with derivative recurrences; all FMA. kVec: the 64 coefficients are
+// fetched as 16 x 128-bit read-only loads (legal whenever leaf blocks are 16-byte aligned, which holds
+// for every start grid with G^3 % 4 == 0 because all blocks are 8 or 64 words long).
+template <bool kGrad, bool kVec> __device__ __forceinline__ float evalLeaf(const float* c, float x, float y, float z, f3& g) {
+    float v = 0.0f, vx = 0.0f, vy = 0.0f, vz = 0.0f;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {
+        float a = 0.0f, ax = 0.0f, ay = 0.0f;
+#pragma unroll
+        for (int j = 3; j >= 0; j--) {
+            float c0, c1, c2, c3;
+            if (kVec) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(c) + 4 * k + j);
+                c0 = q.x; c1 = q.y; c2 = q.z; c3 = q.w;
+            } else {
+                c0 = __ldg(c + 16 * k + 4 * j); c1 = __ldg(c + 16 * k + 4 * j + 1);
+                c2 = __ldg(c + 16 * k + 4 * j + 2); c3 = __ldg(c + 16 * k + 4 * j + 3);
+            }
+            const float r = fmaf(fmaf(fmaf(c3, x, c2), x, c1), x, c0);
+            if (kGrad) {
+                const float rx = fmaf(fmaf(3.0f * c3, x, 2.0f * c2), x, c1);
+                ay = fmaf(ay, y, a);
+                ax = fmaf(ax, y, rx);
+            }
+            a = fmaf(a, y, r);
+        }
+        if (kGrad) {
+            vz = fmaf(vz, z, v);
+            vx = fmaf(vx, z, ax);
+            vy = fmaf(vy, z, ay);
+        }
+        v = fmaf(v, z, a);
+    }
+    if (kGrad) g = normalize3(mk3(vx, vy, vz));
+    return v;
+}
+#endif
+
+template <bool kGrad, bool kVec>
+__global__ void __launch_bounds__(256)
+octreeQueryKernel(const uint32_t* __restrict__ oct, const QueryParams q, const float* __restrict__ xyz, uint64_t n,
+                  float* __restrict__ dist, float* __restrict__ grad) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f3 p = mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+    float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const int ix = int(flx), iy = int(fly), iz = int(flz);
+    fx -= flx; fy -= fly; fz -= flz;
+    f3 g = mk3(0.0f, 0.0f, 0.0f);
+    float d;
+    if (ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid) {
+        d = (kGrad ? boxDistanceGrad(q, p, g) : boxDistance(q, p)) + q.minBorder;
+    } else {
+        // The reference descends with child = (frac >= 0.5) per axis and frac <- fract(2 frac). Both
+        // steps are exact in binary floating point (doubling, floor and the subtraction introduce no
+        // rounding), so the same path and the same final frac are obtained from the leading bits of the
+        // start-cell fraction: level j uses bit j of floor(frac * 2^kPathBits), and a leaf reached after k
+        // steps evaluates at frac * 2^k - floor(frac * 2^k).
+        constexpr int kPathBits = 16;
+        const uint32_t bx = uint32_t(fx * float(1 << kPathBits)), by = uint32_t(fy * float(1 << kPathBits)),
+                       bz = uint32_t(fz * float(1 << kPathBits));
+        uint32_t node = __ldg(oct + (iz * q.grid + iy) * q.grid + ix);
+        int k = 0;
+        while (!(node & kLeafBit)) {
+            const int sh = kPathBits - 1 - k;
+            const uint32_t child = ((bx >> sh) & 1u) | (((by >> sh) & 1u) << 1) | (((bz >> sh) & 1u) << 2);
+            node = __ldg(oct + (node & kOctIndexMask) + child);
+            k++;
+        }
+        const float scale = float(1u << k);
+        fx *= scale; fy *= scale; fz *= scale;
+        fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
+        const float* c = reinterpret_cast<const float*>(oct + (node & kOctIndexMask));
+        d = evalLeaf<kGrad, kVec>(c, fx, fy, fz, g);
+    }
+    dist[i] = d;
+    if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
+}
+
+// ---- EXPERIMENTAL (off unless SDFB200_QUERY_INDEX=1; not yet measured on a GPU) -------------------
+// Dense leaf index: one word per cell of the grid at depth startDepth + L holding the leaf that contains the cell,
+//   bit 31 set : leaf;  bits 27-30 = steps below the start grid at which it was reached, bits 0-26 = (block - G^3) / 8
+//   bit 31 clear: the cell is still an inner node at that depth; bits 0-26 = (children block - G^3) / 8
+// (every block of the array is 8 or 64 words long and starts after the G^3 start words, so block - G^3 is a multiple
+// of 8). A query then replaces its chain of dependent node gathers — about 32 of the 112 L1 wavefronts a warp of the
+// 256^3 workload issues — by ONE load, which is coalesced for grid-ordered queries (32 consecutive cells = 128 bytes).
+constexpr uint32_t kIndexLeaf = 1u << 31;
+constexpr uint32_t kIndexBlockMask = (1u << 27) - 1u;
+
+__global__ void __launch_bounds__(256)
+leafIndexKernel(const uint32_t* __restrict__ oct, int grid, int levels, uint32_t* __restrict__ index, uint32_t* __restrict__ bad) {
+    const uint32_t N = uint32_t(grid) << levels;
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= uint64_t(N) * N * N) return;
+    const uint32_t cx = uint32_t(i % N), cy = uint32_t((i / N) % N), cz = uint32_t(i / (uint64_t(N) * N));
+    const uint32_t G3 = uint32_t(grid) * uint32_t(grid) * uint32_t(grid);
+    uint32_t node = __ldg(oct + ((cz >> levels) * uint32_t(grid) + (cy >> levels)) * uint32_t(grid) + (cx >> levels));
+    int k = 0;
+    while (!(node & kLeafBit) && k < levels) {
+        const int sh = levels - 1 - k;
+        const uint32_t child = ((cx >> sh) & 1u) | (((cy >> sh) & 1u) << 1) | (((cz >> sh) & 1u) << 2);
+        node = __ldg(oct + (node & kOctIndexMask) + child);
+        k++;
+    }
+    const uint32_t block = node & kOctIndexMask;
+    if (block < G3 || ((block - G3) & 7u)) { atomicOr(bad, 1u); return; }
+    index[i] = ((block - G3) >> 3) | ((node & kLeafBit) ? (kIndexLeaf | (uint32_t(k) << 27)) : 0u);
+}
+
+template <bool kGrad, bool kVec>
+__global__ void __launch_bounds__(256)
+octreeQueryIndexedKernel(const uint32_t* __restrict__ oct, const uint32_t* __restrict__ index, int levels, const QueryParams q,
+                         const float* __restrict__ xyz, uint64_t n, float* __restrict__ dist, float* __restrict__ grad) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f3 p = mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+    float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const int ix = int(flx), iy = int(fly), iz = int(flz);
+    fx -= flx; fy -= fly; fz -= flz;
+    f3 g = mk3(0.0f, 0.0f, 0.0f);
+    float d;
+    if (ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid) {
+        d = (kGrad ? boxDistanceGrad(q, p, g) : boxDistance(q, p)) + q.minBorder;
+    } else {
+        // same path bits as octreeQueryKernel; the first `levels` of them select the index cell
+        constexpr int kPathBits = 16;
+        const uint32_t bx = uint32_t(fx * float(1 << kPathBits)), by = uint32_t(fy * float(1 << kPathBits)),
+                       bz = uint32_t(fz * float(1 << kPathBits));
+        const uint32_t N = uint32_t(q.grid) << levels;
+        const uint32_t cx = (uint32_t(ix) << levels) | (bx >> (kPathBits - levels)), cy = (uint32_t(iy) << levels) | (by >> (kPathBits - levels)),
+                       cz = (uint32_t(iz) << levels) | (bz >> (kPathBits - levels));
+        const uint32_t e = __ldg(index + (uint64_t(cz) * N + cy) * N + cx);
+        const uint32_t G3 = uint32_t(q.grid) * uint32_t(q.grid) * uint32_t(q.grid);
+        uint32_t block = ((e & kIndexBlockMask) << 3) + G3;
+        int k;
+        if (e & kIndexLeaf) k = int((e >> 27) & 15u);
+        else {
+            k = levels;
+            for (;;) {   // trees deeper than the index: finish the descent from the cell's node
+                const int sh = kPathBits - 1 - k;
+                const uint32_t child = ((bx >> sh) & 1u) | (((by >> sh) & 1u) << 1) | (((bz >> sh) & 1u) << 2);
+                const uint32_t node = __ldg(oct + block + child);
+                k++;
+                block = node & kOctIndexMask;
+                if (node & kLeafBit) break;
+            }
+        }
+        const float scale = float(1u << k);
+        fx *= scale; fy *= scale; fz *= scale;
+        fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
+        d = evalLeaf<kGrad, kVec>(reinterpret_cast<const float*>(oct + block), fx, fy, fz, g);
+    }
+    dist[i] = d;
+    if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
+}
+
+#ifndef SDFB_QUERY_EXACT
+// ---- EXPERIMENTAL (off unless SDFB200_QUERY_COOP=1; not yet measured on a GPU) --------------------
+// Quad-cooperative evaluation. In octreeQueryKernel 88 % of the L1 wavefronts are the coefficient fill: a warp issues
+// 16 x 128-bit loads and each costs one wavefront per DISTINCT leaf among its lanes (6.2 on average for the 256^3
+// workload: 99 of ~115 wavefronts per warp), every wavefront delivering only 16 useful bytes per lane. Here the four
+// lanes of an aligned quad share the work of one (leaf, y, z) class at a time: lane r loads the 4 vectors
+// c[0..3][j = r][k = 0..3] (the quad reads 64 contiguous bytes per step), forms its part of
+//     A_i(y, z) = sum_jk c_ijk y^j z^k,   i = 0..3,
+// the parts are summed with two butterfly shuffles (every lane gets the same bits: float addition commutes), and each
+// member evaluates the cubic in its own x. Grid-ordered queries put 4-8 neighbours of a row into the same class, so
+// most quads finish in one round (1.31 rounds per warp on the 256^3 workload: ~25 load wavefronts + ~16 shuffles
+// instead of 99); unrelated points cost one round per lane and still use the full width of every wavefront.
+// Same leaf and same final fractions as octreeQueryKernel; only the summation order of the polynomial differs, and it
+// does not depend on where in the batch a query sits.
+template <bool kGrad>
+__global__ void __launch_bounds__(256)
+octreeQueryCoopKernel(const uint32_t* __restrict__ oct, const QueryParams q, const float* __restrict__ xyz, uint64_t n,
+                      float* __restrict__ dist, float* __restrict__ grad) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool valid = i < n;   // no early exit: the shuffles below need the whole warp
+    const f3 p = valid ? mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2)) : mk3(0.0f, 0.0f, 0.0f);
+    float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const int ix = int(flx), iy = int(fly), iz = int(flz);
+    fx -= flx; fy -= fly; fz -= flz;
+    f3 g = mk3(0.0f, 0.0f, 0.0f);
+    float d = 0.0f;
+    uint32_t block = 0;
+    const bool inside = valid && !(ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid);
+    if (valid && !inside) d = (kGrad ? boxDistanceGrad(q, p, g) : boxDistance(q, p)) + q.minBorder;
+    if (inside) {
+        constexpr int kPathBits = 16;
+        const uint32_t bx = uint32_t(fx * float(1 << kPathBits)), by = uint32_t(fy * float(1 << kPathBits)),
+                       bz = uint32_t(fz * float(1 << kPathBits));
+        uint32_t node = __ldg(oct + (iz * q.grid + iy) * q.grid + ix);
+        int k = 0;
+        while (!(node & kLeafBit)) {
+            const int sh = kPathBits - 1 - k;
+            const uint32_t child = ((bx >> sh) & 1u) | (((by >> sh) & 1u) << 1) | (((bz >> sh) & 1u) << 2);
+            node = __ldg(oct + (node & kOctIndexMask) + child);
+            k++;
+        }
+        const float scale = float(1u << k);
+        fx *= scale; fy *= scale; fz *= scale;
+        fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
+        block = node & kOctIndexMask;
+    }
+    bool pending = inside;
+    const unsigned quadBase = lane & ~3u, r = lane & 3u;
+    const unsigned quadMask = 0xFu << quadBase;
+    for (;;) {
+        const unsigned pend = __ballot_sync(kFull, pending);
+        if (pend == 0) break;                                   // warp-uniform
+        const unsigned mine = pend & quadMask;
+        const int leader = mine ? __ffs(int(mine)) - 1 : int(quadBase);   // a finished quad idles through the shuffles
+        const uint32_t lb = __shfl_sync(kFull, block, leader);
+        const float ly = __shfl_sync(kFull, fy, leader), lz = __shfl_sync(kFull, fz, leader);
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;       // this lane's part of A_i
+        float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f, y3 = 0.0f;       // ... of dA_i/dy
+        float z0 = 0.0f, z1 = 0.0f, z2 = 0.0f, z3 = 0.0f;       // ... of dA_i/dz
+        if (mine) {
+            const float4* c = reinterpret_cast<const float4*>(oct + lb) + r;   // vector m = r + 4 k holds c[0..3][j = r][k]
+            const float4 c0 = __ldg(c), c1 = __ldg(c + 4), c2 = __ldg(c + 8), c3 = __ldg(c + 12);
+            const float yy = ly * ly;
+            const float yr = r == 0 ? 1.0f : (r == 1 ? ly : (r == 2 ? yy : yy * ly));           // y^r
+            // Horner in z over k = 3..0, for each i
+            a0 = yr * fmaf(fmaf(fmaf(c3.x, lz, c2.x), lz, c1.x), lz, c0.x);
+            a1 = yr * fmaf(fmaf(fmaf(c3.y, lz, c2.y), lz, c1.y), lz, c0.y);
+            a2 = yr * fmaf(fmaf(fmaf(c3.z, lz, c2.z), lz, c1.z), lz, c0.z);
+            a3 = yr * fmaf(fmaf(fmaf(c3.w, lz, c2.w), lz, c1.w), lz, c0.w);
+            if (kGrad) {
+                const float dyr = r == 0 ? 0.0f : (r == 1 ? 1.0f : (r == 2 ? 2.0f * ly : 3.0f * yy));   // d y^r / dy
+                const float h0 = fmaf(fmaf(fmaf(c3.x, lz, c2.x), lz, c1.x), lz, c0.x), h1 = fmaf(fmaf(fmaf(c3.y, lz, c2.y), lz, c1.y), lz, c0.y);
+                const float h2 = fmaf(fmaf(fmaf(c3.z, lz, c2.z), lz, c1.z), lz, c0.z), h3 = fmaf(fmaf(fmaf(c3.w, lz, c2.w), lz, c1.w), lz, c0.w);
+                y0 = dyr * h0; y1 = dyr * h1; y2 = dyr * h2; y3 = dyr * h3;
+                z0 = yr * fmaf(fmaf(3.0f * c3.x, lz, 2.0f * c2.x), lz, c1.x);
+                z1 = yr * fmaf(fmaf(3.0f * c3.y, lz, 2.0f * c2.y), lz, c1.y);
+                z2 = yr * fmaf(fmaf(3.0f * c3.z, lz, 2.0f * c2.z), lz, c1.z);
+                z3 = yr * fmaf(fmaf(3.0f * c3.w, lz, 2.0f * c2.w), lz, c1.w);
+            }
+        }
+#pragma unroll
+        for (int m = 1; m <= 2; m <<= 1) {                     // butterfly over the quad: all four lanes end with the same sums
+            a0 += __shfl_xor_sync(kFull, a0, m); a1 += __shfl_xor_sync(kFull, a1, m);
+            a2 += __shfl_xor_sync(kFull, a2, m); a3 += __shfl_xor_sync(kFull, a3, m);
+            if (kGrad) {
+                y0 += __shfl_xor_sync(kFull, y0, m); y1 += __shfl_xor_sync(kFull, y1, m);
+                y2 += __shfl_xor_sync(kFull, y2, m); y3 += __shfl_xor_sync(kFull, y3, m);
+                z0 += __shfl_xor_sync(kFull, z0, m); z1 += __shfl_xor_sync(kFull, z1, m);
+                z2 += __shfl_xor_sync(kFull, z2, m); z3 += __shfl_xor_sync(kFull, z3, m);
+            }
+        }
+        if (pending && block == lb && __float_as_uint(fy) == __float_as_uint(ly) && __float_as_uint(fz) == __float_as_uint(lz)) {
+            d = fmaf(fmaf(fmaf(a3, fx, a2), fx, a1), fx, a0);
+            if (kGrad) {
+                const float gx = fmaf(fmaf(3.0f * a3, fx, 2.0f * a2), fx, a1);
+                const float gy = fmaf(fmaf(fmaf(y3, fx, y2), fx, y1), fx, y0);
+                const float gz = fmaf(fmaf(fmaf(z3, fx, z2), fx, z1), fx, z0);
+                g = normalize3(mk3(gx, gy, gz));
+            }
+            pending = false;   // the leader always matches itself bit for bit, so every round retires at least one lane per quad
+        }
+    }
+    if (valid) {
+        dist[i] = d;
+        if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
+    }
+}
+#endif
+

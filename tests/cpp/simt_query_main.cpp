@@ -1,0 +1,159 @@
+// Runs the OctreeSdf query kernels of sdflib_b200/csrc/octree_query_kernels.cuh ON THE CPU, from the very same source,
+// under a lock-step warp emulation: every lane of a warp is a host thread, and the warp collectives (__ballot_sync,
+// __shfl_sync, __shfl_xor_sync) are barrier exchanges between the 32 threads. Purpose: the experimental kernels
+// (quad-cooperative evaluation, dense leaf index) were written without a GPU at hand; this checks their control flow —
+// rounds, leader choice, class membership, index packing, partial last warp — against the plain kernel and (in the
+// pytest wrapper, tests/test_query_variants_model.py) against the oracle. Host fmaf is a true fused multiply-add and
+// the file is compiled with -ffp-contract=off, so the arithmetic is the device's FMA-kernel arithmetic.
+//
+//   simt_query_main <in.bin> <out.bin>
+//   in : 6 f32 box, f32 cell, i32 grid, f32 minBorder, u32 maxDepth, u64 nWords, words, u64 nPoints, points (xyz f32)
+//   out: for each of plain, indexed, coop: distances (n f32), then distances + gradients of the gradient kernels
+#include <barrier>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#include "sdf_internal.h"   // f3 algebra (tri_math.cuh), node word constants; __device__ & co. are inert attributes for g++
+
+namespace simt {
+struct Dim { unsigned x = 0, y = 0, z = 0; };
+struct Warp {
+    std::barrier<> bar{32};
+    uint64_t slot[32];
+};
+thread_local Dim tThread, tBlock, tBlockDim;
+thread_local Warp* tWarp = nullptr;
+thread_local unsigned tLane = 0;
+
+template <class T> T exchange(T v, unsigned src) {   // every lane publishes v, reads lane src's
+    static_assert(sizeof(T) <= 8, "shuffle payload");
+    uint64_t raw = 0;
+    std::memcpy(&raw, &v, sizeof(T));
+    tWarp->slot[tLane] = raw;
+    tWarp->bar.arrive_and_wait();
+    raw = tWarp->slot[src & 31u];
+    tWarp->bar.arrive_and_wait();
+    T out;
+    std::memcpy(&out, &raw, sizeof(T));
+    return out;
+}
+inline unsigned ballot(bool pred) {
+    tWarp->slot[tLane] = pred ? 1u : 0u;
+    tWarp->bar.arrive_and_wait();
+    unsigned r = 0;
+    for (unsigned l = 0; l < 32; l++) r |= unsigned(tWarp->slot[l]) << l;
+    tWarp->bar.arrive_and_wait();
+    return r;
+}
+
+// grid x block launch, one warp at a time; blockDim must be a multiple of 32 (the kernels use 256)
+template <class K> void launch(unsigned grid, unsigned block, K kernel) {
+    for (unsigned b = 0; b < grid; b++)
+        for (unsigned w = 0; w < block / 32; w++) {
+            Warp warp;
+            std::vector<std::thread> lanes;
+            for (unsigned l = 0; l < 32; l++)
+                lanes.emplace_back([&, b, w, l] {
+                    tWarp = &warp; tLane = l;
+                    tThread.x = w * 32 + l; tBlock.x = b; tBlockDim.x = block;
+                    kernel();
+                    warp.bar.arrive_and_drop();   // a lane that left (early return / end) no longer takes part
+                });
+            for (std::thread& t : lanes) t.join();
+        }
+}
+}  // namespace simt
+
+#define __launch_bounds__(...)
+#define threadIdx simt::tThread
+#define blockIdx simt::tBlock
+#define blockDim simt::tBlockDim
+template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return simt::exchange(v, unsigned(src)); }
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return simt::exchange(v, simt::tLane ^ unsigned(m)); }
+inline unsigned __ballot_sync(unsigned, bool p) { return simt::ballot(p); }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+
+namespace sdfb200 {
+namespace {
+#include "octree_query_kernels.cuh"
+}
+}  // namespace sdfb200
+
+using namespace sdfb200;
+
+template <class T> static void readVec(FILE* f, std::vector<T>& v) {
+    uint64_t n = 0;
+    if (std::fread(&n, 8, 1, f) != 1) std::exit(2);
+    v.resize(n);
+    if (n && std::fread(v.data(), sizeof(T), n, f) != n) std::exit(2);
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) return 2;
+    FILE* f = std::fopen(argv[1], "rb");
+    if (!f) return 2;
+    float box[6], cell, minBorder;
+    int grid;
+    uint32_t maxDepth;
+    if (std::fread(box, 4, 6, f) != 6 || std::fread(&cell, 4, 1, f) != 1 || std::fread(&grid, 4, 1, f) != 1 ||
+        std::fread(&minBorder, 4, 1, f) != 1 || std::fread(&maxDepth, 4, 1, f) != 1) return 2;
+    std::vector<uint32_t> oct;
+    std::vector<float> xyz;
+    readVec(f, oct);
+    readVec(f, xyz);
+    std::fclose(f);
+    const uint64_t n = xyz.size() / 3;
+    QueryParams q;
+    q.minx = box[0]; q.miny = box[1]; q.minz = box[2];
+    q.maxx = box[3]; q.maxy = box[4]; q.maxz = box[5];
+    q.cell = cell; q.grid = grid; q.minBorder = minBorder;
+    const unsigned blocks = unsigned((n + 255) / 256);
+
+    // leaf index exactly as buildLeafIndex (octree_query.cu) sizes it
+    int startDepth = 0;
+    while ((1 << startDepth) < grid) startDepth++;
+    int levels = int(maxDepth) - startDepth;
+    if (argc > 3) levels = std::min(levels, std::atoi(argv[3]));   // shallower index: the finishing descent gets exercised
+    const uint64_t cells = uint64_t(1) << (3 * (startDepth + levels));
+    std::vector<uint32_t> index(cells + 1, 0u);
+    simt::launch(unsigned((cells + 255) / 256), 256, [&] { leafIndexKernel(oct.data(), grid, levels, index.data(), index.data() + cells); });
+    if (index[cells]) { std::fprintf(stderr, "leafIndexKernel flagged the array\n"); return 1; }
+
+    FILE* o = std::fopen(argv[2], "wb");
+    if (!o) return 2;
+    std::vector<float> dist(n), grad(3 * n);
+    auto emit = [&](bool withGrad) {
+        std::fwrite(dist.data(), 4, n, o);
+        if (withGrad) std::fwrite(grad.data(), 4, 3 * n, o);
+    };
+    const float* pts = xyz.data();
+    // plain
+    simt::launch(blocks, 256, [&] { octreeQueryKernel<false, true>(oct.data(), q, pts, n, dist.data(), nullptr); });
+    emit(false);
+    simt::launch(blocks, 256, [&] { octreeQueryKernel<true, true>(oct.data(), q, pts, n, dist.data(), grad.data()); });
+    emit(true);
+    // indexed
+    simt::launch(blocks, 256, [&] { octreeQueryIndexedKernel<false, true>(oct.data(), index.data(), levels, q, pts, n, dist.data(), nullptr); });
+    emit(false);
+    simt::launch(blocks, 256, [&] { octreeQueryIndexedKernel<true, true>(oct.data(), index.data(), levels, q, pts, n, dist.data(), grad.data()); });
+    emit(true);
+    // quad-cooperative
+    std::fill(dist.begin(), dist.end(), -123.0f);
+    simt::launch(blocks, 256, [&] { octreeQueryCoopKernel<false>(oct.data(), q, pts, n, dist.data(), nullptr); });
+    emit(false);
+    std::fill(dist.begin(), dist.end(), -123.0f);
+    std::fill(grad.begin(), grad.end(), -123.0f);
+    simt::launch(blocks, 256, [&] { octreeQueryCoopKernel<true>(oct.data(), q, pts, n, dist.data(), grad.data()); });
+    emit(true);
+    std::fclose(o);
+    std::printf("ok %llu queries, index levels %d\n", (unsigned long long)n, levels);
+    return 0;
+}
