@@ -194,3 +194,22 @@ def test_kernel_sources_under_warp_emulation(port, tmp_path, index_levels):
     outside = ((pts < area[:3]) | (pts >= area[3:])).any(1)
     assert outside.sum() > 50      # box-distance path: identical code in both kernels
     assert (parts["plain"]["d"][outside].view(np.uint32) == parts["coop"]["d"][outside].view(np.uint32)).all()
+
+
+def test_refill_sampler_source_under_warp_emulation(sdf, tmp_path):
+    """The lane-refill BVH sampler (bvh_sampler.cuh) run from its CUDA source under the warp emulation
+    (tests/cpp/simt_sampler_main.cpp): it must terminate and reproduce the plain sampler's bits sample for sample."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "simt_sampler_main")
+    lib_dir = os.path.join(ROOT, "sdflib_b200")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-std=c++20", "-O1", "-ffp-contract=off", "-w", "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(lib_dir, "csrc"), "-x", "c++", os.path.join(ROOT, "tests", "cpp", "simt_sampler_main.cpp"), "-o", exe,
+           "-L" + lib_dir, "-lsdfb200", "-Wl,-rpath," + lib_dir, "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for subdivisions, nodes in ((4, 120), (0, 3), (2, 1)):
+        r = subprocess.run([exe, str(subdivisions), str(nodes)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "identical" in r.stdout, (subdivisions, nodes, r.stdout, r.stderr)
