@@ -146,3 +146,42 @@ def test_bvh_builder_equals_serial_reference_order(sdf, tmp_path):
     for subdivisions, displace, threads in ((2, 0, 4), (6, 0, 1), (6, 0, 8), (7, 0, 16), (7, 1, 3), (7, 1, 16)):
         r = subprocess.run([exe, str(subdivisions), str(displace), str(threads)], capture_output=True, text=True)
         assert r.returncode == 0 and r.stdout.startswith("ok "), (subdivisions, displace, threads, r.stdout, r.stderr)
+
+
+def test_bin_loader_survives_corrupted_files(sdf, port, tmp_path):
+    """Untrusted .bin input: byte flips in the header and in the arrays, truncations and wild 64-bit lengths must come
+    back as error codes (or load, when the damage is harmless) — never a crash, hang or exit. Parsing and structure
+    validation run on the host before a device is needed, so this runs without a GPU."""
+    from sdflib_b200 import _capi, meshes
+    L = sdf.lib()
+    v, i = meshes.isosphere(2)
+    box = np.float32([-1.3] * 3 + [1.3] * 3)
+    port.build_octree(v, i, box, 4, 2, use_cache=False).save(str(tmp_path / "o.bin"))
+    port.build_exact(v, i, box, 4, 2, min_tris=16, use_cache=False).save(str(tmp_path / "e.bin"))
+    rng = np.random.default_rng(5)
+    seen = set()
+    for name in ("o.bin", "e.bin"):
+        raw = (tmp_path / name).read_bytes()
+        for t in range(240):
+            b = bytearray(raw)
+            mode = t % 4
+            if mode == 0:
+                for _ in range(rng.integers(1, 4)):
+                    b[rng.integers(0, 200)] = rng.integers(0, 256)
+            elif mode == 1:
+                for _ in range(rng.integers(1, 6)):
+                    b[rng.integers(0, len(b))] = rng.integers(0, 256)
+            elif mode == 2:
+                b = b[:rng.integers(0, len(b))]
+            else:
+                k = int(rng.integers(0, len(b) - 8))
+                b[k:k + 8] = np.uint64(rng.integers(0, 2 ** 63)).tobytes()
+            p = tmp_path / "m.bin"
+            p.write_bytes(bytes(b))
+            h = C.c_void_p()
+            code = L.sdfb200_load(str(p).encode(), C.byref(h))
+            seen.add(code)
+            assert code in (_capi.OK, _capi.ERR_IO, _capi.ERR_INVALID, _capi.ERR_CUDA), code
+            if h.value:
+                L.sdfb200_free(h)
+    assert _capi.ERR_IO in seen
