@@ -110,8 +110,9 @@ private:
                 while (ls >> ref)
                 {
                     const long i = std::strtol(ref.c_str(), nullptr, 10);   // "v", "v/vt", "v//vn", "v/vt/vn"
-                    if (i == 0) throw std::runtime_error("Mesh: malformed face in " + path);
-                    poly.push_back(uint32_t(i > 0 ? i - 1 : long(mVertices.size()) + i));
+                    const long at = i > 0 ? i - 1 : long(mVertices.size()) + i;   // negative = relative to the vertices read so far
+                    if (i == 0 || at < 0 || at > 0x7FFFFFFFL) throw std::runtime_error("Mesh: malformed face in " + path);
+                    poly.push_back(uint32_t(at));
                 }
                 addPolygon(poly);
             }
@@ -180,6 +181,9 @@ private:
         }
         std::vector<uint32_t> poly;
         for (const Element& e : elements)
+        {
+            if (e.props.empty()) continue;   // nothing to read per entry: a huge count must not spin
+            if (e.count > 0xFFFFFFFFull) throw std::runtime_error("Mesh: " + path + " declares an implausible element count");
             for (size_t i = 0; i < e.count; i++)
             {
                 glm::vec3 v(0.0f);
@@ -187,9 +191,17 @@ private:
                 {
                     if (p.list)
                     {
-                        const size_t n = size_t(plyRead(in, p.countType, ascii));
+                        // a damaged file must end in an exception, not in a loop over 2^32 entries or a wild cast
+                        const double count = plyRead(in, p.countType, ascii);
+                        if (!in || !(count >= 0.0 && count <= 65536.0)) throw std::runtime_error("Mesh: " + path + " holds a malformed list");
+                        const size_t n = size_t(count);
                         poly.clear();
-                        for (size_t k = 0; k < n; k++) poly.push_back(uint32_t(plyRead(in, p.type, ascii)));
+                        for (size_t k = 0; k < n; k++)
+                        {
+                            const double x = plyRead(in, p.type, ascii);
+                            if (!in || !(x >= 0.0 && x <= 4294967295.0)) throw std::runtime_error("Mesh: " + path + " holds a malformed list");
+                            poly.push_back(uint32_t(x));
+                        }
                         if (e.name == "face" && (p.name == "vertex_indices" || p.name == "vertex_index")) addPolygon(poly);
                     }
                     else
@@ -201,6 +213,7 @@ private:
                 if (e.name == "vertex") mVertices.push_back(v);
                 if (!in) throw std::runtime_error("Mesh: " + path + " ends early");
             }
+        }
         for (uint32_t i : mIndices) if (i >= mVertices.size()) throw std::runtime_error("Mesh: face index out of range in " + path);
     }
 

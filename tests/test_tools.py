@@ -188,7 +188,15 @@ def test_mesh_reader_polygons_extra_properties_and_relative_indices(mesh_reader,
 
 def test_mesh_reader_rejects_bad_files(mesh_reader, tmp_path):
     cases = {"empty.obj": "", "bad.ply": "not a ply\n", "big.ply": "ply\nformat binary_big_endian 1.0\nend_header\n",
-             "range.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n", "model.stl": "solid\n"}
+             "range.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 9\n", "model.stl": "solid\n",
+             # damaged headers / lists found by fuzzing: must end in an exception, not in a loop over 2^32 entries
+             "wrap.obj": "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 4294967297\n",
+             "shifted.ply": "ply\nformat ascii 1.0\nelement vertex 3\nproperXy float x\nproperty float y\nproperty float z\n"
+                            "element face 1\nproperty list uchar int vertex_indices\nend_header\n-0.5 0 0.8\n0.5 0 0.8\n0 1 -1e30\n3 0 1 2\n",
+             "neglist.ply": "ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+                            "element face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0\n-7 0 1 2\n",
+             "negindex.ply": "ply\nformat ascii 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+                             "element face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0\n3 0 -1 2\n"}
     for name, text in cases.items():
         path = str(tmp_path / name)
         open(path, "w").write(text)
@@ -196,3 +204,11 @@ def test_mesh_reader_rejects_bad_files(mesh_reader, tmp_path):
         assert r.returncode == 1 and "Mesh:" in r.stderr, (name, r.stderr)
     r = subprocess.run([mesh_reader, str(tmp_path / "missing.ply")], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot open" in r.stderr
+
+
+def test_mesh_reader_skips_property_less_elements(mesh_reader, tmp_path):
+    path = str(tmp_path / "spin.ply")
+    open(path, "w").write("ply\nformat ascii 1.0\nelement foo 99999999999999\nelement vertex 3\nproperty float x\nproperty float y\n"
+                          "property float z\nelement face 1\nproperty list uchar int vertex_indices\nend_header\n0 0 0\n1 0 0\n0 1 0\n3 0 1 2\n")
+    r = subprocess.run([mesh_reader, path], capture_output=True, text=True, timeout=30)
+    assert r.returncode == 0 and r.stdout.startswith("3 3"), r.stderr
