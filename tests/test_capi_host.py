@@ -185,3 +185,51 @@ def test_bin_loader_survives_corrupted_files(sdf, port, tmp_path):
             if h.value:
                 L.sdfb200_free(h)
     assert _capi.ERR_IO in seen
+
+
+def _random_meshes(rng, count):
+    """Triangle soups that stress calculateMeshTriangleData: tiny vertex sets (edges shared by many triangles),
+    spheres with duplicated vertices (open edges the repair merges) or missing triangles (true boundaries), large
+    random soups. Degenerate triangles are left out (0/0 in the frame on every implementation)."""
+    from sdflib_b200 import meshes
+    for t in range(count):
+        kind = t % 4
+        if kind == 0:
+            nv, nt = rng.integers(4, 12), rng.integers(1, 30)
+            v, i = rng.standard_normal((nv, 3)), rng.integers(0, nv, size=nt * 3)
+        elif kind == 1:
+            v, i = meshes.isosphere(1)
+            v, i = v.copy(), i.copy()
+            for _ in range(rng.integers(1, 20)):
+                c = rng.integers(0, i.size)
+                v = np.vstack([v, v[i[c]][None] + (rng.standard_normal(3) * 1e-7)])
+                i[c] = len(v) - 1
+        elif kind == 2:
+            v, i = meshes.isosphere(2)
+            i = i.reshape(-1, 3)[rng.random(i.size // 3) > 0.2].ravel()
+        else:
+            nv, nt = rng.integers(50, 400), rng.integers(50, 2000)
+            v, i = rng.standard_normal((nv, 3)), rng.integers(0, nv, size=nt * 3)
+        tri = np.asarray(i).reshape(-1, 3)
+        tri = tri[(tri[:, 0] != tri[:, 1]) & (tri[:, 1] != tri[:, 2]) & (tri[:, 0] != tri[:, 2])]
+        if len(tri):
+            yield np.ascontiguousarray(v, np.float32), np.ascontiguousarray(tri.ravel(), np.uint32)
+
+
+def test_triangle_data_on_random_non_manifold_meshes(sdf, port):
+    """The multi-threaded host TriangleData (sorted edge pairing, chunked by edge groups, non-manifold repair) against
+    the oracle's serial map-based restatement, bit for bit, on meshes where every branch of the repair is taken."""
+    from sdflib_b200 import _capi
+    L = sdf.lib()
+    for v, i in _random_meshes(np.random.default_rng(3), 80):
+        out = np.empty((i.size // 3, 37), np.float32)
+        assert L.sdfb200_triangle_data(_capi.ptr(v), len(v), _capi.ptr(i), i.size, _capi.ptr(out)) == _capi.OK
+        want = port.triangle_data(v, i)
+        same = (out.view(np.uint32) == want.view(np.uint32)) | (np.isnan(out) & np.isnan(want))
+        assert same.all(), (len(v), i.size)
+
+
+def test_oracle_triangle_data_equals_reference_on_random_meshes(port, ref):
+    for v, i in _random_meshes(np.random.default_rng(8), 40):
+        a, b = port.triangle_data(v, i), ref.triangle_data(v, i)
+        assert ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all(), (len(v), i.size)
