@@ -305,3 +305,25 @@ def test_port_equals_reference_on_edge_case_meshes(port, ref, name):
     assert np.array_equal(a.octree_data(), b.octree_data())
     q = (box[:3] + np.random.default_rng(3).uniform(0, 1, (2000, 3)) * (box[3:] - box[:3])).astype(np.float32)
     assert_bit_equal(a.query(q), b.query(q))
+
+
+def test_port_builds_equal_reference_on_random_non_manifold_meshes(port, ref):
+    """Random triangle soups, spheres with duplicated vertices or holes: every builder, random depths / start depths /
+    rules / thresholds (a longer run of the same loop — 80 meshes — found no difference either)."""
+    from test_capi_host import _random_meshes
+    rng = np.random.default_rng(21)
+    for n, (v, i) in enumerate(_random_meshes(rng, 16)):
+        lo, hi = v.min(0), v.max(0)
+        m = 0.2 * float((hi - lo).max())
+        box = np.concatenate([lo - m, hi + m]).astype(np.float32)
+        depth = int(rng.integers(3, 5)); start = int(rng.integers(0, 4)); thr = float(rng.choice([1e-2, 1e-1])); rule = int(rng.integers(1, 4))
+        for alg in (1, 2):
+            a = ref.build_octree(v, i, box, depth, start, thr, alg, 1, termination_rule=rule, param1=0.1).octree_data()
+            b = port.build_octree(v, i, box, depth, start, thr, alg, 1, termination_rule=rule, param1=0.1, use_cache=True).octree_data()
+            assert np.array_equal(a, b), (n, alg, depth, start, rule, thr)
+        if i.size // 3 >= 2:
+            start = int(rng.integers(0, 3)); depth = start + int(rng.integers(2, 4)); min_tris = int(rng.choice([1, 4, 16, 64]))
+            ea, eb = ref.build_exact(v, i, box, depth, start, min_tris, 1), port.build_exact(v, i, box, depth, start, min_tris, 1, use_cache=True)
+            assert np.array_equal(ea.octree_data(), eb.octree_data()), (n, depth, start, min_tris)
+            q = (box[:3] + rng.random((300, 3)) * (box[3:] - box[:3])).astype(np.float32)
+            assert_bit_equal(ea.query(q), eb.query(q))
