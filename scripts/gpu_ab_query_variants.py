@@ -93,6 +93,9 @@ def main():
                     select(variant)
                     best, mean = timed(lambda: sdf.getDistance(pts, gradient=gradient, out=dist, out_gradient=grad))
                     line += f" | {variant}: best {best:.3f} ms, mean {mean:.3f} ms ({pts.shape[0] / best / 1e6:.1f} Gq/s)"
+                select("plain")   # the bit-exact reference-order kernel, for the price of parity (never recorded in round 1)
+                best, mean = timed(lambda: sdf.getDistance(pts, gradient=gradient, exact_order=True, out=dist, out_gradient=grad))
+                line += f" | exact order: best {best:.3f} ms, mean {mean:.3f} ms ({pts.shape[0] / best / 1e6:.1f} Gq/s)"
                 print(line, flush=True)
         sdf.close()
     print("ALL CHECKS PASSED" if ok else "CHECK FAILED")
