@@ -9,6 +9,8 @@
 //   simt_query_main <in.bin> <out.bin>
 //   in : 6 f32 box, f32 cell, i32 grid, f32 minBorder, u32 maxDepth, u64 nWords, words, u64 nPoints, points (xyz f32)
 //   out: for each of plain, indexed, coop: distances (n f32), then distances + gradients of the gradient kernels
+// With -DSDFB_QUERY_EXACT the same header yields the reference-order kernels (no cooperative one): their output must
+// equal the oracle bit for bit, which also pins the emulation itself (host arithmetic = device arithmetic, -fmad=false).
 #include <barrier>
 #include <cstdint>
 #include <cstdio>
@@ -145,6 +147,7 @@ int main(int argc, char** argv) {
     emit(false);
     simt::launch(blocks, 256, [&] { octreeQueryIndexedKernel<true, true>(oct.data(), index.data(), levels, q, pts, n, dist.data(), grad.data()); });
     emit(true);
+#ifndef SDFB_QUERY_EXACT   // compiled with -DSDFB_QUERY_EXACT the header holds the reference-order kernels and no cooperative one
     // quad-cooperative
     std::fill(dist.begin(), dist.end(), -123.0f);
     simt::launch(blocks, 256, [&] { octreeQueryCoopKernel<false>(oct.data(), q, pts, n, dist.data(), nullptr); });
@@ -153,6 +156,7 @@ int main(int argc, char** argv) {
     std::fill(grad.begin(), grad.end(), -123.0f);
     simt::launch(blocks, 256, [&] { octreeQueryCoopKernel<true>(oct.data(), q, pts, n, dist.data(), grad.data()); });
     emit(true);
+#endif
     std::fclose(o);
     std::printf("ok %llu queries, index levels %d\n", (unsigned long long)n, levels);
     return 0;

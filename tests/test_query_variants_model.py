@@ -8,6 +8,8 @@ the oracle on the GPU, tests/test_gpu_octree.py), on octrees built by the oracle
 import numpy as np
 import pytest
 
+from conftest import assert_bit_equal
+
 LEAF, MASK = np.uint32(1 << 31), np.uint32(~(3 << 30) & 0xFFFFFFFF)
 PATH_BITS = 16
 
@@ -124,31 +126,23 @@ def test_quad_cooperative_evaluation_is_the_same_polynomial(port):
         np.testing.assert_allclose(g, want_g[0].astype(np.float64), atol=6e-6 * scale)   # raw (un-normalised) gradient
 
 
-def _compile_simt(tmp_path):
+def _compile_simt(tmp_path, exact=False):
     import os
     import subprocess
     from conftest import ROOT
-    exe = str(tmp_path / "simt_query_main")
+    exe = str(tmp_path / ("simt_query_exact" if exact else "simt_query_main"))
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     cuda_inc = "/usr/local/cuda/include"
     cmd = [cxx, "-std=c++20", "-O1", "-ffp-contract=off", "-w", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "include"),
            "-I" + os.path.join(ROOT, "sdflib_b200", "csrc"), "-x", "c++", os.path.join(ROOT, "tests", "cpp", "simt_query_main.cpp"),
-           "-o", exe, "-lpthread"]
+           "-o", exe, "-lpthread"] + (["-DSDFB_QUERY_EXACT"] if exact else [])
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return exe
 
 
-@pytest.mark.parametrize("index_levels", [None, 1])
-def test_kernel_sources_under_warp_emulation(port, tmp_path, index_levels):
-    """The CUDA source of the query kernels (octree_query_kernels.cuh), compiled for the host and run under a lock-step
-    warp emulation (tests/cpp/simt_query_main.cpp): the indexed kernels must equal the plain ones bit for bit, the
-    quad-cooperative ones must find the same leaf and stay within the FMA kernel's tolerance of the reference's
-    evaluation order (oracle), including points outside the box, rows of a grid (shared classes), unrelated points
-    (one class per lane) and a batch that ends in the middle of a warp."""
-    import subprocess
+def _query_case(port, tmp_path):
     from sdflib_b200 import meshes
-    exe = _compile_simt(tmp_path)
     v, i = meshes.isosphere(2)
     v = (v * np.float32([1.0, 0.8, 0.6]) + np.float32([0.013, -0.007, 0.003])).astype(np.float32)
     box = np.float32([-1.3, -1.3, -1.3, 1.3, 1.3, 1.3])
@@ -161,7 +155,6 @@ def test_kernel_sources_under_warp_emulation(port, tmp_path, index_levels):
     rand_pts = (area[:3] + rng.random((1500, 3), np.float32) * (area[3:] - area[:3])).astype(np.float32)
     out_pts = (area[:3] - 0.3 + rng.random((400, 3), np.float32) * (area[3:] - area[:3] + 0.6)).astype(np.float32)
     pts = np.concatenate([grid_pts, rand_pts, out_pts])[:-7].astype(np.float32)        # n % 32 != 0
-    n = len(pts)
     with open(tmp_path / "in.bin", "wb") as f:
         f.write(area.astype(np.float32).tobytes())
         f.write(np.float32(size / hdr["start_grid_size"]).tobytes())
@@ -170,6 +163,41 @@ def test_kernel_sources_under_warp_emulation(port, tmp_path, index_levels):
         f.write(np.uint32(depth).tobytes())
         f.write(np.uint64(len(oct_)).tobytes()); f.write(oct_.tobytes())
         f.write(np.uint64(pts.size).tobytes()); f.write(pts.tobytes())
+    return sdf, pts, area, size
+
+
+def test_reference_order_kernels_under_warp_emulation_equal_the_oracle(port, tmp_path):
+    """Pins the emulation: the -DSDFB_QUERY_EXACT build of the same header (the kernels behind
+    SDFB200_QUERY_EXACT_ORDER, bit-exact on the GPU) must give the oracle's bits on the CPU too — in-box distances and
+    gradients, plain and indexed."""
+    import subprocess
+    exe = _compile_simt(tmp_path, exact=True)
+    sdf, pts, area, size = _query_case(port, tmp_path)
+    n = len(pts)
+    r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), "2"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), (r.stdout, r.stderr)
+    raw = np.fromfile(tmp_path / "out.bin", np.float32)
+    assert raw.size == 2 * 5 * n
+    ref_d, ref_g = sdf.query(pts, gradient=True)
+    inside = ~((pts < area[:3]) | (pts >= area[3:])).any(1)
+    for k in range(2):                                   # plain, indexed
+        d, dg, g = raw[5 * n * k:5 * n * k + n], raw[5 * n * k + n:5 * n * k + 2 * n], raw[5 * n * k + 2 * n:5 * n * (k + 1)].reshape(n, 3)
+        assert_bit_equal(d, sdf.query(pts), "distance")
+        assert_bit_equal(dg[inside], ref_d[inside], "distance of the gradient kernel")
+        assert_bit_equal(g[inside], ref_g[inside], "gradient")
+
+
+@pytest.mark.parametrize("index_levels", [None, 1])
+def test_kernel_sources_under_warp_emulation(port, tmp_path, index_levels):
+    """The CUDA source of the query kernels (octree_query_kernels.cuh), compiled for the host and run under a lock-step
+    warp emulation (tests/cpp/simt_query_main.cpp): the indexed kernels must equal the plain ones bit for bit, the
+    quad-cooperative ones must find the same leaf and stay within the FMA kernel's tolerance of the reference's
+    evaluation order (oracle), including points outside the box, rows of a grid (shared classes), unrelated points
+    (one class per lane) and a batch that ends in the middle of a warp."""
+    import subprocess
+    exe = _compile_simt(tmp_path)
+    sdf, pts, area, size = _query_case(port, tmp_path)
+    n = len(pts)
     cmd = [exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")] + ([str(index_levels)] if index_levels is not None else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.startswith("ok "), (r.stdout, r.stderr)
