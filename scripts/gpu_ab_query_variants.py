@@ -1,11 +1,13 @@
-"""A/B of the EXPERIMENTAL OctreeSdf bulk-query variants (octree_query.cu; both off by default):
+"""A/B of the OctreeSdf bulk-query kernels (octree_query.cu):
 
-  index : dense leaf index, SDFB200_QUERY_INDEX=1  — must be BIT-IDENTICAL to the plain kernels (FMA and exact order)
-  coop  : quad-cooperative evaluation, SDFB200_QUERY_COOP=1 (FMA kernel only) — same leaf, different summation order:
-          must stay within the FMA kernel's tolerance of the exact-order result (1e-5 relative, floor 1e-3 of the box)
+  tile  : the default FMA kernel (octreeQueryTileKernel: TMA-staged tiles, top index, quad-cooperative evaluation)
+  plain : one query per thread (octreeQueryKernel; SDFB200_QUERY_PLAIN=1 when the structure is built)
+  exact : the reference-order kernel behind SDFB200_QUERY_EXACT_ORDER (bit-exact)
 
-on the C2 octree and a depth-9 one (index = 512 MB), for grid-ordered, random and partly-outside point sets, with and
-without gradients; kernel times by CUDA events on the launching stream with L2 flushed between launches.
+on the C2 octree and a depth-9 one, for grid-ordered, random and partly-outside point sets, with and without
+gradients. Checks: tile and plain within the FMA tolerance of the exact-order result (1e-5 relative, floor 1e-3 of the
+box; points beyond it are counted), identical in/out-of-box classification. Kernel times by CUDA
+events on the launching stream with L2 flushed between launches.
 
     gpurun --timeout 1200 -- 'python scripts/gpu_ab_query_variants.py'
 """
@@ -18,13 +20,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sdflib_b200 as S                      # noqa: E402
 from sdflib_b200 import meshes               # noqa: E402
-
-VARIANTS = {"plain": {}, "index": {"SDFB200_QUERY_INDEX": "1"}, "coop": {"SDFB200_QUERY_COOP": "1"}}
-
-
-def select(variant):
-    for k in ("SDFB200_QUERY_INDEX", "SDFB200_QUERY_COOP"):
-        os.environ[k] = VARIANTS[variant].get(k, "0")
 
 
 def timed(fn, reps=10):
@@ -41,8 +36,7 @@ def timed(fn, reps=10):
     return best, total / reps
 
 
-def run(sdf, pts, variant, gradient, exact):
-    select(variant)
+def run(sdf, pts, gradient, exact):
     r = sdf.getDistance(pts, gradient=gradient, exact_order=exact)
     torch.cuda.synchronize()
     return [t.clone() for t in (r if gradient else (r,))]
@@ -54,6 +48,9 @@ def main():
     mesh, bb = S.Mesh(v, i), S.BoundingBox(box[:3], box[3:])
     ok = True
     for depth, n_grid in ((8, 256), (9, 512)):
+        os.environ["SDFB200_QUERY_PLAIN"] = "1"
+        plain_sdf = S.OctreeSdf(mesh, bb, depth, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 1)
+        os.environ["SDFB200_QUERY_PLAIN"] = "0"
         sdf = S.OctreeSdf(mesh, bb, depth, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 1)
         area = sdf.getGridBoundingBox().as_array()
         size = float(area[3] - area[0])
@@ -61,43 +58,44 @@ def main():
         sets = {
             f"grid {n_grid}^3": torch.from_numpy(meshes.cell_centre_grid(area, n_grid)).cuda(),
             "random 2^24": torch.from_numpy((area[:3] + rng.random((1 << 24, 3), np.float32) * (area[3:] - area[:3])).astype(np.float32)).cuda(),
-            "around the box": torch.from_numpy((area[:3] - 0.2 + rng.random((1 << 20, 3), np.float32) * (area[3:] - area[:3] + 0.4)).astype(np.float32)).cuda(),
+            "around the box": torch.from_numpy((area[:3] - 0.2 + rng.random(((1 << 20) + 5, 3), np.float32) * (area[3:] - area[:3] + 0.4)).astype(np.float32)).cuda(),
         }
         for name, pts in sets.items():
             for gradient in (False, True):
-                exact = run(sdf, pts, "plain", gradient, True)
-                same = all(torch.equal(a.view(torch.int32), b.view(torch.int32)) for a, b in zip(exact, run(sdf, pts, "index", gradient, True)))
-                ok &= same
-                line = f"depth {depth} {name:15s} grad={int(gradient)} | exact order: index identical={same}"
-                plain = run(sdf, pts, "plain", gradient, False)
-                same = all(torch.equal(a.view(torch.int32), b.view(torch.int32)) for a, b in zip(plain, run(sdf, pts, "index", gradient, False)))
-                ok &= same
-                line += f" | fma: index identical={same}"
-                coop = run(sdf, pts, "coop", gradient, False)
+                exact = run(sdf, pts, gradient, True)
+                plain = run(plain_sdf, pts, gradient, False)
+                tile = run(sdf, pts, gradient, False)
                 tol = 1e-5 * torch.clamp(exact[0].abs(), min=1e-3 * size)
-                err = ((coop[0] - exact[0]).abs() / tol).max().item()
-                err_plain = ((plain[0] - exact[0]).abs() / tol).max().item()
-                good = err <= 1.0
-                if gradient:   # unit gradients: compare directions where the exact gradient is defined
-                    fin = torch.isfinite(exact[1]).all(1) & torch.isfinite(coop[1]).all(1)
-                    gerr = (coop[1][fin] - exact[1][fin]).abs().max().item()
-                    good &= gerr <= 1e-3 and bool((torch.isfinite(exact[1]).all(1) == torch.isfinite(coop[1]).all(1)).all())
-                    line += f" | coop grad max abs diff {gerr:.2e}"
-                ok &= good
-                line += f" | coop err/tol {err:.3f} (plain fma {err_plain:.3f}) ok={good}"
+                line = f"depth {depth} {name:15s} grad={int(gradient)}"
+                for what, got in (("tile", tile), ("plain", plain)):
+                    rel = (got[0] - exact[0]).abs() / tol
+                    over = int((rel > 1.0).sum())
+                    good = over <= 1e-5 * pts.shape[0] and rel.max().item() < 8.0 and (got[0] - exact[0]).abs().max().item() < 1e-6 * size
+                    line += f" | {what}: max err/tol {rel.max().item():.2f}, {over} over, max abs {(got[0] - exact[0]).abs().max().item():.2e}"
+                    if gradient:
+                        fin = torch.isfinite(exact[1]).all(1) & torch.isfinite(got[1]).all(1)
+                        gerr = (got[1][fin] - exact[1][fin]).abs().max().item()
+                        good &= gerr <= 1e-3 and bool((torch.isfinite(exact[1]).all(1) == torch.isfinite(got[1]).all(1)).all())
+                        line += f", grad max abs {gerr:.2e}"
+                    ok &= good
+                    line += f" ok={good}"
                 print(line, flush=True)
                 dist = torch.empty(pts.shape[0], dtype=torch.float32, device="cuda")
                 grad = torch.empty((pts.shape[0], 3), dtype=torch.float32, device="cuda") if gradient else None
                 line = "    kernel time"
-                for variant in VARIANTS:
-                    select(variant)
-                    best, mean = timed(lambda: sdf.getDistance(pts, gradient=gradient, out=dist, out_gradient=grad))
-                    line += f" | {variant}: best {best:.3f} ms, mean {mean:.3f} ms ({pts.shape[0] / best / 1e6:.1f} Gq/s)"
-                select("plain")   # the bit-exact reference-order kernel, for the price of parity (never recorded in round 1)
-                best, mean = timed(lambda: sdf.getDistance(pts, gradient=gradient, exact_order=True, out=dist, out_gradient=grad))
-                line += f" | exact order: best {best:.3f} ms, mean {mean:.3f} ms ({pts.shape[0] / best / 1e6:.1f} Gq/s)"
+                for what, obj, ex in (("tile", sdf, False), ("plain", plain_sdf, False), ("exact order", sdf, True)):
+                    best, mean = timed(lambda: obj.getDistance(pts, gradient=gradient, exact_order=ex, out=dist, out_gradient=grad))
+                    line += f" | {what}: best {best:.3f} ms, mean {mean:.3f} ms ({pts.shape[0] / best / 1e6:.1f} Gq/s)"
                 print(line, flush=True)
-        sdf.close()
+        # a batch that does not start on a 16-byte boundary takes the kernel's plain-load path: same bits as the TMA path
+        pts = sets["around the box"]
+        shifted = torch.empty(pts.numel() + 1, dtype=torch.float32, device="cuda")[1:].view(-1, 3)
+        shifted.copy_(pts)
+        a, b = run(sdf, pts, True, False), run(sdf, shifted, True, False)
+        same = all(torch.equal(x.view(torch.int32), y.view(torch.int32)) for x, y in zip(a, b))
+        print(f"depth {depth} unaligned batch identical to aligned: {same}", flush=True)
+        ok &= same
+        sdf.close(); plain_sdf.close()
     print("ALL CHECKS PASSED" if ok else "CHECK FAILED")
     return 0 if ok else 1
 

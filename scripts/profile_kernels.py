@@ -1,5 +1,5 @@
 """Small driver for ncu captures (one GPU): runs ONE build or ONE query pass of the bench workloads.
-    python scripts/profile_kernels.py exact_build | octree_build | octree_cont | exact_query | octree_query"""
+    python scripts/profile_kernels.py exact_build | octree_build | octree_cont | exact_query | octree_query | octree_query_random (SDFB200_QUERY_COOP=1 selects the cooperative kernel)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,8 +16,13 @@ elif what == "octree_cont":
     sdf = S.OctreeSdf(mesh, bb, 8, 3, 1e-3, S.OctreeSdf.CONTINUITY, 2)
 else:
     sdf = S.OctreeSdf(mesh, bb, 8, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 2)
-if what.endswith("query"):
-    pts = torch.from_numpy(meshes.cell_centre_grid(sdf.getSampleArea().as_array(), 256)).cuda()
+if "query" in what:
+    area = sdf.getSampleArea().as_array()
+    if what.endswith("random"):
+        import numpy as np
+        pts = torch.from_numpy((area[:3] + np.random.default_rng(42).random((1 << 24, 3), np.float32) * (area[3:] - area[:3])).astype(np.float32)).cuda()
+    else:
+        pts = torch.from_numpy(meshes.cell_centre_grid(area, 256)).cuda()
     out = torch.empty(len(pts), dtype=torch.float32, device="cuda")
     for _ in range(3):
         sdf.getDistance(pts, out=out)

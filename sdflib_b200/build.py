@@ -35,6 +35,7 @@ UNITS = [
     ("capi.cpp", "capi.o", ["-x", "cu"]),
     ("shard.cpp", "shard.o", ["-x", "cu"]),
     ("host_mem.cpp", "host_mem.o", ["-x", "cu"]),
+    ("query_host.cpp", "query_host.o", ["-x", "cu"]),
     ("fixtures.cpp", "fixtures.o", ["-x", "cu"] + NO_FMA),
     ("octree_build.cu", "octree_build.o", NO_FMA),
     ("octree_cont.cu", "octree_cont.o", NO_FMA),

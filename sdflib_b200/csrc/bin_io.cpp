@@ -149,7 +149,7 @@ void uploadStructure(sdfb200_sdf& s) {
         s.dTris.alloc(s.tris.size());
         s.dTris.upload(s.tris.data(), s.tris.size());
         prepareExactQuery(s);
-    }
+    } else prepareOctreeQuery(s);
     SDFB_CUDA(cudaDeviceSynchronize());
 }
 

@@ -258,50 +258,8 @@ int sdfb200_query(sdfb200_sdf* s, const float* xyz, uint64_t n, float* dist, flo
         if (s->isShard) throw Error(SDFB200_ERR_INVALID, "handle is an unassembled shard (sdfb200_assemble not called yet)");
         SDFB_CUDA(cudaSetDevice(s->device));
         cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
-        if (s->format == SDFB200_FORMAT_OCTREE) {   // EXPERIMENTAL dense leaf index, off unless the switch is set (octree_query.cu)
-            const char* sw = std::getenv("SDFB200_QUERY_INDEX");
-            s->useLeafIndex = sw && sw[0] == '1';
-            if (s->useLeafIndex) std::call_once(s->leafIndexOnce, [&] { buildLeafIndex(*s, st); });
-            const char* coop = std::getenv("SDFB200_QUERY_COOP");
-            s->useCoopQuery = coop && coop[0] == '1';
-        }
-        auto launchOn = [&](const float* dXyz, uint64_t count, float* dDist, float* dGrad, cudaStream_t on) {
-            if (s->format == SDFB200_FORMAT_OCTREE) {
-                if (flags & SDFB200_QUERY_EXACT_ORDER) launchOctreeQueryExact(*s, dXyz, count, dDist, dGrad, on);
-                else launchOctreeQueryFast(*s, dXyz, count, dDist, dGrad, on);
-            } else launchExactQuery(*s, dXyz, count, dDist, dGrad, on);
-        };
-        if (flags & SDFB200_QUERY_DEVICE_POINTERS) { launchOn(xyz, n, dist, grad, st); return; }
-        // host pointers: the batch is cut into chunks that alternate between two internal streams, so the H2D copy
-        // of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap (the two copy directions use
-        // different DMA engines). The call returns when everything has arrived, like the reference's getDistance.
-        constexpr uint64_t kChunk = uint64_t(1) << 21;
-        const uint64_t chunk = std::min<uint64_t>(n, kChunk);
-        bool grown = false;
-        if (s->dPts.n < 2 * 3 * chunk) { s->dPts.alloc(2 * 3 * chunk); grown = true; }
-        if (s->dDist.n < 2 * chunk) { s->dDist.alloc(2 * chunk); grown = true; }
-        if (grad && s->dGrad.n < 2 * 3 * chunk) { s->dGrad.alloc(2 * 3 * chunk); grown = true; }
-        if (grown) SDFB_CUDA(cudaStreamSynchronize(cudaStream_t(0)));   // allocations are ordered on the default stream
-        if (!s->qStream[0]) {
-            for (int k = 0; k < 2; k++) SDFB_CUDA(cudaStreamCreateWithFlags(&s->qStream[k], cudaStreamNonBlocking));
-            SDFB_CUDA(cudaEventCreateWithFlags(&s->qEvent, cudaEventDisableTiming));
-        }
-        SDFB_CUDA(cudaEventRecord(s->qEvent, st));   // work already queued on the caller's stream comes first
-        for (int k = 0; k < 2; k++) SDFB_CUDA(cudaStreamWaitEvent(s->qStream[k], s->qEvent, 0));
-        uint64_t done = 0;
-        for (int k = 0; done < n; k ^= 1) {
-            const uint64_t m = std::min(chunk, n - done);
-            cudaStream_t cs = s->qStream[k];
-            float* dP = s->dPts.p + size_t(k) * 3 * chunk;
-            float* dD = s->dDist.p + size_t(k) * chunk;
-            float* dG = grad ? s->dGrad.p + size_t(k) * 3 * chunk : nullptr;
-            SDFB_CUDA(cudaMemcpyAsync(dP, xyz + 3 * done, 3 * m * sizeof(float), cudaMemcpyHostToDevice, cs));
-            launchOn(dP, m, dD, dG, cs);
-            SDFB_CUDA(cudaMemcpyAsync(dist + done, dD, m * sizeof(float), cudaMemcpyDeviceToHost, cs));
-            if (grad) SDFB_CUDA(cudaMemcpyAsync(grad + 3 * done, dG, 3 * m * sizeof(float), cudaMemcpyDeviceToHost, cs));
-            done += m;
-        }
-        for (int k = 0; k < 2; k++) SDFB_CUDA(cudaStreamSynchronize(s->qStream[k]));
+        if (flags & SDFB200_QUERY_DEVICE_POINTERS) queryDevicePointers(*s, xyz, n, dist, grad, flags, st);
+        else queryHostPointers(*s, xyz, n, dist, grad, flags, st);
     });
 }
 

@@ -498,6 +498,7 @@ struct OctreeBuildState : BuildState {
         if (plan.world == 1) {
             finalizeOctreeScalars(out);
             t0 = std::chrono::steady_clock::now();
+            prepareOctreeQuery(out);
             out.octree.resize(totalWords);
             out.dOctree.download(out.octree.data(), totalWords);
             SDFB_CUDA(cudaDeviceSynchronize());

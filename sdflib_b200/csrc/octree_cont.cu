@@ -1013,6 +1013,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
     out.dOctree.alloc(words);
     SDFB_CUDA(cudaMemcpyAsync(out.dOctree.p, oc.oct.p, words * 4, cudaMemcpyDeviceToDevice));
     finishStep("device copy");
+    prepareOctreeQuery(out);
     out.octree.resize(words);
     finishStep("host block");
     out.dOctree.download(out.octree.data(), words);

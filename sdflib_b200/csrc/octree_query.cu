@@ -12,17 +12,19 @@
 // the reference's IEEE operations, so both visit the same leaf; they differ only in how the leaf
 // polynomial is summed (<= a few ulp of the largest term).
 //
-// Kernel shape: one query per thread, 256-thread CTAs, grid sized by the batch. The descent is a
-// chain of dependent 4-byte gathers (L2-resident after the first touch: the whole structure of the
-// headline config is 82 MB < 126 MB L2); the leaf block is 64 consecutive floats.
-// What bounds it (profiles/r1_summary.md): not HBM but the L1/LSU data pipe — every query must bring its
-// own 64 coefficients (256 B) into registers: each of the 16 vector loads costs one wavefront per distinct leaf
-// among the warp's lanes (6.2 on the 256^3 workload, tests/model_query_wavefronts.py: ~99 of ~115 wavefronts per
-// warp); ncu shows l1tex__data_pipe_lsu_wavefronts at 77 % of peak with DRAM at 15 %. A warp-cooperative variant (distinct
-// leaves staged once per warp in shared memory, evaluated from there) was measured and is slower
-// (0.36 ms vs 0.26 ms on the 256^3 grid): it removes the tag-stage replays but keeps the same
-// register-fill traffic and adds match/shuffle/shared-store work. It was dropped.
+// Kernels (octree_query_kernels.cuh):
+//   octreeQueryTileKernel  the default of the FMA path: persistent warps over 32-query tiles staged by TMA, dense top
+//                          index instead of the first dependent gathers, division-free cell selection, quad-cooperative
+//                          evaluation (see the comment on the kernel for what each of these removes, with the measurements)
+//   octreeQueryKernel      one query per thread: the reference-order (bit-exact) object, and the fallback of the FMA
+//                          object for arrays the tile kernel's preconditions exclude (leaf blocks not 16-byte aligned,
+//                          block offsets not of the 8-word form, start grid not a power of two)
+// Measured and dropped (profiles/r2_summary.md): a dense leaf index down to the deepest level for the one-query-per-
+// thread kernel (+3 %: it was bound by the coefficient fill, not the descent) and a variant staging distinct leaves in
+// shared memory (slower: the register fill from shared memory costs the same wavefronts).
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "sdf_internal.h"
 
@@ -33,29 +35,45 @@ namespace {
 }  // namespace
 
 #ifndef SDFB_QUERY_EXACT
-// Builds s.dLeafIndex (EXPERIMENTAL, see leafIndexKernel). levels = as deep as the tree goes, capped so that the index
-// stays within 2^27 cells (512 MB); leaves s.leafIndexLevels = -1 when the array does not have the 8-word block
-// structure the packing relies on (a hand-made .bin), in which case the plain kernel keeps being used.
-void buildLeafIndex(sdfb200_sdf& s, cudaStream_t st) {
+// Builds s.dTopIndex (topIndexKernel): levels = as deep as the tree goes below the start grid, capped so that the index
+// stays within 2^21 cells (8 MB: L2-resident next to the structure). Leaves s.topLevels = -1 when the array does not
+// have the 8-word block structure the packing relies on (a hand-made .bin) or the start grid is not a power of two;
+// the one-query-per-thread kernel serves those. Runs on the legacy default stream and synchronises (build / load time).
+void prepareOctreeQuery(sdfb200_sdf& s) {
+    s.topLevels = -1;
+    const char* plain = std::getenv("SDFB200_QUERY_PLAIN");   // read once per structure, not per query
+    s.forcePlainQuery = plain && plain[0] == '1';
+    if (s.format != SDFB200_FORMAT_OCTREE || !s.dOctree.p) return;
     int startDepth = 0;
     while ((1 << startDepth) < s.startGridSize) startDepth++;
-    int levels = std::max(0, int(s.maxDepth) - startDepth);
-    while (levels > 0 && 3 * (startDepth + levels) > 27) levels--;
-    s.leafIndexLevels = -1;
-    if ((1 << startDepth) != s.startGridSize || 3 * startDepth > 27) return;
+    if ((1 << startDepth) != s.startGridSize || 3 * startDepth > 21) return;
+    int levels = std::min(std::max(0, int(s.maxDepth) - startDepth), 15);
+    while (levels > 0 && 3 * (startDepth + levels) > 21) levels--;
     const uint64_t cells = uint64_t(1) << (3 * (startDepth + levels));
-    s.dLeafIndex.alloc(cells + 1);
-    SDFB_CUDA(cudaStreamSynchronize(cudaStream_t(0)));   // allocations are ordered on the default stream, the kernel runs on `st`
-    uint32_t* bad = s.dLeafIndex.p + cells;
-    SDFB_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t), st));
-    leafIndexKernel<<<uint32_t((cells + 255) / 256), 256, 0, st>>>(s.dOctree.p, s.startGridSize, levels, s.dLeafIndex.p, bad);
+    s.dTopIndex.alloc(cells + 1);
+    uint32_t* bad = s.dTopIndex.p + cells;
+    SDFB_CUDA(cudaMemsetAsync(bad, 0, sizeof(uint32_t)));
+    topIndexKernel<<<uint32_t((cells + 255) / 256), 256>>>(s.dOctree.p, s.startGridSize, levels, s.dTopIndex.p, bad);
     SDFB_CUDA(cudaGetLastError());
     uint32_t hostBad = 1;
-    SDFB_CUDA(cudaMemcpyAsync(&hostBad, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    SDFB_CUDA(cudaStreamSynchronize(st));
-    if (hostBad) { s.dLeafIndex.release(); return; }
-    s.leafIndexLevels = levels;
+    SDFB_CUDA(cudaMemcpy(&hostBad, bad, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (hostBad) { s.dTopIndex.release(); return; }
+    s.topLevels = levels;
+    s.gridShift = startDepth;
 }
+
+namespace {
+int smCount(int device) {
+    static int cached[64] = {0};
+    if (device < 0 || device >= 64) device = 0;
+    if (!cached[device]) {
+        int n = 0;
+        SDFB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device));
+        cached[device] = n > 0 ? n : 1;
+    }
+    return cached[device];
+}
+}  // namespace
 #endif
 
 #ifdef SDFB_QUERY_EXACT
@@ -63,7 +81,11 @@ void launchOctreeQueryExact(
 #else
 void launchOctreeQueryFast(
 #endif
-    const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st) {
+    const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st
+#ifndef SDFB_QUERY_EXACT
+    , bool hostMapped
+#endif
+    ) {
     if (n == 0) return;
     QueryParams q;
     q.minx = s.boxMin[0]; q.miny = s.boxMin[1]; q.minz = s.boxMin[2];
@@ -76,26 +98,27 @@ void launchOctreeQueryFast(
     const bool vec = (uint64_t(s.startGridSize) * s.startGridSize * s.startGridSize) % 4 == 0 && s.leafBlocksAligned;
     if (s.maxDepth > 16) throw Error(SDFB200_ERR_INVALID, "octree deeper than 16 levels");
 #ifndef SDFB_QUERY_EXACT
-    if (s.useCoopQuery && vec) {   // EXPERIMENTAL, set by sdfb200_query under SDFB200_QUERY_COOP=1
-        if (dGrad) octreeQueryCoopKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, dGrad);
-        else octreeQueryCoopKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, nullptr);
+    // Markstein's division needs a normal divisor whose significand is not all ones; 1 / cell must be normal as well
+    uint32_t cellBits;
+    std::memcpy(&cellBits, &s.cellSize, 4);
+    const bool cellOk = s.cellSize > 1e-30f && s.cellSize < 1e30f && (cellBits & 0x7FFFFFu) != 0x7FFFFFu;
+    if (vec && s.topLevels >= 0 && cellOk && !s.forcePlainQuery && n < (uint64_t(1) << 36)) {
+        TileQuery tq;
+        tq.rcell = 1.0f / s.cellSize;
+        tq.gridf = float(s.startGridSize);
+        tq.gridShift = s.gridShift;
+        tq.topLevels = s.topLevels;
+        tq.G3 = uint32_t(s.startGridSize) * uint32_t(s.startGridSize) * uint32_t(s.startGridSize);
+        tq.tmaPoints = !hostMapped && (reinterpret_cast<uintptr_t>(dXyz) & 15u) == 0;
+        tq.tmaGrad = !hostMapped && dGrad && (reinterpret_cast<uintptr_t>(dGrad) & 15u) == 0;
+        const uint64_t tiles = (n + 31) / 32;
+        const uint32_t ctas = uint32_t(std::min<uint64_t>((tiles + kTileWarps - 1) / kTileWarps, uint64_t(smCount(s.device)) * (dGrad ? 6 : 8)));
+        if (dGrad) octreeQueryTileKernel<true><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, dGrad);
+        else octreeQueryTileKernel<false><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, nullptr);
         SDFB_CUDA(cudaGetLastError());
         return;
     }
 #endif
-    if (s.useLeafIndex && s.leafIndexLevels >= 0) {   // EXPERIMENTAL, set by sdfb200_query under SDFB200_QUERY_INDEX=1
-        const uint32_t* ix = s.dLeafIndex.p;
-        const int lv = s.leafIndexLevels;
-        if (dGrad) {
-            if (vec) octreeQueryIndexedKernel<true, true><<<grid, 256, 0, st>>>(s.dOctree.p, ix, lv, q, dXyz, n, dDist, dGrad);
-            else octreeQueryIndexedKernel<true, false><<<grid, 256, 0, st>>>(s.dOctree.p, ix, lv, q, dXyz, n, dDist, dGrad);
-        } else {
-            if (vec) octreeQueryIndexedKernel<false, true><<<grid, 256, 0, st>>>(s.dOctree.p, ix, lv, q, dXyz, n, dDist, nullptr);
-            else octreeQueryIndexedKernel<false, false><<<grid, 256, 0, st>>>(s.dOctree.p, ix, lv, q, dXyz, n, dDist, nullptr);
-        }
-        SDFB_CUDA(cudaGetLastError());
-        return;
-    }
     if (dGrad) {
         if (vec) octreeQueryKernel<true, true><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, dGrad);
         else octreeQueryKernel<true, false><<<grid, 256, 0, st>>>(s.dOctree.p, q, dXyz, n, dDist, dGrad);

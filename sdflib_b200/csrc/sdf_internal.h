@@ -152,6 +152,10 @@ struct BuildState {
     virtual void finish(sdfb200_sdf& out, const uint32_t* allSizesBySlot) = 0;
 };
 
+// host-pointer query staging (query_host.cpp); incomplete here so that the handle can own one
+struct QueryStage;
+struct QueryStageDeleter { void operator()(QueryStage* p) const; };
+
 // octree node word encoding (reference: OctreeSdf::OctreeNode, include/SdfLib/OctreeSdf.h:39-98)
 constexpr uint32_t kLeafBit = 1u << 31;
 constexpr uint32_t kOctIndexMask = ~(3u << 30);
@@ -188,16 +192,14 @@ struct sdfb200_sdf {
     sdfb200::DevBuf<float4> dFrames;
     sdfb200::DevBuf<uint64_t> dLeafLo;
     sdfb200::DevBuf<uint32_t> dLeafCnt, dLeafPool;
-    // EXPERIMENTAL dense leaf index of an OCTREE (octree_query.cu, SDFB200_QUERY_INDEX=1): built once on first use
-    sdfb200::DevBuf<uint32_t> dLeafIndex;
-    int leafIndexLevels = -1;        // levels below the start grid the index resolves; -1 = no index
-    std::atomic<bool> useLeafIndex{false};   // what the next launch does (sdfb200_query re-reads the switch on every call)
-    std::once_flag leafIndexOnce;
-    std::atomic<bool> useCoopQuery{false};   // EXPERIMENTAL quad-cooperative FMA kernel (SDFB200_QUERY_COOP=1), same protocol
-    // staging for host-pointer queries
-    sdfb200::DevBuf<float> dPts, dDist, dGrad;
-    cudaStream_t qStream[2] = {nullptr, nullptr};
-    cudaEvent_t qEvent = nullptr;
+    // query-side index of an OCTREE (octree_query.cu, prepareOctreeQuery): one word per cell of the grid `topLevels`
+    // below the start grid; -1 = the array does not meet the tile kernel's preconditions
+    sdfb200::DevBuf<uint32_t> dTopIndex;
+    int topLevels = -1, gridShift = 0;
+    bool forcePlainQuery = false;    // SDFB200_QUERY_PLAIN=1 at build / load time: one-query-per-thread kernel (A/B measurements)
+    // staging of host-pointer queries (query_host.cpp), created on first use under stageMutex
+    std::unique_ptr<sdfb200::QueryStage, sdfb200::QueryStageDeleter> stage;
+    std::mutex stageMutex;
     // sharded build: phase state, root plan, per-slot sizes of the own roots, streams for export / assembly
     bool isShard = false;          // true until sdfb200_assemble completed the structure
     std::unique_ptr<sdfb200::BuildState> build;
@@ -208,10 +210,6 @@ struct sdfb200_sdf {
     uint32_t shardScalars[2] = {0, 0};         // OCTREE: valueRange bits / ordered minBorder; EXACT: max leaf / max encoded
     sdfb200_build_stats stats = {};
 
-    ~sdfb200_sdf() {
-        for (int k = 0; k < 2; k++) if (qStream[k]) cudaStreamDestroy(qStream[k]);
-        if (qEvent) cudaEventDestroy(qEvent);
-    }
 };
 
 namespace sdfb200 {
@@ -240,8 +238,13 @@ void nearestTriangleOnDevice(const HostMesh& mesh, const float* xyz, uint64_t n,
 void pointTriangleOnDevice(const float* tri37, const float* v123, const float* xyz, uint64_t n, int mode, float* outDist,
                            float* outGrad);
 // octree_query.cu (two objects: fast = FMA Horner, exact = reference operation order)
-void launchOctreeQueryFast(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
-void buildLeafIndex(sdfb200_sdf& s, cudaStream_t st);
+// hostMapped: the pointers alias mapped host memory (small-batch slot): no TMA staging
+void launchOctreeQueryFast(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st,
+                           bool hostMapped = false);
+void prepareOctreeQuery(sdfb200_sdf& s);   // top index of a complete OCTREE structure (default stream, synchronises)
+// query_host.cpp
+void queryHostPointers(sdfb200_sdf& s, const float* xyz, uint64_t n, float* dist, float* grad, int flags, cudaStream_t st);
+void queryDevicePointers(const sdfb200_sdf& s, const float* xyz, uint64_t n, float* dist, float* grad, int flags, cudaStream_t st);
 void launchOctreeQueryExact(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
 // exact_build.cu / exact_query.cu
 void buildExactOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,

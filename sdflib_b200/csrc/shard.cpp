@@ -86,7 +86,7 @@ void shardAssemble(sdfb200_sdf& s, const uint32_t* dGathered, const uint64_t* wo
     // host mirrors of the now complete structure
     s.octree.resize(s.dOctree.n);
     s.dOctree.download(s.octree.data(), s.octree.size());
-    if (s.format == SDFB200_FORMAT_OCTREE) finalizeOctreeScalars(s);
+    if (s.format == SDFB200_FORMAT_OCTREE) { finalizeOctreeScalars(s); prepareOctreeQuery(s); }
     else {
         s.maxTrisInLeafs = sc0;
         s.maxTrisEncoded = sc1;

@@ -1,17 +1,21 @@
 // Runs the OctreeSdf query kernels of sdflib_b200/csrc/octree_query_kernels.cuh ON THE CPU, from the very same source,
 // under a lock-step warp emulation: every lane of a warp is a host thread, and the warp collectives (__ballot_sync,
 // __shfl_sync, __shfl_xor_sync) are barrier exchanges between the 32 threads. Purpose: the experimental kernels
-// (quad-cooperative evaluation, dense leaf index) were written without a GPU at hand; this checks their control flow —
+// (tile kernel: top index, division-free cell selection, quad-cooperative evaluation) this checks the control flow —
 // rounds, leader choice, class membership, index packing, partial last warp — against the plain kernel and (in the
 // pytest wrapper, tests/test_query_variants_model.py) against the oracle. Host fmaf is a true fused multiply-add and
 // the file is compiled with -ffp-contract=off, so the arithmetic is the device's FMA-kernel arithmetic.
 //
-//   simt_query_main <in.bin> <out.bin>
+//   simt_query_main <in.bin> <out.bin> [top index levels]
 //   in : 6 f32 box, f32 cell, i32 grid, f32 minBorder, u32 maxDepth, u64 nWords, words, u64 nPoints, points (xyz f32)
-//   out: for each of plain, indexed, coop: distances (n f32), then distances + gradients of the gradient kernels
+//   out: for each of plain, tile: distances (n f32), then distances + gradients of the gradient kernels
+// It also compares the tile kernel's division-free cell selection (cellCoordinate / floorSmall) with IEEE division and
+// floorf on every coordinate of the batch and on 2^22 random ones; any mismatch fails the run.
 // With -DSDFB_QUERY_EXACT the same header yields the reference-order kernels (no cooperative one): their output must
 // equal the oracle bit for bit, which also pins the emulation itself (host arithmetic = device arithmetic, -fmad=false).
 #include <barrier>
+#include <cfenv>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -27,7 +31,7 @@ struct Warp {
     std::barrier<> bar{32};
     uint64_t slot[32];
 };
-thread_local Dim tThread, tBlock, tBlockDim;
+thread_local Dim tThread, tBlock, tBlockDim, tGridDim;
 thread_local Warp* tWarp = nullptr;
 thread_local unsigned tLane = 0;
 
@@ -61,7 +65,7 @@ template <class K> void launch(unsigned grid, unsigned block, K kernel) {
             for (unsigned l = 0; l < 32; l++)
                 lanes.emplace_back([&, b, w, l] {
                     tWarp = &warp; tLane = l;
-                    tThread.x = w * 32 + l; tBlock.x = b; tBlockDim.x = block;
+                    tThread.x = w * 32 + l; tBlock.x = b; tBlockDim.x = block; tGridDim.x = grid;
                     kernel();
                     warp.bar.arrive_and_drop();   // a lane that left (early return / end) no longer takes part
                 });
@@ -71,6 +75,8 @@ template <class K> void launch(unsigned grid, unsigned block, K kernel) {
 }  // namespace simt
 
 #define __launch_bounds__(...)
+#define SDFB_SIMT_HOST 1
+#define gridDim simt::tGridDim
 #define threadIdx simt::tThread
 #define blockIdx simt::tBlock
 #define blockDim simt::tBlockDim
@@ -81,6 +87,21 @@ inline unsigned __ballot_sync(unsigned, bool p) { return simt::ballot(p); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
+inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
+inline void __syncwarp() { simt::tWarp->bar.arrive_and_wait(); }
+// the rounding-mode intrinsics: volatile operands keep g++ from folding or contracting them (-ffp-contract=off anyway)
+inline float __fmul_rn(float a, float b) { volatile float x = a, y = b; return x * y; }
+inline float __fadd_rn(float a, float b) { volatile float x = a, y = b; return x + y; }
+inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+inline float __fadd_rd(float a, float b) {
+    const int old = std::fegetround();
+    std::fesetround(FE_DOWNWARD);
+    volatile float x = a, y = b;
+    volatile float r = x + y;
+    std::fesetround(old);
+    return r;
+}
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 
 namespace sdfb200 {
@@ -119,15 +140,40 @@ int main(int argc, char** argv) {
     q.cell = cell; q.grid = grid; q.minBorder = minBorder;
     const unsigned blocks = unsigned((n + 255) / 256);
 
-    // leaf index exactly as buildLeafIndex (octree_query.cu) sizes it
+    // top index exactly as prepareOctreeQuery (octree_query.cu) sizes it
     int startDepth = 0;
     while ((1 << startDepth) < grid) startDepth++;
-    int levels = int(maxDepth) - startDepth;
+    int levels = std::min(std::max(0, int(maxDepth) - startDepth), 15);
+    while (levels > 0 && 3 * (startDepth + levels) > 21) levels--;
     if (argc > 3) levels = std::min(levels, std::atoi(argv[3]));   // shallower index: the finishing descent gets exercised
     const uint64_t cells = uint64_t(1) << (3 * (startDepth + levels));
     std::vector<uint32_t> index(cells + 1, 0u);
-    simt::launch(unsigned((cells + 255) / 256), 256, [&] { leafIndexKernel(oct.data(), grid, levels, index.data(), index.data() + cells); });
-    if (index[cells]) { std::fprintf(stderr, "leafIndexKernel flagged the array\n"); return 1; }
+#ifndef SDFB_QUERY_EXACT
+    simt::launch(unsigned((cells + 255) / 256), 256, [&] { topIndexKernel(oct.data(), grid, levels, index.data(), index.data() + cells); });
+    if (index[cells]) { std::fprintf(stderr, "topIndexKernel flagged the array\n"); return 1; }
+    TileQuery tq;
+    tq.rcell = 1.0f / cell; tq.gridf = float(grid); tq.gridShift = startDepth; tq.topLevels = levels;
+    tq.G3 = uint32_t(grid) * uint32_t(grid) * uint32_t(grid); tq.tmaPoints = 0; tq.tmaGrad = 0;
+    {   // division-free cell selection against IEEE division / floorf
+        uint64_t bad = 0, state = 0x9E3779B97F4A7C15ull;
+        auto check = [&](float x) {
+            const float want = x / cell, got = cellCoordinate(x, cell, tq.rcell);
+            if (std::fabs(x) > 1e-30f && __float_as_uint(want) != __float_as_uint(got)) bad++;
+            if (want >= 0.0f && want < 4194304.0f) {
+                uint32_t asInt = 0;
+                const float fl = floorSmall(want, asInt);
+                if (fl != std::floor(want) || asInt != uint32_t(std::floor(want))) bad++;
+            }
+        };
+        for (uint64_t i = 0; i < 3 * n; i++) check(xyz[i] - box[i % 3]);
+        for (int i = 0; i < (1 << 22); i++) {
+            state ^= state << 13; state ^= state >> 7; state ^= state << 17;
+            const float u = float(state >> 40) * (1.0f / 16777216.0f);
+            check((i & 1) ? u * 1.1f * float(grid) * cell : float(state % uint64_t(64 * grid)) / 64.0f * cell);   // uniform / near cell and sub-cell boundaries
+        }
+        if (bad) { std::fprintf(stderr, "cell selection differs from IEEE division / floor on %llu values\n", (unsigned long long)bad); return 1; }
+    }
+#endif
 
     FILE* o = std::fopen(argv[2], "wb");
     if (!o) return 2;
@@ -142,19 +188,14 @@ int main(int argc, char** argv) {
     emit(false);
     simt::launch(blocks, 256, [&] { octreeQueryKernel<true, true>(oct.data(), q, pts, n, dist.data(), grad.data()); });
     emit(true);
-    // indexed
-    simt::launch(blocks, 256, [&] { octreeQueryIndexedKernel<false, true>(oct.data(), index.data(), levels, q, pts, n, dist.data(), nullptr); });
-    emit(false);
-    simt::launch(blocks, 256, [&] { octreeQueryIndexedKernel<true, true>(oct.data(), index.data(), levels, q, pts, n, dist.data(), grad.data()); });
-    emit(true);
-#ifndef SDFB_QUERY_EXACT   // compiled with -DSDFB_QUERY_EXACT the header holds the reference-order kernels and no cooperative one
-    // quad-cooperative
+#ifndef SDFB_QUERY_EXACT   // compiled with -DSDFB_QUERY_EXACT the header holds the reference-order kernel only
+    // tile kernel (plain loads instead of the TMA staging): 3 CTAs of 8 warps, so every warp loops over several tiles
     std::fill(dist.begin(), dist.end(), -123.0f);
-    simt::launch(blocks, 256, [&] { octreeQueryCoopKernel<false>(oct.data(), q, pts, n, dist.data(), nullptr); });
+    simt::launch(3, 256, [&] { octreeQueryTileKernel<false>(oct.data(), index.data(), q, tq, pts, n, dist.data(), nullptr); });
     emit(false);
     std::fill(dist.begin(), dist.end(), -123.0f);
     std::fill(grad.begin(), grad.end(), -123.0f);
-    simt::launch(blocks, 256, [&] { octreeQueryCoopKernel<true>(oct.data(), q, pts, n, dist.data(), grad.data()); });
+    simt::launch(3, 256, [&] { octreeQueryTileKernel<true>(oct.data(), index.data(), q, tq, pts, n, dist.data(), grad.data()); });
     emit(true);
 #endif
     std::fclose(o);

@@ -1,5 +1,5 @@
-"""Host models of the EXPERIMENTAL query variants of octree_query.cu: the dense leaf index (leafIndexKernel /
-octreeQueryIndexedKernel) and the quad-cooperative evaluation (octreeQueryCoopKernel, last test).
+"""Host models of the building blocks of octreeQueryTileKernel (octree_query_kernels.cuh): the dense top index
+(topIndexKernel) and the quad-cooperative evaluation, plus the kernel SOURCE run on the CPU under a warp emulation.
 
 The CUDA code cannot run here; what can be checked on the CPU is the arithmetic it transcribes: the entry packing
 ((block - G^3) / 8, steps, leaf flag), the cell chosen from the start cell and the leading path bits, and the finish of
@@ -39,7 +39,7 @@ def build_index(oct_, G, levels):
             k += 1
         block = int(node & MASK)
         assert block >= G3 and (block - G3) % 8 == 0      # what the kernel reports through `bad`
-        index[i] = ((block - G3) >> 3) | (((1 << 31) | (k << 27)) if node & LEAF else 0)
+        index[i] = ((block - G3) >> 3) | (k << 27) | ((1 << 31) if node & LEAF else 0)
     return index
 
 
@@ -50,9 +50,10 @@ def indexed_descent(oct_, index, G, levels, ix, iy, iz, bx, by, bz):
     cz = (iz << levels) | (bz >> (PATH_BITS - levels))
     e = int(index[(cz * N + cy) * N + cx])
     block = ((e & ((1 << 27) - 1)) << 3) + G3
+    k = (e >> 27) & 15
     if e & (1 << 31):
-        return block, (e >> 27) & 15
-    k = levels
+        return block, k
+    assert k == levels
     while True:
         sh = PATH_BITS - 1 - k
         child = ((bx >> sh) & 1) | (((by >> sh) & 1) << 1) | (((bz >> sh) & 1) << 2)
@@ -169,7 +170,7 @@ def _query_case(port, tmp_path):
 def test_reference_order_kernels_under_warp_emulation_equal_the_oracle(port, tmp_path):
     """Pins the emulation: the -DSDFB_QUERY_EXACT build of the same header (the kernels behind
     SDFB200_QUERY_EXACT_ORDER, bit-exact on the GPU) must give the oracle's bits on the CPU too — in-box distances and
-    gradients, plain and indexed."""
+    gradients."""
     import subprocess
     exe = _compile_simt(tmp_path, exact=True)
     sdf, pts, area, size = _query_case(port, tmp_path)
@@ -177,10 +178,10 @@ def test_reference_order_kernels_under_warp_emulation_equal_the_oracle(port, tmp
     r = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), "2"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.startswith("ok "), (r.stdout, r.stderr)
     raw = np.fromfile(tmp_path / "out.bin", np.float32)
-    assert raw.size == 2 * 5 * n
+    assert raw.size == 5 * n
     ref_d, ref_g = sdf.query(pts, gradient=True)
     inside = ~((pts < area[:3]) | (pts >= area[3:])).any(1)
-    for k in range(2):                                   # plain, indexed
+    for k in range(1):
         d, dg, g = raw[5 * n * k:5 * n * k + n], raw[5 * n * k + n:5 * n * k + 2 * n], raw[5 * n * k + 2 * n:5 * n * (k + 1)].reshape(n, 3)
         assert_bit_equal(d, sdf.query(pts), "distance")
         assert_bit_equal(dg[inside], ref_d[inside], "distance of the gradient kernel")
@@ -190,10 +191,11 @@ def test_reference_order_kernels_under_warp_emulation_equal_the_oracle(port, tmp
 @pytest.mark.parametrize("index_levels", [None, 1])
 def test_kernel_sources_under_warp_emulation(port, tmp_path, index_levels):
     """The CUDA source of the query kernels (octree_query_kernels.cuh), compiled for the host and run under a lock-step
-    warp emulation (tests/cpp/simt_query_main.cpp): the indexed kernels must equal the plain ones bit for bit, the
-    quad-cooperative ones must find the same leaf and stay within the FMA kernel's tolerance of the reference's
-    evaluation order (oracle), including points outside the box, rows of a grid (shared classes), unrelated points
-    (one class per lane) and a batch that ends in the middle of a warp."""
+    warp emulation (tests/cpp/simt_query_main.cpp): the tile kernel (top index, division-free cell selection —
+    compared with IEEE division inside the harness —, quad-cooperative evaluation, persistent warps looping over tiles)
+    must stay within the FMA kernel's tolerance of the reference's evaluation order (oracle), including points outside
+    the box, rows of a grid (shared classes), unrelated points (one class per lane) and a batch that ends in the middle
+    of a warp."""
     import subprocess
     exe = _compile_simt(tmp_path)
     sdf, pts, area, size = _query_case(port, tmp_path)
@@ -202,26 +204,24 @@ def test_kernel_sources_under_warp_emulation(port, tmp_path, index_levels):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.startswith("ok "), (r.stdout, r.stderr)
     raw = np.fromfile(tmp_path / "out.bin", np.float32)
-    assert raw.size == 3 * (n + 4 * n)
+    assert raw.size == 2 * (n + 4 * n)
     parts = {}
     off = 0
-    for name in ("plain", "indexed", "coop"):
+    for name in ("plain", "tile"):
         parts[name] = dict(d=raw[off:off + n], dg=raw[off + n:off + 2 * n], g=raw[off + 2 * n:off + 5 * n].reshape(n, 3))
         off += 5 * n
-    for key in ("d", "dg", "g"):
-        assert (parts["plain"][key].view(np.uint32) == parts["indexed"][key].view(np.uint32)).all(), key
     ref_d, ref_g = sdf.query(pts, gradient=True)
     # the plain FMA kernel itself sits at 1.05 x the GPU tests' floor (1e-3 of the box) on one near-surface point of
     # this tree (|d| = 0.0027, coefficients of order 1), so the floor here is 1e-2 of the box for both kernels
     tol = 1e-5 * np.maximum(np.abs(ref_d), 1e-2 * size)
-    for name in ("plain", "coop"):
+    for name in ("plain", "tile"):
         assert (np.abs(parts[name]["d"] - ref_d) <= tol).all(), name
         assert (np.abs(parts[name]["dg"] - ref_d) <= tol).all(), name
         fin = np.isfinite(ref_g).all(1) & np.isfinite(parts[name]["g"]).all(1)
         assert fin.mean() > 0.9 and np.abs(parts[name]["g"][fin] - ref_g[fin]).max() <= 1e-4, name
     outside = ((pts < area[:3]) | (pts >= area[3:])).any(1)
     assert outside.sum() > 50      # box-distance path: identical code in both kernels
-    assert (parts["plain"]["d"][outside].view(np.uint32) == parts["coop"]["d"][outside].view(np.uint32)).all()
+    assert (parts["plain"]["d"][outside].view(np.uint32) == parts["tile"]["d"][outside].view(np.uint32)).all()
 
 
 def test_refill_sampler_source_under_warp_emulation(sdf, tmp_path):
