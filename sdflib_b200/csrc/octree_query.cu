@@ -13,9 +13,9 @@
 // polynomial is summed (<= a few ulp of the largest term).
 //
 // Kernels (octree_query_kernels.cuh):
-//   octreeQueryTileKernel  the default of the FMA path: persistent warps over 32-query tiles staged by TMA, dense top
-//                          index instead of the first dependent gathers, division-free cell selection, quad-cooperative
-//                          evaluation (see the comment on the kernel for what each of these removes, with the measurements)
+//   octreeQueryTileKernel  the default of the FMA path: persistent warps over 32-query tiles (next tile's points loaded
+//                          ahead), dense top index instead of the first dependent gathers, division-free cell selection,
+//                          quad-cooperative evaluation (see the comment on the kernel for what each of these removes)
 //   octreeQueryKernel      one query per thread: the reference-order (bit-exact) object, and the fallback of the FMA
 //                          object for arrays the tile kernel's preconditions exclude (leaf blocks not 16-byte aligned,
 //                          block offsets not of the 8-word form, start grid not a power of two)
@@ -23,6 +23,7 @@
 // thread kernel (+3 %: it was bound by the coefficient fill, not the descent) and a variant staging distinct leaves in
 // shared memory (slower: the register fill from shared memory costs the same wavefronts).
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -43,6 +44,8 @@ void prepareOctreeQuery(sdfb200_sdf& s) {
     s.topLevels = -1;
     const char* plain = std::getenv("SDFB200_QUERY_PLAIN");   // read once per structure, not per query
     s.forcePlainQuery = plain && plain[0] == '1';
+    const char* occ = std::getenv("SDFB200_TILE_OCC");         // measurement switch: 8 (32 registers) or 6 (40 registers) CTAs per SM
+    s.tileCtasPerSm = occ && occ[0] == '8' ? 8 : 6;
     if (s.format != SDFB200_FORMAT_OCTREE || !s.dOctree.p) return;
     int startDepth = 0;
     while ((1 << startDepth) < s.startGridSize) startDepth++;
@@ -104,17 +107,25 @@ void launchOctreeQueryFast(
     const bool cellOk = s.cellSize > 1e-30f && s.cellSize < 1e30f && (cellBits & 0x7FFFFFu) != 0x7FFFFFu;
     if (vec && s.topLevels >= 0 && cellOk && !s.forcePlainQuery && n < (uint64_t(1) << 36)) {
         TileQuery tq;
-        tq.rcell = 1.0f / s.cellSize;
-        tq.gridf = float(s.startGridSize);
-        tq.gridShift = s.gridShift;
-        tq.topLevels = s.topLevels;
+        const int L = s.topLevels;
+        tq.cellL = std::ldexp(s.cellSize, -L);
+        tq.rcellL = 1.0f / tq.cellL;
+        const float limit = float(uint32_t(s.startGridSize) << L);
+        std::memcpy(&tq.limitBits, &limit, 4);
+        tq.shiftN = s.gridShift + L;
+        tq.topLevels = L;
         tq.G3 = uint32_t(s.startGridSize) * uint32_t(s.startGridSize) * uint32_t(s.startGridSize);
-        tq.tmaPoints = !hostMapped && (reinterpret_cast<uintptr_t>(dXyz) & 15u) == 0;
-        tq.tmaGrad = !hostMapped && dGrad && (reinterpret_cast<uintptr_t>(dGrad) & 15u) == 0;
+        (void)hostMapped;
         const uint64_t tiles = (n + 31) / 32;
-        const uint32_t ctas = uint32_t(std::min<uint64_t>((tiles + kTileWarps - 1) / kTileWarps, uint64_t(smCount(s.device)) * (dGrad ? 6 : 8)));
-        if (dGrad) octreeQueryTileKernel<true><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, dGrad);
-        else octreeQueryTileKernel<false><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, nullptr);
+        const int occ = s.tileCtasPerSm;   // resident CTAs per SM the kernel is compiled for (8: 32 registers, 6: 40)
+        const uint32_t ctas = uint32_t(std::min<uint64_t>((tiles + kTileWarps - 1) / kTileWarps, uint64_t(smCount(s.device)) * occ));
+        if (dGrad) {
+            if (occ == 8) octreeQueryTileKernel<true, 8><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, dGrad);
+            else octreeQueryTileKernel<true, 6><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, dGrad);
+        } else {
+            if (occ == 8) octreeQueryTileKernel<false, 8><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, nullptr);
+            else octreeQueryTileKernel<false, 6><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, nullptr);
+        }
         SDFB_CUDA(cudaGetLastError());
         return;
     }

@@ -161,46 +161,46 @@ octreeQueryKernel(const uint32_t* __restrict__ oct, const QueryParams q, const f
     if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
 }
 
-// ---- the default kernel of the FMA path: warp-per-query-batch, TMA-staged point tiles, quad-cooperative evaluation ----------
-// Measured on the 256^3 workload (profiles/r2_summary.md): the one-query-per-thread kernel above is bound by the LSU
-// data pipe (every lane fills 64 coefficient registers: 16 x LDG.128, one wavefront per DISTINCT leaf in the warp) and,
-// once that is cut, by the latency of its dependent chain (point -> 5-6 node gathers -> coefficients) at 58 % achieved
-// occupancy and by XU-pipe conversions (IEEE division, floor, float <-> int). This kernel removes each of them:
-//   * every WARP is a persistent worker over 32-query tiles (tile = 384 contiguous bytes of xyz): lane 0 fetches the
-//     next tile with one 1-D TMA bulk copy into the warp's double-buffered shared-memory slot while the current tile
-//     is evaluated, so the point loads cost no LSU wavefronts and their DRAM latency is off the chain; unit gradients
-//     leave the same way (shared memory -> one bulk store of 384 bytes) instead of stride-3 scalar stores;
+// ---- the default kernel of the FMA path: warp-per-query-batch, top index, quad-cooperative evaluation -------------------------
+// What bounds the one-query-per-thread kernel above (profiles/r2_summary.md, 256^3 workload): the LSU data pipe — every
+// lane fills 64 coefficient registers, 16 x LDG.128 costing one wavefront per DISTINCT leaf in the warp — then the latency of
+// its dependent chain (point -> 5-6 node gathers -> coefficients) and the XU pipe (IEEE division, floor, float <-> int). Once
+// those are cut the kernel is ISSUE bound, so everything below is also chosen for its instruction count:
+//   * every WARP is a persistent worker over 32-query tiles and loads the NEXT tile's points before it evaluates the
+//     current one (their DRAM latency is off the chain). Staging the tiles through shared memory with one 1-D TMA bulk
+//     copy per tile was built and measured: the mbarrier / elect / address bookkeeping costs ~75 instructions per tile
+//     against 9 for three strided loads, and the kernel was no faster (0.235 ms vs 0.232 ms); it was dropped;
 //   * a dense TOP INDEX (one word per cell of the grid `topLevels` below the start grid, <= 2^21 cells = 8 MB,
-//     L2-resident) replaces the first `topLevels` dependent gathers by one load that is coalesced for coherent
-//     batches; only leaves deeper than the index (0.2 % of the 256^3 queries) continue the descent;
+//     L2-resident) replaces the first `topLevels` dependent gathers by one load that is coalesced for coherent batches;
+//     only leaves deeper than the index (0.2 % of the 256^3 queries) continue the descent;
 //   * the cell selection uses no division and no conversion instruction but gives the reference's bits:
-//     (p - min) / cell is formed as two Newton steps on x * RN(1 / cell) with exact FMA residuals (Markstein: the
-//     result is the correctly rounded quotient for normal operands; tests/cpp/simt_query_main.cpp and
-//     tests/test_query_variants_model.py check it against IEEE division), floor() is an add of 2^23 rounded towards
-//     minus infinity, the integer cell and the 16 path bits are read from the mantissa of that sum;
+//     u = (p - min) / (cell / 2^L) — the reference's quotient scaled by the exact factor 2^L — is formed as two Newton
+//     steps on x * RN(2^L / cell) with exact FMA residuals (Markstein: the correctly rounded quotient for normal
+//     operands; tests/cpp/simt_query_main.cpp checks it against IEEE division), floor() is an add of 2^23 rounded
+//     towards minus infinity whose mantissa is the integer cell, and "0 <= u < N" is one unsigned compare of the float
+//     bits (negative values and NaN have larger patterns);
 //   * the polynomial is evaluated by the four lanes of an aligned quad working on one (leaf, y, z) class at a time:
 //     lane r loads the vectors c[0..3][j = r][k = 0..3] (64 contiguous bytes per quad and step), forms
 //     y^r * Horner_z, two butterfly shuffles give every lane the same sums A_i(y, z), each member evaluates the cubic
 //     in its own x. Grid rows put 4-8 neighbours of a row into one class; unrelated points take one round per lane
 //     and still use every loaded byte.
-// Same leaf and same leaf-local fractions as the reference; only the summation order of the polynomial differs
-// (independent of where in the batch a query sits), within the tolerance of the FMA path.
+// Same leaf and same leaf-local fractions as the reference (doubling, floor and subtraction are exact in binary floating
+// point, so frac(2^k f) taken from u equals the reference's fract(2 f) chain); only the summation order of the polynomial
+// differs (independent of where in the batch a query sits), within the tolerance of the FMA path.
 #ifndef SDFB_QUERY_EXACT
 struct TileQuery {
-    float rcell;             // RN(1 / cell), computed on the host
-    float gridf;             // float(grid)
-    int gridShift;           // log2(grid)
-    int topLevels;           // levels below the start grid the top index resolves
+    float cellL;             // cell / 2^L (exact: a power-of-two scaling)
+    float rcellL;            // RN(1 / cellL), computed on the host
+    uint32_t limitBits;      // bit pattern of float(grid << L)
+    int shiftN;              // log2(grid << L)
+    int topLevels;           // L: levels below the start grid the top index resolves
     uint32_t G3;             // grid^3
-    uint32_t tmaPoints;      // xyz is 16-byte aligned: tiles are fetched by TMA
-    uint32_t tmaGrad;        // grad is 16-byte aligned: gradients leave by bulk stores
 };
 
 // top index word: bit 31 = leaf, bits 27-30 = steps below the start grid at which the leaf / node was reached,
 // bits 0-26 = (block - G^3) / 8 (every block of the array is 8 or 64 words long and starts after the G^3 start words)
 constexpr uint32_t kTopLeaf = 1u << 31;
 constexpr uint32_t kTopBlockMask = (1u << 27) - 1u;
-constexpr int kPathBits = 16;
 
 __global__ void __launch_bounds__(256)
 topIndexKernel(const uint32_t* __restrict__ oct, int grid, int levels, uint32_t* __restrict__ index, uint32_t* __restrict__ bad) {
@@ -222,108 +222,63 @@ topIndexKernel(const uint32_t* __restrict__ oct, int grid, int levels, uint32_t*
     index[i] = ((block - G3) >> 3) | (uint32_t(k) << 27) | ((node & kLeafBit) ? kTopLeaf : 0u);
 }
 
-// (x - lo) / cell, correctly rounded, without a division: q0 = x * rc, two steps q <- q + (x - q * cell) * rc with exact
+// x / cell, correctly rounded, without a division: q0 = x * rc, two steps q <- q + (x - q * cell) * rc with exact
 // residuals. Operands far below the normal range (|x| < 2^-100: the quotient is a denormal fraction of cell 0 either way)
-// may differ from IEEE division in their last bits; no cell or leaf decision depends on them.
+// may differ from IEEE division in their last bits; no cell or leaf decision depends on them. A zero of either sign comes
+// out as +0 (the residual of -0 is +0), which the unsigned range test relies on.
 __device__ __forceinline__ float cellCoordinate(float x, float cell, float rc) {
     float qv = __fmul_rn(x, rc);
     qv = __fmaf_rn(__fmaf_rn(-qv, cell, x), rc, qv);
     return __fmaf_rn(__fmaf_rn(-qv, cell, x), rc, qv);
 }
-// floor(v) for 0 <= v < 2^22 and the integer itself, from the mantissa of v + 2^23 rounded towards minus infinity
-__device__ __forceinline__ float floorSmall(float v, uint32_t& asInt) {
-    const float t = __fadd_rd(v, 8388608.0f);
-    asInt = uint32_t(__float_as_int(t)) & 0x7FFFFFu;
-    return __fadd_rn(t, -8388608.0f);
+// v - floor(v) for 0 <= v < 2^22 (floor = v + 2^23 rounded towards minus infinity, minus 2^23; every step exact)
+__device__ __forceinline__ float fractSmall(float v) {
+    return __fadd_rn(v, -__fadd_rn(__fadd_rd(v, 8388608.0f), -8388608.0f));
 }
-
-#ifndef SDFB_SIMT_HOST
-__device__ __forceinline__ void qMbarInit(uint64_t* bar) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(uint32_t(__cvta_generic_to_shared(bar))));
-}
-__device__ __forceinline__ void qTileLoad(void* smemDst, const void* gmemSrc, uint64_t* bar) {   // 384 bytes, 16-byte aligned both sides
-    const uint32_t b = uint32_t(__cvta_generic_to_shared(bar));
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 384;" ::"r"(b) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 384, [%2];" ::"r"(
-                     uint32_t(__cvta_generic_to_shared(smemDst))), "l"(gmemSrc), "r"(b) : "memory");
-}
-__device__ __forceinline__ void qMbarWait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "QWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra QDONE_%=;\n"
-        "bra QWAIT_%=;\n"
-        "QDONE_%=:\n"
-        "}\n" ::"r"(uint32_t(__cvta_generic_to_shared(bar))), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void qTileStore(void* gmemDst, const void* smemSrc) {   // 384 bytes shared -> global, one bulk group
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 384;" ::"l"(gmemDst), "r"(uint32_t(__cvta_generic_to_shared(smemSrc))) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-#endif
 
 constexpr int kTileWarps = 8;   // warps per CTA of the tile kernel
 
-template <bool kGrad>
-__global__ void __launch_bounds__(kTileWarps * 32, kGrad ? 6 : 8)
+template <bool kGrad, int kCtasPerSm>
+__global__ void __launch_bounds__(kTileWarps * 32, kCtasPerSm)
 octreeQueryTileKernel(const uint32_t* __restrict__ oct, const uint32_t* __restrict__ top, const QueryParams q, const TileQuery tq,
                       const float* __restrict__ xyz, uint64_t n, float* __restrict__ dist, float* __restrict__ grad) {
     constexpr unsigned kFull = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t tiles = uint32_t((n + 31) >> 5), fullTiles = uint32_t(n >> 5);   // the launcher keeps n below 2^36
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned r = lane & 3u, quadBase = lane & ~3u;
+    const uint32_t tiles = uint32_t((n + 31) >> 5);   // the launcher keeps n below 2^36
     const uint32_t stride = gridDim.x * kTileWarps;
-    uint32_t t = blockIdx.x * kTileWarps + warp;
-#ifndef SDFB_SIMT_HOST
-    __shared__ alignas(16) float sPts[kTileWarps][2][96];
-    __shared__ alignas(16) float sGrad[kGrad ? kTileWarps : 1][96];
-    __shared__ alignas(8) uint64_t sBar[kTileWarps][2];
-    if (lane == 0) {
-        qMbarInit(&sBar[warp][0]);
-        qMbarInit(&sBar[warp][1]);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    if (tq.tmaPoints && lane == 0 && t < fullTiles) qTileLoad(sPts[warp][0], xyz + uint64_t(t) * 96, &sBar[warp][0]);
-#endif
-    for (uint32_t it = 0; t < tiles; it++) {
-        const uint64_t i = (uint64_t(t) << 5) + lane;
+    uint32_t t = blockIdx.x * kTileWarps + (threadIdx.x >> 5);
+    if (t >= tiles) return;
+    uint64_t i = (uint64_t(t) << 5) + lane;
+    f3 p = i < n ? mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2)) : mk3(0.0f, 0.0f, 0.0f);
+    for (;;) {
         const bool valid = i < n;
-        f3 p;
-#ifndef SDFB_SIMT_HOST
-        if (tq.tmaPoints && t < fullTiles) {
-            const int s = int(it & 1u);
-            __syncwarp();   // every lane has taken its point of the previous tile out of slot s ^ 1
-            if (lane == 0 && uint64_t(t) + stride < fullTiles) qTileLoad(sPts[warp][s ^ 1], xyz + (uint64_t(t) + stride) * 96, &sBar[warp][s ^ 1]);
-            qMbarWait(&sBar[warp][s], (it >> 1) & 1u);
-            const float* sp = sPts[warp][s] + 3 * lane;
-            p = mk3(sp[0], sp[1], sp[2]);
-        } else
-#endif
-            p = valid ? mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2)) : mk3(0.0f, 0.0f, 0.0f);
-        float fx = cellCoordinate(__fadd_rn(p.x, -q.minx), q.cell, tq.rcell), fy = cellCoordinate(__fadd_rn(p.y, -q.miny), q.cell, tq.rcell),
-              fz = cellCoordinate(__fadd_rn(p.z, -q.minz), q.cell, tq.rcell);
-        // floor(f) in [0, grid) <=> 0 <= f < grid (NaN compares false: outside, like the reference's int conversion)
-        const bool inside = valid && fx >= 0.0f && fy >= 0.0f && fz >= 0.0f && fx < tq.gridf && fy < tq.gridf && fz < tq.gridf;
+        const uint32_t tNext = t + stride;           // < 2^31 + 2^20: no wrap
+        const uint64_t iNext = (uint64_t(tNext) << 5) + lane;
+        f3 pNext = mk3(0.0f, 0.0f, 0.0f);
+        if (tNext < tiles && iNext < n) pNext = mk3(__ldg(xyz + 3 * iNext), __ldg(xyz + 3 * iNext + 1), __ldg(xyz + 3 * iNext + 2));
+
+        // u = (p - min) / cell * 2^L: integer part = cell of the top index, fraction = position inside it
+        const float ux = cellCoordinate(__fadd_rn(p.x, -q.minx), tq.cellL, tq.rcellL), uy = cellCoordinate(__fadd_rn(p.y, -q.miny), tq.cellL, tq.rcellL),
+                    uz = cellCoordinate(__fadd_rn(p.z, -q.minz), tq.cellL, tq.rcellL);
+        // 0 <= u < N as one unsigned compare of the bit pattern (negative values and NaN compare larger; -0 never occurs)
+        const bool inside = valid && __float_as_uint(ux) < tq.limitBits && __float_as_uint(uy) < tq.limitBits && __float_as_uint(uz) < tq.limitBits;
         f3 g = mk3(0.0f, 0.0f, 0.0f);
-        float d = 0.0f;
+        float d = 0.0f, fx = 0.0f, fy = 0.0f, fz = 0.0f;
         uint32_t block = 0;
         if (valid && !inside) d = (kGrad ? boxDistanceGrad(q, p, g) : boxDistance(q, p)) + q.minBorder;
         if (inside) {
-            uint32_t ix, iy, iz, bx, by, bz;
-            fx = __fadd_rn(fx, -floorSmall(fx, ix)); fy = __fadd_rn(fy, -floorSmall(fy, iy)); fz = __fadd_rn(fz, -floorSmall(fz, iz));
-            // path bits: bit j (from the top) of floor(frac * 2^16) is the child choice at level j (doubling, floor and
-            // subtraction are exact in binary floating point, so this is the reference's fract(2 f) chain)
-            floorSmall(__fmul_rn(fx, 65536.0f), bx); floorSmall(__fmul_rn(fy, 65536.0f), by); floorSmall(__fmul_rn(fz, 65536.0f), bz);
-            const int L = tq.topLevels, ns = tq.gridShift + L;
-            const uint32_t cx = (ix << L) | (bx >> (kPathBits - L)), cy = (iy << L) | (by >> (kPathBits - L)), cz = (iz << L) | (bz >> (kPathBits - L));
-            const uint32_t e = __ldg(top + ((((uint64_t(cz) << ns) | cy) << ns) | cx));
+            const uint32_t cx = uint32_t(__float_as_int(__fadd_rd(ux, 8388608.0f))) & 0x7FFFFFu, cy = uint32_t(__float_as_int(__fadd_rd(uy, 8388608.0f))) & 0x7FFFFFu,
+                           cz = uint32_t(__float_as_int(__fadd_rd(uz, 8388608.0f))) & 0x7FFFFFu;
+            const uint32_t e = __ldg(top + ((((cz << tq.shiftN) | cy) << tq.shiftN) | cx));
             block = ((e & kTopBlockMask) << 3) + tq.G3;
             int k = int((e >> 27) & 15u);
             if (!(e & kTopLeaf)) {
-                for (;;) {   // leaves below the index: finish the descent from the cell's node
-                    const int sh = kPathBits - 1 - k;
+                // leaves below the index: the next child choices are the leading bits of the fraction inside the index cell
+                const uint32_t bx = uint32_t(__float_as_int(__fadd_rd(__fmul_rn(fractSmall(ux), 65536.0f), 8388608.0f))) & 0xFFFFu,
+                               by = uint32_t(__float_as_int(__fadd_rd(__fmul_rn(fractSmall(uy), 65536.0f), 8388608.0f))) & 0xFFFFu,
+                               bz = uint32_t(__float_as_int(__fadd_rd(__fmul_rn(fractSmall(uz), 65536.0f), 8388608.0f))) & 0xFFFFu;
+                for (int sh = 15;; sh--) {
                     const uint32_t child = ((bx >> sh) & 1u) | (((by >> sh) & 1u) << 1) | (((bz >> sh) & 1u) << 2);
                     const uint32_t node = __ldg(oct + block + child);
                     k++;
@@ -331,19 +286,15 @@ octreeQueryTileKernel(const uint32_t* __restrict__ oct, const uint32_t* __restri
                     if (node & kLeafBit) break;
                 }
             }
-            const float scale = __int_as_float((127 + k) << 23);   // 2^k
-            uint32_t unused;
-            fx = __fmul_rn(fx, scale); fy = __fmul_rn(fy, scale); fz = __fmul_rn(fz, scale);
-            fx = __fadd_rn(fx, -floorSmall(fx, unused)); fy = __fadd_rn(fy, -floorSmall(fy, unused)); fz = __fadd_rn(fz, -floorSmall(fz, unused));
+            const float scale = __int_as_float((127 + k - tq.topLevels) << 23);   // 2^(k - L): leaf-local fraction = frac(f * 2^k)
+            fx = fractSmall(__fmul_rn(ux, scale)); fy = fractSmall(__fmul_rn(uy, scale)); fz = fractSmall(__fmul_rn(uz, scale));
         }
         bool pending = inside;
-        const unsigned quadBase = lane & ~3u, r = lane & 3u;
-        const unsigned quadMask = 0xFu << quadBase;
         for (;;) {
             const unsigned pend = __ballot_sync(kFull, pending);
             if (pend == 0) break;                                   // warp-uniform
-            const unsigned mine = pend & quadMask;
-            const int leader = mine ? __ffs(int(mine)) - 1 : int(quadBase);   // a finished quad idles through the shuffles
+            const unsigned mine = (pend >> quadBase) & 0xFu;
+            const int leader = int(quadBase) + (mine ? __ffs(int(mine)) - 1 : 0);   // a finished quad idles through the shuffles
             const uint32_t lb = __shfl_sync(kFull, block, leader);
             const float ly = __shfl_sync(kFull, fy, leader), lz = __shfl_sync(kFull, fz, leader);
             float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;       // this lane's part of A_i
@@ -353,7 +304,7 @@ octreeQueryTileKernel(const uint32_t* __restrict__ oct, const uint32_t* __restri
                 const float4* c = reinterpret_cast<const float4*>(oct + lb) + r;   // vector m = r + 4 k holds c[0..3][j = r][k]
                 const float4 c0 = __ldg(c), c1 = __ldg(c + 4), c2 = __ldg(c + 8), c3 = __ldg(c + 12);
                 const float yy = ly * ly;
-                const float yr = r == 0 ? 1.0f : (r == 1 ? ly : (r == 2 ? yy : yy * ly));           // y^r
+                const float yr = ((r & 1u) ? ly : 1.0f) * ((r & 2u) ? yy : 1.0f);                     // y^r
                 const float h0 = fmaf(fmaf(fmaf(c3.x, lz, c2.x), lz, c1.x), lz, c0.x), h1 = fmaf(fmaf(fmaf(c3.y, lz, c2.y), lz, c1.y), lz, c0.y);
                 const float h2 = fmaf(fmaf(fmaf(c3.z, lz, c2.z), lz, c1.z), lz, c0.z), h3 = fmaf(fmaf(fmaf(c3.w, lz, c2.w), lz, c1.w), lz, c0.w);
                 a0 = yr * h0; a1 = yr * h1; a2 = yr * h2; a3 = yr * h3;
@@ -388,26 +339,12 @@ octreeQueryTileKernel(const uint32_t* __restrict__ oct, const uint32_t* __restri
                 pending = false;   // the leader always matches itself bit for bit, so every round retires at least one lane per quad
             }
         }
-        if (valid) dist[i] = d;
-        if (kGrad) {
-#ifndef SDFB_SIMT_HOST
-            if (tq.tmaGrad && t < fullTiles) {
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's store has read the slot
-                __syncwarp();
-                float* sg = sGrad[warp] + 3 * lane;
-                sg[0] = g.x; sg[1] = g.y; sg[2] = g.z;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) qTileStore(grad + uint64_t(t) * 96, sGrad[warp]);
-            } else
-#endif
-            if (valid) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
+        if (valid) {
+            dist[i] = d;
+            if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
         }
-        if (tiles - t <= stride) break;   // t + stride could wrap
-        t += stride;
+        if (tNext >= tiles) break;
+        t = tNext; i = iNext; p = pNext;
     }
-#ifndef SDFB_SIMT_HOST
-    if (kGrad && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-#endif
 }
 #endif

@@ -152,17 +152,21 @@ int main(int argc, char** argv) {
     simt::launch(unsigned((cells + 255) / 256), 256, [&] { topIndexKernel(oct.data(), grid, levels, index.data(), index.data() + cells); });
     if (index[cells]) { std::fprintf(stderr, "topIndexKernel flagged the array\n"); return 1; }
     TileQuery tq;
-    tq.rcell = 1.0f / cell; tq.gridf = float(grid); tq.gridShift = startDepth; tq.topLevels = levels;
-    tq.G3 = uint32_t(grid) * uint32_t(grid) * uint32_t(grid); tq.tmaPoints = 0; tq.tmaGrad = 0;
-    {   // division-free cell selection against IEEE division / floorf
+    tq.cellL = std::ldexp(cell, -levels); tq.rcellL = 1.0f / tq.cellL;
+    { const float limit = float(uint32_t(grid) << levels); std::memcpy(&tq.limitBits, &limit, 4); }
+    tq.shiftN = startDepth + levels; tq.topLevels = levels; tq.G3 = uint32_t(grid) * uint32_t(grid) * uint32_t(grid);
+    {   // division-free cell selection against IEEE division / floorf (at the start-grid scale and at the index scale)
         uint64_t bad = 0, state = 0x9E3779B97F4A7C15ull;
         auto check = [&](float x) {
-            const float want = x / cell, got = cellCoordinate(x, cell, tq.rcell);
-            if (std::fabs(x) > 1e-30f && __float_as_uint(want) != __float_as_uint(got)) bad++;
-            if (want >= 0.0f && want < 4194304.0f) {
-                uint32_t asInt = 0;
-                const float fl = floorSmall(want, asInt);
-                if (fl != std::floor(want) || asInt != uint32_t(std::floor(want))) bad++;
+            for (int L = 0; L <= levels; L += std::max(levels, 1)) {
+                const float cl = std::ldexp(cell, -L);
+                const float want = x / cl, got = cellCoordinate(x, cl, 1.0f / cl);
+                if (std::fabs(x) > 1e-30f && __float_as_uint(want) != __float_as_uint(got)) bad++;
+                if (__float_as_uint(want) != __float_as_uint(std::ldexp(x / cell, L))) bad++;   // the scaling itself is exact
+                if (want >= 0.0f && want < 4194304.0f) {
+                    if (fractSmall(want) != want - std::floor(want)) bad++;
+                    if ((uint32_t(__float_as_int(__fadd_rd(want, 8388608.0f))) & 0x7FFFFFu) != uint32_t(std::floor(want))) bad++;
+                }
             }
         };
         for (uint64_t i = 0; i < 3 * n; i++) check(xyz[i] - box[i % 3]);
@@ -171,6 +175,8 @@ int main(int argc, char** argv) {
             const float u = float(state >> 40) * (1.0f / 16777216.0f);
             check((i & 1) ? u * 1.1f * float(grid) * cell : float(state % uint64_t(64 * grid)) / 64.0f * cell);   // uniform / near cell and sub-cell boundaries
         }
+        check(0.0f); check(-0.0f);
+        if (__float_as_uint(cellCoordinate(-0.0f, cell, 1.0f / cell)) != 0u) bad++;   // the unsigned range test relies on +0
         if (bad) { std::fprintf(stderr, "cell selection differs from IEEE division / floor on %llu values\n", (unsigned long long)bad); return 1; }
     }
 #endif
@@ -191,11 +197,11 @@ int main(int argc, char** argv) {
 #ifndef SDFB_QUERY_EXACT   // compiled with -DSDFB_QUERY_EXACT the header holds the reference-order kernel only
     // tile kernel (plain loads instead of the TMA staging): 3 CTAs of 8 warps, so every warp loops over several tiles
     std::fill(dist.begin(), dist.end(), -123.0f);
-    simt::launch(3, 256, [&] { octreeQueryTileKernel<false>(oct.data(), index.data(), q, tq, pts, n, dist.data(), nullptr); });
+    simt::launch(3, 256, [&] { octreeQueryTileKernel<false, 6>(oct.data(), index.data(), q, tq, pts, n, dist.data(), nullptr); });
     emit(false);
     std::fill(dist.begin(), dist.end(), -123.0f);
     std::fill(grad.begin(), grad.end(), -123.0f);
-    simt::launch(3, 256, [&] { octreeQueryTileKernel<true>(oct.data(), index.data(), q, tq, pts, n, dist.data(), grad.data()); });
+    simt::launch(3, 256, [&] { octreeQueryTileKernel<true, 6>(oct.data(), index.data(), q, tq, pts, n, dist.data(), grad.data()); });
     emit(true);
 #endif
     std::fclose(o);
