@@ -51,9 +51,6 @@ def main():
         os.environ["SDFB200_QUERY_PLAIN"] = "1"
         plain_sdf = S.OctreeSdf(mesh, bb, depth, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 1)
         os.environ["SDFB200_QUERY_PLAIN"] = "0"
-        os.environ["SDFB200_TILE_OCC"] = "8"
-        sdf8 = S.OctreeSdf(mesh, bb, depth, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 1)
-        os.environ["SDFB200_TILE_OCC"] = "6"
         sdf = S.OctreeSdf(mesh, bb, depth, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 1)
         area = sdf.getGridBoundingBox().as_array()
         size = float(area[3] - area[0])
@@ -86,7 +83,7 @@ def main():
                 dist = torch.empty(pts.shape[0], dtype=torch.float32, device="cuda")
                 grad = torch.empty((pts.shape[0], 3), dtype=torch.float32, device="cuda") if gradient else None
                 line = "    kernel time"
-                for what, obj, ex in (("tile", sdf, False), ("tile occ8", sdf8, False), ("plain", plain_sdf, False), ("exact order", sdf, True)):
+                for what, obj, ex in (("tile", sdf, False), ("plain", plain_sdf, False), ("exact order", sdf, True)):
                     best, mean = timed(lambda: obj.getDistance(pts, gradient=gradient, exact_order=ex, out=dist, out_gradient=grad))
                     line += f" | {what}: best {best:.3f} ms, mean {mean:.3f} ms ({pts.shape[0] / best / 1e6:.1f} Gq/s)"
                 print(line, flush=True)
@@ -98,7 +95,7 @@ def main():
         same = all(torch.equal(x.view(torch.int32), y.view(torch.int32)) for x, y in zip(a, b))
         print(f"depth {depth} unaligned batch identical to aligned: {same}", flush=True)
         ok &= same
-        sdf.close(); sdf8.close(); plain_sdf.close()
+        sdf.close(); plain_sdf.close()
     print("ALL CHECKS PASSED" if ok else "CHECK FAILED")
     return 0 if ok else 1
 

@@ -44,8 +44,6 @@ void prepareOctreeQuery(sdfb200_sdf& s) {
     s.topLevels = -1;
     const char* plain = std::getenv("SDFB200_QUERY_PLAIN");   // read once per structure, not per query
     s.forcePlainQuery = plain && plain[0] == '1';
-    const char* occ = std::getenv("SDFB200_TILE_OCC");         // measurement switch: 8 (32 registers) or 6 (40 registers) CTAs per SM
-    s.tileCtasPerSm = occ && occ[0] == '8' ? 8 : 6;
     if (s.format != SDFB200_FORMAT_OCTREE || !s.dOctree.p) return;
     int startDepth = 0;
     while ((1 << startDepth) < s.startGridSize) startDepth++;
@@ -117,15 +115,9 @@ void launchOctreeQueryFast(
         tq.G3 = uint32_t(s.startGridSize) * uint32_t(s.startGridSize) * uint32_t(s.startGridSize);
         (void)hostMapped;
         const uint64_t tiles = (n + 31) / 32;
-        const int occ = s.tileCtasPerSm;   // resident CTAs per SM the kernel is compiled for (8: 32 registers, 6: 40)
-        const uint32_t ctas = uint32_t(std::min<uint64_t>((tiles + kTileWarps - 1) / kTileWarps, uint64_t(smCount(s.device)) * occ));
-        if (dGrad) {
-            if (occ == 8) octreeQueryTileKernel<true, 8><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, dGrad);
-            else octreeQueryTileKernel<true, 6><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, dGrad);
-        } else {
-            if (occ == 8) octreeQueryTileKernel<false, 8><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, nullptr);
-            else octreeQueryTileKernel<false, 6><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, nullptr);
-        }
+        const uint32_t ctas = uint32_t(std::min<uint64_t>((tiles + kTileWarps - 1) / kTileWarps, uint64_t(smCount(s.device)) * 6));   // persistent: 6 CTAs per SM
+        if (dGrad) octreeQueryTileKernel<true><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, dGrad);
+        else octreeQueryTileKernel<false><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, nullptr);
         SDFB_CUDA(cudaGetLastError());
         return;
     }

@@ -195,7 +195,7 @@ struct sdfb200_sdf {
     // query-side index of an OCTREE (octree_query.cu, prepareOctreeQuery): one word per cell of the grid `topLevels`
     // below the start grid; -1 = the array does not meet the tile kernel's preconditions
     sdfb200::DevBuf<uint32_t> dTopIndex;
-    int topLevels = -1, gridShift = 0, tileCtasPerSm = 6;
+    int topLevels = -1, gridShift = 0;
     bool forcePlainQuery = false;    // SDFB200_QUERY_PLAIN=1 at build / load time: one-query-per-thread kernel (A/B measurements)
     // staging of host-pointer queries (query_host.cpp), created on first use under stageMutex
     std::unique_ptr<sdfb200::QueryStage, sdfb200::QueryStageDeleter> stage;

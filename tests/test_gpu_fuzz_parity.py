@@ -1,13 +1,13 @@
-"""GPU product against the oracle on random NON-MANIFOLD meshes (not collected by pytest; run by hand on the GPU box):
+"""GPU product against the oracle on random NON-MANIFOLD meshes (a `-m gpu` test with 12 meshes; by hand for more):
 
-    python tests/fuzz_gpu_parity.py [meshes=40] [seed=21]
+    python tests/test_gpu_fuzz_parity.py [meshes=40] [seed=21]
 
 The committed GPU parity tests use sphere-like and hand-made edge-case meshes. This loop throws triangle soups,
 duplicated vertices, duplicated triangles and holes at all three builders (random depth / start depth / rule /
 threshold / minTrianglesPerNode) and at the queries, and compares with the history-free oracle bit for bit — the same
 comparison as tests/test_gpu_octree.py::test_edge_case_meshes_bit_exact. The oracle itself is pinned against the
-compiled reference on the same family of meshes (tests/test_oracle.py). Written after round 1's last GPU minute: once
-it has passed on a B200 it should become a `-m gpu` test."""
+compiled reference on the same family of meshes (tests/test_oracle.py). First passed on a B200 in round 2 (40 meshes,
+0 differing builds: profiles/r2_summary.md)."""
 import os
 import sys
 
@@ -20,9 +20,16 @@ from oracle.binding import port                 # noqa: E402
 from test_capi_host import _random_meshes       # noqa: E402
 
 
-def main():
-    count = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 21)
+import pytest                                   # noqa: E402
+
+
+@pytest.mark.gpu
+def test_random_non_manifold_meshes_bit_exact():
+    assert run(12, 21) == 0
+
+
+def run(count, seed):
+    rng = np.random.default_rng(seed)
     bad = 0
     for n, (v, i) in enumerate(_random_meshes(rng, count)):
         lo, hi = v.min(0), v.max(0)
@@ -54,8 +61,8 @@ def main():
                 print(f"mesh {n}: ExactOctreeSdf differs (nodes {same}, queries {same_q}): tris {i.size // 3} depth {depth} start {start} minTris {min_tris}", flush=True)
             e.close()
     print(f"{count} meshes, {bad} differing builds")
-    return 1 if bad else 0
+    return bad
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    sys.exit(1 if run(int(sys.argv[1]) if len(sys.argv) > 1 else 40, int(sys.argv[2]) if len(sys.argv) > 2 else 21) else 0)
