@@ -37,6 +37,7 @@ UNITS = [
     ("host_mem.cpp", "host_mem.o", ["-x", "cu"]),
     ("query_host.cpp", "query_host.o", ["-x", "cu"]),
     ("fixtures.cpp", "fixtures.o", ["-x", "cu"] + NO_FMA),
+    ("mesh_device.cu", "mesh_device.o", NO_FMA),
     ("octree_build.cu", "octree_build.o", NO_FMA),
     ("octree_cont.cu", "octree_cont.o", NO_FMA),
     ("octree_query.cu", "octree_query_fast.o", []),

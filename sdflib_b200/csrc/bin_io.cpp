@@ -54,7 +54,7 @@ void saveBin(const sdfb200_sdf& s, const char* path) {
         os.write(reinterpret_cast<const char*>(s.octree.data()), std::streamsize(s.octree.size() * 4));
         putArray(os, s.sets.data(), uint64_t(s.sets.size()));
         putArray(os, s.masks.data(), uint64_t(s.masks.size()));
-        putArray(os, s.tris.data(), uint64_t(s.tris.size()));
+        { const TriVec& t = const_cast<sdfb200_sdf&>(s).hostTris(); putArray(os, t.data(), uint64_t(t.size())); }
     }
     if (!os) throw Error(SDFB200_ERR_IO, std::string("write failed on ") + path);
 }
@@ -146,6 +146,7 @@ void uploadStructure(sdfb200_sdf& s) {
         s.dMasks.alloc(s.masks.size() + 8);
         SDFB_CUDA(cudaMemsetAsync(s.dMasks.p, 0, s.masks.size() + 8));
         s.dMasks.upload(s.masks.data(), s.masks.size());
+        s.numTris = uint32_t(s.tris.size());
         s.dTris.alloc(s.tris.size());
         s.dTris.upload(s.tris.data(), s.tris.size());
         prepareExactQuery(s);

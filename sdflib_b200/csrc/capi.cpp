@@ -2,6 +2,7 @@
 // staging. No compute happens here; every entry point that needs the GPU fails with SDFB200_ERR_CUDA
 // when no device is present — there is no CPU fallback.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -103,11 +104,15 @@ int sdfb200_build_octree_shard(const float* vertices, uint32_t numVertices, cons
         if (initAlgorithm == SDFB200_ALG_CONTINUITY && worldSize > 1)
             throw Error(SDFB200_ERR_UNSUPPORTED, "CONTINUITY does not shard by start voxels (its neighbour probes cross them): use sdfb200_build_octree_collective");
         requireDevice();
+        const auto tStart = std::chrono::steady_clock::now();
+        const std::shared_ptr<PreparedMesh> pm = prepareMesh(mesh, true, false);
+        const double prepMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count();
         std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
         if (initAlgorithm == SDFB200_ALG_CONTINUITY)
-            buildOctreeContinuityOnDevice(*s, mesh, box6, depth, startDepth, terminationRule, param0, param1);
+            buildOctreeContinuityOnDevice(*s, *pm, box6, depth, startDepth, terminationRule, param0, param1);
         else
-            buildOctreeOnDevice(*s, mesh, box6, depth, startDepth, terminationRule, param0, param1, numThreads, rank, worldSize);
+            buildOctreeOnDevice(*s, *pm, box6, depth, startDepth, terminationRule, param0, param1, numThreads, rank, worldSize);
+        s->stats.total_ms += prepMs;
         *out = s.release();
     });
 }
@@ -129,10 +134,14 @@ int sdfb200_build_octree_collective(const float* vertices, uint32_t numVertices,
             throw Error(SDFB200_ERR_INVALID, "unknown termination rule");
         if (worldSize > 1 && !allgather) throw Error(SDFB200_ERR_INVALID, "worldSize > 1 needs an allgather hook");
         requireDevice();
+        const auto tStart = std::chrono::steady_clock::now();
+        const std::shared_ptr<PreparedMesh> pm = prepareMesh(mesh, true, false);
+        const double prepMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count();
         std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
         SampleExchange ex;
         ex.rank = rank; ex.world = worldSize; ex.allgather = allgather; ex.user = user;
-        buildOctreeContinuityOnDevice(*s, mesh, box6, depth, startDepth, terminationRule, param0, param1, ex);
+        buildOctreeContinuityOnDevice(*s, *pm, box6, depth, startDepth, terminationRule, param0, param1, ex);
+        s->stats.total_ms += prepMs;
         *out = s.release();
     });
 }
@@ -154,8 +163,12 @@ int sdfb200_build_exact_shard(const float* vertices, uint32_t numVertices, const
         checkBox(box6);
         if (worldSize == 0 || rank >= worldSize) throw Error(SDFB200_ERR_INVALID, "rank/worldSize out of range");
         requireDevice();
+        const auto tStart = std::chrono::steady_clock::now();
+        const std::shared_ptr<PreparedMesh> pm = prepareMesh(mesh, false, true);
+        const double prepMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count();
         std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
-        buildExactOnDevice(*s, mesh, box6, maxDepth, startDepth, minTrianglesPerNode, numThreads, rank, worldSize);
+        buildExactOnDevice(*s, pm, box6, maxDepth, startDepth, minTrianglesPerNode, numThreads, rank, worldSize);
+        s->stats.total_ms += prepMs;
         *out = s.release();
     });
 }
@@ -212,7 +225,7 @@ int sdfb200_get_info(const sdfb200_sdf* s, sdfb200_info* o) {
         o->octree_words = s->format == SDFB200_FORMAT_OCTREE ? s->octree.size() : s->octree.size() / 2;
         o->triangle_sets_words = s->sets.size();
         o->triangle_masks_bytes = s->masks.size();
-        o->num_triangles = s->tris.size();
+        o->num_triangles = s->format == SDFB200_FORMAT_EXACT_OCTREE ? s->numTris : 0;
         o->device = s->device;
     });
 }
@@ -239,7 +252,7 @@ int sdfb200_get_exact_arrays(const sdfb200_sdf* s, uint32_t* sets, uint8_t* mask
         if (s->format != SDFB200_FORMAT_EXACT_OCTREE) throw Error(SDFB200_ERR_INVALID, "not an ExactOctreeSdf");
         if (sets) std::memcpy(sets, s->sets.data(), s->sets.size() * 4);
         if (masks) std::memcpy(masks, s->masks.data(), s->masks.size());
-        if (tris37) std::memcpy(tris37, s->tris.data(), s->tris.size() * sizeof(TriData));
+        if (tris37) { const TriVec& t = const_cast<sdfb200_sdf*>(s)->hostTris(); std::memcpy(tris37, t.data(), t.size() * sizeof(TriData)); }
     });
 }
 

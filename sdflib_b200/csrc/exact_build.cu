@@ -639,43 +639,27 @@ struct ExactBuildState : BuildState {
     DevBuf<uint32_t> scalars;   // [0] maxTrianglesInLeafs, [1] maxTrianglesEncodedInLeafs
     uint32_t numStreams() const override { return 3; }
 
-    void buildLevels(sdfb200_sdf& out, const HostMesh& mesh, uint32_t numThreads, uint32_t rank, uint32_t world) {
+    void buildLevels(sdfb200_sdf& out, const std::shared_ptr<PreparedMesh>& meshPtr, uint32_t numThreads, uint32_t rank, uint32_t world) {
         sdfb200_build_stats& st = out.stats;
-        // ---- serial set-up of the reference, on the host ---------------------------------------------------
-        auto t0 = std::chrono::steady_clock::now();
-        out.tris = computeTriangleData(mesh);
-        const uint32_t nT = uint32_t(out.tris.size());
+        const PreparedMesh& mesh = *meshPtr;
+        if (!mesh.hasExactParts) throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf needs a mesh prepared with its frames (SDFB200_MESH_EXACT)");
+        // ---- set-up of the reference (TriangleData, degenerate filter): done by mesh_device.cu ---------------------------
+        st.triangle_data_ms = mesh.triangleDataMs;
+        st.upload_ms = mesh.uploadMs;
+        const uint32_t nT = mesh.nTris;
+        out.mesh = meshPtr;          // the structure's queries read the mesh's TriangleData and frames
+        out.numTris = nT;
+        out.qTris = mesh.dev.tris.p;
+        out.qFrames = mesh.frames.p;
         out.bitsPerIndex = uint32_t(int32_t(std::ceil(std::log2(float(nT)))));   // ExactOctreeSdfDepthFirst.h:61
         bits = out.bitsPerIndex;
         if (bits == 0 || bits > 31) throw Error(SDFB200_ERR_INVALID, "ExactOctreeSdf needs between 2 and 2^31 triangles");
-        RawVec<float4> frames(size_t(nT) * 5);
-#pragma omp parallel for schedule(static) num_threads(hostThreads())
-        for (int64_t t = 0; t < int64_t(nT); t++) {
-            float tmp[20];
-            std::memcpy(tmp, &out.tris[size_t(t)], 19 * sizeof(float));
-            tmp[19] = 0.0f;
-            std::memcpy(&frames[size_t(t) * 5], tmp, sizeof(tmp));
-        }
-        std::vector<uint32_t> all;
-        all.reserve(nT);
-        for (uint32_t t = 0; t < nT; t++) {
-            const f3 nrm = triNormal(out.tris[t]);
-            if (dot3(nrm, nrm) > 1e-3f) all.push_back(t);   // ExactOctreeSdfDepthFirst.h:106 (false for NaN)
-        }
-        st.triangle_data_ms = msSince(t0);
-        t0 = std::chrono::steady_clock::now();
-        DevBuf<f3> dVerts(mesh.nVerts);
-        DevBuf<uint32_t> dIdx(mesh.nIdx), dAll(all.size() + 8);
-        DevBuf<float4> dFrames(frames.size());
-        dVerts.upload(mesh.verts, mesh.nVerts);
-        dIdx.upload(mesh.idx, mesh.nIdx);
-        dFrames.upload(frames.data(), frames.size());
-        dAll.upload(all.data(), all.size());
-        SDFB_CUDA(cudaDeviceSynchronize());
-        st.upload_ms = msSince(t0);
-        const DeviceMesh dmesh{dVerts.p, dIdx.p, nullptr, nullptr, nT};
+        const float4* dFramesP = mesh.frames.p;
+        const uint32_t* dAllP = mesh.valid.p;
+        const uint32_t numAll = mesh.numValid;
+        const DeviceMesh dmesh{mesh.dev.verts.p, mesh.dev.idx.p, nullptr, nullptr, nT};
 
-        t0 = std::chrono::steady_clock::now();
+        auto t0 = std::chrono::steady_clock::now();
         const uint32_t d0 = std::min(startDepth, 1u);
         const f3 boxMin = mk3(out.boxMin[0], out.boxMin[1], out.boxMin[2]);
         const float boxSize = out.boxMax[0] - out.boxMin[0];
@@ -696,7 +680,7 @@ struct ExactBuildState : BuildState {
             const uint64_t nKeys = uint64_t(L.count) * kPts;
             if (best.n < nKeys) best.alloc(nKeys);
             fillU64<<<divUp(nKeys, 256), 256>>>(best.p, kNoKey, nKeys);
-            if (nChunks) sampleKernel<kPts><<<nChunks, kSampleThreads>>>(dFrames.p, L.centerHalf.p, list, lo, cnt, chOff, L.count, best.p);
+            if (nChunks) sampleKernel<kPts><<<nChunks, kSampleThreads>>>(dFramesP, L.centerHalf.p, list, lo, cnt, chOff, L.count, best.p);
             resolveKernel<<<divUp(nKeys, 256), 256>>>(best.p, list, lo, kPts, outInfo, nKeys);
             st.kernel_launches += 3;
             SDFB_CUDA(cudaGetLastError());
@@ -721,20 +705,29 @@ struct ExactBuildState : BuildState {
             L.allocNodes(n, d0);
             L.centerHalf.upload(ch.data(), n);
             L.coord.upload(coord.data(), n);
-            std::vector<uint32_t> zero(n, 0u), cntAll(n, uint32_t(all.size())), chOff(n + 1);
-            const uint32_t perNode = divUp(all.size(), kChunk);
+            std::vector<uint32_t> zero(n, 0u), cntAll(n, numAll), chOff(n + 1);
+            const uint32_t perNode = divUp(numAll, kChunk);
             for (uint32_t i = 0; i <= n; i++) chOff[i] = i * perNode;
             L.parent.upload(zero.data(), n);
             L.parentLo.upload(zero.data(), n);
             L.parentCnt.upload(cntAll.data(), n);
             chunkOff.alloc(n + 1);
             chunkOff.upload(chOff.data(), n + 1);
-            runSample(std::integral_constant<int, 8>(), L, dAll.p, L.parentLo.p, L.parentCnt.p, chunkOff.p, n * perNode, L.info.p);
+            runSample(std::integral_constant<int, 8>(), L, dAllP, L.parentLo.p, L.parentCnt.p, chunkOff.p, n * perNode, L.info.p);
         }
 
+        static const bool timing = std::getenv("SDFB200_TIMING") != nullptr;
+        auto tLevel = std::chrono::steady_clock::now();
+        auto levelDone = [&](uint32_t d, const Level& L) {   // SDFB200_TIMING: synchronised per-depth times (diagnostic runs only)
+            if (!timing) return;
+            SDFB_CUDA(cudaDeviceSynchronize());
+            std::fprintf(stderr, "[sdfb200] exact depth %u: %9u nodes %12llu pairs %10u kept %8.2f ms\n", d, L.count,
+                         (unsigned long long)L.numPairs, L.listTotal, msSince(tLevel));
+            tLevel = std::chrono::steady_clock::now();
+        };
         for (uint32_t d = d0; d <= maxDepth; d++) {
             Level& L = *levels[d];
-            const uint32_t* parentList = d == d0 ? dAll.p : levels[d - 1]->list.p;
+            const uint32_t* parentList = d == d0 ? dAllP : levels[d - 1]->list.p;
             if (d == startDepth) {
                 makePlan(out, L, numThreads, rank, world);
                 if (world > 1) {   // roots of other ranks: empty list -> terminal, nothing below them is built here
@@ -753,7 +746,7 @@ struct ExactBuildState : BuildState {
             // pair indices are 64-bit everywhere; list positions (kept pairs) are 32-bit and are checked after the filter
             if (L.numPairs >= (uint64_t(1) << 38)) throw Error(SDFB200_ERR_INVALID, "more than 2^38 (node, triangle) pairs on one octree level");
             if (region.n < size_t(L.count) * 72) region.alloc(size_t(L.count) * 72);
-            regionKernel<<<divUp(L.count, 4), 256>>>(dFrames.p, L.view(), region.p);
+            regionKernel<<<divUp(L.count, 4), 256>>>(dFramesP, L.view(), region.p);
             L.flags.alloc(L.numPairs + 1);
             L.pos.alloc(L.numPairs + 1);
             if (L.numPairs) filterRefillKernel<<<divUp(L.numPairs, 8 * kFilterChunk), 256>>>(dmesh, L.view(), parentList, region.p, L.flags.p, L.numPairs);
@@ -773,7 +766,7 @@ struct ExactBuildState : BuildState {
             // terminal rule
             subdivide.alloc(L.count); chunks.alloc(L.count); childIdx.alloc(L.count); chunkOff.alloc(size_t(L.count) + 1);
             decideKernel<<<divUp(L.count, 256), 256>>>(L.listCnt.p, L.count, d, startDepth, maxDepth, minTris, subdivide.p, chunks.p, scalars.p);
-            if (d == maxDepth) { SDFB_CUDA(cudaMemsetAsync(L.childOf.p, 0xFF, size_t(L.count) * 4)); break; }
+            if (d == maxDepth) { SDFB_CUDA(cudaMemsetAsync(L.childOf.p, 0xFF, size_t(L.count) * 4)); levelDone(d, L); break; }
             const uint32_t nSub = scan32.run(subdivide.p, childIdx.p, L.count);
             const uint32_t nChunks = scan32.run(chunks.p, chunkOff.p, L.count, true);
             // HOT LOOP B
@@ -788,6 +781,7 @@ struct ExactBuildState : BuildState {
             st.kernel_launches += 8;
             SDFB_CUDA(cudaGetLastError());
             if (d + 1 < maxDepth) { L.flags.release(); L.pos.release(); }   // only the flags of levels maxDepth-1 and maxDepth feed the merge
+            levelDone(d, L);
         }
         SDFB_CUDA(cudaDeviceSynchronize());
         st.levels_ms = msSince(t0);
@@ -919,8 +913,6 @@ struct ExactBuildState : BuildState {
         out.octree.resize(size_t(rn) * 2);
         out.sets.resize(size_t(rs));
         out.masks.resize(size_t(rm));
-        out.dTris.alloc(out.tris.size());
-        out.dTris.upload(out.tris.data(), out.tris.size());
         if (plan.world == 1) {
             out.maxTrisInLeafs = out.shardScalars[0];
             out.maxTrisEncoded = out.shardScalars[1];
@@ -941,7 +933,7 @@ struct ExactBuildState : BuildState {
 
 void cubifyBox(sdfb200_sdf& s, const float* box6, uint32_t startDepth);   // octree_build.cu
 
-void buildExactOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
+void buildExactOnDevice(sdfb200_sdf& out, const std::shared_ptr<PreparedMesh>& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
                         uint32_t minTris, uint32_t numThreads, uint32_t rank, uint32_t world) {
     const auto tStart = std::chrono::steady_clock::now();
     out.stats = sdfb200_build_stats{};

@@ -449,10 +449,14 @@ exactBinnedKernel(const uint64_t* __restrict__ leafLo, const uint32_t* __restric
 // Decode the public arrays into the private per-leaf pool (see the header comment). Throws ERR_IO when the
 // arrays are inconsistent (untrusted .bin input).
 void prepareExactQuery(sdfb200_sdf& s) {
-    const uint32_t nT = uint32_t(s.tris.size());
+    const uint32_t nT = s.numTris;
     const uint64_t numNodes = s.octree.size() / 2;
-    s.dFrames.alloc(size_t(nT) * 5);
-    if (nT) framesFromTriData<<<divUp(uint64_t(nT) * 5, 256), 256>>>(s.dTris.p, s.dFrames.p, nT);
+    if (!s.qFrames) {   // loaded from a .bin: frames from the file's TriangleData (built structures share their mesh's)
+        s.dFrames.alloc(size_t(nT) * 5);
+        if (nT) framesFromTriData<<<divUp(uint64_t(nT) * 5, 256), 256>>>(s.dTris.p, s.dFrames.p, nT);
+        s.qFrames = s.dFrames.p;
+        s.qTris = s.dTris.p;
+    }
     s.dLeafLo.alloc(numNodes);
     s.dLeafCnt.alloc(numNodes);
     SDFB_CUDA(cudaMemsetAsync(s.dLeafLo.p, 0, numNodes * 8));
@@ -575,20 +579,20 @@ void launchExactQuery(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float
         exactScatterKernel<<<grid, 256, 0, st>>>(leafOf, n, start, counts, order);
         const uint32_t segGrid = divUp(n, 8 * kBinSegment);
         if (dGrad) {
-            exactBinnedKernel<true><<<segGrid, 256, 0, st>>>(s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, dXyz, leafOf, order, total, useBins, dDist, dGrad);
-            exactQueryWarpKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, dGrad, useBins);
+            exactBinnedKernel<true><<<segGrid, 256, 0, st>>>(s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.qFrames, s.qTris, dXyz, leafOf, order, total, useBins, dDist, dGrad);
+            exactQueryWarpKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.qFrames, s.qTris, q, dXyz, n, dDist, dGrad, useBins);
         } else {
-            exactBinnedKernel<false><<<segGrid, 256, 0, st>>>(s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, dXyz, leafOf, order, total, useBins, dDist, nullptr);
-            exactQueryWarpKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, nullptr, useBins);
+            exactBinnedKernel<false><<<segGrid, 256, 0, st>>>(s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.qFrames, s.qTris, dXyz, leafOf, order, total, useBins, dDist, nullptr);
+            exactQueryWarpKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.qFrames, s.qTris, q, dXyz, n, dDist, nullptr, useBins);
         }
         SDFB_CUDA(cudaGetLastError());
         cudaFreeAsync(leafOf, st); cudaFreeAsync(order, st); cudaFreeAsync(counts, st); cudaFreeAsync(start, st); cudaFreeAsync(blockSums, st);
         return;
     }
     if (dGrad)
-        exactQueryWarpKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, dGrad, nullptr);
+        exactQueryWarpKernel<true><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.qFrames, s.qTris, q, dXyz, n, dDist, dGrad, nullptr);
     else
-        exactQueryWarpKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.dFrames.p, s.dTris.p, q, dXyz, n, dDist, nullptr, nullptr);
+        exactQueryWarpKernel<false><<<grid, 256, 0, st>>>(s.dOctree.p, s.dLeafLo.p, s.dLeafCnt.p, s.dLeafPool.p, s.qFrames, s.qTris, q, dXyz, n, dDist, nullptr, nullptr);
     SDFB_CUDA(cudaGetLastError());
 }
 

@@ -1,5 +1,6 @@
 #include "mesh_host.h"
 #include "host_sort.h"
+#include "tri_data_build.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -33,51 +34,85 @@ int hostThreads() {
 
 namespace {
 
-TriData makeTriData(f3 p1, f3 p2, f3 p3) {   // TriangleData ctor, include/SdfLib/utils/TriangleUtils.h:23-42
-    TriData d;
-    d.origin[0] = p1.x; d.origin[1] = p1.y; d.origin[2] = p1.z;
-    const f3 e12 = p2 - p1, e13 = p3 - p1;
-    const f3 sx = normalize3(e12);
-    const f3 crs = mk3(e12.y * e13.z - e13.y * e12.z, e12.z * e13.x - e13.z * e12.x, e12.x * e13.y - e13.x * e12.y);
-    const f3 sz = normalize3(crs);
-    const f3 sy = mk3(sz.y * sx.z - sx.y * sz.z, sz.z * sx.x - sx.z * sz.x, sz.x * sx.y - sx.x * sz.y);
-    // inverse of the matrix with columns (sx, sy, sz): cofactors times 1/det, det along the first row
-    const float m[3][3] = {{sx.x, sx.y, sx.z}, {sy.x, sy.y, sy.z}, {sz.x, sz.y, sz.z}};
-    const float c00 = m[1][1] * m[2][2] - m[2][1] * m[1][2];
-    const float c10 = m[0][1] * m[2][2] - m[2][1] * m[0][2];
-    const float c20 = m[0][1] * m[1][2] - m[1][1] * m[0][2];
-    const float inv = 1.0f / (+m[0][0] * c00 - m[1][0] * c10 + m[2][0] * c20);
-    d.T[0][0] = +c00 * inv;
-    d.T[1][0] = -(m[1][0] * m[2][2] - m[2][0] * m[1][2]) * inv;
-    d.T[2][0] = +(m[1][0] * m[2][1] - m[2][0] * m[1][1]) * inv;
-    d.T[0][1] = -c10 * inv;
-    d.T[1][1] = +(m[0][0] * m[2][2] - m[2][0] * m[0][2]) * inv;
-    d.T[2][1] = -(m[0][0] * m[2][1] - m[2][0] * m[0][1]) * inv;
-    d.T[0][2] = +c20 * inv;
-    d.T[1][2] = -(m[0][0] * m[1][2] - m[1][0] * m[0][2]) * inv;
-    d.T[2][2] = +(m[0][0] * m[1][1] - m[1][0] * m[0][1]) * inv;
-    auto unit2 = [](f3 v, float* out) {
-        const float tx = v.x * v.x, ty = v.y * v.y;
-        const float s = 1.0f / std::sqrt(tx + ty);
-        out[0] = v.x * s; out[1] = v.y * s;
-    };
-    unit2(matMul(d.T, p3 - p2), d.b);
-    unit2(matMul(d.T, p1 - p3), d.c);
-    d.v2 = matMul(d.T, p2 - p1).x;
-    const f3 l3 = matMul(d.T, p3 - p1);
-    d.v3[0] = l3.x; d.v3[1] = l3.y;
-    for (int k = 0; k < 3; k++) {
-        d.edgesNormal[k][0] = 0.f; d.edgesNormal[k][1] = 0.f; d.edgesNormal[k][2] = 1.f;
-        d.verticesNormal[k][0] = 0.f; d.verticesNormal[k][1] = 0.f; d.verticesNormal[k][2] = 1.f;
-    }
-    return d;
-}
-
 inline void st3(float* dst, f3 v) { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; }
 
 struct EdgeUse { uint64_t key; uint32_t corner; };   // key = min<<32 | max, corner = 3*t + k
 
 }  // namespace
+
+// Non-manifold repair (src/utils/TriangleUtils.cpp:292-420) over the OPEN edge uses (those left unpaired by the edge
+// pairing), given in key order: vertices of open edges that lie within 1e-5/extent of each other (found through two
+// staggered 2048^3 hash grids) are merged with a union-find, open edges are re-paired under the merged ids, and merged
+// vertices share the sum of their normals. Returns the patches instead of applying them, so that the host path
+// (computeTriangleData) and the device path (mesh_device.cu) share it; the triangles involved are rebuilt from their
+// vertices with the same constructor both paths use.
+OpenEdgeRepair repairOpenEdges(const HostMesh& mesh, const std::vector<OpenEdgeUse>& open, const f3* vNormalIn) {
+    OpenEdgeRepair out;
+    auto triOf = [&](uint32_t t) { return makeTriData(mesh.verts[mesh.idx[3 * size_t(t)]], mesh.verts[mesh.idx[3 * size_t(t) + 1]], mesh.verts[mesh.idx[3 * size_t(t) + 2]]); };
+    std::map<uint32_t, uint32_t> parentOf;
+    auto root = [&](uint32_t v) {
+        auto it = parentOf.find(v);
+        while (it != parentOf.end() && it->second != v) { v = it->second; it = parentOf.find(v); }
+        return v;
+    };
+    std::vector<uint32_t> nm;
+    for (const OpenEdgeUse& e : open) { nm.push_back(e.lo); nm.push_back(e.hi); }
+    std::sort(nm.begin(), nm.end());
+    nm.erase(std::unique(nm.begin(), nm.end()), nm.end());
+    std::map<uint32_t, f3> vNormal;   // working copy of the normals the repair touches
+    for (uint32_t v : nm) vNormal[v] = vNormalIn[v];
+    f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
+    for (uint32_t i = 0; i < mesh.nVerts; i++) {
+        const f3 v = mesh.verts[i];
+        lo = mk3(gmin(lo.x, v.x), gmin(lo.y, v.y), gmin(lo.z, v.z));
+        hi = mk3(gmax(hi.x, v.x), gmax(hi.y, v.y), gmax(hi.z, v.z));
+    }
+    const f3 ext = hi - lo;
+    const float maxExt = gmax(ext.x, gmax(ext.y, ext.z));
+    const uint32_t res = 2048;
+    const float scale = float(res) / maxExt;
+    const float thr = float(1e-5 / double(maxExt));
+    const float sqThr = thr * thr;
+    auto cell = [&](f3 p, float off) {
+        const f3 q = (p - lo) * scale;
+        const int x = int(q.x + off), y = int(q.y + off), z = int(q.z + off);
+        return uint64_t(uint32_t(x + y * res + z * res * res));
+    };
+    std::map<uint64_t, std::vector<uint32_t>> grid[2];
+    for (uint32_t v : nm) { grid[0][cell(mesh.verts[v], 0.0f)].push_back(v); grid[1][cell(mesh.verts[v], 0.5f)].push_back(v); }
+    for (uint32_t v : nm)
+        for (int gsel = 0; gsel < 2; gsel++) {
+            auto it = grid[gsel].find(cell(mesh.verts[v], gsel ? 0.5f : 0.0f));
+            if (it == grid[gsel].end()) continue;
+            for (uint32_t u : it->second) {
+                const f3 diff = mesh.verts[v] - mesh.verts[u];
+                if (dot3(diff, diff) < sqThr) {
+                    const uint32_t p1 = root(v), p2 = root(u);
+                    if (v == p1) parentOf[p1] = p1;
+                    parentOf[p2] = p1;
+                    break;
+                }
+            }
+        }
+    // open edges in key order (the reference iterates its ordered map)
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> merged;
+    for (const OpenEdgeUse& e : open) {
+        const uint32_t a = root(e.lo), b = root(e.hi);
+        auto ins = merged.insert(std::make_pair(std::make_pair(std::min(a, b), std::max(a, b)), e.corner));
+        if (!ins.second) {
+            const uint32_t t = e.corner / 3, t2 = ins.first->second / 3;
+            const TriData dt = triOf(t), dt2 = triOf(t2);
+            const f3 n = triNormal(dt) + triNormal(dt2);
+            out.edgeCorner.push_back(e.corner); out.edgeNormal.push_back(matMul(dt.T, n));
+            out.edgeCorner.push_back(ins.first->second); out.edgeNormal.push_back(matMul(dt2.T, n));
+            merged.erase(ins.first);
+        }
+    }
+    for (uint32_t v : nm) { const uint32_t p = root(v); if (p != v) vNormal[p] = vNormal[p] + vNormal[v]; }
+    for (uint32_t v : nm) vNormal[v] = vNormal[root(v)];
+    for (uint32_t v : nm) { out.vertex.push_back(v); out.vertexNormal.push_back(vNormal[v]); }
+    return out;
+}
 
 TriVec computeTriangleData(const HostMesh& mesh) {
     const uint32_t nT = mesh.numTriangles();
@@ -102,7 +137,7 @@ TriVec computeTriangleData(const HostMesh& mesh) {
         for (uint32_t k = 0; k < 3; k++) {
             const uint32_t a = ix[k], b = ix[(k + 1) % 3], c = ix[(k + 2) % 3];
             const float cosA = dot3(normalize3(mesh.verts[b] - mesh.verts[a]), normalize3(mesh.verts[c] - mesh.verts[a]));
-            const float angle = std::acos(gmin(gmax(cosA, -1.0f), 1.0f));
+            const float angle = std::acos(gmin(gmax(cosA, -1.0f), 1.0f));   // == acosfLibm (tri_data_build.cuh), checked in tests/cpp
             cornerContribution[size_t(3 * t + k)] = angle * n;
             uses[size_t(3 * t + k)] = EdgeUse{(uint64_t(std::min(a, b)) << 32) | std::max(a, b), uint32_t(3 * t + k)};
         }
@@ -164,68 +199,11 @@ TriVec computeTriangleData(const HostMesh& mesh) {
 
     lap("vertex normals");
     if (!open.empty()) {
-        // Non-manifold repair (src/utils/TriangleUtils.cpp:292-420): vertices of open edges that lie
-        // within 1e-5/extent of each other (found through two staggered 2048^3 hash grids) are merged
-        // with a union-find, open edges are re-paired under the merged ids, and merged vertices share
-        // the sum of their normals.
-        std::map<uint32_t, uint32_t> parentOf;
-        auto root = [&](uint32_t v) {
-            auto it = parentOf.find(v);
-            while (it != parentOf.end() && it->second != v) { v = it->second; it = parentOf.find(v); }
-            return v;
-        };
-        std::vector<uint32_t> nm;
-        for (const EdgeUse& e : open) { nm.push_back(uint32_t(e.key >> 32)); nm.push_back(uint32_t(e.key)); }
-        std::sort(nm.begin(), nm.end());
-        nm.erase(std::unique(nm.begin(), nm.end()), nm.end());
-        f3 lo = mk3(INFINITY, INFINITY, INFINITY), hi = mk3(-INFINITY, -INFINITY, -INFINITY);
-        for (uint32_t i = 0; i < mesh.nVerts; i++) {
-            const f3 v = mesh.verts[i];
-            lo = mk3(gmin(lo.x, v.x), gmin(lo.y, v.y), gmin(lo.z, v.z));
-            hi = mk3(gmax(hi.x, v.x), gmax(hi.y, v.y), gmax(hi.z, v.z));
-        }
-        const f3 ext = hi - lo;
-        const float maxExt = gmax(ext.x, gmax(ext.y, ext.z));
-        const uint32_t res = 2048;
-        const float scale = float(res) / maxExt;
-        const float thr = float(1e-5 / double(maxExt));
-        const float sqThr = thr * thr;
-        auto cell = [&](f3 p, float off) {
-            const f3 q = (p - lo) * scale;
-            const int x = int(q.x + off), y = int(q.y + off), z = int(q.z + off);
-            return uint64_t(uint32_t(x + y * res + z * res * res));
-        };
-        std::map<uint64_t, std::vector<uint32_t>> grid[2];
-        for (uint32_t v : nm) { grid[0][cell(mesh.verts[v], 0.0f)].push_back(v); grid[1][cell(mesh.verts[v], 0.5f)].push_back(v); }
-        for (uint32_t v : nm)
-            for (int gsel = 0; gsel < 2; gsel++) {
-                auto it = grid[gsel].find(cell(mesh.verts[v], gsel ? 0.5f : 0.0f));
-                if (it == grid[gsel].end()) continue;
-                for (uint32_t u : it->second) {
-                    const f3 diff = mesh.verts[v] - mesh.verts[u];
-                    if (dot3(diff, diff) < sqThr) {
-                        const uint32_t p1 = root(v), p2 = root(u);
-                        if (v == p1) parentOf[p1] = p1;
-                        parentOf[p2] = p1;
-                        break;
-                    }
-                }
-            }
-        // open edges in key order (the reference iterates its ordered map)
-        std::map<std::pair<uint32_t, uint32_t>, uint32_t> merged;
-        for (const EdgeUse& e : open) {
-            const uint32_t a = root(uint32_t(e.key >> 32)), b = root(uint32_t(e.key));
-            auto ins = merged.insert(std::make_pair(std::make_pair(std::min(a, b), std::max(a, b)), e.corner));
-            if (!ins.second) {
-                const uint32_t t = e.corner / 3, t2 = ins.first->second / 3;
-                const f3 n = triNormal(tris[t]) + triNormal(tris[t2]);
-                st3(tris[t].edgesNormal[e.corner % 3], matMul(tris[t].T, n));
-                st3(tris[t2].edgesNormal[ins.first->second % 3], matMul(tris[t2].T, n));
-                merged.erase(ins.first);
-            }
-        }
-        for (uint32_t v : nm) { const uint32_t p = root(v); if (p != v) vNormal[p] = vNormal[p] + vNormal[v]; }
-        for (uint32_t v : nm) vNormal[v] = vNormal[root(v)];
+        std::vector<OpenEdgeUse> uses(open.size());
+        for (size_t i = 0; i < open.size(); i++) uses[i] = OpenEdgeUse{uint32_t(open[i].key >> 32), uint32_t(open[i].key), open[i].corner};
+        const OpenEdgeRepair rep = repairOpenEdges(mesh, uses, vNormal.data());
+        for (size_t i = 0; i < rep.edgeCorner.size(); i++) st3(tris[rep.edgeCorner[i] / 3].edgesNormal[rep.edgeCorner[i] % 3], rep.edgeNormal[i]);
+        for (size_t i = 0; i < rep.vertex.size(); i++) vNormal[rep.vertex[i]] = rep.vertexNormal[i];
     }
 
 #pragma omp parallel for schedule(static) num_threads(hostThreads()) if (nT > 8192)

@@ -1,8 +1,7 @@
-// Host-side mesh preprocessing of the product path: TriangleData precompute and the float64
-// bounding-sphere BVH whose traversal order defines the reference's nearest-triangle choice.
-// These are the serial set-up steps of the reference constructors; they stay on the host because
-// (a) vertex pseudo-normals use acosf, which must match the host libm bit for bit, and (b) the BVH
-// shape depends on std::sort's (unstable) tie order. Everything per-node / per-query runs on the GPU.
+// Host-side mesh preprocessing: the float64 bounding-sphere BVH whose traversal order defines the reference's
+// nearest-triangle choice (it stays on the host: its shape depends on std::sort's unstable tie order), the host
+// restatement of TriangleData (sdfb200_triangle_data, and the A/B switch SDFB200_HOST_TRIANGLE_DATA; the builders use the
+// device path of mesh_device.cu) and the non-manifold repair both TriangleData paths share.
 #pragma once
 #include <cstdint>
 #include <memory>
@@ -32,6 +31,14 @@ int hostThreads();   // SDFB200_HOST_THREADS or the OpenMP default
 
 // reference: TriangleUtils::calculateMeshTriangleData, src/utils/TriangleUtils.cpp:7-428
 TriVec computeTriangleData(const HostMesh& mesh);
+
+// Non-manifold repair over the edge uses the pairing left open (shared by the host and the device path; mesh_host.cpp)
+struct OpenEdgeUse { uint32_t lo, hi, corner; };   // vertex ids (lo <= hi), corner = 3 * triangle + edge
+struct OpenEdgeRepair {
+    std::vector<uint32_t> edgeCorner; std::vector<f3> edgeNormal;   // edgesNormal[corner % 3] of triangle corner / 3, in its frame, in application order
+    std::vector<uint32_t> vertex; std::vector<f3> vertexNormal;     // final (merged) vertex normals, world frame
+};
+OpenEdgeRepair repairOpenEdges(const HostMesh& mesh, const std::vector<OpenEdgeUse>& openInKeyOrder, const f3* vNormal);
 
 // Device-friendly BVH node: both child spheres + child links, 80 bytes, 16-byte aligned
 // (reference: tmd::TriangleMeshDistance::Node, TriangleMeshDistance.h:96-109).

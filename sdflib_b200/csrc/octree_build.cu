@@ -332,22 +332,14 @@ struct OctreeBuildState : BuildState {
     uint32_t numStreams() const override { return 1; }
 
     // phase 1: candidate levels top-down (only the subtrees of the own roots below the start depth), subtree sizes
-    void buildLevels(sdfb200_sdf& out, const HostMesh& mesh, int rule, float param0, float param1, uint32_t numThreads,
+    void buildLevels(sdfb200_sdf& out, const PreparedMesh& mesh, int rule, float param0, float param1, uint32_t numThreads,
                      uint32_t rank, uint32_t world) {
         sdfb200_build_stats& st = out.stats;
-        // serial set-up steps of the reference, on the host (see mesh_host.h)
-        auto t0 = std::chrono::steady_clock::now();
-        TriVec tris;
-        RawVec<BvhNode> bvh;
-        buildHostStructures(mesh, tris, bvh, st);
-        t0 = std::chrono::steady_clock::now();
-        MeshOnDevice dm;
-        uploadMesh(dm, mesh, tris, &bvh);
-        SDFB_CUDA(cudaDeviceSynchronize());
-        st.upload_ms = msSince(t0);
-        const DeviceMesh dmesh = dm.view();
+        if (!mesh.hasBvh) throw Error(SDFB200_ERR_INVALID, "OctreeSdf needs a mesh prepared with its BVH (SDFB200_MESH_BVH)");
+        meshStats(mesh, st);
+        const DeviceMesh dmesh = mesh.dev.view();
 
-        t0 = std::chrono::steady_clock::now();
+        auto t0 = std::chrono::steady_clock::now();
         const uint32_t d0 = std::min(startDepth, 1u);
         const f3 boxMin = mk3(out.boxMin[0], out.boxMin[1], out.boxMin[2]);
         const float boxSize = out.boxMax[0] - out.boxMin[0];
@@ -521,7 +513,7 @@ void finalizeOctreeScalars(sdfb200_sdf& s) {
     s.minBorderValue = (o == 0xFFFFFFFFu) ? INFINITY : mb;
 }
 
-void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+void buildOctreeOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
                          int rule, float param0, float param1, uint32_t numThreads, uint32_t rank, uint32_t world) {
     const auto tStart = std::chrono::steady_clock::now();
     out.stats = sdfb200_build_stats{};
@@ -544,10 +536,8 @@ void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* bo
 }
 
 void nearestTriangleOnDevice(const HostMesh& mesh, const float* xyz, uint64_t n, uint32_t* outTri) {
-    TriVec tris = computeTriangleData(mesh);
-    RawVec<BvhNode> bvh = buildBvh(mesh);
-    MeshOnDevice dm;
-    uploadMesh(dm, mesh, tris, &bvh);
+    const std::shared_ptr<PreparedMesh> pm = prepareMesh(mesh, true, false);
+    const MeshOnDevice& dm = pm->dev;
     DevBuf<f3> pts(n);
     DevBuf<uint32_t> out(n);
     pts.upload(reinterpret_cast<const f3*>(xyz), n);

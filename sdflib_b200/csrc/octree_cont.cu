@@ -720,7 +720,7 @@ struct GrowingOctree {
 
 }  // namespace
 
-void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
                                    int rule, float param0, float param1, const SampleExchange& exchange) {
     const auto tStart = std::chrono::steady_clock::now();
     out.stats = sdfb200_build_stats{};
@@ -757,18 +757,11 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const
         SDFB_CUDA(cudaMemcpyToSymbol(cFaceMask, table, sizeof(table)));
     }
 
-    auto t0 = std::chrono::steady_clock::now();
-    TriVec tris;
-    RawVec<BvhNode> bvh;
-    buildHostStructures(mesh, tris, bvh, st);
-    t0 = std::chrono::steady_clock::now();
-    MeshOnDevice dm;
-    uploadMesh(dm, mesh, tris, &bvh);
-    SDFB_CUDA(cudaDeviceSynchronize());
-    st.upload_ms = msSince(t0);
-    const DeviceMesh dmesh = dm.view();
+    if (!mesh.hasBvh) throw Error(SDFB200_ERR_INVALID, "OctreeSdf needs a mesh prepared with its BVH (SDFB200_MESH_BVH)");
+    meshStats(mesh, st);
+    const DeviceMesh dmesh = mesh.dev.view();
 
-    t0 = std::chrono::steady_clock::now();
+    auto t0 = std::chrono::steady_clock::now();
     const uint32_t G = uint32_t(out.startGridSize), G3 = G * G * G;
     Grid grid{G, startDepth, {out.boxMin[0], out.boxMin[1], out.boxMin[2]}, out.cellSize};
     const float sqThreshold = param0 * param0;

@@ -202,13 +202,6 @@ inline const float4* LevelSampler::runPoints(const DeviceMesh& mesh, const float
     });
 }
 
-__global__ void gatherTriVertsKernel(const f3* verts, const uint32_t* idx, uint32_t nTris, float4* triVerts) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nTris * 3) return;
-    const f3 v = verts[idx[t]];
-    triVerts[t] = make_float4(v.x, v.y, v.z, 0.f);
-}
-
 // interpolateValue, scalar branch: acc = 0 + sum_n ((c_n * x^i) * y^j) * z^k, n ascending, left to right.
 __device__ __forceinline__ float polyValueExact(const float* c, float x, float y, float z) {
     float acc = 0.0f;
@@ -257,33 +250,11 @@ void uploadHermite() {
     if (dev < 64) done[dev] = true;
 }
 
-inline void uploadMesh(MeshOnDevice& m, const HostMesh& mesh, const TriVec& tris, const RawVec<BvhNode>* bvh) {
-    m.numTriangles = mesh.numTriangles();
-    m.verts.alloc(mesh.nVerts); m.verts.upload(mesh.verts, mesh.nVerts);
-    m.idx.alloc(mesh.nIdx); m.idx.upload(mesh.idx, mesh.nIdx);
-    m.tris.alloc(tris.size()); m.tris.upload(tris.data(), tris.size());
-    if (bvh) {
-        m.bvh.alloc(bvh->size()); m.bvh.upload(bvh->data(), bvh->size());
-        m.rootLink = (*bvh)[0].pad[0] ? ~(*bvh)[0].right : 0;   // single-triangle mesh: the root is a leaf
-        // height of the median-split tree (mesh_host.cpp: halves of floor / ceil size) = deepest possible stack, + 1 spare
-        uint32_t n = m.numTriangles, h = 0;
-        while (n > 1) { n = n - n / 2; h++; }
-        m.stackDepth = int(h) + 1;
-        m.triVerts.alloc(size_t(m.numTriangles) * 3);
-        gatherTriVertsKernel<<<divUp(uint64_t(m.numTriangles) * 3, 256), 256>>>(m.verts.p, m.idx.p, m.numTriangles, m.triVerts.p);
-    }
-}
-
-// The two serial set-up steps of the reference constructors. Running them side by side was measured twice (OpenMP
-// task team and plain threads in the BVH builder): TriangleData saturates every host core, so the BVH thread only
-// gets going once it is done — no gain; they run one after the other.
-inline void buildHostStructures(const HostMesh& mesh, TriVec& tris, RawVec<BvhNode>& bvh, sdfb200_build_stats& st) {
-    auto t0 = std::chrono::steady_clock::now();
-    tris = computeTriangleData(mesh);
-    st.triangle_data_ms = msSince(t0);
-    t0 = std::chrono::steady_clock::now();
-    bvh = buildBvh(mesh);
-    st.bvh_ms = msSince(t0);
+// host-side phases of the mesh preparation into the build statistics (mesh_device.cu measured them)
+inline void meshStats(const PreparedMesh& pm, sdfb200_build_stats& st) {
+    st.triangle_data_ms = pm.triangleDataMs;
+    st.bvh_ms = pm.bvhMs;
+    st.upload_ms = pm.uploadMs;
 }
 
 // Weight of a mid-point in the error integral: trapezoid / by-distance 2^k/64 (OctreeSdfUtils.h:60-138),

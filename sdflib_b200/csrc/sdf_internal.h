@@ -122,6 +122,27 @@ struct MeshOnDevice {
     DeviceMesh view() const { return DeviceMesh{verts.p, idx.p, tris.p, bvh.p, numTriangles, triVerts.p, rootLink, stackDepth}; }
 };
 
+// ---- prepared mesh (mesh_device.cu): what every builder reads; computed once per mesh and device ------------------------
+struct PreparedMesh {
+    int device = 0;
+    uint32_t nVerts = 0, nIdx = 0, nTris = 0;
+    MeshOnDevice dev;                 // verts, idx, TriangleData; with hasBvh also bvh, triVerts, rootLink, stackDepth
+    bool hasBvh = false;              // OctreeSdf builders (nearest-triangle queries)
+    bool hasExactParts = false;       // ExactOctreeSdf builder / query: 80-byte frames + ids of the non-degenerate triangles
+    DevBuf<float4> frames;
+    DevBuf<uint32_t> valid;           // ascending triangle ids passing ExactOctreeSdfDepthFirst.h:106, padded by 8 words
+    uint32_t numValid = 0;
+    double triangleDataMs = 0, bvhMs = 0, uploadMs = 0;   // host wall clock of the phases (0 for clones / imports)
+    std::mutex lazy;
+    TriVec hostTris;                  // host copy of TriangleData, fetched from the device on first use
+    const TriVec& hostTriangleData();
+};
+std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bool withExactParts);
+uint64_t meshBlobBytes(const PreparedMesh& pm);
+void meshBlobExport(const PreparedMesh& pm, void* dDst, uint64_t capacity, cudaStream_t st);
+std::shared_ptr<PreparedMesh> meshBlobImport(const void* dSrc, uint64_t bytes);
+std::shared_ptr<PreparedMesh> cloneMeshToCurrentDevice(const PreparedMesh& src);
+
 // ---- sharded construction: state shared by both builders ---------------------------------
 // Roots = nodes of the start depth. Their order in the output arrays follows the reference's drivers
 // (numThreads < 2: one global stack, virtual levels popped 7-first; numThreads >= 2: start-grid order);
@@ -181,7 +202,12 @@ struct sdfb200_sdf {
     sdfb200::HostArray<uint32_t> octree;   // OCTREE: words; EXACT: (childrenIndex, trianglesArrayIndex) pairs
     sdfb200::HostArray<uint32_t> sets;
     sdfb200::HostArray<uint8_t> masks;
-    sdfb200::TriVec tris;
+    sdfb200::TriVec tris;            // EXACT: loaded from a .bin; built structures fetch it from `mesh` on demand (hostTris())
+    uint32_t numTris = 0;
+    std::shared_ptr<sdfb200::PreparedMesh> mesh;   // EXACT, built here: owner of the device TriangleData / frames the queries read
+    const sdfb200::TriData* qTris = nullptr;       // what the exact query kernels read (mesh->dev.tris or dTris)
+    const float4* qFrames = nullptr;               // (mesh->frames or dFrames)
+    const sdfb200::TriVec& hostTris() { return mesh ? mesh->hostTriangleData() : tris; }
     // device copies (what the query kernels read)
     sdfb200::DevBuf<uint32_t> dOctree;
     sdfb200::DevBuf<uint32_t> dSets;
@@ -217,7 +243,7 @@ namespace sdfb200 {
 // octree_build.cu
 // Builders: with world == 1 the structure is complete on return; with world > 1 only phase 1 (levels + sizes of
 // the own roots) has run and out.build holds the state for finish().
-void buildOctreeOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+void buildOctreeOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
                          int rule, float param0, float param1, uint32_t numThreads, uint32_t rank, uint32_t world);
 void finalizeOctreeScalars(sdfb200_sdf& s);   // shardScalars -> valueRange / minBorderValue
 void cubifyBox(sdfb200_sdf& s, const float* box6, uint32_t startDepth);
@@ -228,7 +254,7 @@ struct SampleExchange {
     sdfb200_allgather_fn allgather = nullptr;
     void* user = nullptr;
 };
-void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
                                    int rule, float param0, float param1, const SampleExchange& exchange = SampleExchange());
 // shard.cpp
 uint64_t shardPayloadWords(const sdfb200_sdf& s);
@@ -247,7 +273,7 @@ void queryHostPointers(sdfb200_sdf& s, const float* xyz, uint64_t n, float* dist
 void queryDevicePointers(const sdfb200_sdf& s, const float* xyz, uint64_t n, float* dist, float* grad, int flags, cudaStream_t st);
 void launchOctreeQueryExact(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);
 // exact_build.cu / exact_query.cu
-void buildExactOnDevice(sdfb200_sdf& out, const HostMesh& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
+void buildExactOnDevice(sdfb200_sdf& out, const std::shared_ptr<PreparedMesh>& mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
                         uint32_t minTris, uint32_t numThreads, uint32_t rank, uint32_t world);
 void prepareExactQuery(sdfb200_sdf& s);
 void launchExactQuery(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st);

@@ -233,3 +233,19 @@ def test_oracle_triangle_data_equals_reference_on_random_meshes(port, ref):
     for v, i in _random_meshes(np.random.default_rng(8), 40):
         a, b = port.triangle_data(v, i), ref.triangle_data(v, i)
         assert ((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all(), (len(v), i.size)
+
+
+def test_device_acosf_equals_host_libm_on_every_float(tmp_path):
+    """acosfLibm (tri_data_build.cuh: what the device uses for the corner angles of TriangleData) against the host libm's
+    acosf — the reference's std::acos(float) — on all 2 130 706 434 floats of [-1, 1] (tests/cpp/acosf_libm_main.cpp)."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "acosf_libm_main")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [cxx, "-O2", "-fopenmp", "-ffp-contract=off", "-fno-builtin", "-std=c++17", "-w", "-I/usr/local/cuda/include",
+           "-I" + os.path.join(ROOT, "sdflib_b200", "csrc"), "-x", "c++", os.path.join(ROOT, "tests", "cpp", "acosf_libm_main.cpp"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and r.stdout.startswith("ok 2130706434"), r.stdout[-500:]
