@@ -66,9 +66,23 @@ public:
               TerminationRuleParams params, InitAlgorithm initAlgorithm, uint32_t numThreads = 1)
     {
         const float b[6] = {box.min.x, box.min.y, box.min.z, box.max.x, box.max.y, box.max.z};
-        check(sdfb200_build_octree(reinterpret_cast<const float*>(mesh.getVertices().data()), uint32_t(mesh.getVertices().size()),
-                                   mesh.getIndices().data(), uint32_t(mesh.getIndices().size()), b, depth, startDepth,
-                                   int(terminationRule), params.params[0], params.params[1], int(initAlgorithm), numThreads, &mHandle));
+        const std::vector<int>& devices = getDevices();
+        if (devices.size() > 1)
+        {
+            std::vector<sdfb200_sdf*> handles(devices.size(), nullptr);
+            check(sdfb200_build_octree_multi(reinterpret_cast<const float*>(mesh.getVertices().data()), uint32_t(mesh.getVertices().size()),
+                                             mesh.getIndices().data(), uint32_t(mesh.getIndices().size()), b, depth, startDepth,
+                                             int(terminationRule), params.params[0], params.params[1], int(initAlgorithm), numThreads,
+                                             devices.data(), uint32_t(devices.size()), handles.data()));
+            adopt(handles);
+        }
+        else
+        {
+            if (devices.size() == 1) check(sdfb200_set_device(devices[0]));
+            check(sdfb200_build_octree(reinterpret_cast<const float*>(mesh.getVertices().data()), uint32_t(mesh.getVertices().size()),
+                                       mesh.getIndices().data(), uint32_t(mesh.getIndices().size()), b, depth, startDepth,
+                                       int(terminationRule), params.params[0], params.params[1], int(initAlgorithm), numThreads, &mHandle));
+        }
         fetch();
     }
 

@@ -101,7 +101,8 @@ int sdfb200_build_exact(const float* vertices, uint32_t numVertices, const uint3
 
 /* Sharded construction (one process per GPU). The start-depth voxels ("roots") are the reference's
  * own task decomposition (src/sdf/OctreeSdfDepthFirst.h:433-469, include/SdfLib/ExactOctreeSdfDepthFirst.h:534-574);
- * root i of the layout order is built by rank i % worldSize. Protocol, identical on every rank:
+ * a root's owner is chosen by estimated work (longest-processing-time greedy over per-root weights that every rank
+ * derives from the replicated levels above the start depth). Protocol, identical on every rank:
  *   1. sdfb200_build_*_shard      levels + subtree sizes of the own roots (GPU)
  *   2. sdfb200_shard_sizes        K values per start-grid slot (K = 1 OCTREE: words; K = 3 EXACT: node records, set
  *                                 words, mask bytes), 0 for roots of other ranks  -> caller all-reduces (SUM)
@@ -130,6 +131,49 @@ int sdfb200_build_octree_collective(const float* vertices, uint32_t numVertices,
 int sdfb200_build_exact_shard(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
                               const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
                               uint32_t numThreads, uint32_t rank, uint32_t worldSize, sdfb200_sdf** out);
+
+/* ---- prepared meshes (mesh ingestion on the device; reference: calculateMeshTriangleData, src/utils/TriangleUtils.cpp:7-428,
+ * and tmd::TriangleMeshDistance's BVH, libs/InteractiveComputerGraphics/.../TriangleMeshDistance.h:421-490).
+ * A prepared mesh holds, on the current device, everything the builders read: vertices, indices, TriangleData (computed on
+ * the GPU, same bits as the reference's host loop), with SDFB200_MESH_BVH the nearest-triangle BVH (built on the host:
+ * its shape is std::sort's tie order) and with SDFB200_MESH_EXACT the ExactOctreeSdf side arrays. One mesh serves any
+ * number of builds; sdfb200_mesh_export / sdfb200_mesh_import replicate it on other ranks (broadcast the blob). */
+typedef struct sdfb200_mesh sdfb200_mesh;
+enum { SDFB200_MESH_BVH = 1, SDFB200_MESH_EXACT = 2,
+       SDFB200_MESH_ALL_HOST_THREADS = 4 /* the host part may use every core although other ranks share the node */ };
+int sdfb200_mesh_create(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices, int parts,
+                        sdfb200_mesh** out);
+void sdfb200_mesh_free(sdfb200_mesh* mesh);
+int sdfb200_mesh_blob_bytes(const sdfb200_mesh* mesh, uint64_t* outBytes);
+int sdfb200_mesh_export(const sdfb200_mesh* mesh, void* devicePtr, uint64_t capacityBytes);   /* device buffer on the mesh's GPU */
+int sdfb200_mesh_import(const void* devicePtr, uint64_t bytes, sdfb200_mesh** out);          /* device buffer on the current GPU */
+int sdfb200_mesh_stats(const sdfb200_mesh* mesh, double* triangleDataMs, double* bvhMs, double* uploadMs);
+/* The builders of this header with the mesh given as a prepared mesh (same arguments otherwise). */
+int sdfb200_build_octree_from_mesh(const sdfb200_mesh* mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+                                   int terminationRule, float param0, float param1, int initAlgorithm, uint32_t numThreads,
+                                   uint32_t rank, uint32_t worldSize, sdfb200_sdf** out);
+int sdfb200_build_octree_collective_from_mesh(const sdfb200_mesh* mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+                                              int terminationRule, float param0, float param1, uint32_t rank, uint32_t worldSize,
+                                              sdfb200_allgather_fn allgather, void* user, sdfb200_sdf** out);
+int sdfb200_build_exact_from_mesh(const sdfb200_mesh* mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
+                                  uint32_t minTrianglesPerNode, uint32_t numThreads, uint32_t rank, uint32_t worldSize,
+                                  sdfb200_sdf** out);
+
+/* ---- one process, several GPUs of one box: what the C++ drop-in classes call when more than one device
+ * is requested. Host set-up once, the mesh replicated by peer copies, one host thread per device building the
+ * start-depth voxels it owns (assigned by estimated work), ONE ncclAllGather over NVLink (libnccl.so.2 is loaded at run
+ * time; peer copies when it is absent) assembling the complete structure on EVERY listed device. CONTINUITY shares the
+ * per-depth BVH sampling instead (see sdfb200_build_octree_collective). outHandles receives nDevices handles,
+ * outHandles[k] living on devices[k]; each is a complete SdfFunction (free every one with sdfb200_free). */
+int sdfb200_build_octree_multi(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                               const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule, float param0,
+                               float param1, int initAlgorithm, uint32_t numThreads, const int* devices, uint32_t nDevices,
+                               sdfb200_sdf** outHandles);
+int sdfb200_build_exact_multi(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                              const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
+                              uint32_t numThreads, const int* devices, uint32_t nDevices, sdfb200_sdf** outHandles);
+int sdfb200_nccl_available(void);   /* 1 when libnccl.so.2 could be loaded (SDFB200_NCCL_LIB overrides the name) */
+
 int sdfb200_shard_sizes(const sdfb200_sdf* shard, uint32_t* outSizes, uint64_t capacity, uint64_t* outCount);
 int sdfb200_shard_finish(sdfb200_sdf* shard, const uint32_t* allSizes, uint64_t count);
 int sdfb200_shard_words(const sdfb200_sdf* shard, uint64_t* outWords);
@@ -154,9 +198,15 @@ int sdfb200_get_device_octree(const sdfb200_sdf* sdf, const uint32_t** outDevice
 
 /* ---- bulk getDistance (hot path 2) ------------------------------------------------------------
  * xyz: n packed float3. dist: n floats. grad: NULL or n packed float3 (getDistance(p, grad)).
- * Host pointers by default (copied through pinned staging inside the call); with
- * SDFB200_QUERY_DEVICE_POINTERS they are device pointers and the call only enqueues the kernel on
- * `cudaStream` (a cudaStream_t, NULL = default stream) without synchronising. */
+ * Host pointers by default: the call returns when the results are in the caller's memory. Pinned (cudaHostAlloc /
+ * cudaHostRegister) buffers are copied directly in 2 M-query chunks alternating between two streams; pageable buffers
+ * go through a pinned ring owned by the handle (filled by all host threads); batches of up to 2048 queries — the
+ * scalar getDistance(p) of the reference API — use one mapped pinned slot and cost a kernel launch and a stream
+ * synchronisation. With SDFB200_QUERY_DEVICE_POINTERS the pointers are device pointers and the call only enqueues the
+ * kernel on `cudaStream` (a cudaStream_t, NULL = default stream) without synchronising.
+ * Threading: device-pointer calls are re-entrant (they share no mutable state). Host-pointer calls on ONE handle are
+ * serialised by a mutex inside the handle — correct from any number of threads (the reference's getDistance is a const
+ * read its users call from OpenMP loops), but they do not run concurrently; use one bulk call, or device pointers. */
 int sdfb200_query(sdfb200_sdf* sdf, const float* xyz, uint64_t n, float* dist, float* grad, int flags,
                   void* cudaStream);
 

@@ -44,7 +44,9 @@ SYMBOLS = ["sdfb200_last_error", "sdfb200_version", "sdfb200_device_count", "sdf
            "sdfb200_assemble", "sdfb200_save", "sdfb200_load", "sdfb200_free", "sdfb200_get_info",
            "sdfb200_get_build_stats", "sdfb200_get_octree_data", "sdfb200_get_exact_arrays", "sdfb200_get_device_octree",
            "sdfb200_query", "sdfb200_triangle_data", "sdfb200_nearest_triangle", "sdfb200_point_triangle",
-           "sdfb200_make_isosphere"]
+           "sdfb200_make_isosphere", "sdfb200_mesh_create", "sdfb200_mesh_free", "sdfb200_mesh_blob_bytes", "sdfb200_mesh_export",
+           "sdfb200_mesh_import", "sdfb200_mesh_stats", "sdfb200_build_octree_from_mesh", "sdfb200_build_octree_collective_from_mesh",
+           "sdfb200_build_exact_from_mesh", "sdfb200_build_octree_multi", "sdfb200_build_exact_multi", "sdfb200_nccl_available"]
 
 # int (*sdfb200_allgather_fn)(void* user, const void* dSend, void* dRecv, uint64_t bytesPerRank)
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
@@ -62,6 +64,7 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.sdfb200_last_error.restype = C.c_char_p
         L.sdfb200_free.restype = None
+        L.sdfb200_mesh_free.restype = None
         _lib = L
     return _lib
 

@@ -36,6 +36,7 @@ UNITS = [
     ("shard.cpp", "shard.o", ["-x", "cu"]),
     ("host_mem.cpp", "host_mem.o", ["-x", "cu"]),
     ("query_host.cpp", "query_host.o", ["-x", "cu"]),
+    ("multi_device.cpp", "multi_device.o", ["-x", "cu"]),
     ("fixtures.cpp", "fixtures.o", ["-x", "cu"] + NO_FMA),
     ("mesh_device.cu", "mesh_device.o", NO_FMA),
     ("octree_build.cu", "octree_build.o", NO_FMA),
@@ -93,7 +94,7 @@ def build(force=False, verbose=True):
                     f.write(r.stderr)
     objs = [os.path.join(OBJ, o) for _, o, _ in UNITS]
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc] + _ccbin() + ["-shared", "-o", LIB] + objs + ARCH + ["-Xcompiler", "-fopenmp", "-lgomp", "-cudart", "static"]
+        cmd = [nvcc] + _ccbin() + ["-shared", "-o", LIB] + objs + ARCH + ["-Xcompiler", "-fopenmp", "-lgomp", "-ldl", "-cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

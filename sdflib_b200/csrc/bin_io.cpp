@@ -88,6 +88,8 @@ void loadBin(sdfb200_sdf& s, const char* path) {
         getArray(is, s.tris);
     }
     s.cellSize = (s.boxMax[0] - s.boxMin[0]) / float(s.startGridSize);
+    s.nOctree = s.octree.size(); s.nSets = s.sets.size(); s.nMasks = s.masks.size();
+    s.hostMirror = true;
     validateStructure(s);
 }
 

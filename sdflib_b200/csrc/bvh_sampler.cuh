@@ -192,7 +192,7 @@ sampleOwnersKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const
     results[u] = samplePoint(mesh, latticeSamplePosition(centerHalf, owners[first + u]));
 }
 
-// ---- EXPERIMENTAL (off unless SDFB200_SAMPLE_REFILL=1; not yet measured on a GPU) ----------------
+// ---- default schedule (SDFB200_SAMPLE_REFILL=0 selects sampleOwnersKernel above) ------------------------------------------
 // Lane-refill schedule for the same traversals. With one sample per thread a lane whose traversal ends waits for the
 // longest one of its warp: on the C2 levels the lanes are busy 62-68 % of the warp's trips (tests/model_bvh_traversal.py;
 // ~650 node visits per sample, spread widely). Here a lane that runs out of work takes the next unassigned sample of

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <memory>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "sdf_internal.h"
 
@@ -63,7 +65,181 @@ void checkBox(const float* b) {
 
 using namespace sdfb200;
 
+struct sdfb200_mesh { std::shared_ptr<PreparedMesh> pm; };
+
+namespace {
+void checkOctreeOptions(int initAlgorithm, int terminationRule) {
+    if (initAlgorithm != SDFB200_ALG_NO_CONTINUITY && initAlgorithm != SDFB200_ALG_CONTINUITY)
+        throw Error(SDFB200_ERR_UNSUPPORTED, "InitAlgorithm::UNIFORM (the reference's testing variant) is not built: see DESIGN.md");
+    if (terminationRule < SDFB200_RULE_NONE || terminationRule > SDFB200_RULE_BY_DISTANCE)
+        throw Error(SDFB200_ERR_INVALID, "unknown termination rule");
+}
+const PreparedMesh& meshOnCurrentDevice(const sdfb200_mesh* m) {
+    if (!m || !m->pm) throw Error(SDFB200_ERR_INVALID, "null mesh handle");
+    requireDevice();
+    SDFB_CUDA(cudaSetDevice(m->pm->device));
+    return *m->pm;
+}
+std::vector<int> checkedDevices(const int* devices, uint32_t nDevices) {
+    if (!devices || nDevices == 0) throw Error(SDFB200_ERR_INVALID, "empty device list");
+    const int n = sdfb200_device_count();
+    if (n == 0) throw Error(SDFB200_ERR_CUDA, "no CUDA device available (sdfb200 has no CPU fallback)");
+    std::vector<int> d(devices, devices + nDevices);
+    // test switch: several "ranks" on one device exercise the thread choreography on a single-GPU box (peer copies, no NCCL)
+    const char* dup = std::getenv("SDFB200_ALLOW_DUPLICATE_DEVICES");
+    for (size_t i = 0; i < d.size(); i++) {
+        if (d[i] < 0 || d[i] >= n) throw Error(SDFB200_ERR_INVALID, "device index out of range");
+        for (size_t j = 0; j < i; j++)
+            if (d[j] == d[i] && !(dup && dup[0] == '1')) throw Error(SDFB200_ERR_INVALID, "device listed twice");
+    }
+    return d;
+}
+void runMulti(const HostMesh& mesh, const MultiBuildRequest& req, const int* devices, uint32_t nDevices, sdfb200_sdf** outHandles) {
+    if (!outHandles) throw Error(SDFB200_ERR_INVALID, "null output handles");
+    for (uint32_t k = 0; k < nDevices; k++) outHandles[k] = nullptr;
+    const std::vector<int> dev = checkedDevices(devices, nDevices);
+    std::vector<std::unique_ptr<sdfb200_sdf>> built;
+    buildMulti(mesh, req, dev, built);
+    for (uint32_t k = 0; k < nDevices; k++) outHandles[k] = built[k].release();
+}
+}  // namespace
+
 extern "C" {
+
+// ---- prepared meshes ---------------------------------------------------------------------------------------------
+int sdfb200_mesh_create(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices, int parts,
+                        sdfb200_mesh** out) {
+    return guarded([&] {
+        if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
+        *out = nullptr;
+        HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
+        requireDevice();
+        if (parts & SDFB200_MESH_ALL_HOST_THREADS) setHostThreadsForThisThread(int(std::thread::hardware_concurrency()));
+        std::unique_ptr<sdfb200_mesh> m(new sdfb200_mesh());
+        try { m->pm = prepareMesh(mesh, (parts & SDFB200_MESH_BVH) != 0, (parts & SDFB200_MESH_EXACT) != 0); }
+        catch (...) { setHostThreadsForThisThread(0); throw; }
+        setHostThreadsForThisThread(0);
+        *out = m.release();
+    });
+}
+
+void sdfb200_mesh_free(sdfb200_mesh* mesh) {
+    if (!mesh) return;
+    if (mesh->pm) { cudaSetDevice(mesh->pm->device); cudaDeviceSynchronize(); }
+    delete mesh;
+}
+
+int sdfb200_mesh_blob_bytes(const sdfb200_mesh* mesh, uint64_t* outBytes) {
+    return guarded([&] {
+        if (!mesh || !mesh->pm || !outBytes) throw Error(SDFB200_ERR_INVALID, "null argument");
+        *outBytes = meshBlobBytes(*mesh->pm);
+    });
+}
+
+int sdfb200_mesh_export(const sdfb200_mesh* mesh, void* devicePtr, uint64_t capacityBytes) {
+    return guarded([&] {
+        if (!devicePtr) throw Error(SDFB200_ERR_INVALID, "null argument");
+        meshBlobExport(meshOnCurrentDevice(mesh), devicePtr, capacityBytes, cudaStream_t(0));
+    });
+}
+
+int sdfb200_mesh_import(const void* devicePtr, uint64_t bytes, sdfb200_mesh** out) {
+    return guarded([&] {
+        if (!devicePtr || !out) throw Error(SDFB200_ERR_INVALID, "null argument");
+        *out = nullptr;
+        requireDevice();
+        std::unique_ptr<sdfb200_mesh> m(new sdfb200_mesh());
+        m->pm = meshBlobImport(devicePtr, bytes);
+        *out = m.release();
+    });
+}
+
+int sdfb200_mesh_stats(const sdfb200_mesh* mesh, double* triangleDataMs, double* bvhMs, double* uploadMs) {
+    return guarded([&] {
+        if (!mesh || !mesh->pm) throw Error(SDFB200_ERR_INVALID, "null mesh handle");
+        if (triangleDataMs) *triangleDataMs = mesh->pm->triangleDataMs;
+        if (bvhMs) *bvhMs = mesh->pm->bvhMs;
+        if (uploadMs) *uploadMs = mesh->pm->uploadMs;
+    });
+}
+
+int sdfb200_build_octree_from_mesh(const sdfb200_mesh* mesh, const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule,
+                                   float param0, float param1, int initAlgorithm, uint32_t numThreads, uint32_t rank, uint32_t worldSize,
+                                   sdfb200_sdf** out) {
+    return guarded([&] {
+        if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
+        *out = nullptr;
+        checkBox(box6);
+        if (worldSize == 0 || rank >= worldSize) throw Error(SDFB200_ERR_INVALID, "rank/worldSize out of range");
+        checkOctreeOptions(initAlgorithm, terminationRule);
+        if (initAlgorithm == SDFB200_ALG_CONTINUITY && worldSize > 1)
+            throw Error(SDFB200_ERR_UNSUPPORTED, "CONTINUITY does not shard by start voxels (its neighbour probes cross them): use sdfb200_build_octree_collective_from_mesh");
+        const PreparedMesh& pm = meshOnCurrentDevice(mesh);
+        std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
+        if (initAlgorithm == SDFB200_ALG_CONTINUITY) buildOctreeContinuityOnDevice(*s, pm, box6, depth, startDepth, terminationRule, param0, param1);
+        else buildOctreeOnDevice(*s, pm, box6, depth, startDepth, terminationRule, param0, param1, numThreads, rank, worldSize);
+        *out = s.release();
+    });
+}
+
+int sdfb200_build_octree_collective_from_mesh(const sdfb200_mesh* mesh, const float* box6, uint32_t depth, uint32_t startDepth,
+                                              int terminationRule, float param0, float param1, uint32_t rank, uint32_t worldSize,
+                                              sdfb200_allgather_fn allgather, void* user, sdfb200_sdf** out) {
+    return guarded([&] {
+        if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
+        *out = nullptr;
+        checkBox(box6);
+        if (worldSize == 0 || rank >= worldSize) throw Error(SDFB200_ERR_INVALID, "rank/worldSize out of range");
+        checkOctreeOptions(SDFB200_ALG_CONTINUITY, terminationRule);
+        if (worldSize > 1 && !allgather) throw Error(SDFB200_ERR_INVALID, "worldSize > 1 needs an allgather hook");
+        const PreparedMesh& pm = meshOnCurrentDevice(mesh);
+        std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
+        SampleExchange ex;
+        ex.rank = rank; ex.world = worldSize; ex.allgather = allgather; ex.user = user;
+        buildOctreeContinuityOnDevice(*s, pm, box6, depth, startDepth, terminationRule, param0, param1, ex);
+        *out = s.release();
+    });
+}
+
+int sdfb200_build_exact_from_mesh(const sdfb200_mesh* mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
+                                  uint32_t minTrianglesPerNode, uint32_t numThreads, uint32_t rank, uint32_t worldSize, sdfb200_sdf** out) {
+    return guarded([&] {
+        if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
+        *out = nullptr;
+        checkBox(box6);
+        if (worldSize == 0 || rank >= worldSize) throw Error(SDFB200_ERR_INVALID, "rank/worldSize out of range");
+        meshOnCurrentDevice(mesh);
+        std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
+        buildExactOnDevice(*s, mesh->pm, box6, maxDepth, startDepth, minTrianglesPerNode, numThreads, rank, worldSize);
+        *out = s.release();
+    });
+}
+
+// ---- one process, several devices ----------------------------------------------------------------------------------
+int sdfb200_nccl_available(void) { return ncclAvailable() ? 1 : 0; }
+
+int sdfb200_build_octree_multi(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                               const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule, float param0, float param1,
+                               int initAlgorithm, uint32_t numThreads, const int* devices, uint32_t nDevices, sdfb200_sdf** outHandles) {
+    return guarded([&] {
+        HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
+        checkBox(box6);
+        checkOctreeOptions(initAlgorithm, terminationRule);
+        MultiBuildRequest req{SDFB200_FORMAT_OCTREE, box6, depth, startDepth, numThreads, terminationRule, param0, param1, initAlgorithm, 0};
+        runMulti(mesh, req, devices, nDevices, outHandles);
+    });
+}
+
+int sdfb200_build_exact_multi(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                              const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode, uint32_t numThreads,
+                              const int* devices, uint32_t nDevices, sdfb200_sdf** outHandles) {
+    return guarded([&] {
+        HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
+        checkBox(box6);
+        MultiBuildRequest req{SDFB200_FORMAT_EXACT_OCTREE, box6, maxDepth, startDepth, numThreads, 0, 0.0f, 0.0f, 0, minTrianglesPerNode};
+        runMulti(mesh, req, devices, nDevices, outHandles);
+    });
+}
 
 const char* sdfb200_last_error(void) { return gLastError.c_str(); }
 int sdfb200_version(void) { return SDFB200_VERSION; }
@@ -184,6 +360,7 @@ int sdfb200_save(const sdfb200_sdf* sdf, const char* path) {
     return guarded([&] {
         if (!sdf || !path) throw Error(SDFB200_ERR_INVALID, "null argument");
         if (sdf->isShard) throw Error(SDFB200_ERR_INVALID, "handle is an unassembled shard (sdfb200_assemble not called yet)");
+        ensureHostMirror(*const_cast<sdfb200_sdf*>(sdf));
         saveBin(*sdf, path);
     });
 }
@@ -222,9 +399,9 @@ int sdfb200_get_info(const sdfb200_sdf* s, sdfb200_info* o) {
         o->max_triangles_encoded_in_leafs = s->maxTrisEncoded;
         o->bit_encoding_start_depth = s->bitEncodingStartDepth;
         o->bits_per_index = s->bitsPerIndex;
-        o->octree_words = s->format == SDFB200_FORMAT_OCTREE ? s->octree.size() : s->octree.size() / 2;
-        o->triangle_sets_words = s->sets.size();
-        o->triangle_masks_bytes = s->masks.size();
+        o->octree_words = s->format == SDFB200_FORMAT_OCTREE ? s->nOctree : s->nOctree / 2;
+        o->triangle_sets_words = s->nSets;
+        o->triangle_masks_bytes = s->nMasks;
         o->num_triangles = s->format == SDFB200_FORMAT_EXACT_OCTREE ? s->numTris : 0;
         o->device = s->device;
     });
@@ -241,8 +418,9 @@ int sdfb200_get_octree_data(const sdfb200_sdf* s, uint32_t* out, uint64_t capaci
     return guarded([&] {
         if (!s || !out) throw Error(SDFB200_ERR_INVALID, "null argument");
         if (s->isShard) throw Error(SDFB200_ERR_INVALID, "handle is an unassembled shard (sdfb200_assemble not called yet)");
-        if (capacityWords < s->octree.size()) throw Error(SDFB200_ERR_INVALID, "output buffer too small");
-        std::memcpy(out, s->octree.data(), s->octree.size() * sizeof(uint32_t));
+        if (capacityWords < s->nOctree) throw Error(SDFB200_ERR_INVALID, "output buffer too small");
+        ensureHostMirror(*const_cast<sdfb200_sdf*>(s));
+        std::memcpy(out, s->octree.data(), s->nOctree * sizeof(uint32_t));
     });
 }
 
@@ -250,8 +428,9 @@ int sdfb200_get_exact_arrays(const sdfb200_sdf* s, uint32_t* sets, uint8_t* mask
     return guarded([&] {
         if (!s) throw Error(SDFB200_ERR_INVALID, "null argument");
         if (s->format != SDFB200_FORMAT_EXACT_OCTREE) throw Error(SDFB200_ERR_INVALID, "not an ExactOctreeSdf");
-        if (sets) std::memcpy(sets, s->sets.data(), s->sets.size() * 4);
-        if (masks) std::memcpy(masks, s->masks.data(), s->masks.size());
+        if (sets || masks) ensureHostMirror(*const_cast<sdfb200_sdf*>(s));
+        if (sets) std::memcpy(sets, s->sets.data(), s->nSets * 4);
+        if (masks) std::memcpy(masks, s->masks.data(), s->nMasks);
         if (tris37) { const TriVec& t = const_cast<sdfb200_sdf*>(s)->hostTris(); std::memcpy(tris37, t.data(), t.size() * sizeof(TriData)); }
     });
 }

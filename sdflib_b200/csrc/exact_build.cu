@@ -841,10 +841,13 @@ struct ExactBuildState : BuildState {
         if (R.count != G3) throw Error(SDFB200_ERR_INVALID, "internal: start level is not a full grid");
         std::vector<float4> rootCH(G3);
         std::vector<uint32_t> rootCoord(G3);
+        std::vector<uint32_t> weight(G3);   // work estimate of a start voxel: the triangles its parent kept (its own candidates)
         R.centerHalf.download(rootCH.data(), G3);
         R.coord.download(rootCoord.data(), G3);
+        R.parentCnt.download(weight.data(), G3);
         SDFB_CUDA(cudaDeviceSynchronize());
-        out.plan = makeRootPlan(rootCH.data(), rootCoord.data(), G, startDepth, out.boxMin, out.cellSize, numThreads, rank, world);
+        out.plan = makeRootPlan(rootCH.data(), rootCoord.data(), G, startDepth, out.boxMin, out.cellSize, numThreads, rank, world,
+                                world > 1 ? weight.data() : nullptr);
     }
 
     void finish(sdfb200_sdf& out, const uint32_t* allSizesBySlot) override {
@@ -910,17 +913,13 @@ struct ExactBuildState : BuildState {
         SDFB_CUDA(cudaDeviceSynchronize());
         st.layout_ms += msSince(t0);
         levels.clear();   // release the builder's working set before the query-side pool is allocated
-        out.octree.resize(size_t(rn) * 2);
-        out.sets.resize(size_t(rs));
-        out.masks.resize(size_t(rm));
+        out.nOctree = rn * 2; out.nSets = rs; out.nMasks = rm;
+        out.hostMirror = false;
         if (plan.world == 1) {
             out.maxTrisInLeafs = out.shardScalars[0];
             out.maxTrisEncoded = out.shardScalars[1];
             t0 = std::chrono::steady_clock::now();
-            out.dOctree.download(out.octree.data(), out.octree.size());
-            out.dSets.download(out.sets.data(), out.sets.size());
-            out.dMasks.download(out.masks.data(), out.masks.size());
-            SDFB_CUDA(cudaDeviceSynchronize());
+            ensureHostMirror(out);
             st.download_ms = msSince(t0);
             prepareExactQuery(out);
             out.isShard = false;

@@ -450,7 +450,7 @@ exactBinnedKernel(const uint64_t* __restrict__ leafLo, const uint32_t* __restric
 // arrays are inconsistent (untrusted .bin input).
 void prepareExactQuery(sdfb200_sdf& s) {
     const uint32_t nT = s.numTris;
-    const uint64_t numNodes = s.octree.size() / 2;
+    const uint64_t numNodes = s.nOctree / 2;
     if (!s.qFrames) {   // loaded from a .bin: frames from the file's TriangleData (built structures share their mesh's)
         s.dFrames.alloc(size_t(nT) * 5);
         if (nT) framesFromTriData<<<divUp(uint64_t(nT) * 5, 256), 256>>>(s.dTris.p, s.dFrames.p, nT);
@@ -461,7 +461,7 @@ void prepareExactQuery(sdfb200_sdf& s) {
     s.dLeafCnt.alloc(numNodes);
     SDFB_CUDA(cudaMemsetAsync(s.dLeafLo.p, 0, numNodes * 8));
     SDFB_CUDA(cudaMemsetAsync(s.dLeafCnt.p, 0, numNodes * 4));
-    PublicView pv{s.dOctree.p, s.dSets.p, s.dMasks.p, numNodes, s.sets.size(), s.masks.size(), nT, s.bitsPerIndex, s.bitEncodingStartDepth};
+    PublicView pv{s.dOctree.p, s.dSets.p, s.dMasks.p, numNodes, s.nSets, s.nMasks, nT, s.bitsPerIndex, s.bitEncodingStartDepth};
     DevBuf<uint32_t> err(1);
     SDFB_CUDA(cudaMemsetAsync(err.p, 0, 4));
 

@@ -20,7 +20,11 @@ namespace sdfb200 {
 // Threads of the host-side set-up steps: SDFB200_HOST_THREADS when set; otherwise the machine's cores divided by
 // the ranks of this node (LOCAL_WORLD_SIZE). OMP_NUM_THREADS is deliberately not consulted: a launcher like
 // torchrun pins it to 1 for every rank, which serialised TriangleData and the BVH build (9x slower at 2 ranks).
+static thread_local int tHostThreadsOverride = 0;
+void setHostThreadsForThisThread(int n) { tHostThreadsOverride = n; }
+
 int hostThreads() {
+    if (tHostThreadsOverride > 0) return tHostThreadsOverride;
     static const int n = [] {
         const char* e = std::getenv("SDFB200_HOST_THREADS");
         const int v = e ? std::atoi(e) : 0;

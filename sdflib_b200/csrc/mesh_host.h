@@ -27,7 +27,8 @@ template <class T> struct DefaultInitAllocator : std::allocator<T> {
 template <class T> using RawVec = std::vector<T, DefaultInitAllocator<T>>;
 using TriVec = RawVec<TriData>;
 
-int hostThreads();   // SDFB200_HOST_THREADS or the OpenMP default
+int hostThreads();   // SDFB200_HOST_THREADS, else the machine's cores divided by the ranks of this node (LOCAL_WORLD_SIZE)
+void setHostThreadsForThisThread(int n);   // > 0: overrides hostThreads() for calls made by this thread (0 = back to the default)
 
 // reference: TriangleUtils::calculateMeshTriangleData, src/utils/TriangleUtils.cpp:7-428
 TriVec computeTriangleData(const HostMesh& mesh);

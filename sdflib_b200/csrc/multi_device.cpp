@@ -1,0 +1,245 @@
+// Construction over several GPUs of one box from ONE process (VERDICT r1 "a native multi-GPU host"):
+// the C++ drop-in classes reach every device of the box through sdfb200_build_*_multi without torch or a launcher.
+//
+//   1. the mesh is prepared once (TriangleData on the first device, BVH on the host threads) and replicated to the
+//      other devices by peer copies over NVLink;
+//   2. one host thread per device builds the sub-octrees of the start-depth voxels it owns (the reference's own task
+//      decomposition: src/sdf/OctreeSdfDepthFirst.h:433-469, include/SdfLib/ExactOctreeSdfDepthFirst.h:534-574), voxels
+//      assigned by estimated work;
+//   3. the per-voxel sizes are summed on the host (same process), every device emits its blocks at their final indices;
+//   4. ONE all-gather of the payloads — ncclAllGather over NVLink (libnccl.so.2, loaded at run time), or peer copies
+//      when NCCL is not installed — and a segmented copy assemble the complete arrays on EVERY device.
+// InitAlgorithm::CONTINUITY does not shard by voxels (its neighbour probes cross them): its ranks share the BVH
+// sampling of every depth and exchange the samples through the same all-gather (octree_cont.cu).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "sdf_internal.h"
+
+namespace sdfb200 {
+
+namespace {
+
+// ---- NCCL through dlopen: the library stays loadable (and single-GPU) on machines without NCCL ----------------------------
+struct Nccl {
+    typedef void* Comm;
+    int (*commInitAll)(Comm*, int, const int*) = nullptr;
+    int (*commDestroy)(Comm) = nullptr;
+    int (*allGather)(const void*, void*, size_t, int, Comm, cudaStream_t) = nullptr;
+    int (*groupStart)() = nullptr;
+    int (*groupEnd)() = nullptr;
+    const char* (*getErrorString)(int) = nullptr;
+    void* handle = nullptr;
+    bool ok = false;
+    static constexpr int kUint8 = 1;   // ncclUint8
+};
+
+Nccl& nccl() {
+    static Nccl n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (const char* off = std::getenv("SDFB200_NO_NCCL")) { if (off[0] == '1') return; }
+        const char* names[] = {std::getenv("SDFB200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* name : names) {
+            if (!name || !name[0]) continue;
+            n.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (n.handle) break;
+        }
+        if (!n.handle) return;
+        n.commInitAll = reinterpret_cast<decltype(n.commInitAll)>(dlsym(n.handle, "ncclCommInitAll"));
+        n.commDestroy = reinterpret_cast<decltype(n.commDestroy)>(dlsym(n.handle, "ncclCommDestroy"));
+        n.allGather = reinterpret_cast<decltype(n.allGather)>(dlsym(n.handle, "ncclAllGather"));
+        n.groupStart = reinterpret_cast<decltype(n.groupStart)>(dlsym(n.handle, "ncclGroupStart"));
+        n.groupEnd = reinterpret_cast<decltype(n.groupEnd)>(dlsym(n.handle, "ncclGroupEnd"));
+        n.getErrorString = reinterpret_cast<decltype(n.getErrorString)>(dlsym(n.handle, "ncclGetErrorString"));
+        n.ok = n.commInitAll && n.commDestroy && n.allGather && n.groupStart && n.groupEnd;
+    });
+    return n;
+}
+
+// communicators are cached per device list (ncclCommInitAll costs ~100 ms per device)
+struct CommSet { std::vector<Nccl::Comm> comm; };
+std::mutex gCommMutex;
+std::map<std::vector<int>, std::shared_ptr<CommSet>> gComms;
+
+std::shared_ptr<CommSet> commsFor(const std::vector<int>& devices) {
+    Nccl& n = nccl();
+    if (!n.ok || devices.size() < 2) return nullptr;
+    for (size_t i = 0; i < devices.size(); i++)
+        for (size_t j = 0; j < i; j++) if (devices[i] == devices[j]) return nullptr;   // NCCL needs distinct devices
+    std::lock_guard<std::mutex> lock(gCommMutex);
+    auto it = gComms.find(devices);
+    if (it != gComms.end()) return it->second;
+    std::shared_ptr<CommSet> cs(new CommSet());
+    cs->comm.resize(devices.size());
+    const int rc = n.commInitAll(cs->comm.data(), int(devices.size()), devices.data());
+    if (rc != 0) {
+        std::fprintf(stderr, "[sdfb200] ncclCommInitAll failed (%s): falling back to peer copies\n", n.getErrorString ? n.getErrorString(rc) : "?");
+        return nullptr;
+    }
+    gComms[devices] = cs;
+    return cs;
+}
+
+// a reusable barrier for the worker threads (C++17: no std::barrier)
+struct Barrier {
+    std::mutex m;
+    std::condition_variable cv;
+    uint32_t count, waiting = 0, generation = 0;
+    bool broken = false;
+    explicit Barrier(uint32_t n) : count(n) {}
+    void arriveAndWait() {
+        std::unique_lock<std::mutex> lock(m);
+        if (broken) throw Error(SDFB200_ERR_CUDA, "another device of the multi-GPU build failed");
+        const uint32_t gen = generation;
+        if (++waiting == count) { waiting = 0; generation++; cv.notify_all(); return; }
+        cv.wait(lock, [&] { return gen != generation || broken; });
+        if (broken) throw Error(SDFB200_ERR_CUDA, "another device of the multi-GPU build failed");
+    }
+    void breakAll() { std::lock_guard<std::mutex> lock(m); broken = true; cv.notify_all(); }
+};
+
+struct MultiContext {
+    std::vector<int> devices;
+    std::shared_ptr<CommSet> comms;
+    Barrier barrier;
+    // exchange slots (one writer per rank, read after a barrier)
+    std::vector<const void*> sendPtr;
+    std::vector<uint64_t> words;
+    std::vector<std::vector<uint32_t>> sizes;
+    explicit MultiContext(uint32_t n) : barrier(n), sendPtr(n), words(n), sizes(n) {}
+};
+
+// all-gather of `bytesPerRank` bytes: dRecv[q * bytesPerRank ...] = rank q's dSend, on every rank. Called by all rank threads.
+void allGatherBytes(MultiContext& ctx, uint32_t rank, const void* dSend, void* dRecv, uint64_t bytesPerRank) {
+    const uint32_t world = uint32_t(ctx.devices.size());
+    if (ctx.comms) {
+        Nccl& n = nccl();
+        const int rc = n.allGather(dSend, dRecv, size_t(bytesPerRank), Nccl::kUint8, ctx.comms->comm[rank], cudaStream_t(0));
+        if (rc != 0) throw Error(SDFB200_ERR_CUDA, std::string("ncclAllGather: ") + (n.getErrorString ? n.getErrorString(rc) : "failed"));
+        SDFB_CUDA(cudaStreamSynchronize(cudaStream_t(0)));
+        return;
+    }
+    // no NCCL: every rank publishes its buffer, then pulls the others' with peer copies
+    ctx.sendPtr[rank] = dSend;
+    SDFB_CUDA(cudaStreamSynchronize(cudaStream_t(0)));   // dSend is complete
+    ctx.barrier.arriveAndWait();
+    for (uint32_t q = 0; q < world; q++)
+        SDFB_CUDA(cudaMemcpyPeerAsync(static_cast<uint8_t*>(dRecv) + q * bytesPerRank, ctx.devices[rank], ctx.sendPtr[q], ctx.devices[q], bytesPerRank));
+    SDFB_CUDA(cudaStreamSynchronize(cudaStream_t(0)));
+    ctx.barrier.arriveAndWait();   // nobody reuses its send buffer before every peer has read it
+}
+
+struct HookUser { MultiContext* ctx; uint32_t rank; };
+int contAllGatherHook(void* user, const void* dSend, void* dRecv, uint64_t bytesPerRank) {
+    HookUser* u = static_cast<HookUser*>(user);
+    try {
+        allGatherBytes(*u->ctx, u->rank, dSend, dRecv, bytesPerRank);
+        return 0;
+    } catch (const std::exception& e) {
+        setLastError(e.what());
+        return 1;
+    }
+}
+
+void enablePeerAccess(const std::vector<int>& devices) {
+    for (int a : devices)
+        for (int b : devices) {
+            if (a == b) continue;
+            int can = 0;
+            SDFB_CUDA(cudaDeviceCanAccessPeer(&can, a, b));
+            if (!can) continue;
+            SDFB_CUDA(cudaSetDevice(a));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) SDFB_CUDA(e);
+            cudaGetLastError();
+        }
+}
+
+}  // namespace
+
+// Runs `req` over `devices`; out[k] = complete structure on devices[k].
+void buildMulti(const HostMesh& mesh, const MultiBuildRequest& req, const std::vector<int>& devices, std::vector<std::unique_ptr<sdfb200_sdf>>& out) {
+    const uint32_t world = uint32_t(devices.size());
+    const auto tStart = std::chrono::steady_clock::now();
+    enablePeerAccess(devices);
+    SDFB_CUDA(cudaSetDevice(devices[0]));
+    configureDevicePool(devices[0]);
+    const bool exact = req.format == SDFB200_FORMAT_EXACT_OCTREE;
+    std::shared_ptr<PreparedMesh> mesh0 = prepareMesh(mesh, !exact, exact);
+    MultiContext ctx(world);
+    ctx.devices = devices;
+    ctx.comms = commsFor(devices);
+    out.clear();
+    out.resize(world);
+    std::vector<std::exception_ptr> errors(world);
+    std::vector<std::shared_ptr<PreparedMesh>> meshes(world);
+    meshes[0] = mesh0;
+    const double prepMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count();
+
+    auto worker = [&](uint32_t rank) {
+        try {
+            SDFB_CUDA(cudaSetDevice(devices[rank]));
+            configureDevicePool(devices[rank]);
+            const auto t0 = std::chrono::steady_clock::now();
+            if (rank) meshes[rank] = cloneMeshToCurrentDevice(*mesh0);
+            std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
+            if (!exact && req.algorithm == SDFB200_ALG_CONTINUITY) {
+                HookUser user{&ctx, rank};
+                SampleExchange ex;
+                ex.rank = rank; ex.world = world; ex.allgather = contAllGatherHook; ex.user = &user;
+                buildOctreeContinuityOnDevice(*s, *meshes[rank], req.box6, req.depth, req.startDepth, req.rule, req.param0, req.param1, ex);
+            } else {
+                if (exact) buildExactOnDevice(*s, meshes[rank], req.box6, req.depth, req.startDepth, req.minTris, req.numThreads, rank, world);
+                else buildOctreeOnDevice(*s, *meshes[rank], req.box6, req.depth, req.startDepth, req.rule, req.param0, req.param1, req.numThreads, rank, world);
+                if (world > 1) {
+                    // sizes of every root: each rank contributes its own (others are 0), summed on the host
+                    ctx.sizes[rank] = s->shardSizes;
+                    ctx.barrier.arriveAndWait();
+                    std::vector<uint32_t> all(s->shardSizes.size(), 0u);
+                    for (uint32_t q = 0; q < world; q++)
+                        for (size_t i = 0; i < all.size(); i++) all[i] += ctx.sizes[q][i];
+                    s->build->finish(*s, all.data());
+                    ctx.words[rank] = shardPayloadWords(*s);
+                    ctx.barrier.arriveAndWait();
+                    uint64_t stride = 0;
+                    for (uint32_t q = 0; q < world; q++) stride = std::max(stride, ctx.words[q]);
+                    stride = (stride + 3) / 4 * 4;
+                    DevBuf<uint32_t> send(stride), recv(stride * world);
+                    shardExport(*s, send.p, stride);
+                    allGatherBytes(ctx, rank, send.p, recv.p, stride * 4);
+                    shardAssemble(*s, recv.p, ctx.words.data(), stride, world);
+                    SDFB_CUDA(cudaDeviceSynchronize());
+                }
+            }
+            s->stats.total_ms = prepMs + std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            out[rank] = std::move(s);
+        } catch (...) {
+            errors[rank] = std::current_exception();
+            ctx.barrier.breakAll();
+        }
+    };
+    std::vector<std::thread> threads;
+    for (uint32_t k = 1; k < world; k++) threads.emplace_back(worker, k);
+    worker(0);
+    for (std::thread& t : threads) t.join();
+    SDFB_CUDA(cudaSetDevice(devices[0]));
+    for (uint32_t k = 0; k < world; k++)
+        if (errors[k]) { out.clear(); std::rethrow_exception(errors[k]); }
+}
+
+bool ncclAvailable() { return nccl().ok; }
+
+}  // namespace sdfb200
+

@@ -287,7 +287,7 @@ void cubifyBox(sdfb200_sdf& s, const float* box6, uint32_t startDepth) {   // Oc
 }
 
 RootPlan makeRootPlan(const float4* rootCH, const uint32_t* rootCoord, uint32_t G, uint32_t startDepth, const float* boxMin3,
-                      float cellSize, uint32_t numThreads, uint32_t rank, uint32_t world) {
+                      float cellSize, uint32_t numThreads, uint32_t rank, uint32_t world, const uint32_t* weight) {
     RootPlan plan;
     const uint32_t G3 = G * G * G;
     plan.G3 = G3; plan.world = world; plan.rank = rank;
@@ -311,10 +311,20 @@ RootPlan makeRootPlan(const float4* rootCH, const uint32_t* rootCoord, uint32_t 
         plan.order[r] = r;
     }
     std::sort(plan.order.begin(), plan.order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    // Owners by estimated work: longest-processing-time greedy over the roots' weights — heaviest root
+    // first (ties in layout order), each to the rank with the least load so far (ties to the lowest rank). Every rank
+    // computes the same weights from the replicated levels above the start depth, hence the same plan.
+    std::vector<uint32_t> byWeight(plan.order);
+    if (weight) std::stable_sort(byWeight.begin(), byWeight.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+    std::vector<uint64_t> load(world, 0);
     for (uint32_t i = 0; i < G3; i++) {
-        const uint32_t r = plan.order[i];
-        plan.ownerOf[r] = i % world;
-        plan.owned[r] = (i % world) == rank;
+        const uint32_t r = byWeight[i];
+        uint32_t q = 0;
+        if (weight) { for (uint32_t k = 1; k < world; k++) if (load[k] < load[q]) q = k; }
+        else q = i % world;
+        load[q] += weight ? uint64_t(weight[r]) + 1 : 1;
+        plan.ownerOf[r] = q;
+        plan.owned[r] = q == rank;
     }
     return plan;
 }
@@ -434,10 +444,21 @@ struct OctreeBuildState : BuildState {
         if (R.count != G3) throw Error(SDFB200_ERR_INVALID, "internal: start level is not a full grid");
         std::vector<float4> rootCH(G3);
         std::vector<uint32_t> rootCoord(G3);
+        std::vector<float4> corners(size_t(G3) * 8);
         R.centerHalf.download(rootCH.data(), G3);
         R.coord.download(rootCoord.data(), G3);
+        R.corners.download(corners.data(), corners.size());
         SDFB_CUDA(cudaDeviceSynchronize());
-        out.plan = makeRootPlan(rootCH.data(), rootCoord.data(), G, startDepth, out.boxMin, out.cellSize, numThreads, rank, world);
+        // work estimate of a start voxel: it is refined down to the leaves where the surface passes through or next to it
+        // (some corner closer than the voxel's diagonal), and ends after a few levels elsewhere
+        std::vector<uint32_t> weight(G3);
+        for (uint32_t r = 0; r < G3; r++) {
+            float nearest = INFINITY;
+            for (int c = 0; c < 8; c++) nearest = std::min(nearest, std::fabs(corners[size_t(r) * 8 + c].x));
+            weight[r] = nearest < 3.4641f * rootCH[r].w ? 64u : 1u;   // 2 * half * sqrt(3)
+        }
+        out.plan = makeRootPlan(rootCH.data(), rootCoord.data(), G, startDepth, out.boxMin, out.cellSize, numThreads, rank, world,
+                                world > 1 ? weight.data() : nullptr);
     }
 
     // phase 2: global offsets, node words + leaf blocks of the own roots at their final positions
@@ -491,9 +512,9 @@ struct OctreeBuildState : BuildState {
             finalizeOctreeScalars(out);
             t0 = std::chrono::steady_clock::now();
             prepareOctreeQuery(out);
-            out.octree.resize(totalWords);
-            out.dOctree.download(out.octree.data(), totalWords);
-            SDFB_CUDA(cudaDeviceSynchronize());
+            out.nOctree = totalWords;
+            out.hostMirror = false;
+            ensureHostMirror(out);
             st.download_ms = msSince(t0);
             out.isShard = false;
         }

@@ -1007,10 +1007,9 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
     SDFB_CUDA(cudaMemcpyAsync(out.dOctree.p, oc.oct.p, words * 4, cudaMemcpyDeviceToDevice));
     finishStep("device copy");
     prepareOctreeQuery(out);
-    out.octree.resize(words);
-    finishStep("host block");
-    out.dOctree.download(out.octree.data(), words);
-    SDFB_CUDA(cudaDeviceSynchronize());
+    out.nOctree = words;
+    out.hostMirror = false;
+    ensureHostMirror(out);
     finishStep("download");
     st.download_ms = msSince(t0);
     out.isShard = false;

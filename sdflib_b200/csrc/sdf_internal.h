@@ -145,8 +145,8 @@ std::shared_ptr<PreparedMesh> cloneMeshToCurrentDevice(const PreparedMesh& src);
 
 // ---- sharded construction: state shared by both builders ---------------------------------
 // Roots = nodes of the start depth. Their order in the output arrays follows the reference's drivers
-// (numThreads < 2: one global stack, virtual levels popped 7-first; numThreads >= 2: start-grid order);
-// root i of that order is built by rank i % world. Identical on every rank.
+// (numThreads < 2: one global stack, virtual levels popped 7-first; numThreads >= 2: start-grid order); the owner of a
+// root is chosen by estimated work (longest-processing-time greedy over per-root weights). Identical on every rank.
 struct RootPlan {
     uint32_t G3 = 0, world = 1, rank = 0;
     std::vector<uint32_t> rootSlot;   // by root index (position in the start-depth level): start-grid slot
@@ -155,7 +155,7 @@ struct RootPlan {
     std::vector<uint32_t> ownerOf;    // by root index
 };
 RootPlan makeRootPlan(const float4* rootCenterHalf, const uint32_t* rootCoord, uint32_t G, uint32_t startDepth, const float* boxMin,
-                      float cellSize, uint32_t numThreads, uint32_t rank, uint32_t world);
+                      float cellSize, uint32_t numThreads, uint32_t rank, uint32_t world, const uint32_t* weight = nullptr);
 
 // One output array of a structure, as the shard exporter / assembler sees it.
 struct ShardStream {
@@ -202,6 +202,10 @@ struct sdfb200_sdf {
     sdfb200::HostArray<uint32_t> octree;   // OCTREE: words; EXACT: (childrenIndex, trianglesArrayIndex) pairs
     sdfb200::HostArray<uint32_t> sets;
     sdfb200::HostArray<uint8_t> masks;
+    // element counts of the arrays (valid as soon as the structure is complete on the device) and whether the host mirrors
+    // above hold them: replicas of a multi-GPU build fetch their mirrors on first use (ensureHostMirror, shard.cpp)
+    uint64_t nOctree = 0, nSets = 0, nMasks = 0;   // uint32 words / uint32 words / bytes
+    bool hostMirror = false;
     sdfb200::TriVec tris;            // EXACT: loaded from a .bin; built structures fetch it from `mesh` on demand (hostTris())
     uint32_t numTris = 0;
     std::shared_ptr<sdfb200::PreparedMesh> mesh;   // EXACT, built here: owner of the device TriangleData / frames the queries read
@@ -256,7 +260,18 @@ struct SampleExchange {
 };
 void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, const float* box6, uint32_t depth, uint32_t startDepth,
                                    int rule, float param0, float param1, const SampleExchange& exchange = SampleExchange());
+// multi_device.cpp: one process, several devices
+struct MultiBuildRequest {
+    int format;   // SDFB200_FORMAT_OCTREE / SDFB200_FORMAT_EXACT_OCTREE
+    const float* box6;
+    uint32_t depth, startDepth, numThreads;
+    int rule; float param0, param1; int algorithm;   // OCTREE
+    uint32_t minTris;                                // EXACT_OCTREE
+};
+void buildMulti(const HostMesh& mesh, const MultiBuildRequest& req, const std::vector<int>& devices, std::vector<std::unique_ptr<sdfb200_sdf>>& out);
+bool ncclAvailable();
 // shard.cpp
+void ensureHostMirror(sdfb200_sdf& s);   // downloads the structure arrays into the host mirrors once (synchronises)
 uint64_t shardPayloadWords(const sdfb200_sdf& s);
 void shardExport(const sdfb200_sdf& s, uint32_t* dDst, uint64_t capacityWords);
 void shardAssemble(sdfb200_sdf& s, const uint32_t* dGathered, const uint64_t* wordsPerRank, uint64_t strideWords, uint32_t world);

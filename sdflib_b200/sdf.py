@@ -61,6 +61,59 @@ class Mesh:
         return self._bbox
 
 
+class PreparedMesh:
+    """sdfb200_mesh: a mesh ingested on the current device (TriangleData on the GPU; with bvh=True the nearest-triangle BVH
+    of the OctreeSdf builders, with exact=True the side arrays of ExactOctreeSdf). One prepared mesh serves any number of
+    builds; export_blob()/from_blob() replicate it on another rank or device without repeating the host work."""
+    BVH, EXACT, ALL_HOST_THREADS = 1, 2, 4
+
+    def __init__(self, mesh=None, bvh=True, exact=True, all_host_threads=False, _handle=None):
+        if _handle is not None:
+            self._h = C.c_void_p(_handle)
+            return
+        parts = (self.BVH if bvh else 0) | (self.EXACT if exact else 0) | (self.ALL_HOST_THREADS if all_host_threads else 0)
+        h = C.c_void_p()
+        _capi.check(_capi.lib().sdfb200_mesh_create(_capi.ptr(mesh.vertices), C.c_uint32(len(mesh.vertices)), _capi.ptr(mesh.indices),
+                                                    C.c_uint32(mesh.indices.size), C.c_int(parts), C.byref(h)))
+        self._h = h
+
+    def blob_bytes(self):
+        n = C.c_uint64()
+        _capi.check(_capi.lib().sdfb200_mesh_blob_bytes(self._h, C.byref(n)))
+        return n.value
+
+    def export_blob(self, device_ptr, capacity):
+        _capi.check(_capi.lib().sdfb200_mesh_export(self._h, C.c_void_p(device_ptr), C.c_uint64(capacity)))
+
+    @staticmethod
+    def from_blob(device_ptr, nbytes):
+        h = C.c_void_p()
+        _capi.check(_capi.lib().sdfb200_mesh_import(C.c_void_p(device_ptr), C.c_uint64(nbytes), C.byref(h)))
+        return PreparedMesh(_handle=h.value)
+
+    def stats(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _capi.check(_capi.lib().sdfb200_mesh_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"triangle_data_ms": a.value, "bvh_ms": b.value, "upload_ms": c.value}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _capi.lib().sdfb200_mesh_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _adopt(cls, handle):
+    obj = cls.__new__(cls)
+    SdfFunction.__init__(obj, handle)
+    return obj
+
+
 def _is_torch_cuda(x):
     return hasattr(x, "is_cuda") and x.is_cuda
 
@@ -83,6 +136,10 @@ class SdfFunction:
             if pts.dtype != torch.float32 or not pts.is_contiguous():
                 pts = pts.float().contiguous()
             n = pts.shape[0]
+            for name, buf, need in (("out", out, n), ("out_gradient", out_gradient if gradient else None, 3 * n)):
+                if buf is not None and not (_is_torch_cuda(buf) and buf.dtype == torch.float32 and buf.is_contiguous()
+                                            and buf.numel() >= need and buf.device == pts.device):
+                    raise ValueError(f"{name} must be a contiguous float32 CUDA tensor on {pts.device} with at least {need} elements")
             dist = out if out is not None else torch.empty(n, dtype=torch.float32, device=pts.device)
             grad = None
             if gradient:
@@ -96,6 +153,9 @@ class SdfFunction:
         single = pts.ndim == 1
         pts = pts.reshape(-1, 3)
         n = len(pts)
+        for name, buf, need in (("out", out, n), ("out_gradient", out_gradient if gradient else None, 3 * n)):
+            if buf is not None and not (isinstance(buf, np.ndarray) and buf.dtype == np.float32 and buf.flags.c_contiguous and buf.size >= need):
+                raise ValueError(f"{name} must be a C-contiguous float32 numpy array with at least {need} elements")
         dist = out if out is not None else np.empty(n, np.float32)
         grad = (out_gradient if out_gradient is not None else np.zeros((n, 3), np.float32)) if gradient else None
         _capi.check(L.sdfb200_query(self._h, _capi.ptr(pts), C.c_uint64(n), _capi.ptr(dist), _capi.ptr(grad), C.c_int(flags), None))
@@ -173,11 +233,31 @@ class OctreeSdf(SdfFunction):
         params = list(terminationRuleParams) if terminationRuleParams is not None else [maxError]
         params += [0.0] * (2 - len(params))
         h = C.c_void_p()
-        _capi.check(_capi.lib().sdfb200_build_octree(
+        if isinstance(mesh, PreparedMesh):
+            _capi.check(_capi.lib().sdfb200_build_octree_from_mesh(
+                mesh._h, _capi.ptr(_capi.f32(box.as_array())), C.c_uint32(depth), C.c_uint32(startDepth), C.c_int(terminationRule),
+                C.c_float(params[0]), C.c_float(params[1]), C.c_int(initAlgorithm), C.c_uint32(numThreads), C.c_uint32(0), C.c_uint32(1),
+                C.byref(h)))
+        else:
+            _capi.check(_capi.lib().sdfb200_build_octree(
+                _capi.ptr(mesh.vertices), C.c_uint32(len(mesh.vertices)), _capi.ptr(mesh.indices), C.c_uint32(mesh.indices.size),
+                _capi.ptr(_capi.f32(box.as_array())), C.c_uint32(depth), C.c_uint32(startDepth), C.c_int(terminationRule),
+                C.c_float(params[0]), C.c_float(params[1]), C.c_int(initAlgorithm), C.c_uint32(numThreads), C.byref(h)))
+        super().__init__(h.value)
+
+    @staticmethod
+    def build_on_devices(mesh, box, depth, startDepth, devices, maxError=1e-3, initAlgorithm=1, numThreads=2,
+                         terminationRule=1, terminationRuleParams=None):
+        """sdfb200_build_octree_multi: ONE process, the listed devices of this box; returns one complete OctreeSdf per device."""
+        params = list(terminationRuleParams) if terminationRuleParams is not None else [maxError]
+        params += [0.0] * (2 - len(params))
+        dev = (C.c_int * len(devices))(*devices)
+        handles = (C.c_void_p * len(devices))()
+        _capi.check(_capi.lib().sdfb200_build_octree_multi(
             _capi.ptr(mesh.vertices), C.c_uint32(len(mesh.vertices)), _capi.ptr(mesh.indices), C.c_uint32(mesh.indices.size),
             _capi.ptr(_capi.f32(box.as_array())), C.c_uint32(depth), C.c_uint32(startDepth), C.c_int(terminationRule),
-            C.c_float(params[0]), C.c_float(params[1]), C.c_int(initAlgorithm), C.c_uint32(numThreads), C.byref(h)))
-        super().__init__(h.value)
+            C.c_float(params[0]), C.c_float(params[1]), C.c_int(initAlgorithm), C.c_uint32(numThreads), dev, C.c_uint32(len(devices)), handles))
+        return [_adopt(OctreeSdf, h) for h in handles]
 
     def getOctreeData(self):
         out = np.empty(self.info().octree_words, np.uint32)
@@ -194,11 +274,27 @@ class OctreeSdf(SdfFunction):
 class ExactOctreeSdf(SdfFunction):
     def __init__(self, mesh, box, maxDepth, startDepth=1, minTrianglesPerNode=128, numThreads=1):
         h = C.c_void_p()
-        _capi.check(_capi.lib().sdfb200_build_exact(
-            _capi.ptr(mesh.vertices), C.c_uint32(len(mesh.vertices)), _capi.ptr(mesh.indices), C.c_uint32(mesh.indices.size),
-            _capi.ptr(_capi.f32(box.as_array())), C.c_uint32(maxDepth), C.c_uint32(startDepth),
-            C.c_uint32(minTrianglesPerNode), C.c_uint32(numThreads), C.byref(h)))
+        if isinstance(mesh, PreparedMesh):
+            _capi.check(_capi.lib().sdfb200_build_exact_from_mesh(
+                mesh._h, _capi.ptr(_capi.f32(box.as_array())), C.c_uint32(maxDepth), C.c_uint32(startDepth), C.c_uint32(minTrianglesPerNode),
+                C.c_uint32(numThreads), C.c_uint32(0), C.c_uint32(1), C.byref(h)))
+        else:
+            _capi.check(_capi.lib().sdfb200_build_exact(
+                _capi.ptr(mesh.vertices), C.c_uint32(len(mesh.vertices)), _capi.ptr(mesh.indices), C.c_uint32(mesh.indices.size),
+                _capi.ptr(_capi.f32(box.as_array())), C.c_uint32(maxDepth), C.c_uint32(startDepth),
+                C.c_uint32(minTrianglesPerNode), C.c_uint32(numThreads), C.byref(h)))
         super().__init__(h.value)
+
+    @staticmethod
+    def build_on_devices(mesh, box, maxDepth, startDepth, devices, minTrianglesPerNode=128, numThreads=2):
+        """sdfb200_build_exact_multi: ONE process, the listed devices of this box; returns one complete ExactOctreeSdf per device."""
+        dev = (C.c_int * len(devices))(*devices)
+        handles = (C.c_void_p * len(devices))()
+        _capi.check(_capi.lib().sdfb200_build_exact_multi(
+            _capi.ptr(mesh.vertices), C.c_uint32(len(mesh.vertices)), _capi.ptr(mesh.indices), C.c_uint32(mesh.indices.size),
+            _capi.ptr(_capi.f32(box.as_array())), C.c_uint32(maxDepth), C.c_uint32(startDepth), C.c_uint32(minTrianglesPerNode),
+            C.c_uint32(numThreads), dev, C.c_uint32(len(devices)), handles))
+        return [_adopt(ExactOctreeSdf, h) for h in handles]
 
     def getOctreeData(self):
         out = np.empty(2 * self.info().octree_words, np.uint32)

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
-from .sdf import OctreeSdf, ExactOctreeSdf, SdfFunction
+from .sdf import OctreeSdf, ExactOctreeSdf, PreparedMesh, SdfFunction
 
 
 class Shard:
@@ -89,9 +89,35 @@ def exchange(shard, group=None, device=None):
     return stride * 4, stride
 
 
+def prepare_mesh(mesh, bvh, exact, group=None):
+    """The mesh prepared ONCE per node (the host set-up used to be repeated by every rank with
+    cores / ranks threads). Without a BVH every rank ingests the mesh on its own GPU (TriangleData is a few kernels).
+    With a BVH — host work whose result depends on std::sort's tie order — rank 0 builds it with all host cores and the
+    prepared mesh travels as one device blob through a broadcast over NCCL/NVLink."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if world == 1 or not bvh:
+        return PreparedMesh(mesh, bvh=bvh, exact=exact)
+    rank = dist.get_rank(group)
+    device = torch.device("cuda", torch.cuda.current_device())
+    own = PreparedMesh(mesh, bvh=True, exact=exact, all_host_threads=True) if rank == 0 else None
+    size = torch.tensor([own.blob_bytes() if own is not None else 0], dtype=torch.int64, device=device)
+    dist.broadcast(size, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    blob = torch.empty(int(size.item()), dtype=torch.uint8, device=device)
+    if own is not None:
+        own.export_blob(blob.data_ptr(), blob.numel())
+    dist.broadcast(blob, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return own if own is not None else PreparedMesh.from_blob(blob.data_ptr(), blob.numel())
+
+
 def _mesh_args(mesh, box):
     return (_capi.ptr(mesh.vertices), C.c_uint32(len(mesh.vertices)), _capi.ptr(mesh.indices), C.c_uint32(mesh.indices.size),
             _capi.ptr(_capi.f32(box.as_array())))
+
+
+def _box_arg(box):
+    return _capi.ptr(_capi.f32(box.as_array()))
 
 
 class _DevicePointer:
@@ -135,26 +161,30 @@ def build_octree_collective(mesh, box, depth, startDepth, params, terminationRul
     """InitAlgorithm::CONTINUITY over `world` ranks: replicated octree logic, BVH sampling sliced over the ranks and
     all-gathered per depth through `hook` (an _capi.ALLGATHER_FN). Returns the complete OctreeSdf on every rank."""
     h = C.c_void_p()
-    _capi.check(_capi.lib().sdfb200_build_octree_collective(
-        *_mesh_args(mesh, box), C.c_uint32(depth), C.c_uint32(startDepth), C.c_int(terminationRule), C.c_float(params[0]),
-        C.c_float(params[1]), C.c_int(OctreeSdf.CONTINUITY), C.c_uint32(1), C.c_uint32(rank), C.c_uint32(world), hook, None, C.byref(h)))
+    pm = mesh if isinstance(mesh, PreparedMesh) else PreparedMesh(mesh, bvh=True, exact=False)
+    _capi.check(_capi.lib().sdfb200_build_octree_collective_from_mesh(
+        pm._h, _box_arg(box), C.c_uint32(depth), C.c_uint32(startDepth), C.c_int(terminationRule), C.c_float(params[0]),
+        C.c_float(params[1]), C.c_uint32(rank), C.c_uint32(world), hook, None, C.byref(h)))
     return Shard(h.value).into(OctreeSdf)
 
 
 def build_octree_sharded(mesh, box, depth, startDepth, maxError=1e-3, initAlgorithm=OctreeSdf.NO_CONTINUITY, numThreads=2,
                          terminationRule=OctreeSdf.TRAPEZOIDAL_RULE, terminationRuleParams=None, group=None):
-    """OctreeSdf(...) built cooperatively by all ranks of `group`; every rank returns the complete structure."""
+    """OctreeSdf(...) built cooperatively by all ranks of `group`; every rank returns the complete structure.
+    `mesh`: a Mesh (prepared here, once per node) or a PreparedMesh from prepare_mesh() to reuse across builds."""
     import torch.distributed as dist
     params = list(terminationRuleParams) if terminationRuleParams is not None else [maxError]
     params += [0.0] * (2 - len(params))
+    if not isinstance(mesh, PreparedMesh):
+        mesh = prepare_mesh(mesh, True, False, group)
     if initAlgorithm == OctreeSdf.CONTINUITY:
         import torch
         hook = torch_allgather_hook(group, torch.device("cuda", torch.cuda.current_device()))
         return build_octree_collective(mesh, box, depth, startDepth, params, terminationRule, dist.get_rank(group),
                                        dist.get_world_size(group), hook)
     h = C.c_void_p()
-    _capi.check(_capi.lib().sdfb200_build_octree_shard(
-        *_mesh_args(mesh, box), C.c_uint32(depth), C.c_uint32(startDepth), C.c_int(terminationRule), C.c_float(params[0]),
+    _capi.check(_capi.lib().sdfb200_build_octree_from_mesh(
+        mesh._h, _box_arg(box), C.c_uint32(depth), C.c_uint32(startDepth), C.c_int(terminationRule), C.c_float(params[0]),
         C.c_float(params[1]), C.c_int(initAlgorithm), C.c_uint32(numThreads), C.c_uint32(dist.get_rank(group)),
         C.c_uint32(dist.get_world_size(group)), C.byref(h)))
     if dist.get_world_size(group) == 1:
@@ -168,8 +198,10 @@ def build_exact_sharded(mesh, box, maxDepth, startDepth=1, minTrianglesPerNode=1
     """ExactOctreeSdf(...) built cooperatively by all ranks of `group`; every rank returns the complete structure."""
     import torch.distributed as dist
     h = C.c_void_p()
-    _capi.check(_capi.lib().sdfb200_build_exact_shard(
-        *_mesh_args(mesh, box), C.c_uint32(maxDepth), C.c_uint32(startDepth), C.c_uint32(minTrianglesPerNode),
+    if not isinstance(mesh, PreparedMesh):
+        mesh = prepare_mesh(mesh, False, True, group)
+    _capi.check(_capi.lib().sdfb200_build_exact_from_mesh(
+        mesh._h, _box_arg(box), C.c_uint32(maxDepth), C.c_uint32(startDepth), C.c_uint32(minTrianglesPerNode),
         C.c_uint32(numThreads), C.c_uint32(dist.get_rank(group)), C.c_uint32(dist.get_world_size(group)), C.byref(h)))
     if dist.get_world_size(group) == 1:
         return Shard(h.value).into(ExactOctreeSdf)
