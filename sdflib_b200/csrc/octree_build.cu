@@ -492,6 +492,8 @@ struct OctreeBuildState : BuildState {
             st.kernel_launches++;
         }
         out.dOctree.alloc(totalWords);
+        out.nOctree = totalWords;
+        out.hostMirror = false;
         S.dBase = reinterpret_cast<uint8_t*>(out.dOctree.p);
         SDFB_CUDA(cudaMemsetAsync(out.dOctree.p, 0, totalWords * sizeof(uint32_t)));
         DevBuf<uint32_t> scalars(2);
@@ -512,8 +514,6 @@ struct OctreeBuildState : BuildState {
             finalizeOctreeScalars(out);
             t0 = std::chrono::steady_clock::now();
             prepareOctreeQuery(out);
-            out.nOctree = totalWords;
-            out.hostMirror = false;
             ensureHostMirror(out);
             st.download_ms = msSince(t0);
             out.isShard = false;
