@@ -194,6 +194,11 @@ void buildMulti(const HostMesh& mesh, const MultiBuildRequest& req, const std::v
             configureDevicePool(devices[rank]);
             const auto t0 = std::chrono::steady_clock::now();
             if (rank) meshes[rank] = cloneMeshToCurrentDevice(*mesh0);
+            // Nobody starts building before every clone has arrived: a peer copy out of device 0 is ordered behind the work
+            // queued on device 0, so a rank-0 build that is already waiting inside its first collective (CONTINUITY) for a
+            // rank still fetching its mesh would deadlock (reproduced on 2 x B200: profiles/r2_summary.md), and the other
+            // builders would delay the copies behind their first kernels.
+            if (world > 1) ctx.barrier.arriveAndWait();
             std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
             if (!exact && req.algorithm == SDFB200_ALG_CONTINUITY) {
                 HookUser user{&ctx, rank};
