@@ -65,6 +65,10 @@ def main():
                 times.append(time.perf_counter() - t0)
                 if rep == 3:
                     stats = {k: round(x, 1) for k, x in replicas[0].build_stats().items() if k.endswith("_ms")}
+                    per_rank = [r.build_stats() for r in replicas]
+                    stats["levels_ms_max"] = round(max(s["levels_ms"] for s in per_rank), 1)       # load balance of the voxel plan
+                    stats["levels_ms_min"] = round(min(s["levels_ms"] for s in per_rank), 1)
+                    stats["total_ms_max"] = round(max(s["total_ms"] for s in per_rank), 1)
                     digests = [digest(r) for r in (replicas if cfg != "c4" else replicas[:2])]   # c4: 1.5 GB per download, two replicas suffice
                     if reference_digest is None:
                         reference_digest = digests[0]

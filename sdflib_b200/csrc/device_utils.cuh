@@ -3,6 +3,7 @@
 #pragma once
 #include <chrono>
 #include <cstdint>
+#include <cstring>
 
 #include "sdf_internal.h"
 
@@ -12,6 +13,29 @@ inline uint32_t divUp(uint64_t a, uint64_t b) { return uint32_t((a + b - 1) / b)
 
 inline double msSince(std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- small device -> host readbacks ----------------------------------------------------------------------------
+// Scan totals and counters come back through a PINNED slot owned by the calling thread: a copy into pageable memory
+// (a stack variable) is staged by the driver under a process-wide lock, which serialises the host threads of a
+// single-process multi-device build against each other (measured on 8 x B200: profiles/r2_summary.md).
+inline void* pinnedScratch() {   // 256 bytes per host thread, allocated on first use, freed at process exit by the driver
+    static thread_local void* slot = nullptr;
+    if (!slot && cudaHostAlloc(&slot, 256, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); slot = nullptr; }
+    return slot;
+}
+template <class T> inline T readScalar(const T* dSrc, cudaStream_t st = 0) {
+    static_assert(sizeof(T) <= 256, "readScalar payload");
+    T out;
+    if (void* pin = pinnedScratch()) {
+        SDFB_CUDA(cudaMemcpyAsync(pin, dSrc, sizeof(T), cudaMemcpyDeviceToHost, st));
+        SDFB_CUDA(cudaStreamSynchronize(st));
+        std::memcpy(&out, pin, sizeof(T));
+    } else {
+        SDFB_CUDA(cudaMemcpyAsync(&out, dSrc, sizeof(T), cudaMemcpyDeviceToHost, st));
+        SDFB_CUDA(cudaStreamSynchronize(st));
+    }
+    return out;
 }
 
 // ---- exclusive scan (three small kernels) ---------------------------------------------------------------
@@ -107,10 +131,7 @@ template <class In, class Out> struct ScannerT {
         scanOfBlockSums<Out><<<1, kScanBlock, 0, st>>>(blockSums.p, nBlocks, total.p);
         scanFinalize<In, Out><<<nBlocks, kScanBlock, 0, st>>>(in, blockSums.p, out, n, total.p, writeTotal);
         launches += 3;
-        Out t = 0;
-        SDFB_CUDA(cudaMemcpyAsync(&t, total.p, sizeof(Out), cudaMemcpyDeviceToHost, st));
-        SDFB_CUDA(cudaStreamSynchronize(st));
-        return t;
+        return readScalar<Out>(total.p, st);
     }
 };
 using Scanner = ScannerT<uint32_t, uint32_t>;
@@ -188,10 +209,7 @@ struct FlagScanner {
         flagBlockSums<<<nBlocks, kFlagThreads, 0, st>>>(in, blockSums.p, n);
         scanOfBlockSums<uint32_t><<<1, kScanBlock, 0, st>>>(blockSums.p, nBlocks, total.p);
         flagFinalize<<<nBlocks, kFlagThreads, 0, st>>>(in, blockSums.p, out, n);
-        uint32_t t = 0;
-        SDFB_CUDA(cudaMemcpyAsync(&t, total.p, sizeof(t), cudaMemcpyDeviceToHost, st));
-        SDFB_CUDA(cudaStreamSynchronize(st));
-        return t;
+        return readScalar<uint32_t>(total.p, st);
     }
 };
 
@@ -207,9 +225,7 @@ inline uint64_t countFlags64(const uint8_t* flags, uint64_t n) {
     DevBuf<unsigned long long> total(1);
     SDFB_CUDA(cudaMemsetAsync(total.p, 0, 8));
     countFlagsKernel<<<148 * 8, 256>>>(flags, n, total.p);
-    unsigned long long t = 0;
-    SDFB_CUDA(cudaMemcpy(&t, total.p, 8, cudaMemcpyDeviceToHost));
-    return t;
+    return readScalar<unsigned long long>(total.p);
 }
 
 }  // namespace sdfb200

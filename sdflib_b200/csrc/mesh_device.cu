@@ -311,6 +311,14 @@ std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bo
     return pm;
 }
 
+// BVH built elsewhere (one host build shared by the devices of a multi-device build): upload + pre-gathered triangle vertices
+void attachBvh(PreparedMesh& pm, const RawVec<BvhNode>& bvh, double bvhMs) {
+    const auto t0 = std::chrono::steady_clock::now();
+    uploadBvh(pm, bvh);
+    pm.bvhMs = bvhMs;
+    pm.uploadMs += msSince(t0);
+}
+
 const TriVec& PreparedMesh::hostTriangleData() {
     std::lock_guard<std::mutex> lock(lazy);
     if (hostTris.size() != nTris) {

@@ -1,8 +1,10 @@
 // Construction over several GPUs of one box from ONE process (VERDICT r1 "a native multi-GPU host"):
 // the C++ drop-in classes reach every device of the box through sdfb200_build_*_multi without torch or a launcher.
 //
-//   1. the mesh is prepared once (TriangleData on the first device, BVH on the host threads) and replicated to the
-//      other devices by peer copies over NVLink;
+//   1. every device ingests the mesh itself (vertices + indices over its own PCIe link, TriangleData by a few kernels:
+//      cheaper than cloning 250 bytes per triangle from the first device — measured: peer clones of the config-4 mesh
+//      took 36 ms each and serialised); the BVH of the OctreeSdf builders is host work done ONCE, by a thread of its
+//      own, and uploaded to every device;
 //   2. one host thread per device builds the sub-octrees of the start-depth voxels it owns (the reference's own task
 //      decomposition: src/sdf/OctreeSdfDepthFirst.h:433-469, include/SdfLib/ExactOctreeSdfDepthFirst.h:534-574), voxels
 //      assigned by estimated work;
@@ -25,6 +27,7 @@
 #include <thread>
 #include <vector>
 
+#include "device_utils.cuh"
 #include "sdf_internal.h"
 
 namespace sdfb200 {
@@ -177,7 +180,20 @@ void buildMulti(const HostMesh& mesh, const MultiBuildRequest& req, const std::v
     SDFB_CUDA(cudaSetDevice(devices[0]));
     configureDevicePool(devices[0]);
     const bool exact = req.format == SDFB200_FORMAT_EXACT_OCTREE;
-    std::shared_ptr<PreparedMesh> mesh0 = prepareMesh(mesh, !exact, exact);
+    // the one host-side BVH build, overlapped with the per-device ingestion
+    RawVec<BvhNode> sharedBvh;
+    double sharedBvhMs = 0.0;
+    std::exception_ptr bvhError;
+    std::thread bvhThread;
+    if (!exact)
+        bvhThread = std::thread([&] {
+            try {
+                const auto tb = std::chrono::steady_clock::now();
+                sharedBvh = buildBvh(mesh);
+                sharedBvhMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb).count();
+            } catch (...) { bvhError = std::current_exception(); }
+        });
+    struct JoinGuard { std::thread& t; ~JoinGuard() { if (t.joinable()) t.join(); } } joinGuard{bvhThread};
     MultiContext ctx(world);
     ctx.devices = devices;
     ctx.comms = commsFor(devices);
@@ -185,20 +201,34 @@ void buildMulti(const HostMesh& mesh, const MultiBuildRequest& req, const std::v
     out.resize(world);
     std::vector<std::exception_ptr> errors(world);
     std::vector<std::shared_ptr<PreparedMesh>> meshes(world);
-    meshes[0] = mesh0;
+    std::mutex bvhJoinMutex;
     const double prepMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tStart).count();
 
     auto worker = [&](uint32_t rank) {
         try {
             SDFB_CUDA(cudaSetDevice(devices[rank]));
             configureDevicePool(devices[rank]);
+            pinnedScratch();   // pinned allocations touch every context: none of them while a collective is in flight
             const auto t0 = std::chrono::steady_clock::now();
-            if (rank) meshes[rank] = cloneMeshToCurrentDevice(*mesh0);
-            // Nobody starts building before every clone has arrived: a peer copy out of device 0 is ordered behind the work
-            // queued on device 0, so a rank-0 build that is already waiting inside its first collective (CONTINUITY) for a
-            // rank still fetching its mesh would deadlock (reproduced on 2 x B200: profiles/r2_summary.md), and the other
-            // builders would delay the copies behind their first kernels.
-            if (world > 1) ctx.barrier.arriveAndWait();
+            static const bool timing = std::getenv("SDFB200_TIMING") != nullptr;
+            auto tPhase = t0;
+            auto phase = [&](const char* what) {   // SDFB200_TIMING: per-rank phase times (diagnostic runs)
+                if (!timing) return;
+                const auto now = std::chrono::steady_clock::now();
+                std::fprintf(stderr, "[sdfb200] multi rank %u/%u %-12s %8.2f ms\n", rank, world, what, std::chrono::duration<double, std::milli>(now - tPhase).count());
+                tPhase = now;
+            };
+            meshes[rank] = prepareMesh(mesh, false, exact);
+            phase("mesh ingest");
+            if (!exact) {
+                {   // first thread here joins the BVH builder; the others find it joined
+                    std::lock_guard<std::mutex> lock(bvhJoinMutex);
+                    if (bvhThread.joinable()) bvhThread.join();
+                }
+                if (bvhError) std::rethrow_exception(bvhError);
+                attachBvh(*meshes[rank], sharedBvh, sharedBvhMs);
+                phase("bvh upload");
+            }
             std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
             if (!exact && req.algorithm == SDFB200_ALG_CONTINUITY) {
                 HookUser user{&ctx, rank};
@@ -208,24 +238,33 @@ void buildMulti(const HostMesh& mesh, const MultiBuildRequest& req, const std::v
             } else {
                 if (exact) buildExactOnDevice(*s, meshes[rank], req.box6, req.depth, req.startDepth, req.minTris, req.numThreads, rank, world);
                 else buildOctreeOnDevice(*s, *meshes[rank], req.box6, req.depth, req.startDepth, req.rule, req.param0, req.param1, req.numThreads, rank, world);
+                phase("levels");
                 if (world > 1) {
                     // sizes of every root: each rank contributes its own (others are 0), summed on the host
                     ctx.sizes[rank] = s->shardSizes;
                     ctx.barrier.arriveAndWait();
+                    phase("wait sizes");
                     std::vector<uint32_t> all(s->shardSizes.size(), 0u);
                     for (uint32_t q = 0; q < world; q++)
                         for (size_t i = 0; i < all.size(); i++) all[i] += ctx.sizes[q][i];
                     s->build->finish(*s, all.data());
+                    phase("emit");
                     ctx.words[rank] = shardPayloadWords(*s);
                     ctx.barrier.arriveAndWait();
+                    phase("wait words");
                     uint64_t stride = 0;
                     for (uint32_t q = 0; q < world; q++) stride = std::max(stride, ctx.words[q]);
                     stride = (stride + 3) / 4 * 4;
                     DevBuf<uint32_t> send(stride), recv(stride * world);
+                    SDFB_CUDA(cudaDeviceSynchronize());
+                    phase("buffers");
                     shardExport(*s, send.p, stride);
+                    phase("export");
                     allGatherBytes(ctx, rank, send.p, recv.p, stride * 4);
+                    phase("all-gather");
                     shardAssemble(*s, recv.p, ctx.words.data(), stride, world);
                     SDFB_CUDA(cudaDeviceSynchronize());
+                    phase("assemble");
                 }
             }
             s->stats.total_ms = prepMs + std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -1009,7 +1009,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
     prepareOctreeQuery(out);
     out.nOctree = words;
     out.hostMirror = false;
-    ensureHostMirror(out);
+    if (exchange.world == 1) ensureHostMirror(out);   // the ranks of a collective build fetch their mirror when a getter asks
     finishStep("download");
     st.download_ms = msSince(t0);
     out.isShard = false;

@@ -138,6 +138,7 @@ struct PreparedMesh {
     const TriVec& hostTriangleData();
 };
 std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bool withExactParts);
+void attachBvh(PreparedMesh& pm, const RawVec<BvhNode>& bvh, double bvhMs);   // a BVH built once on the host, uploaded to pm's device
 uint64_t meshBlobBytes(const PreparedMesh& pm);
 void meshBlobExport(const PreparedMesh& pm, void* dDst, uint64_t capacity, cudaStream_t st);
 std::shared_ptr<PreparedMesh> meshBlobImport(const void* dSrc, uint64_t bytes);

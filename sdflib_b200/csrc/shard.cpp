@@ -12,6 +12,8 @@
 //     [start-slot record: 1 word (OCTREE) or 2 words (EXACT)]
 //     for every stream (OCTREE: words; EXACT: node records, set words, mask bytes): the root's block, padded to a word
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -140,12 +142,15 @@ void shardAssemble(sdfb200_sdf& s, const uint32_t* dGathered, const uint64_t* wo
     s.shardScalars[1] = sc1;
     // the structure is complete on this device; its host mirrors are fetched when a getter or the .bin writer asks
     s.hostMirror = false;
+    static const bool timing = std::getenv("SDFB200_TIMING") != nullptr;
+    const auto tq = std::chrono::steady_clock::now();
     if (s.format == SDFB200_FORMAT_OCTREE) { finalizeOctreeScalars(s); prepareOctreeQuery(s); }
     else {
         s.maxTrisInLeafs = sc0;
         s.maxTrisEncoded = sc1;
         prepareExactQuery(s);
     }
+    if (timing) { SDFB_CUDA(cudaDeviceSynchronize()); std::fprintf(stderr, "[sdfb200] assemble: query-side structures %8.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tq).count()); }
     s.isShard = false;
     s.build.reset();
 }
