@@ -27,7 +27,8 @@ void parallelCopy(void* dst, const void* src, size_t bytes) {
     constexpr size_t kPiece = size_t(1) << 20;
     const long pieces = long((bytes + kPiece - 1) / kPiece);
     if (pieces <= 2) { std::memcpy(dst, src, bytes); return; }
-#pragma omp parallel for schedule(static)
+    // hostThreads(), not the OpenMP default: launchers like torchrun export OMP_NUM_THREADS=1 to every rank
+#pragma omp parallel for schedule(static) num_threads(hostThreads())
     for (long i = 0; i < pieces; i++) {
         const size_t at = size_t(i) * kPiece;
         std::memcpy(static_cast<char*>(dst) + at, static_cast<const char*>(src) + at, std::min(kPiece, bytes - at));
