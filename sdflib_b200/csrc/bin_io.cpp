@@ -9,6 +9,7 @@
 // Derived members (cell size, scratch sizes) are recomputed on load exactly as the reference does
 // (OctreeSdf.h:233-234, ExactOctreeSdf.h:149-153).
 #include <cstring>
+#include <algorithm>
 #include <fstream>
 
 #include "sdf_internal.h"
@@ -102,14 +103,17 @@ void validateStructure(sdfb200_sdf& s) {
         const uint64_t n = s.octree.size();
         if (n < G3) throw Error(SDFB200_ERR_IO, "octree array smaller than its start grid");
         s.leafBlocksAligned = true;
-        std::vector<uint32_t> stack;
-        stack.reserve(1024);
+        std::vector<uint32_t> stack, depthOf;   // word index and its depth below the start grid
+        stack.reserve(1024); depthOf.reserve(1024);
         uint64_t visited = 0;
+        uint32_t deepest = 0;
         for (uint64_t r = 0; r < G3; r++) {
-            stack.push_back(uint32_t(r));
+            stack.push_back(uint32_t(r)); depthOf.push_back(0u);
             while (!stack.empty()) {
                 const uint32_t w = s.octree[stack.back()];
-                stack.pop_back();
+                const uint32_t dRel = depthOf.back();
+                stack.pop_back(); depthOf.pop_back();
+                deepest = std::max(deepest, dRel);
                 const uint64_t at = w & kOctIndexMask;
                 if (++visited > n) throw Error(SDFB200_ERR_IO, "octree array contains a cycle");
                 if (w & kLeafBit) {
@@ -117,10 +121,15 @@ void validateStructure(sdfb200_sdf& s) {
                     if (at % 4) s.leafBlocksAligned = false;
                 } else {
                     if (at < G3 || at + 8 > n) throw Error(SDFB200_ERR_IO, "children block out of range");
-                    for (uint32_t c = 0; c < 8; c++) stack.push_back(uint32_t(at + c));
+                    for (uint32_t c = 0; c < 8; c++) { stack.push_back(uint32_t(at + c)); depthOf.push_back(dRel + 1); }
                 }
             }
         }
+        // The query kernels take the child choices from 16 path bits of the start-cell fraction: a file whose tree goes
+        // deeper than that below its start grid would silently pick wrong children. The header's maxDepth is
+        // untrusted and counts absolute depth, so the walk above measures it.
+        if (deepest > 16) throw Error(SDFB200_ERR_IO, "octree deeper than 16 levels below its start grid is not supported by the query kernels");
+        s.relativeDepth = deepest;
     } else {
         const uint64_t n = s.octree.size() / 2;
         if (n < G3) throw Error(SDFB200_ERR_IO, "node array smaller than its start grid");

@@ -97,7 +97,8 @@ void launchOctreeQueryFast(
     const uint32_t grid = uint32_t((n + 255) / 256);
     // leaf blocks are 16-byte aligned iff the start grid has a multiple of 4 slots (all blocks are 8 or 64 words)
     const bool vec = (uint64_t(s.startGridSize) * s.startGridSize * s.startGridSize) % 4 == 0 && s.leafBlocksAligned;
-    if (s.maxDepth > 16) throw Error(SDFB200_ERR_INVALID, "octree deeper than 16 levels");
+    // 16 path bits: built structures are at most depth 10 (builders), loaded ones were measured by validateStructure
+    if (s.relativeDepth > 16) throw Error(SDFB200_ERR_INVALID, "octree deeper than 16 levels below its start grid");
 #ifndef SDFB_QUERY_EXACT
     // Markstein's division needs a normal divisor whose significand is not all ones; 1 / cell must be normal as well
     uint32_t cellBits;

@@ -196,6 +196,7 @@ struct sdfb200_sdf {
     // OCTREE
     float valueRange = 0.0f, minBorderValue = 0.0f;
     bool leafBlocksAligned = true;   // every leaf block offset is a multiple of 4 words (checked on load)
+    uint32_t relativeDepth = 0;      // loaded files: measured depth below the start grid (validateStructure); built: maxDepth - startDepth
     // EXACT_OCTREE
     uint32_t startDepth = 0, minTrisInLeafs = 0, maxTrisInLeafs = 0, maxTrisEncoded = 0, bitEncodingStartDepth = 0,
              bitsPerIndex = 0;

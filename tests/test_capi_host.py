@@ -249,3 +249,43 @@ def test_device_acosf_equals_host_libm_on_every_float(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and r.stdout.startswith("ok 2130706434"), r.stdout[-500:]
+
+
+def test_octree_file_deeper_than_the_path_bits_is_rejected(sdf, tmp_path):
+    """A .bin whose tree goes more than 16 levels below its start grid (the query kernels take child choices from 16 path
+    bits) must be refused at load time with a file error — measured by walking the tree, not read from the header."""
+    import struct
+    from sdflib_b200 import _capi
+    import ctypes as C
+
+    def make(levels):
+        g3, leaf = 1, 0x80000000
+        coeff_at = g3 + 8 * levels                      # one shared 64-word coefficient block behind the child blocks
+        words = [0] * (coeff_at + 64)
+        words[0] = g3                                    # start slot -> first child block
+        for k in range(levels):
+            base = g3 + 8 * k
+            for c in range(8):
+                words[base + c] = leaf | coeff_at
+            if k + 1 < levels:
+                words[base] = g3 + 8 * (k + 1)           # child 0 keeps descending
+        return np.asarray(words, np.uint32)
+
+    def write(path, words, header_depth):
+        with open(path, "wb") as f:
+            f.write(struct.pack("<BI6fiIff", 1, 1, 0, 0, 0, 1, 1, 1, 1, header_depth, 1.0, 0.0))
+            f.write(struct.pack("<Q", words.size))
+            f.write(words.tobytes())
+
+    L = sdf.lib()
+    h = C.c_void_p()
+    deep = str(tmp_path / "deep.bin")
+    write(deep, make(17), 3)                             # the header lies about the depth
+    assert L.sdfb200_load(deep.encode(), C.byref(h)) == _capi.ERR_IO
+    assert b"16 levels" in L.sdfb200_last_error()
+    ok = str(tmp_path / "ok.bin")
+    write(ok, make(16), 16)
+    code = L.sdfb200_load(ok.encode(), C.byref(h))       # accepted by the validator; without a GPU the upload then fails
+    assert code in (_capi.OK, _capi.ERR_CUDA)
+    if code == _capi.OK:
+        L.sdfb200_free(h)
