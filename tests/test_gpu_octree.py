@@ -26,6 +26,12 @@ def build_both(sdf, port, v, i, depth, start, thr=1e-3, threads=1, rule=1, param
     return g, p, box
 
 
+def reference_gate(d, ref_d, size):
+    """(fraction of points beyond the north-star tolerance 1e-5 max(|ref|, 1e-3 box), largest absolute difference)."""
+    tol = 1e-5 * np.maximum(np.abs(ref_d), 1e-3 * size)
+    return float((np.abs(d - ref_d) > tol).mean()), float(np.abs(d - ref_d).max())
+
+
 def random_points(area, n, seed, spill=0.1):
     rng = np.random.default_rng(seed)
     return (area[:3] + rng.uniform(-spill, 1 + spill, (n, 3)) * (area[3:] - area[:3])).astype(np.float32)
@@ -63,7 +69,11 @@ def test_config1_against_reference_fixture(sdf):
     assert (leaves, inner) == (17571, 2437)
     assert_bit_equal(np.float32([s.info().value_range]), np.float32([g["value_range"]]))
     dist = s.getDistance(g["query_points"], exact_order=True)
-    assert np.abs(dist - g["distances"]).max() < 5e-3   # tie-broken gradients on a symmetric input
+    # the undisplaced icosphere is symmetric: many lattice points are EXACTLY equidistant from several triangles, and which
+    # one the reference reports depends on its traversal history — about 1 % of the points sit in leaves fed by such a
+    # sample (0.98 % measured, CPU oracle vs reference); the others meet the north-star gate
+    frac, worst = reference_gate(dist, g["distances"], float(g["box"][3] - g["box"][0]))
+    assert frac < 0.02 and worst < 5e-3, (frac, worst)
 
 
 def test_topology_equals_reference_single_thread(sdf, ref):
@@ -223,7 +233,12 @@ def test_continuity_topology_equals_reference(sdf, ref):
     assert np.array_equal(ta, tb) and np.array_equal(a[ta], b[tb])
     q = random_points(s.getSampleArea().as_array(), 200000, 1, spill=0.0)
     d, dr = s.getDistance(q), r.query(q)
-    assert np.abs(d - dr).max() < 5e-4   # tie-broken nearest triangles propagate through the interpolated samples
+    # north-star gate against the reference's own build: |d - ref| <= 1e-5 max(|ref|, 1e-3 box). The reference's vertex
+    # cache breaks ties between triangles by traversal history; the points whose leaf interpolates such a sample may
+    # exceed the gate — their fraction is bounded (1.15e-4 measured for this mesh, CPU oracle vs reference) and so is
+    # their size (the two candidate triangles share an edge: same distance, other gradient)
+    frac, worst = reference_gate(d, dr, float(box[3] - box[0]))
+    assert frac < 2e-4 and worst < 5e-4, (frac, worst)
 
 
 def test_continuity_golden_fixture(sdf):
@@ -234,7 +249,8 @@ def test_continuity_golden_fixture(sdf):
     assert d.size == int(g["trapezoid_words"])
     assert np.array_equal(d[:512], g["start_slots"])
     dist = s.getDistance(g["query_points"], exact_order=True)
-    assert np.abs(dist - g["distances"]).max() < 5e-4
+    frac, worst = reference_gate(dist, g["distances"], float(g["box"][3] - g["box"][0]))
+    assert frac == 0.0 and worst < 1e-5, (frac, worst)      # no tie-affected point in this fixture: the plain north-star gate holds
 
 
 def test_continuity_query_bit_exact_and_continuous(sdf, port):
