@@ -86,6 +86,17 @@ public:
         fetch();
     }
 
+    // Sphere tracing of n rays (the raycast loop of the reference's viewer, src/render_engine/shaders/sdfOctreeRender.comp:392-410,
+    // one ray per GPU thread): outHit = last evaluated position, outTravelled = marched distance or -1 when no surface was reached.
+    void sphereTrace(const glm::vec3* origins, const glm::vec3* directions, size_t n, float farDistance, glm::vec3* outHit, float* outTravelled,
+                     uint32_t* outIterations = nullptr, float epsilon = 1e-5f, uint32_t maxIterations = 1024, bool devicePointers = false,
+                     void* cudaStream = nullptr, bool referenceOperationOrder = false) const
+    {
+        const int flags = (devicePointers ? SDFB200_QUERY_DEVICE_POINTERS : 0) | (referenceOperationOrder ? SDFB200_QUERY_EXACT_ORDER : 0);
+        check(sdfb200_sphere_trace(mHandle, reinterpret_cast<const float*>(origins), reinterpret_cast<const float*>(directions), n, epsilon,
+                                   farDistance, maxIterations, reinterpret_cast<float*>(outHit), outTravelled, outIterations, flags, cudaStream));
+    }
+
     float getOctreeValueRange() const { return mInfo.value_range; }
     float getOctreeMinBorderValue() const { return mInfo.min_border_value; }
     glm::ivec3 getStartGridSize() const { return glm::ivec3(mInfo.start_grid_size); }

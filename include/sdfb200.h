@@ -210,6 +210,19 @@ int sdfb200_get_device_octree(const sdfb200_sdf* sdf, const uint32_t** outDevice
 int sdfb200_query(sdfb200_sdf* sdf, const float* xyz, uint64_t n, float* dist, float* grad, int flags,
                   void* cudaStream);
 
+/* Sphere tracing over an OctreeSdf: the consumer of getDistance in the reference's viewer (raycast() of
+ * src/render_engine/shaders/sdfOctreeRender.comp:392-410), one ray per GPU thread:
+ *     while (last > epsilon && travelled < farDistance && it < maxIterations) { hit = pos; last = getDistance(pos);
+ *                                                                            step = max(last, 0); travelled += step; pos += dir * step; it++; }
+ * origins / directions: n packed float3 (directions as given: normalise them for distances in world units).
+ * outHit: n packed float3, the last position evaluated; outTravelled: n floats, the distance marched when the surface was
+ * reached (last < epsilon), -1 otherwise; outIterations: NULL or n uint32. flags: SDFB200_QUERY_DEVICE_POINTERS and
+ * SDFB200_QUERY_EXACT_ORDER as for sdfb200_query (with the latter the march equals a CPU loop over the reference's
+ * getDistance bit for bit). The shader's constants are epsilon = 1e-5, maxIterations = 1024. */
+int sdfb200_sphere_trace(sdfb200_sdf* sdf, const float* origins, const float* directions, uint64_t n, float epsilon,
+                         float farDistance, uint32_t maxIterations, float* outHit, float* outTravelled,
+                         uint32_t* outIterations, int flags, void* cudaStream);
+
 /* Kernel-level entry points (used by the parity tests; each runs the same device function the
  * builders use). All pointers are HOST pointers. */
 int sdfb200_triangle_data(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,

@@ -455,6 +455,34 @@ int sdfb200_query(sdfb200_sdf* s, const float* xyz, uint64_t n, float* dist, flo
     });
 }
 
+int sdfb200_sphere_trace(sdfb200_sdf* s, const float* origins, const float* directions, uint64_t n, float epsilon, float farDistance,
+                         uint32_t maxIterations, float* outHit, float* outTravelled, uint32_t* outIterations, int flags, void* cudaStream) {
+    return guarded([&] {
+        if (!s || (n && (!origins || !directions || !outHit || !outTravelled))) throw Error(SDFB200_ERR_INVALID, "null argument");
+        if (n == 0) return;
+        if (s->format != SDFB200_FORMAT_OCTREE) throw Error(SDFB200_ERR_UNSUPPORTED, "sphere tracing is built for OctreeSdf structures");
+        if (!s->dOctree.p) throw Error(SDFB200_ERR_CUDA, "structure is not resident on a CUDA device");
+        if (s->isShard) throw Error(SDFB200_ERR_INVALID, "handle is an unassembled shard (sdfb200_assemble not called yet)");
+        SDFB_CUDA(cudaSetDevice(s->device));
+        cudaStream_t st = static_cast<cudaStream_t>(cudaStream);
+        auto launch = [&](const float* dO, const float* dD, float* dH, float* dT, uint32_t* dI) {
+            if (flags & SDFB200_QUERY_EXACT_ORDER) launchOctreeTraceExact(*s, dO, dD, n, epsilon, farDistance, maxIterations, dH, dT, dI, st);
+            else launchOctreeTraceFast(*s, dO, dD, n, epsilon, farDistance, maxIterations, dH, dT, dI, st);
+        };
+        if (flags & SDFB200_QUERY_DEVICE_POINTERS) { launch(origins, directions, outHit, outTravelled, outIterations); return; }
+        DevBuf<float> dO(3 * n), dD(3 * n), dH(3 * n), dT(n);
+        DevBuf<uint32_t> dI(outIterations ? n : 0);
+        SDFB_CUDA(cudaStreamSynchronize(cudaStream_t(0)));   // device blocks are ordered on the default stream
+        SDFB_CUDA(cudaMemcpyAsync(dO.p, origins, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+        SDFB_CUDA(cudaMemcpyAsync(dD.p, directions, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+        launch(dO.p, dD.p, dH.p, dT.p, outIterations ? dI.p : nullptr);
+        SDFB_CUDA(cudaMemcpyAsync(outHit, dH.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        SDFB_CUDA(cudaMemcpyAsync(outTravelled, dT.p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (outIterations) SDFB_CUDA(cudaMemcpyAsync(outIterations, dI.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SDFB_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
 int sdfb200_shard_sizes(const sdfb200_sdf* s, uint32_t* outSizes, uint64_t capacity, uint64_t* outCount) {
     return guarded([&] {
         if (!s || !outCount) throw Error(SDFB200_ERR_INVALID, "null argument");

@@ -133,4 +133,29 @@ void launchOctreeQueryFast(
     SDFB_CUDA(cudaGetLastError());
 }
 
+
+// Sphere tracing over an OCTREE structure (device pointers; see octreeTraceKernel)
+#ifdef SDFB_QUERY_EXACT
+void launchOctreeTraceExact(
+#else
+void launchOctreeTraceFast(
+#endif
+    const sdfb200_sdf& s, const float* dOrigin, const float* dDirection, uint64_t n, float epsilon, float farDistance, uint32_t maxIterations,
+    float* dHit, float* dTravelled, uint32_t* dIterations, cudaStream_t st) {
+    if (n == 0) return;
+    QueryParams q;
+    q.minx = s.boxMin[0]; q.miny = s.boxMin[1]; q.minz = s.boxMin[2];
+    q.maxx = s.boxMax[0]; q.maxy = s.boxMax[1]; q.maxz = s.boxMax[2];
+    q.cell = s.cellSize;
+    q.grid = s.startGridSize;
+    q.minBorder = s.minBorderValue;
+    if (s.relativeDepth > 16) throw Error(SDFB200_ERR_INVALID, "octree deeper than 16 levels below its start grid");
+    const bool vec = (uint64_t(s.startGridSize) * s.startGridSize * s.startGridSize) % 4 == 0 && s.leafBlocksAligned;
+    const TraceParams tp{epsilon, farDistance, maxIterations};
+    const uint32_t grid = uint32_t((n + 127) / 128);
+    if (vec) octreeTraceKernel<true><<<grid, 128, 0, st>>>(s.dOctree.p, q, tp, dOrigin, dDirection, n, dHit, dTravelled, dIterations);
+    else octreeTraceKernel<false><<<grid, 128, 0, st>>>(s.dOctree.p, q, tp, dOrigin, dDirection, n, dHit, dTravelled, dIterations);
+    SDFB_CUDA(cudaGetLastError());
+}
+
 }  // namespace sdfb200

@@ -119,6 +119,39 @@ template <bool kGrad, bool kVec> __device__ __forceinline__ float evalLeaf(const
 }
 #endif
 
+// OctreeSdf::getDistance at one point (src/sdf/OctreeSdf.cpp:93-152): start cell by the reference's float operations, the
+// descent, the leaf polynomial (evalLeaf of this translation unit: FMA Horner, or the reference's literal order).
+template <bool kGrad, bool kVec>
+__device__ __forceinline__ float octreeDistanceAt(const uint32_t* __restrict__ oct, const QueryParams& q, f3 p, f3& g) {
+    float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
+    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    const int ix = int(flx), iy = int(fly), iz = int(flz);
+    fx -= flx; fy -= fly; fz -= flz;
+    g = mk3(0.0f, 0.0f, 0.0f);
+    if (ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid)
+        return (kGrad ? boxDistanceGrad(q, p, g) : boxDistance(q, p)) + q.minBorder;
+    // The reference descends with child = (frac >= 0.5) per axis and frac <- fract(2 frac). Both
+    // steps are exact in binary floating point (doubling, floor and the subtraction introduce no
+    // rounding), so the same path and the same final frac are obtained from the leading bits of the
+    // start-cell fraction: level j uses bit j of floor(frac * 2^kPathBits), and a leaf reached after k
+    // steps evaluates at frac * 2^k - floor(frac * 2^k).
+    constexpr int kPathBits = 16;
+    const uint32_t bx = uint32_t(fx * float(1 << kPathBits)), by = uint32_t(fy * float(1 << kPathBits)),
+                   bz = uint32_t(fz * float(1 << kPathBits));
+    uint32_t node = __ldg(oct + (iz * q.grid + iy) * q.grid + ix);
+    int k = 0;
+    while (!(node & kLeafBit)) {
+        const int sh = kPathBits - 1 - k;
+        const uint32_t child = ((bx >> sh) & 1u) | (((by >> sh) & 1u) << 1) | (((bz >> sh) & 1u) << 2);
+        node = __ldg(oct + (node & kOctIndexMask) + child);
+        k++;
+    }
+    const float scale = float(1u << k);
+    fx *= scale; fy *= scale; fz *= scale;
+    fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
+    return evalLeaf<kGrad, kVec>(reinterpret_cast<const float*>(oct + (node & kOctIndexMask)), fx, fy, fz, g);
+}
+
 template <bool kGrad, bool kVec>
 __global__ void __launch_bounds__(256)
 octreeQueryKernel(const uint32_t* __restrict__ oct, const QueryParams q, const float* __restrict__ xyz, uint64_t n,
@@ -126,39 +159,43 @@ octreeQueryKernel(const uint32_t* __restrict__ oct, const QueryParams q, const f
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const f3 p = mk3(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
-    float fx = (p.x - q.minx) / q.cell, fy = (p.y - q.miny) / q.cell, fz = (p.z - q.minz) / q.cell;
-    const float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-    const int ix = int(flx), iy = int(fly), iz = int(flz);
-    fx -= flx; fy -= fly; fz -= flz;
-    f3 g = mk3(0.0f, 0.0f, 0.0f);
-    float d;
-    if (ix < 0 || ix >= q.grid || iy < 0 || iy >= q.grid || iz < 0 || iz >= q.grid) {
-        d = (kGrad ? boxDistanceGrad(q, p, g) : boxDistance(q, p)) + q.minBorder;
-    } else {
-        // The reference descends with child = (frac >= 0.5) per axis and frac <- fract(2 frac). Both
-        // steps are exact in binary floating point (doubling, floor and the subtraction introduce no
-        // rounding), so the same path and the same final frac are obtained from the leading bits of the
-        // start-cell fraction: level j uses bit j of floor(frac * 2^kPathBits), and a leaf reached after k
-        // steps evaluates at frac * 2^k - floor(frac * 2^k).
-        constexpr int kPathBits = 16;
-        const uint32_t bx = uint32_t(fx * float(1 << kPathBits)), by = uint32_t(fy * float(1 << kPathBits)),
-                       bz = uint32_t(fz * float(1 << kPathBits));
-        uint32_t node = __ldg(oct + (iz * q.grid + iy) * q.grid + ix);
-        int k = 0;
-        while (!(node & kLeafBit)) {
-            const int sh = kPathBits - 1 - k;
-            const uint32_t child = ((bx >> sh) & 1u) | (((by >> sh) & 1u) << 1) | (((bz >> sh) & 1u) << 2);
-            node = __ldg(oct + (node & kOctIndexMask) + child);
-            k++;
-        }
-        const float scale = float(1u << k);
-        fx *= scale; fy *= scale; fz *= scale;
-        fx -= floorf(fx); fy -= floorf(fy); fz -= floorf(fz);
-        const float* c = reinterpret_cast<const float*>(oct + (node & kOctIndexMask));
-        d = evalLeaf<kGrad, kVec>(c, fx, fy, fz, g);
-    }
+    f3 g;
+    const float d = octreeDistanceAt<kGrad, kVec>(oct, q, p, g);
     dist[i] = d;
     if (kGrad) { grad[3 * i] = g.x; grad[3 * i + 1] = g.y; grad[3 * i + 2] = g.z; }
+}
+
+// ---- sphere tracing: the consumer of getDistance in the reference's viewer -----------------------------
+// Reference: raycast() of src/render_engine/shaders/sdfOctreeRender.comp:392-410 —
+//     while (last > eps && acc < far && it < maxIterations) { hit = pos; last = map(pos); step = max(last, 0); acc += step; pos += dir * step; it++ }
+//     return last < eps;
+// one ray per thread, map() = octreeDistanceAt above; the march is three multiplies and three adds per step in the
+// shader's order, so the reference-order object reproduces a CPU loop over getDistance bit for bit.
+struct TraceParams { float epsilon, farDistance; uint32_t maxIterations; };
+
+template <bool kVec>
+__global__ void __launch_bounds__(128)
+octreeTraceKernel(const uint32_t* __restrict__ oct, const QueryParams q, const TraceParams tp, const float* __restrict__ origin,
+                  const float* __restrict__ direction, uint64_t n, float* __restrict__ hitPos, float* __restrict__ travelled,
+                  uint32_t* __restrict__ iterations) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f3 pos = mk3(__ldg(origin + 3 * i), __ldg(origin + 3 * i + 1), __ldg(origin + 3 * i + 2));
+    const f3 dir = mk3(__ldg(direction + 3 * i), __ldg(direction + 3 * i + 1), __ldg(direction + 3 * i + 2));
+    f3 hit = pos, g;
+    float acc = 0.0f, last = 1e8f;
+    uint32_t it = 0;
+    while (last > tp.epsilon && acc < tp.farDistance && it < tp.maxIterations) {
+        hit = pos;
+        last = octreeDistanceAt<false, kVec>(oct, q, pos, g);
+        const float step = gmax(last, 0.0f);
+        acc = acc + step;
+        pos = pos + dir * step;
+        it++;
+    }
+    hitPos[3 * i] = hit.x; hitPos[3 * i + 1] = hit.y; hitPos[3 * i + 2] = hit.z;
+    travelled[i] = last < tp.epsilon ? acc : -1.0f;   // -1: no surface within the limits
+    if (iterations) iterations[i] = it;
 }
 
 // ---- the default kernel of the FMA path: warp-per-query-batch, top index, quad-cooperative evaluation -------------------------

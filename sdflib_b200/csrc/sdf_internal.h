@@ -284,6 +284,10 @@ void pointTriangleOnDevice(const float* tri37, const float* v123, const float* x
 // hostMapped: the pointers alias mapped host memory (small-batch slot): no TMA staging
 void launchOctreeQueryFast(const sdfb200_sdf& s, const float* dXyz, uint64_t n, float* dDist, float* dGrad, cudaStream_t st,
                            bool hostMapped = false);
+void launchOctreeTraceFast(const sdfb200_sdf& s, const float* dOrigin, const float* dDirection, uint64_t n, float epsilon, float farDistance,
+                           uint32_t maxIterations, float* dHit, float* dTravelled, uint32_t* dIterations, cudaStream_t st);
+void launchOctreeTraceExact(const sdfb200_sdf& s, const float* dOrigin, const float* dDirection, uint64_t n, float epsilon, float farDistance,
+                            uint32_t maxIterations, float* dHit, float* dTravelled, uint32_t* dIterations, cudaStream_t st);
 void prepareOctreeQuery(sdfb200_sdf& s);   // top index of a complete OCTREE structure (default stream, synchronises)
 // query_host.cpp
 void queryHostPointers(sdfb200_sdf& s, const float* xyz, uint64_t n, float* dist, float* grad, int flags, cudaStream_t st);

@@ -264,6 +264,30 @@ class OctreeSdf(SdfFunction):
         _capi.check(_capi.lib().sdfb200_get_octree_data(self._h, _capi.ptr(out), C.c_uint64(out.size)))
         return out
 
+    def sphereTrace(self, origins, directions, far_distance, epsilon=1e-5, max_iterations=1024, exact_order=False):
+        """Sphere tracing (the reference viewer's raycast loop over getDistance) of n rays: returns (hit positions (n, 3),
+        travelled distance (n,), -1 where no surface was reached, iterations (n,)). numpy arrays or CUDA torch tensors."""
+        L = _capi.lib()
+        flags = _capi.QUERY_EXACT_ORDER if exact_order else 0
+        if _is_torch_cuda(origins):
+            import torch
+            o, d = origins.reshape(-1, 3).float().contiguous(), directions.reshape(-1, 3).float().contiguous()
+            n = o.shape[0]
+            hit = torch.empty((n, 3), dtype=torch.float32, device=o.device)
+            trav = torch.empty(n, dtype=torch.float32, device=o.device)
+            its = torch.empty(n, dtype=torch.int32, device=o.device)
+            _capi.check(L.sdfb200_sphere_trace(self._h, C.c_void_p(o.data_ptr()), C.c_void_p(d.data_ptr()), C.c_uint64(n), C.c_float(epsilon),
+                                               C.c_float(far_distance), C.c_uint32(max_iterations), C.c_void_p(hit.data_ptr()),
+                                               C.c_void_p(trav.data_ptr()), C.c_void_p(its.data_ptr()),
+                                               C.c_int(flags | _capi.QUERY_DEVICE_POINTERS), C.c_void_p(torch.cuda.current_stream(o.device).cuda_stream)))
+            return hit, trav, its
+        o, d = _capi.f32(origins).reshape(-1, 3), _capi.f32(directions).reshape(-1, 3)
+        n = len(o)
+        hit, trav, its = np.empty((n, 3), np.float32), np.empty(n, np.float32), np.empty(n, np.uint32)
+        _capi.check(L.sdfb200_sphere_trace(self._h, _capi.ptr(o), _capi.ptr(d), C.c_uint64(n), C.c_float(epsilon), C.c_float(far_distance),
+                                           C.c_uint32(max_iterations), _capi.ptr(hit), _capi.ptr(trav), _capi.ptr(its), C.c_int(flags), None))
+        return hit, trav, its
+
     def getOctreeValueRange(self):
         return self.info().value_range
 
