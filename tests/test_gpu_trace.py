@@ -33,7 +33,7 @@ def camera_rays(box, n_side, seed):
     rng = np.random.default_rng(seed)
     centre, size = 0.5 * (box[:3] + box[3:]), float((box[3:] - box[:3]).max())
     eye = (centre + np.float32([0.1, 0.25, 1.4]) * size).astype(np.float32)
-    u = np.linspace(-0.8, 0.8, n_side, dtype=np.float32)
+    u = np.linspace(-1.5, 1.5, n_side, dtype=np.float32)   # wide enough that the outer rays miss the mesh
     px, py = np.meshgrid(u, u)
     target = centre + np.stack([px.ravel() * size * 0.5, py.ravel() * size * 0.5, np.zeros(px.size, np.float32)], -1)
     target = target + rng.normal(0, 1e-3, target.shape)
