@@ -1,5 +1,5 @@
 """Small driver for ncu captures (one GPU): runs ONE build or ONE query pass of the bench workloads.
-    python scripts/profile_kernels.py exact_build | octree_build | octree_cont | exact_query | octree_query | octree_query_random (SDFB200_QUERY_COOP=1 selects the cooperative kernel)"""
+    python scripts/profile_kernels.py exact_build | octree_build | octree_cont | exact_query | octree_query | octree_query_random | octree_query_grad"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -24,7 +24,8 @@ if "query" in what:
     else:
         pts = torch.from_numpy(meshes.cell_centre_grid(area, 256)).cuda()
     out = torch.empty(len(pts), dtype=torch.float32, device="cuda")
+    grad = torch.empty((len(pts), 3), dtype=torch.float32, device="cuda") if what.endswith("grad") else None
     for _ in range(3):
-        sdf.getDistance(pts, out=out)
+        sdf.getDistance(pts, out=out, gradient=grad is not None, out_gradient=grad)
     torch.cuda.synchronize()
 print("done", what)

@@ -29,11 +29,21 @@ def cpu_march(oracle_sdf, origins, directions, far, eps=1e-5, max_it=1024):
     return hit, np.where(last < np.float32(eps), acc, np.float32(-1.0)).astype(np.float32), it
 
 
+def outward_sphere(subdiv):
+    """The reference icosphere winds its triangles so that the field is positive inside; a march needs it positive
+    at the eye, so the winding is flipped here."""
+    v, i = displaced_sphere(subdiv)
+    return v, np.ascontiguousarray(i.reshape(-1, 3)[:, [0, 2, 1]]).reshape(i.shape)
+
+
 def camera_rays(box, n_side, seed):
     rng = np.random.default_rng(seed)
     centre, size = 0.5 * (box[:3] + box[3:]), float((box[3:] - box[:3]).max())
-    eye = (centre + np.float32([0.1, 0.25, 1.4]) * size).astype(np.float32)
-    u = np.linspace(-1.5, 1.5, n_side, dtype=np.float32)   # wide enough that the outer rays miss the mesh
+    # the eye sits inside the box near a corner (outside the box getDistance is the distance to the box, so a march
+    # that starts there converges onto the box face and never reaches the octree); the fan is wide enough that the
+    # outer rays miss the mesh, leave the box and run out to `far`
+    eye = (centre + np.float32([0.42, 0.43, 0.44]) * size).astype(np.float32)
+    u = np.linspace(-1.5, 1.5, n_side, dtype=np.float32)
     px, py = np.meshgrid(u, u)
     target = centre + np.stack([px.ravel() * size * 0.5, py.ravel() * size * 0.5, np.zeros(px.size, np.float32)], -1)
     target = target + rng.normal(0, 1e-3, target.shape)
@@ -44,7 +54,7 @@ def camera_rays(box, n_side, seed):
 
 @pytest.mark.parametrize("algorithm", [1, 2])
 def test_trace_bit_exact_with_cpu_loop(sdf, port, algorithm):
-    v, i = displaced_sphere(3)
+    v, i = outward_sphere(3)
     box = sdf.meshes.bounding_box_with_margin(v)
     g = sdf.OctreeSdf(sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:]), 6, 3, 1e-3, algorithm, 1)
     p = port.build_octree(v, i, box, 6, 3, 1e-3, algorithm, 1, use_cache=False)
@@ -65,7 +75,7 @@ def test_trace_bit_exact_with_cpu_loop(sdf, port, algorithm):
 
 def test_trace_device_pointers_and_errors(sdf):
     import torch
-    v, i = displaced_sphere(2)
+    v, i = outward_sphere(2)
     box = sdf.meshes.bounding_box_with_margin(v)
     bb = sdf.BoundingBox(box[:3], box[3:])
     g = sdf.OctreeSdf(sdf.Mesh(v, i), bb, 5, 3)
