@@ -135,8 +135,8 @@ int sdfb200_build_exact_shard(const float* vertices, uint32_t numVertices, const
 /* ---- prepared meshes (mesh ingestion on the device; reference: calculateMeshTriangleData, src/utils/TriangleUtils.cpp:7-428,
  * and tmd::TriangleMeshDistance's BVH, libs/InteractiveComputerGraphics/.../TriangleMeshDistance.h:421-490).
  * A prepared mesh holds, on the current device, everything the builders read: vertices, indices, TriangleData (computed on
- * the GPU, same bits as the reference's host loop), with SDFB200_MESH_BVH the nearest-triangle BVH (built on the host:
- * its shape is std::sort's tie order) and with SDFB200_MESH_EXACT the ExactOctreeSdf side arrays. One mesh serves any
+ * the GPU, same bits as the reference's host loop), with SDFB200_MESH_BVH the nearest-triangle BVH (built on the GPU
+ * with std::sort's exact tie order, bvh_device.cu; SDFB200_HOST_BVH=1 selects the host builder) and with SDFB200_MESH_EXACT the ExactOctreeSdf side arrays. One mesh serves any
  * number of builds; sdfb200_mesh_export / sdfb200_mesh_import replicate it on other ranks (broadcast the blob). */
 typedef struct sdfb200_mesh sdfb200_mesh;
 enum { SDFB200_MESH_BVH = 1, SDFB200_MESH_EXACT = 2,
@@ -229,6 +229,14 @@ int sdfb200_triangle_data(const float* vertices, uint32_t numVertices, const uin
                           float* out37);
 int sdfb200_nearest_triangle(const float* vertices, uint32_t numVertices, const uint32_t* indices,
                              uint32_t numIndices, const float* xyz, uint64_t n, uint32_t* outTriangle);
+/* The nearest-triangle BVH (reference: tmd::TriangleMeshDistance::_build_tree, TriangleMeshDistance.h:421-490) as the
+ * traversal kernels read it: 2 * triangles - 1 nodes of 80 bytes in the reference's push order — float64 left sphere
+ * (centre xyz, radius), float64 right sphere, int32 left / right links (>= 0: inner child, < 0: ~triangleId), int32 leaf
+ * flag, int32 pad. sdfb200_mesh_bvh copies out the tree a prepared mesh holds (built on the GPU), sdfb200_bvh_host runs the
+ * host builder (libstdc++'s own std::sort routines); the parity tests compare the two node for node. */
+int sdfb200_mesh_bvh(const sdfb200_mesh* mesh, void* outNodes, uint64_t capacityNodes);
+int sdfb200_bvh_host(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
+                     void* outNodes, uint64_t capacityNodes);
 int sdfb200_point_triangle(const float* tri37, const float* v123, const float* xyz, uint64_t n, int mode,
                            float* outDist, float* outGrad);
 

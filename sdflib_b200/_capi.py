@@ -47,7 +47,7 @@ SYMBOLS = ["sdfb200_last_error", "sdfb200_version", "sdfb200_device_count", "sdf
            "sdfb200_make_isosphere", "sdfb200_mesh_create", "sdfb200_mesh_free", "sdfb200_mesh_blob_bytes", "sdfb200_mesh_export",
            "sdfb200_mesh_import", "sdfb200_mesh_stats", "sdfb200_build_octree_from_mesh", "sdfb200_build_octree_collective_from_mesh",
            "sdfb200_build_exact_from_mesh", "sdfb200_build_octree_multi", "sdfb200_build_exact_multi", "sdfb200_nccl_available",
-           "sdfb200_sphere_trace"]
+           "sdfb200_sphere_trace", "sdfb200_mesh_bvh", "sdfb200_bvh_host"]
 
 # int (*sdfb200_allgather_fn)(void* user, const void* dSend, void* dRecv, uint64_t bytesPerRank)
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)

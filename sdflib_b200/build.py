@@ -39,6 +39,7 @@ UNITS = [
     ("multi_device.cpp", "multi_device.o", ["-x", "cu"]),
     ("fixtures.cpp", "fixtures.o", ["-x", "cu"] + NO_FMA),
     ("mesh_device.cu", "mesh_device.o", NO_FMA),
+    ("bvh_device.cu", "bvh_device.o", NO_FMA),
     ("octree_build.cu", "octree_build.o", NO_FMA),
     ("octree_cont.cu", "octree_cont.o", NO_FMA),
     ("octree_query.cu", "octree_query_fast.o", []),

@@ -539,6 +539,30 @@ int sdfb200_triangle_data(const float* vertices, uint32_t numVertices, const uin
     });
 }
 
+int sdfb200_bvh_host(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices, void* outNodes, uint64_t capacityNodes) {
+    return guarded([&] {
+        HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
+        const RawVec<BvhNode> nodes = buildBvh(mesh);
+        if (!outNodes || capacityNodes < nodes.size()) throw Error(SDFB200_ERR_INVALID, "the BVH has 2 * triangles - 1 nodes of 80 bytes");
+        std::memcpy(outNodes, nodes.data(), nodes.size() * sizeof(BvhNode));
+    });
+}
+
+int sdfb200_mesh_bvh(const sdfb200_mesh* mesh, void* outNodes, uint64_t capacityNodes) {
+    return guarded([&] {
+        if (!mesh || !mesh->pm) throw Error(SDFB200_ERR_INVALID, "null mesh handle");
+        const PreparedMesh& pm = *mesh->pm;
+        if (!pm.hasBvh) throw Error(SDFB200_ERR_INVALID, "the mesh was prepared without SDFB200_MESH_BVH");
+        if (!outNodes || capacityNodes < pm.dev.bvh.n) throw Error(SDFB200_ERR_INVALID, "the BVH has 2 * triangles - 1 nodes of 80 bytes");
+        int current = 0;
+        SDFB_CUDA(cudaGetDevice(&current));
+        SDFB_CUDA(cudaSetDevice(pm.device));
+        const cudaError_t e = cudaMemcpy(outNodes, pm.dev.bvh.p, pm.dev.bvh.n * sizeof(BvhNode), cudaMemcpyDeviceToHost);
+        cudaSetDevice(current);
+        SDFB_CUDA(e);
+    });
+}
+
 int sdfb200_nearest_triangle(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
                              const float* xyz, uint64_t n, uint32_t* outTriangle) {
     return guarded([&] {

@@ -247,6 +247,12 @@ static void exactPartsOnDevice(PreparedMesh& pm) {
     pm.hasExactParts = true;
 }
 
+static void gatherTriVerts(MeshOnDevice& m) {   // one 48-byte record per triangle: what the BVH build and the traversal's leaf test read
+    m.triVerts.alloc(size_t(m.numTriangles) * 3);
+    gatherTriVertsKernel<<<divUp(uint64_t(m.numTriangles) * 3, 256), 256>>>(m.verts.p, m.idx.p, m.numTriangles, m.triVerts.p);
+    SDFB_CUDA(cudaGetLastError());
+}
+
 static void uploadBvh(PreparedMesh& pm, const RawVec<BvhNode>& bvh) {
     MeshOnDevice& m = pm.dev;
     m.bvh.alloc(bvh.size());
@@ -256,10 +262,14 @@ static void uploadBvh(PreparedMesh& pm, const RawVec<BvhNode>& bvh) {
     uint32_t n = m.numTriangles, h = 0;
     while (n > 1) { n = n - n / 2; h++; }
     m.stackDepth = int(h) + 1;
-    m.triVerts.alloc(size_t(m.numTriangles) * 3);
-    gatherTriVertsKernel<<<divUp(uint64_t(m.numTriangles) * 3, 256), 256>>>(m.verts.p, m.idx.p, m.numTriangles, m.triVerts.p);
+    gatherTriVerts(m);
     SDFB_CUDA(cudaDeviceSynchronize());
     pm.hasBvh = true;
+}
+
+bool hostBvhRequested() {   // A/B switch: the host builder of mesh_host.cpp (the only one until the end of round 2)
+    static const bool host = std::getenv("SDFB200_HOST_BVH") != nullptr;
+    return host;
 }
 
 std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bool withExactParts) {
@@ -272,10 +282,11 @@ std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bo
     pm->dev.idx.alloc(mesh.nIdx); pm->dev.idx.upload(mesh.idx, mesh.nIdx);
     SDFB_CUDA(cudaDeviceSynchronize());
     pm->uploadMs = msSince(t0);
-    // The BVH is host work (std::sort's tie order is part of the result, mesh_host.cpp) and independent of TriangleData:
-    // it runs on the host threads while the device computes TriangleData.
+    // TriangleData, then the BVH, both on the device (bvh_device.cu). SDFB200_HOST_BVH: the host builder instead, on the host
+    // threads while the device computes TriangleData.
     RawVec<BvhNode> bvh;
     double bvhMs = 0.0;
+    const bool hostBvh = withBvh && hostBvhRequested();
     t0 = std::chrono::steady_clock::now();
     static const bool hostTriangleData = std::getenv("SDFB200_HOST_TRIANGLE_DATA") != nullptr;   // A/B switch: the round-1 host path
     if (hostTriangleData) {
@@ -284,8 +295,8 @@ std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bo
         pm->dev.tris.upload(pm->hostTris.data(), pm->nTris);
         SDFB_CUDA(cudaDeviceSynchronize());
         pm->triangleDataMs = msSince(t0);
-        if (withBvh) { t0 = std::chrono::steady_clock::now(); bvh = buildBvh(mesh); bvhMs = msSince(t0); }
-    } else if (withBvh) {
+        if (hostBvh) { t0 = std::chrono::steady_clock::now(); bvh = buildBvh(mesh); bvhMs = msSince(t0); }
+    } else if (hostBvh) {
         // device work is enqueued by this thread; the BVH build forks its own host threads meanwhile
         std::exception_ptr bvhError;
         std::thread worker([&] {
@@ -303,9 +314,16 @@ std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bo
         triangleDataOnDevice(*pm, mesh);
         pm->triangleDataMs = msSince(t0);
     }
+    if (withBvh && !hostBvh) {
+        t0 = std::chrono::steady_clock::now();
+        gatherTriVerts(pm->dev);
+        buildBvhOnDevice(pm->dev);
+        pm->hasBvh = true;
+        bvhMs = msSince(t0);
+    }
     pm->bvhMs = bvhMs;
     t0 = std::chrono::steady_clock::now();
-    if (withBvh) uploadBvh(*pm, bvh);
+    if (hostBvh) uploadBvh(*pm, bvh);
     if (withExactParts) exactPartsOnDevice(*pm);
     pm->uploadMs += msSince(t0);
     return pm;

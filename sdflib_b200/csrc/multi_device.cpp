@@ -180,12 +180,14 @@ void buildMulti(const HostMesh& mesh, const MultiBuildRequest& req, const std::v
     SDFB_CUDA(cudaSetDevice(devices[0]));
     configureDevicePool(devices[0]);
     const bool exact = req.format == SDFB200_FORMAT_EXACT_OCTREE;
-    // the one host-side BVH build, overlapped with the per-device ingestion
+    // Every device builds its BVH itself (bvh_device.cu). With SDFB200_HOST_BVH: the one host-side BVH build, overlapped
+    // with the per-device ingestion.
+    const bool hostBvh = !exact && hostBvhRequested();
     RawVec<BvhNode> sharedBvh;
     double sharedBvhMs = 0.0;
     std::exception_ptr bvhError;
     std::thread bvhThread;
-    if (!exact)
+    if (hostBvh)
         bvhThread = std::thread([&] {
             try {
                 const auto tb = std::chrono::steady_clock::now();
@@ -218,9 +220,9 @@ void buildMulti(const HostMesh& mesh, const MultiBuildRequest& req, const std::v
                 std::fprintf(stderr, "[sdfb200] multi rank %u/%u %-12s %8.2f ms\n", rank, world, what, std::chrono::duration<double, std::milli>(now - tPhase).count());
                 tPhase = now;
             };
-            meshes[rank] = prepareMesh(mesh, false, exact);
+            meshes[rank] = prepareMesh(mesh, !exact && !hostBvh, exact);
             phase("mesh ingest");
-            if (!exact) {
+            if (hostBvh) {
                 {   // first thread here joins the BVH builder; the others find it joined
                     std::lock_guard<std::mutex> lock(bvhJoinMutex);
                     if (bvhThread.joinable()) bvhThread.join();

@@ -61,6 +61,18 @@ class Mesh:
         return self._bbox
 
 
+# BvhNode of the traversal kernels (include/sdfb200.h, sdfb200_mesh_bvh): two float64 child spheres, links, leaf flag
+BVH_NODE = np.dtype([("left_sphere", "<f8", 4), ("right_sphere", "<f8", 4), ("left", "<i4"), ("right", "<i4"), ("leaf", "<i4"), ("pad", "<i4")])
+
+
+def bvh_host(vertices, indices):
+    """sdfb200_bvh_host: the host builder (libstdc++'s std::sort routines), for the parity tests of the device build."""
+    v, i = _capi.f32(vertices).reshape(-1, 3), _capi.u32(indices).reshape(-1)
+    out = np.zeros(2 * (i.size // 3) - 1, BVH_NODE)
+    _capi.check(_capi.lib().sdfb200_bvh_host(_capi.ptr(v), C.c_uint32(len(v)), _capi.ptr(i), C.c_uint32(i.size), _capi.ptr(out), C.c_uint64(out.size)))
+    return out
+
+
 class PreparedMesh:
     """sdfb200_mesh: a mesh ingested on the current device (TriangleData on the GPU; with bvh=True the nearest-triangle BVH
     of the OctreeSdf builders, with exact=True the side arrays of ExactOctreeSdf). One prepared mesh serves any number of
@@ -95,6 +107,12 @@ class PreparedMesh:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _capi.check(_capi.lib().sdfb200_mesh_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"triangle_data_ms": a.value, "bvh_ms": b.value, "upload_ms": c.value}
+
+    def bvh_nodes(self, num_triangles):
+        """The nearest-triangle BVH this mesh holds on its device (sdfb200_mesh_bvh), as a BVH_NODE record array."""
+        out = np.zeros(2 * num_triangles - 1, BVH_NODE)
+        _capi.check(_capi.lib().sdfb200_mesh_bvh(self._h, _capi.ptr(out), C.c_uint64(out.size)))
+        return out
 
     def close(self):
         if getattr(self, "_h", None):
