@@ -224,23 +224,26 @@ template <class KeyPtr, class IdPtr> __device__ void bvhHeapSort(KeyPtr keys, Id
 //   L_k = k-th position (ascending) with !(a < pivot),   R_k = k-th position (descending) with !(pivot < a),
 //   K = #{k : L_k < R_k} swaps,   cut = min(L_K, R_{K-1})   (tests/cpp/simt_bvh_main.cpp checks this against the library).
 // lpos / rpos: scratch indexed like the range itself (Pos = uint32_t in global memory, uint16_t in shared memory).
+constexpr int kBvhItems = 4;   // elements per thread and pass of the compaction loop
 struct BvhPartitionShared {
-    uint32_t warpL[2][32], warpR[2][32];
+    uint32_t count[2][kBvhItems * 32];     // per (item, warp): candidates on the left in the low half, on the right in the high half
+    uint32_t before[2][kBvhItems * 32 + 1];
     float pivot;
     uint32_t swaps;
 };
+__device__ __forceinline__ int32_t bvhMedianOfThree(float ka, float kb, float kc, int32_t a, int32_t b, int32_t c) {   // __move_median_to_first
+    if (ka < kb) return kb < kc ? b : (ka < kc ? c : a);
+    return ka < kc ? a : (kb < kc ? c : b);
+}
 template <int kThreads, class Pos, class KeyPtr, class IdPtr>
 __device__ int32_t bvhPartitionStep(KeyPtr keys, IdPtr ids, int32_t first, int32_t last, Pos* lpos, Pos* rpos, BvhPartitionShared& sh) {
     constexpr unsigned kFull = 0xffffffffu;
-    constexpr int kWarps = kThreads / 32;
+    constexpr int kWarps = kThreads / 32, kEntries = kBvhItems * kWarps, kPerLane = (kEntries + 31) / 32;
     const int tid = int(threadIdx.x), lane = tid & 31, warp = tid >> 5;
     __syncthreads();                                                       // the range as the previous step left it
     if (tid == 0) {                                                        // __move_median_to_first(first, first + 1, mid, last - 1)
         const int32_t a = first + 1, b = first + (last - first) / 2, c = last - 1;
-        const float ka = keys[a], kb = keys[b], kc = keys[c];
-        int32_t med;
-        if (ka < kb) med = kb < kc ? b : (ka < kc ? c : a);
-        else med = ka < kc ? a : (kb < kc ? c : b);
+        const int32_t med = bvhMedianOfThree(keys[a], keys[b], keys[c], a, b, c);
         const float kf = keys[first], km = keys[med];
         const int32_t idf = ids[first], idm = ids[med];
         keys[first] = km; keys[med] = kf; ids[first] = idm; ids[med] = idf;
@@ -252,35 +255,85 @@ __device__ int32_t bvhPartitionStep(KeyPtr keys, IdPtr ids, int32_t first, int32
     const int32_t base0 = first + 1;
     uint32_t nL = 0, nR = 0;
     int buf = 0;
-    for (int32_t base = base0; base < last; base += kThreads, buf ^= 1) {
-        const int32_t i = base + tid;
-        const bool in = i < last;
-        const float k = in ? float(keys[i]) : 0.0f;
-        const bool fl = in && !(k < pivot), fr = in && !(pivot < k);
-        const unsigned bl = __ballot_sync(kFull, fl), br = __ballot_sync(kFull, fr);
-        if (lane == 0) { sh.warpL[buf][warp] = uint32_t(__popc(bl)); sh.warpR[buf][warp] = uint32_t(__popc(br)); }
-        __syncthreads();
-        uint32_t beforeL = 0, beforeR = 0, totalL = 0, totalR = 0;
-        for (int w = 0; w < kWarps; w++) {
-            const uint32_t cl = sh.warpL[buf][w], cr = sh.warpR[buf][w];
-            if (w < warp) { beforeL += cl; beforeR += cr; }
-            totalL += cl; totalR += cr;
+    for (int32_t base = base0; base < last; base += kThreads * kBvhItems, buf ^= 1) {
+        bool fl[kBvhItems], fr[kBvhItems];
+        unsigned bl[kBvhItems], br[kBvhItems];
+        float k[kBvhItems];
+#pragma unroll
+        for (int j = 0; j < kBvhItems; j++) {                              // the loads of a pass are independent: all in flight together
+            const int32_t i = base + j * kThreads + tid;
+            k[j] = i < last ? float(keys[i]) : 0.0f;
         }
+#pragma unroll
+        for (int j = 0; j < kBvhItems; j++) {
+            const bool in = base + j * kThreads + tid < last;
+            fl[j] = in && !(k[j] < pivot); fr[j] = in && !(pivot < k[j]);
+            bl[j] = __ballot_sync(kFull, fl[j]); br[j] = __ballot_sync(kFull, fr[j]);
+            if (lane == 0) sh.count[buf][j * kWarps + warp] = uint32_t(__popc(bl[j])) | (uint32_t(__popc(br[j])) << 16);
+        }
+        __syncthreads();
+        if (warp == 0) {                                                   // exclusive prefix over the (item, warp) counts: both halves at once
+            uint32_t c[kPerLane], sum = 0;
+#pragma unroll
+            for (int q = 0; q < kPerLane; q++) {
+                const int e = lane * kPerLane + q;
+                c[q] = e < kEntries ? sh.count[buf][e] : 0u;
+                sum += c[q];
+            }
+            uint32_t incl = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_sync(kFull, incl, lane >= o ? lane - o : lane);
+                if (lane >= o) incl += t;
+            }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int q = 0; q < kPerLane; q++) {
+                const int e = lane * kPerLane + q;
+                if (e < kEntries) sh.before[buf][e] = run;
+                run += c[q];
+            }
+            if (lane == 31) sh.before[buf][kEntries] = incl;
+        }
+        __syncthreads();
         const unsigned below = (1u << lane) - 1u;
-        if (fl) lpos[base0 + nL + beforeL + uint32_t(__popc(bl & below))] = Pos(i);
-        if (fr) rpos[base0 + nR + beforeR + uint32_t(__popc(br & below))] = Pos(i);
-        nL += totalL; nR += totalR;
+#pragma unroll
+        for (int j = 0; j < kBvhItems; j++) {
+            const uint32_t bef = sh.before[buf][j * kWarps + warp];
+            const int32_t i = base + j * kThreads + tid;
+            if (fl[j]) lpos[base0 + nL + (bef & 0xFFFFu) + uint32_t(__popc(bl[j] & below))] = Pos(i);
+            if (fr[j]) rpos[base0 + nR + (bef >> 16) + uint32_t(__popc(br[j] & below))] = Pos(i);
+        }
+        const uint32_t total = sh.before[buf][kEntries];
+        nL += total & 0xFFFFu; nR += total >> 16;
     }
     __syncthreads();                                                       // both lists complete
     const uint32_t nMin = nL < nR ? nL : nR;
     uint32_t mine = 0;
-    for (uint32_t k = uint32_t(tid); k < nMin; k += kThreads) {
-        const int32_t pl = int32_t(lpos[base0 + k]), pr = int32_t(rpos[base0 + nR - 1 - k]);
-        if (!(pl < pr)) break;                                             // monotone in k: no later pair swaps either
-        const float kl = keys[pl], kr = keys[pr];
-        const int32_t il = ids[pl], ir = ids[pr];
-        keys[pl] = kr; keys[pr] = kl; ids[pl] = ir; ids[pr] = il;
-        mine++;
+    for (uint32_t k0 = uint32_t(tid); k0 < nMin; k0 += kThreads * kBvhItems) {
+        int32_t pl[kBvhItems], pr[kBvhItems];
+        bool ok[kBvhItems];
+#pragma unroll
+        for (int u = 0; u < kBvhItems; u++) {
+            const uint32_t k = k0 + uint32_t(u) * kThreads;
+            ok[u] = k < nMin;
+            pl[u] = ok[u] ? int32_t(lpos[base0 + k]) : 0;
+            pr[u] = ok[u] ? int32_t(rpos[base0 + nR - 1 - k]) : 0;
+        }
+        bool done = false;
+#pragma unroll
+        for (int u = 0; u < kBvhItems; u++) {
+            ok[u] = ok[u] && pl[u] < pr[u];                                // monotone in k: once a pair does not swap, no later pair does
+            if (!ok[u]) done = true;
+        }
+        float kl[kBvhItems], kr[kBvhItems];
+        int32_t il[kBvhItems], ir[kBvhItems];
+#pragma unroll
+        for (int u = 0; u < kBvhItems; u++)
+            if (ok[u]) { kl[u] = keys[pl[u]]; kr[u] = keys[pr[u]]; il[u] = ids[pl[u]]; ir[u] = ids[pr[u]]; }
+#pragma unroll
+        for (int u = 0; u < kBvhItems; u++)
+            if (ok[u]) { keys[pl[u]] = kr[u]; keys[pr[u]] = kl[u]; ids[pl[u]] = ir[u]; ids[pr[u]] = il[u]; mine++; }
+        if (done) break;
     }
     if (mine) atomicAdd(&sh.swaps, mine);
     __syncthreads();
@@ -315,18 +368,48 @@ bvhBigPartitionKernel(float* keys, int32_t* ids, uint32_t* lpos, uint32_t* rpos,
     }
 }
 
-// the rest of std::sort for a range that fits shared memory: introsort loop (explicit stack), then the final insertion pass.
-// After the loop the range is a sequence of pieces (<= 16 elements each, or heap-sorted), every piece <= the next one, so the
-// insertion pass — a stable sort — is a stable sort of each piece: every element counts the piece members that precede it.
+// std::__unguarded_partition_pivot by ONE thread, literally (ranges of <= kBvhSequential elements in shared memory). The scans
+// are bounded by the range as well: with the median in front they never get there, but NaN keys must not walk out of the array.
+template <class KeyPtr, class IdPtr> __device__ int32_t bvhSequentialPartition(KeyPtr keys, IdPtr ids, int32_t first, int32_t last) {
+    {
+        const int32_t a = first + 1, b = first + (last - first) / 2, c = last - 1;
+        const int32_t med = bvhMedianOfThree(keys[a], keys[b], keys[c], a, b, c);
+        const float kf = keys[first]; const int32_t idf = ids[first];
+        keys[first] = keys[med]; ids[first] = ids[med]; keys[med] = kf; ids[med] = idf;
+    }
+    const float pivot = keys[first];
+    int32_t lo = first + 1, hi = last;
+    for (;;) {
+        while (lo < last && keys[lo] < pivot) lo++;
+        hi--;
+        while (hi > first && pivot < keys[hi]) hi--;
+        if (!(lo < hi)) return lo;
+        const float k = keys[lo]; const int32_t id = ids[lo];
+        keys[lo] = keys[hi]; ids[lo] = ids[hi]; keys[hi] = k; ids[hi] = id;
+        lo++;
+    }
+}
+
+constexpr int kBvhSequential = 64;   // ranges of at most this many elements are finished by one thread each
+
+// the rest of std::sort for a range that fits shared memory: introsort loop, then the final insertion pass. The CTA partitions
+// together (bvhPartitionStep, explicit stack) while ranges are longer than kBvhSequential; the shorter ranges are then taken
+// one per thread and partitioned literally. After the loop the range is a sequence of pieces (<= 16 elements each, or
+// heap-sorted), every piece <= the next one, so the insertion pass — a stable sort — is a stable sort of each piece: every
+// element counts the piece members that precede it.
+constexpr int kBvhShortMax = kBvhSmallMax / (kBvhInsertion + 1) + 2;       // disjoint ranges of more than 16 elements
+
 __global__ void __launch_bounds__(kBvhSmallThreads)
 bvhSmallSortKernel(float* keys, int32_t* ids, const BvhSortTask* __restrict__ tasks, const uint32_t* __restrict__ taskCount) {
     __shared__ float sKey[kBvhSmallMax];
     __shared__ int32_t sId[kBvhSmallMax];
-    __shared__ uint16_t sL[kBvhSmallMax], sR[kBvhSmallMax];
-    __shared__ uint32_t sStart[kBvhSmallMax / 32];                         // bit p set: a piece starts at p
+    __shared__ uint16_t sL[kBvhSmallMax], sR[kBvhSmallMax];                // scratch of the CTA-wide partition steps
+    __shared__ uint16_t sShortFirst[kBvhShortMax], sShortLast[kBvhShortMax];
+    __shared__ uint8_t sShortDepth[kBvhShortMax];
+    __shared__ uint32_t sStart[kBvhSmallMax / 32 + 1];                     // bit p set: a piece starts at p
     __shared__ BvhSortTask sStack[64];
     __shared__ BvhPartitionShared sh;
-    __shared__ int sTop;
+    __shared__ int sTop, sShort;
     const int tid = int(threadIdx.x);
     const uint32_t count = *taskCount;
     for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) {
@@ -334,31 +417,58 @@ bvhSmallSortKernel(float* keys, int32_t* ids, const BvhSortTask* __restrict__ ta
         const int32_t m = task.last - task.first;
         __syncthreads();                                                   // previous task's shared arrays are free
         for (int32_t i = tid; i < m; i += kBvhSmallThreads) { sKey[i] = keys[task.first + i]; sId[i] = ids[task.first + i]; }
-        for (int32_t i = tid; i < kBvhSmallMax / 32; i += kBvhSmallThreads) sStart[i] = i == 0 ? 1u : 0u;
-        if (tid == 0) { sStack[0] = BvhSortTask{0, m, task.depth}; sTop = 1; }
+        for (int32_t i = tid; i < kBvhSmallMax / 32 + 1; i += kBvhSmallThreads) sStart[i] = i == 0 ? 1u : 0u;
+        if (tid == 0) { sStack[0] = BvhSortTask{0, m, task.depth}; sTop = 1; sShort = 0; }
         __syncthreads();
         while (sTop > 0) {                                                 // CTA-uniform: sTop changes only between barriers
             const BvhSortTask cur = sStack[sTop - 1];
             __syncthreads();
             if (tid == 0) sTop--;
             int32_t first = cur.first, last = cur.last, depth = cur.depth;
-            while (last - first > kBvhInsertion) {
-                if (depth == 0) {
+            while (last - first > kBvhSequential) {
+                if (depth == 0) {                                          // depth limit spent: std::__partial_sort, nothing left of this range
                     __syncthreads();
                     if (tid == 0) bvhHeapSort(sKey, sId, first, last);
                     for (int32_t i = first + tid; i < last; i += kBvhSmallThreads) atomicOr(&sStart[i >> 5], 1u << (i & 31));   // sorted: every element its own piece
+                    first = last;
                     break;
                 }
                 depth--;
                 const int32_t cut = bvhPartitionStep<kBvhSmallThreads, uint16_t>(sKey, sId, first, last, sL, sR, sh);
                 if (tid == 0) {
                     atomicOr(&sStart[cut >> 5], 1u << (cut & 31));
-                    sStack[sTop++] = BvhSortTask{cut, last, depth};        // __introsort_loop(cut, last, depth): later
+                    if (last - cut > kBvhSequential) sStack[sTop++] = BvhSortTask{cut, last, depth};   // __introsort_loop(cut, last, depth): later
+                    else if (last - cut > kBvhInsertion) { sShortFirst[sShort] = uint16_t(cut); sShortLast[sShort] = uint16_t(last); sShortDepth[sShort++] = uint8_t(depth); }
                 }
                 last = cut;                                                // ... and loop on [first, cut)
             }
+            if (tid == 0 && last - first > kBvhInsertion) { sShortFirst[sShort] = uint16_t(first); sShortLast[sShort] = uint16_t(last); sShortDepth[sShort++] = uint8_t(depth); }
             __syncthreads();
         }
+        // the short ranges: the same loop, one thread per range, partitions done literally
+        for (int q = tid; q < sShort; q += kBvhSmallThreads) {
+            int32_t stackFirst[4], stackLast[4], stackDepth[4];            // pending right parts: longer than 16, disjoint, inside 64 elements
+            int top = 0;
+            int32_t first = sShortFirst[q], last = sShortLast[q], depth = sShortDepth[q];
+            for (;;) {
+                while (last - first > kBvhInsertion) {
+                    if (depth == 0) {
+                        bvhHeapSort(sKey, sId, first, last);
+                        for (int32_t i = first; i < last; i++) atomicOr(&sStart[i >> 5], 1u << (i & 31));
+                        break;
+                    }
+                    depth--;
+                    const int32_t cut = bvhSequentialPartition(sKey, sId, first, last);
+                    atomicOr(&sStart[cut >> 5], 1u << (cut & 31));
+                    if (last - cut > kBvhInsertion && top < 4) { stackFirst[top] = cut; stackLast[top] = last; stackDepth[top++] = depth; }
+                    last = cut;
+                }
+                if (top == 0) break;
+                top--;
+                first = stackFirst[top]; last = stackLast[top]; depth = stackDepth[top];
+            }
+        }
+        __syncthreads();
         // final insertion pass, piece by piece, as ranks
         float rk[kBvhSmallMax / kBvhSmallThreads];
         int32_t rid[kBvhSmallMax / kBvhSmallThreads], rdst[kBvhSmallMax / kBvhSmallThreads];
@@ -392,15 +502,15 @@ __device__ __forceinline__ double* bvhSphereSlot(BvhNode* nodes, const BvhSeg& s
 // shared memory (coalesced index loads, one 48-byte record per lane, the next batch in flight) and lanes 0-2 add, one axis each.
 __global__ void __launch_bounds__(128)
 bvhCentreKernel(int32_t n, int level, int wide, const int32_t* __restrict__ order, const float4* __restrict__ triVerts, BvhNode* nodes) {
-    __shared__ float buf[4][32][10];
+    __shared__ double2 buf[4][3][48];                                     // per warp and axis: the 96 float64 operands of a batch of 32 triangles, in order
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t unit = wide ? (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5 : uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (unit >= (uint64_t(1) << level)) return;                            // warp-uniform when wide
     const BvhSeg s = bvhSegOfSlot(n, level, uint32_t(unit));
     const int32_t m = s.e - s.b;
     if (!s.valid || m <= 1 || s.parent < 0) return;
-    double c[3] = {0.0, 0.0, 0.0};
     if (!wide) {
+        double c[3] = {0.0, 0.0, 0.0};
         for (int32_t i = s.b; i < s.e; i++) {
             const int32_t id = order[i];
             for (int k = 0; k < 3; k++) {
@@ -413,26 +523,37 @@ bvhCentreKernel(int32_t n, int level, int wide, const int32_t* __restrict__ orde
         for (int a = 0; a < 3; a++) out[a] = c[a] / count;
         return;
     }
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v0 = zero, v1 = zero, v2 = zero;
     {
         const int32_t i = s.b + int32_t(lane);
         if (i < s.e) { const int32_t id = order[i]; v0 = triVerts[size_t(id) * 3]; v1 = triVerts[size_t(id) * 3 + 1]; v2 = triVerts[size_t(id) * 3 + 2]; }
     }
     double acc = 0.0;                                                      // lanes 0-2: the axis `lane`
     for (int32_t base = s.b; base < s.e; base += 32) {
-        float* mine = buf[warp][lane];
-        mine[0] = v0.x; mine[1] = v0.y; mine[2] = v0.z; mine[3] = v1.x; mine[4] = v1.y; mine[5] = v1.z; mine[6] = v2.x; mine[7] = v2.y; mine[8] = v2.z;
+        // lanes past the end of the range stage +0.0: the running sum never is -0.0 (it starts at +0.0, and x + (-x) = +0.0),
+        // so adding +0.0 leaves it unchanged and every batch runs the same 96 additions
+        double* bx = reinterpret_cast<double*>(buf[warp][0]) + 3 * lane;
+        double* by = reinterpret_cast<double*>(buf[warp][1]) + 3 * lane;
+        double* bz = reinterpret_cast<double*>(buf[warp][2]) + 3 * lane;
+        bx[0] = double(v0.x); bx[1] = double(v1.x); bx[2] = double(v2.x);
+        by[0] = double(v0.y); by[1] = double(v1.y); by[2] = double(v2.y);
+        bz[0] = double(v0.z); bz[1] = double(v1.z); bz[2] = double(v2.z);
         __syncwarp();
         {
             const int32_t i = base + 32 + int32_t(lane);                   // next batch: in flight while lanes 0-2 add
+            v0 = zero; v1 = zero; v2 = zero;
             if (i < s.e) { const int32_t id = order[i]; v0 = triVerts[size_t(id) * 3]; v1 = triVerts[size_t(id) * 3 + 1]; v2 = triVerts[size_t(id) * 3 + 2]; }
         }
         if (lane < 3) {
-            const int32_t cnt = s.e - base < 32 ? s.e - base : 32;
-            for (int32_t j = 0; j < cnt; j++) {
-                acc += double(buf[warp][j][lane]);
-                acc += double(buf[warp][j][3 + lane]);
-                acc += double(buf[warp][j][6 + lane]);
+            const double2* col = buf[warp][lane];                          // 128-bit shared loads: two operands each, issued ahead of the chain
+#pragma unroll
+            for (int q0 = 0; q0 < 48; q0 += 8) {
+                double2 x[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) x[q] = col[q0 + q];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { acc += x[q].x; acc += x[q].y; }
             }
         }
         __syncwarp();
