@@ -1,5 +1,5 @@
 """Small driver for ncu captures (one GPU): runs ONE build or ONE query pass of the bench workloads.
-    python scripts/profile_kernels.py exact_build | octree_build | octree_cont | exact_query | octree_query | octree_query_random | octree_query_grad"""
+    python scripts/profile_kernels.py exact_build | exact_build_c4 | octree_build | octree_cont | exact_query | octree_query | octree_query_random | octree_query_grad"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,10 +7,16 @@ import sdflib_b200 as S
 from sdflib_b200 import meshes
 
 what = sys.argv[1]
-v, i = meshes.config_mesh("M1")
+v, i = meshes.config_mesh("M2" if what.endswith("c4") else "M1")
 box = meshes.bounding_box_with_margin(v)
 mesh, bb = S.Mesh(v, i), S.BoundingBox(box[:3], box[3:])
-if what.startswith("exact"):
+if what == "exact_build_c4":
+    sdf = S.ExactOctreeSdf(mesh, bb, 8, 3, 128, 2)
+    print(sdf.build_stats())
+    sdf.close()
+    sdf = S.ExactOctreeSdf(mesh, bb, 8, 3, 128, 2)   # the second build is the warm one (device pool filled)
+    print(sdf.build_stats())
+elif what.startswith("exact"):
     sdf = S.ExactOctreeSdf(mesh, bb, 7, 3, 128, 2)
 elif what == "octree_cont":
     sdf = S.OctreeSdf(mesh, bb, 8, 3, 1e-3, S.OctreeSdf.CONTINUITY, 2)

@@ -116,6 +116,11 @@ inline bool sampleRefillEnabled() {
     return on;
 }
 
+inline int sampleLeafBatch() {   // lanes of a warp that must hold a leaf before the leaf branch runs (1 = take leaves as they come)
+    static const int v = [] { const char* e = std::getenv("SDFB200_LEAF_BATCH"); const int x = e ? std::atoi(e) : 16; return x < 1 ? 1 : (x > 32 ? 32 : x); }();
+    return v;
+}
+
 __global__ void dedupeScatterKernel(const uint32_t* __restrict__ rep, const uint32_t* __restrict__ pos, const float4* __restrict__ results,
                                     uint32_t nSamples, float4* out, int stride) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,7 +181,7 @@ struct LevelSampler {
                 refillCounter.ensure(1);
                 SDFB_CUDA(cudaMemsetAsync(refillCounter.p, 0, sizeof(uint32_t), stream));
                 const uint32_t blocks = std::min<uint32_t>(divUp(cnt, kBvhThreads), 148u * 8u);
-                sampleOwnersRefillKernel<<<blocks, kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst, refillCounter.p);
+                sampleOwnersRefillKernel<<<blocks, kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst, refillCounter.p, sampleLeafBatch());
                 finishOwnersKernel<<<divUp(cnt, 256), 256, 0, stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst);
                 return;
             }

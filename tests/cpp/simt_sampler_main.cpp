@@ -5,7 +5,7 @@
 // terminate and give, sample for sample, the bits of the plain one-sample-per-thread kernel (sampleOwnersKernel, the
 // measured default path). Mesh set-up (TriangleData, BVH) comes from the product library's host functions.
 //
-//   simt_sampler_main <isosphere subdivisions> <nodes>       prints "ok <samples> identical"
+//   simt_sampler_main <isosphere subdivisions> <nodes> [leaf batch]      prints "ok <samples> identical"
 #include <algorithm>
 #include <barrier>
 #include <cfloat>
@@ -90,6 +90,7 @@ using namespace sdfb200;
 int main(int argc, char** argv) {
     const uint32_t subdivisions = argc > 1 ? uint32_t(std::atoi(argv[1])) : 3;
     const uint32_t nNodes = argc > 2 ? uint32_t(std::atoi(argv[2])) : 60;
+    const int leafBatch = argc > 3 ? std::atoi(argv[3]) : 16;   // lanes that must hold a leaf before the leaf branch runs
     uint32_t nv = 0, ni = 0;
     sdfb200_make_isosphere(subdivisions, nullptr, nullptr, &nv, &ni);
     std::vector<float> verts(size_t(nv) * 3);
@@ -129,7 +130,7 @@ int main(int argc, char** argv) {
     simt::launch((count + 127) / 128, 128, [&] { sampleOwnersKernel(mesh, centerHalf.data(), owners.data(), first, count, plain.data()); });
     uint32_t counter = 0;
     const unsigned blocks = std::min<unsigned>((count + 127) / 128, 148u * 8u);
-    simt::launch(blocks, 128, [&] { sampleOwnersRefillKernel(mesh, centerHalf.data(), owners.data(), first, count, refill.data(), &counter); });
+    simt::launch(blocks, 128, [&] { sampleOwnersRefillKernel(mesh, centerHalf.data(), owners.data(), first, count, refill.data(), &counter, leafBatch); });
     if (counter < count) { std::fprintf(stderr, "counter %u < count %u\n", counter, count); return 1; }
     for (uint32_t u = 0; u < count; u++) {   // parked nearest triangle must be a valid id before the finishing pass
         int t;
