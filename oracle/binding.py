@@ -125,6 +125,16 @@ class Backend:
                                            C.c_uint64(len(pts)), _p(out), _p(visits))
         return out, visits
 
+    def nearest_triangle_visits_seeded(self, verts, idx, pts, seeds):
+        """Port only: as nearest_triangle_visits, the running best of query i starting from seeds[i] (float64)."""
+        verts, idx, pts = _f(verts), _u(idx), _f(pts)
+        seeds = None if seeds is None else np.ascontiguousarray(seeds, np.float64)   # None: the box-pruning model (no seed)
+        out = np.empty(len(pts), np.uint32)
+        visits = np.empty((len(pts), 2), np.uint32)
+        self.fn("nearest_triangle_visits_seeded")(_p(verts), C.c_uint32(len(verts)), _p(idx), C.c_uint32(idx.size), _p(pts),
+                                                  C.c_uint64(len(pts)), None if seeds is None else _p(seeds), _p(out), _p(visits))
+        return out, visits
+
     # ---- structures -----------------------------------------------------------------------
     def build_octree(self, verts, idx, box6, depth, start_depth, threshold=1e-3, algorithm=1, num_threads=1,
                      termination_rule=1, param1=0.0, use_cache=True):

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <array>
 #include <chrono>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -438,6 +439,11 @@ struct Bvh {
     std::vector<std::array<int, 3>> tris;
     std::vector<BvhNode> nodes;
     Sphere root;
+    // traversal model only (tests/model_bvh_boxes.py): axis-aligned box of every subtree, by node id (float, exact: min / max of float coordinates)
+    struct Box { float lo[3], hi[3]; };
+    std::vector<Box> boxes;
+    bool useBoxes = false;
+    double boxMargin = 0.0;
 
     struct BuildTri { D3 v[3]; int id; };
 
@@ -454,6 +460,35 @@ struct Bvh {
         nodes.reserve(2 * tris.size());
         nodes.push_back(BvhNode());
         build(0, -1, 0, bt, 0, int(bt.size()));
+    }
+    // boxes of all subtrees, bottom-up over the finished tree (children have larger ids than their parent)
+    void buildBoxes() {
+        boxes.assign(nodes.size(), Box{{FLT_MAX, FLT_MAX, FLT_MAX}, {-FLT_MAX, -FLT_MAX, -FLT_MAX}});
+        for (size_t k = nodes.size(); k-- > 0;) {
+            Box& b = boxes[k];
+            if (nodes[k].l == -1) {
+                for (int c = 0; c < 3; c++) {
+                    const D3& p = verts[size_t(tris[size_t(nodes[k].r)][size_t(c)])];
+                    const float q[3] = {float(p.x), float(p.y), float(p.z)};
+                    for (int a = 0; a < 3; a++) { b.lo[a] = std::min(b.lo[a], q[a]); b.hi[a] = std::max(b.hi[a], q[a]); }
+                }
+            } else {
+                for (int child : {nodes[k].l, nodes[k].r})
+                    for (int a = 0; a < 3; a++) { b.lo[a] = std::min(b.lo[a], boxes[size_t(child)].lo[a]); b.hi[a] = std::max(b.hi[a], boxes[size_t(child)].hi[a]); }
+            }
+        }
+        double s2 = 0;
+        for (int a = 0; a < 3; a++) s2 += double(boxes[0].hi[a] - boxes[0].lo[a]) * double(boxes[0].hi[a] - boxes[0].lo[a]);
+        boxMargin = 1e-10 * s2;
+        useBoxes = true;
+    }
+    // conservative squared distance from p to the box of node k (float arithmetic, scaled down by more than its rounding error)
+    bool boxBeyondBest(int k, D3 p, double best) const {
+        const Box& b = boxes[size_t(k)];
+        const float q[3] = {float(p.x), float(p.y), float(p.z)};
+        float d2 = 0.f;
+        for (int a = 0; a < 3; a++) { const float d = std::max(std::max(b.lo[a] - q[a], q[a] - b.hi[a]), 0.f); d2 += d * d; }
+        return double(d2 * (1.0f - 1e-6f)) > best * best * (1.0 + 1e-9) + boxMargin;
     }
 
     // :421-490. `slot` says where this subtree's bounding sphere lives: 0 root, 1 parent.left, 2 parent.right.
@@ -523,16 +558,18 @@ struct Bvh {
         }
         const double dl = dnorm(p - nd.left.c) - nd.left.r;
         const double dr = dnorm(p - nd.right.c) - nd.right.r;
-        if (dl < dr) {
-            if (dl < best) query(nodes[size_t(nd.l)], p, best, bestTri);
-            if (dr < best) query(nodes[size_t(nd.r)], p, best, bestTri);
-        } else {
-            if (dr < best) query(nodes[size_t(nd.r)], p, best, bestTri);
-            if (dl < best) query(nodes[size_t(nd.l)], p, best, bestTri);
-        }
+        // model of the device's extra pruning: a child whose box lies beyond the running best (by a margin above every rounding
+        // error of the leaf test) cannot change the result, so it is skipped although its sphere passes
+        auto visit = [&](int child, double d) {
+            if (!(d < best)) return;
+            if (useBoxes && boxBeyondBest(child, p, best)) return;
+            query(nodes[size_t(child)], p, best, bestTri);
+        };
+        if (dl < dr) { visit(nd.l, dl); visit(nd.r, dr); }
+        else { visit(nd.r, dr); visit(nd.l, dl); }
     }
-    uint32_t nearest(V3 p) const {
-        double best = std::numeric_limits<double>::max();
+    uint32_t nearest(V3 p, double seed = std::numeric_limits<double>::max()) const {   // seed: traversal models only (an upper bound the search starts from)
+        double best = seed;
         int tri = -1;
         query(nodes[0], D3{double(p.x), double(p.y), double(p.z)}, best, tri);
         return uint32_t(tri);
@@ -1787,6 +1824,20 @@ void orc_nearest_triangle_visits(const float* verts, uint32_t nVerts, const uint
         outVisits2[2 * i] = outVisits2[2 * i + 1] = 0;
         bvh.visitCount = outVisits2 + 2 * i;
         outTri[i] = bvh.nearest(v3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+    }
+    bvh.visitCount = nullptr;
+}
+
+// Traversal model of a SEEDED search (tests/model_bvh_seed.py): the running best starts from seeds[i] instead of DBL_MAX.
+void orc_nearest_triangle_visits_seeded(const float* verts, uint32_t nVerts, const uint32_t* idx, uint32_t nIdx, const float* pts,
+                                        uint64_t n, const double* seeds, uint32_t* outTri, uint32_t* outVisits2) {
+    MeshView m{reinterpret_cast<const V3*>(verts), nVerts, idx, nIdx};
+    Bvh bvh(m);
+    if (seeds == nullptr) bvh.buildBoxes();   // no seeds: the box-pruning model instead
+    for (uint64_t i = 0; i < n; i++) {
+        outVisits2[2 * i] = outVisits2[2 * i + 1] = 0;
+        bvh.visitCount = outVisits2 + 2 * i;
+        outTri[i] = bvh.nearest(v3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]), seeds ? seeds[i] : std::numeric_limits<double>::max());
     }
     bvh.visitCount = nullptr;
 }

@@ -37,6 +37,8 @@ void orc_nearest_triangle(const float* verts, uint32_t nVerts, const uint32_t* i
 
 void orc_nearest_triangle_visits(const float* verts, uint32_t nVerts, const uint32_t* idx, uint32_t nIdx, const float* pts,
                                  uint64_t n, uint32_t* outTri, uint32_t* outVisits2);
+void orc_nearest_triangle_visits_seeded(const float* verts, uint32_t nVerts, const uint32_t* idx, uint32_t nIdx, const float* pts,
+                                        uint64_t n, const double* seeds, uint32_t* outTri, uint32_t* outVisits2);
 
 /* whole structures. useCache=1 emulates the reference's 32^3 direct-mapped vertex cache
  * (TrianglesInfluence.h:934-991) — required for bit-identity with the reference's single-thread

@@ -280,58 +280,63 @@ __device__ __forceinline__ void tmaLoad1d(void* smemDst, const void* gmemSrc, ui
                  : "memory");
 }
 
+// One WARP per chunk of 512 list entries (a CTA of four warps works on four chunks, usually four different nodes). With
+// a CTA per chunk (round 1) a 129-500 entry list filled its 128 threads for one to four trips, the last one partly: 14 of 32
+// threads per instruction (profiles/r1_summary.md). A warp walks its chunk in trips of 32 entries — at most the last trip of a
+// chunk is partly filled — and the 19 (distance, position) minima are folded once per chunk instead of once per warp and CTA.
 template <int kPts>
 __global__ void __launch_bounds__(kSampleThreads)
 sampleKernel(const float4* __restrict__ frames, const float4* __restrict__ centerHalf, const uint32_t* __restrict__ list,
              const uint32_t* __restrict__ listLo, const uint32_t* __restrict__ listCnt, const uint32_t* __restrict__ chunkOff,
-             uint32_t numNodes, unsigned long long* __restrict__ best) {
+             uint32_t numNodes, uint32_t numChunks, unsigned long long* __restrict__ best) {
+    constexpr int kWarps = kSampleThreads / 32;
     // The chunk's index block is fetched as the 16-byte aligned window that covers it: [winLo, winLo + winBytes)
-    __shared__ alignas(16) uint32_t sIdx[kChunk + 8];
-    __shared__ alignas(8) uint64_t sBar;
-    __shared__ float sPts[kPts][3];
-    __shared__ unsigned long long sKeys[kSampleThreads / 32][kPts];
-    __shared__ uint32_t sNode;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        sNode = lastLessEqual<uint32_t>(chunkOff, numNodes + 1, blockIdx.x);
-        mbarInit(&sBar, 1);
+    __shared__ alignas(16) uint32_t sIdx[kWarps][kChunk + 8];
+    __shared__ alignas(8) uint64_t sBar[kWarps];
+    __shared__ float sPts[kWarps][kPts][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * kWarps + warp;
+    if (chunk >= numChunks) return;                                       // warp-uniform; no CTA-wide barrier below
+    uint32_t node = 0;
+    if (lane == 0) {
+        node = lastLessEqual<uint32_t>(chunkOff, numNodes + 1, chunk);
+        mbarInit(&sBar[warp], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    const uint32_t node = sNode;
-    const uint32_t first = (blockIdx.x - chunkOff[node]) * kChunk;       // position of the chunk inside the node's list
+    node = __shfl_sync(0xffffffffu, node, 0);
+    const uint32_t first = (chunk - chunkOff[node]) * kChunk;            // position of the chunk inside the node's list
     const uint32_t cnt = min(uint32_t(kChunk), listCnt[node] - first);   // entries of this chunk
     const size_t gFirst = size_t(listLo[node]) + first;                   // index of the first entry in `list`
     const size_t winFirst = gFirst & ~size_t(3);                          // 16-byte aligned window start
     const uint32_t skip = uint32_t(gFirst - winFirst);
     const uint32_t winBytes = ((skip + cnt + 3u) & ~3u) * 4u;             // the list array is padded by 8 words
-    if (tid == 0) {
-        mbarExpectTx(&sBar, winBytes);
-        tmaLoad1d(sIdx, list + winFirst, winBytes, &sBar);
+    if (lane == 0) {
+        mbarExpectTx(&sBar[warp], winBytes);
+        tmaLoad1d(sIdx[warp], list + winFirst, winBytes, &sBar[warp]);
     }
-    if (tid < kPts) {
+    if (lane < kPts) {
         const float4 ch = centerHalf[node];
         f3 rel;
-        if (kPts == 8) rel = cornerDir(uint32_t(tid));
+        if (kPts == 8) rel = cornerDir(uint32_t(lane));
         else {
-            const int L = cMidLattice[tid];
+            const int L = cMidLattice[lane];
             rel = mk3(float(L % 3 - 1), float((L / 3) % 3 - 1), float(L / 9 - 1));
         }
         const f3 p = mk3(ch.x, ch.y, ch.z) + rel * ch.w;
-        sPts[tid][0] = p.x; sPts[tid][1] = p.y; sPts[tid][2] = p.z;
+        sPts[warp][lane][0] = p.x; sPts[warp][lane][1] = p.y; sPts[warp][lane][2] = p.z;
     }
-    __syncthreads();
-    mbarWait(&sBar, 0);
+    __syncwarp();
+    mbarWait(&sBar[warp], 0);
 
     float bestD[kPts];
     uint32_t bestJ[kPts];
 #pragma unroll
     for (int s = 0; s < kPts; s++) { bestD[s] = INFINITY; bestJ[s] = kNone; }
-    for (uint32_t k = uint32_t(tid); k < cnt; k += kSampleThreads) {   // ascending positions per thread
-        const TriFrame f = loadFrame(frames, sIdx[skip + k]);
+    for (uint32_t k = uint32_t(lane); k < cnt; k += 32) {                 // ascending positions per thread
+        const TriFrame f = loadFrame(frames, sIdx[warp][skip + k]);
 #pragma unroll
         for (int s = 0; s < kPts; s++) {
-            const float d = sqDistPointTriangle(mk3(sPts[s][0], sPts[s][1], sPts[s][2]), f);
+            const float d = sqDistPointTriangle(mk3(sPts[warp][s][0], sPts[warp][s][1], sPts[warp][s][2]), f);
             if (d < bestD[s]) { bestD[s] = d; bestJ[s] = first + k; }
         }
     }
@@ -345,14 +350,7 @@ sampleKernel(const float4* __restrict__ frames, const float4* __restrict__ cente
         const uint32_t j = __reduce_min_sync(0xffffffffu, bits == m ? bestJ[s] : kNone);
         if (lane == s) mine = (static_cast<unsigned long long>(m) << 32) | j;
     }
-    if (lane < kPts) sKeys[warp][lane] = mine;
-    __syncthreads();
-    if (tid < kPts) {
-        unsigned long long k = sKeys[0][tid];
-#pragma unroll
-        for (int w = 1; w < kSampleThreads / 32; w++) k = min(k, sKeys[w][tid]);
-        if ((k >> 32) != 0xFFFFFFFFull) atomicMin(best + size_t(node) * kPts + tid, k);
-    }
+    if (lane < kPts && (mine >> 32) != 0xFFFFFFFFull) atomicMin(best + size_t(node) * kPts + lane, mine);
 }
 
 // best keys -> triangle ids (0 when the list was empty: deterministic stand-in for the reference's untouched slot)
@@ -680,7 +678,7 @@ struct ExactBuildState : BuildState {
             const uint64_t nKeys = uint64_t(L.count) * kPts;
             if (best.n < nKeys) best.alloc(nKeys);
             fillU64<<<divUp(nKeys, 256), 256>>>(best.p, kNoKey, nKeys);
-            if (nChunks) sampleKernel<kPts><<<nChunks, kSampleThreads>>>(dFramesP, L.centerHalf.p, list, lo, cnt, chOff, L.count, best.p);
+            if (nChunks) sampleKernel<kPts><<<divUp(nChunks, kSampleThreads / 32), kSampleThreads>>>(dFramesP, L.centerHalf.p, list, lo, cnt, chOff, L.count, nChunks, best.p);
             resolveKernel<<<divUp(nKeys, 256), 256>>>(best.p, list, lo, kPts, outInfo, nKeys);
             st.kernel_launches += 3;
             SDFB_CUDA(cudaGetLastError());

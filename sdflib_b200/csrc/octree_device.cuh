@@ -117,7 +117,7 @@ inline bool sampleRefillEnabled() {
 }
 
 inline int sampleLeafBatch() {   // lanes of a warp that must hold a leaf before the leaf branch runs (1 = take leaves as they come)
-    static const int v = [] { const char* e = std::getenv("SDFB200_LEAF_BATCH"); const int x = e ? std::atoi(e) : 16; return x < 1 ? 1 : (x > 32 ? 32 : x); }();
+    static const int v = [] { const char* e = std::getenv("SDFB200_LEAF_BATCH"); const int x = e ? std::atoi(e) : 1; return x < 1 ? 1 : (x > 32 ? 32 : x); }();
     return v;
 }
 

@@ -238,6 +238,8 @@ def test_refill_sampler_source_under_warp_emulation(sdf, tmp_path):
            "-L" + lib_dir, "-lsdfb200", "-Wl,-rpath," + lib_dir, "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
-    for subdivisions, nodes in ((4, 120), (0, 3), (2, 1)):
-        r = subprocess.run([exe, str(subdivisions), str(nodes)], capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0 and "identical" in r.stdout, (subdivisions, nodes, r.stdout, r.stderr)
+    # third argument: the leaf-batch threshold of the refill kernel (1 = the default schedule; larger values were measured slower
+    # on the GPU but must stay correct: they are reachable through SDFB200_LEAF_BATCH)
+    for subdivisions, nodes, leaf_batch in ((4, 120, 1), (0, 3, 1), (2, 1, 1), (3, 40, 8), (3, 40, 32)):
+        r = subprocess.run([exe, str(subdivisions), str(nodes), str(leaf_batch)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "identical" in r.stdout, (subdivisions, nodes, leaf_batch, r.stdout, r.stderr)
