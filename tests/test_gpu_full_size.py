@@ -135,6 +135,31 @@ def test_config3_exact_octree_at_full_size(sdf, ref, m1, tmp_path):
     assert_bit_equal(r.query(q[::16], False, 8), dist[::16], "reference query of the GPU-built .bin")
 
 
+def test_config4_dragon_class_exact_octree_at_full_size(sdf):
+    """BASELINE configs[3]: 5 242 880 triangles, ExactOctreeSdf depth 8 / start depth 3 / minTrianglesPerNode 128 — 11.3 M nodes,
+    162 M set words, 812 MB of masks, more than 2^32 (node, triangle) pairs on the two deepest levels. Hashes and a 256^3
+    distance sample from the history-free CPU oracle (tests/golden/make_golden_c4.py, about an hour of CPU)."""
+    gold = golden("config4.npz")
+    v, i = sdf.meshes.config_mesh("M2")
+    assert sha(v) + sha(i) == str(gold["mesh_sha256"]), "config mesh M2 differs from the one the fixture was generated on"
+    box = gold["box"]
+    s = sdf.ExactOctreeSdf(sdf.Mesh(v, i), sdf.BoundingBox(box[:3], box[3:]), 8, 3, 128, 1)
+    try:
+        nodes, sets, masks = s.getOctreeData(), s.getTrianglesSets(), s.getTrianglesMasks()
+        assert nodes.shape[0] == int(gold["nodes"]) and sets.size == int(gold["sets_words"]) and masks.size == int(gold["masks_bytes"])
+        assert sha(nodes) == str(gold["nodes_sha256"])
+        assert sha(sets) == str(gold["sets_sha256"])
+        assert sha(masks) == str(gold["masks_sha256"])
+        assert sha(s.getTrianglesData()) == str(gold["triangle_data_sha256"])
+        q = grid_sample(s.getSampleArea().as_array(), 61)[::int(gold["sample_every"])]   # make_golden_full.grid_sample (STRIDE = 61), then every 16th
+        dist, grad = s.getDistance(q, gradient=True)
+        assert_bit_equal(dist, gold["distances"], "distances against the oracle's build")
+        assert_bit_equal(grad, gold["gradients"], "gradients against the oracle's build")
+    finally:
+        s.close()
+        sdf.lib().sdfb200_release_cached_memory()   # ~95 GB of level arrays: back to the driver before the next test
+
+
 def test_exact_octree_against_reference_build(sdf, ref):
     """GPU build <-> the compiled reference's own build (not the port): same distances and gradients bit for bit; the
     node arrays agree except where the reference's vertex cache changed a tie (counted)."""
