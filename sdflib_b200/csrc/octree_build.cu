@@ -107,6 +107,21 @@ __global__ void fillOnesKernel(uint32_t* p, uint32_t n) {
     if (i < n) p[i] = 1u;
 }
 
+// Geometry of the children of a level whose nodes all subdivide (the virtual levels above the start depth): centres, half
+// sizes and packed coordinates, exactly as emitChildrenKernel computes them — they do not depend on any sample.
+__global__ void childGeometryKernel(LevelView lv, float4* nextCenterHalf, uint32_t* nextCoord) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= lv.count * 8u) return;
+    const uint32_t node = e >> 3, lane = e & 7u;
+    const float4 ch = lv.centerHalf[node];
+    const float h = 0.5f * ch.w;
+    const f3 c = mk3(ch.x, ch.y, ch.z) + cornerDir(lane) * h;
+    nextCenterHalf[e] = make_float4(c.x, c.y, c.z, h);
+    const uint32_t pc = lv.coord[node];
+    const uint32_t ix = ((pc & 1023u) << 1) | (lane & 1u), iy = (((pc >> 10) & 1023u) << 1) | ((lane >> 1) & 1u), iz = (((pc >> 20) & 1023u) << 1) | (lane >> 2);
+    nextCoord[e] = ix | (iy << 10) | (iz << 20);
+}
+
 // Children of the subdividing nodes: 8 records each, corner values inherited from the 27-point lattice
 // (child c, corner k  <-  lattice point (c+k) per axis; OctreeSdfDepthFirst.h:225-336).
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -372,7 +387,6 @@ struct OctreeBuildState : BuildState {
             L.alloc(uint32_t(ch.size()));
             L.centerHalf.upload(ch.data(), ch.size());
             L.coord.upload(coord.data(), coord.size());
-            seedCornersKernel<<<divUp(L.count * 8, 64), 64, bvhStackBytes(dmesh, 64)>>>(dmesh, L.centerHalf.p, L.corners.p, L.count);
             st.kernel_launches++;
             st.samples_evaluated += L.count * 8;
         }
@@ -381,18 +395,67 @@ struct OctreeBuildState : BuildState {
         DevBuf<uint32_t> flags, scan;
         DevBuf<uint8_t> dOwned;
         Scanner scanner;
+        // The levels above the start depth always subdivide (OctreeSdfDepthFirst.h:397-416), so their nodes are known before any
+        // sample is: the mid-point samples of ALL of them and of the start level are taken in ONE batch, with the seed corners on a
+        // side stream next to it. Each of these launches is a handful of CTAs that lasts as long as its longest far-field
+        // traversal (2.5 - 4.7 ms each on the C2 mesh: seeds, depth 1, 2, 3 = 13.3 ms in a row, profiles/r2_summary.md); together
+        // they last as long as the longest one. Same positions, same kernels per sample: same bits.
+        static const bool batchVirtual = [] { const char* e = std::getenv("SDFB200_BATCH_VIRTUAL_LEVELS"); return !(e && e[0] == '0'); }();
+        const bool batched = batchVirtual && startDepth > d0;
+        struct SeedStream {
+            cudaStream_t s = nullptr; cudaEvent_t ready = nullptr, done = nullptr;
+            ~SeedStream() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } if (ready) cudaEventDestroy(ready); if (done) cudaEventDestroy(done); }
+        } seed;
+        {
+            Level& L = *levels[d0];
+            if (batched) {
+                SDFB_CUDA(cudaStreamCreateWithFlags(&seed.s, cudaStreamNonBlocking));
+                SDFB_CUDA(cudaEventCreateWithFlags(&seed.ready, cudaEventDisableTiming));
+                SDFB_CUDA(cudaEventCreateWithFlags(&seed.done, cudaEventDisableTiming));
+                SDFB_CUDA(cudaEventRecord(seed.ready, 0));                     // the uploads above
+                SDFB_CUDA(cudaStreamWaitEvent(seed.s, seed.ready, 0));
+            }
+            seedCornersKernel<<<divUp(L.count * 8, 64), 64, bvhStackBytes(dmesh, 64), seed.s>>>(dmesh, L.centerHalf.p, L.corners.p, L.count);
+            if (batched) SDFB_CUDA(cudaEventRecord(seed.done, seed.s));
+        }
+        DevBuf<float4> preMids, preCentres;
+        std::vector<uint32_t> preOffset(depth + 2, 0u);
+        if (batched) {
+            uint32_t total = 0;
+            for (uint32_t d = d0; d <= startDepth; d++) {
+                Level& L = *levels[d];
+                preOffset[d] = total;
+                total += L.count;
+                if (d == startDepth) break;
+                levels[d + 1].reset(new Level());
+                Level& N = *levels[d + 1];
+                N.alloc(L.count * 8);
+                childGeometryKernel<<<divUp(uint64_t(L.count) * 8, 256), 256>>>(L.view(), N.centerHalf.p, N.coord.p);
+                st.kernel_launches++;
+            }
+            preCentres.alloc(total);
+            for (uint32_t d = d0; d <= startDepth; d++)
+                SDFB_CUDA(cudaMemcpyAsync(preCentres.p + preOffset[d], levels[d]->centerHalf.p, size_t(levels[d]->count) * sizeof(float4), cudaMemcpyDeviceToDevice));
+            preMids.alloc(size_t(total) * 19);
+            const uint32_t ran = levelSampler.run(dmesh, preCentres.p, total, preMids.p, 1);
+            st.leaves += ran == 0xFFFFFFFFu ? uint64_t(total) * 19 : ran;
+            SDFB_CUDA(cudaStreamWaitEvent(0, seed.done, 0));                    // corner values of the seeds, before the first children inherit them
+        }
         for (uint32_t d = d0; d <= depth; d++) {
             Level& L = *levels[d];
             if (d == startDepth) makePlan(out, L, numThreads, rank, world);
             if (d == depth) break;
             if (L.count == 0) { levels[d + 1].reset(new Level()); continue; }
-            mids.alloc(size_t(L.count) * 19);
+            const bool presampled = batched && d <= startDepth;
+            if (!presampled) mids.alloc(size_t(L.count) * 19);
+            const float4* midsPtr = presampled ? preMids.p + size_t(preOffset[d]) * 19 : mids.p;
             flags.alloc(L.count);
             scan.alloc(L.count);
             const uint32_t grid = divUp(L.count, kWarpsPerCta);
+            if (!presampled)
             { const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 1); st.leaves += ran == 0xFFFFFFFFu ? uint64_t(L.count) * 19 : ran; }   // stats.leaves: BVH traversals run
             if (d >= startDepth)
-                levelDecideKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), mids.p, flags.p, rule, param0 * param0, param1);
+                levelDecideKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), midsPtr, flags.p, rule, param0 * param0, param1);
             else
                 fillOnesKernel<<<divUp(L.count, 256), 256>>>(flags.p, L.count);   // virtual levels always subdivide
             st.kernel_launches++;
@@ -404,10 +467,12 @@ struct OctreeBuildState : BuildState {
             const uint32_t nSubdivide = scanner.run(flags.p, scan.p, L.count);
             st.kernel_launches += 4;
             st.samples_evaluated += uint64_t(L.count) * 19;
-            levels[d + 1].reset(new Level());
+            if (!(batched && d < startDepth)) {   // (the children of a virtual level exist already: their geometry was needed for the batch)
+                levels[d + 1].reset(new Level());
+                levels[d + 1]->alloc(nSubdivide * 8);
+            }
             Level& N = *levels[d + 1];
-            N.alloc(nSubdivide * 8);
-            emitChildrenKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), mids.p, flags.p, scan.p, L.childOf.p, N.centerHalf.p,
+            emitChildrenKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), midsPtr, flags.p, scan.p, L.childOf.p, N.centerHalf.p,
                                                             N.corners.p, N.coord.p);
             st.kernel_launches++;
             st.nodes_processed += L.count;

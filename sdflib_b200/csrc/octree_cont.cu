@@ -189,6 +189,20 @@ struct LevelArrays {
     uint8_t* terminal;
 };
 
+// geometry of the children of a level whose nodes all subdivide (virtual levels): as contEmitKernel computes it, no sample needed
+__global__ void contChildGeometryKernel(uint32_t count, const float4* centerHalf, const uint32_t* coord, float4* nextCenterHalf, uint32_t* nextCoord) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= count * 8u) return;
+    const uint32_t node = e >> 3, lane = e & 7u;
+    const float4 ch = centerHalf[node];
+    const float h = 0.5f * ch.w;
+    const f3 c = mk3(ch.x, ch.y, ch.z) + cornerDir(lane) * h;
+    nextCenterHalf[e] = make_float4(c.x, c.y, c.z, h);
+    const uint32_t pc = coord[node];
+    const uint32_t ix = ((pc & 1023u) << 1) | (lane & 1u), iy = (((pc >> 10) & 1023u) << 1) | ((lane >> 1) & 1u), iz = (((pc >> 20) & 1023u) << 1) | (lane >> 2);
+    nextCoord[e] = ix | (iy << 10) | (iz << 20);
+}
+
 // corner samples of the seed nodes (:197-221)
 __global__ void contSeedKernel(DeviceMesh mesh, Grid g, LevelArrays lv, uint32_t depth) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -782,6 +796,15 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
     scalars.upload(scalarInit, 2);
 
     const uint32_t d0 = std::min(startDepth, 1u);
+    // The levels above the start depth always subdivide: their nodes are known before any sample is, so their Iter-1 samples and
+    // those of the start level are taken in ONE batch, with the seed corners on a side stream next to it (octree_build.cu has the
+    // measurements: each of these launches lasts as long as its longest far-field traversal). Same positions: same bits.
+    static const bool batchVirtual = [] { const char* e = std::getenv("SDFB200_BATCH_VIRTUAL_LEVELS"); return !(e && e[0] == '0'); }();
+    const bool batched = batchVirtual && startDepth > d0;
+    struct SeedStream {
+        cudaStream_t s = nullptr; cudaEvent_t done = nullptr;
+        ~SeedStream() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } if (done) cudaEventDestroy(done); }
+    } seed;
     {
         const float boxSize = out.boxMax[0] - out.boxMin[0];
         const float h0 = float(0.5f * boxSize * std::pow(0.5f, d0));
@@ -802,8 +825,13 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
         L.alloc(uint32_t(ch.size()));
         L.centerHalf.upload(ch.data(), ch.size());
         L.coord.upload(coord.data(), coord.size());
-        contSeedKernel<<<divUp(L.count * 8, 64), 64, bvhStackBytes(dmesh, 64)>>>(dmesh, grid, L.arrays(), d0);
         SDFB_CUDA(cudaStreamSynchronize(0));   // ch / coord are stack vectors
+        if (batched) {   // seeds next to the batch of the virtual levels (below), not before it
+            SDFB_CUDA(cudaStreamCreateWithFlags(&seed.s, cudaStreamNonBlocking));
+            SDFB_CUDA(cudaEventCreateWithFlags(&seed.done, cudaEventDisableTiming));
+        }
+        contSeedKernel<<<divUp(L.count * 8, 64), 64, bvhStackBytes(dmesh, 64), seed.s>>>(dmesh, grid, L.arrays(), d0);
+        if (batched) SDFB_CUDA(cudaEventRecord(seed.done, seed.s));
         st.kernel_launches++;
         st.samples_evaluated += L.count * 8;
     }
@@ -921,11 +949,36 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
         SDFB_CUDA(cudaEventCreateWithFlags(&emitted, cudaEventDisableTiming));
     }
     uint32_t pendingDepth = 0, pendingCand = 0;
+    DevBuf<float4> preMids, preCentres;
+    std::vector<uint32_t> preOffset(depth + 2, 0u);
+    if (batched) {
+        uint32_t total = 0;
+        for (uint32_t d = d0; d <= startDepth; d++) {
+            NodeLevel& L = *levels[d];
+            preOffset[d] = total;
+            total += L.count;
+            if (d == startDepth) break;
+            levels[d + 1].reset(new NodeLevel());
+            NodeLevel& N = *levels[d + 1];
+            N.alloc(L.count * 8);
+            contChildGeometryKernel<<<divUp(uint64_t(L.count) * 8, 256), 256>>>(L.count, L.centerHalf.p, L.coord.p, N.centerHalf.p, N.coord.p);
+            st.kernel_launches++;
+        }
+        preCentres.alloc(total);
+        for (uint32_t d = d0; d <= startDepth; d++)
+            SDFB_CUDA(cudaMemcpyAsync(preCentres.p + preOffset[d], levels[d]->centerHalf.p, size_t(levels[d]->count) * sizeof(float4), cudaMemcpyDeviceToDevice));
+        preMids.alloc(size_t(total) * 38);
+        const uint32_t ran = levelSampler.run(dmesh, preCentres.p, total, preMids.p, 2);
+        st.leaves += ran == 0xFFFFFFFFu ? uint64_t(total) * 19 : ran;
+        SDFB_CUDA(cudaStreamWaitEvent(0, seed.done, 0));   // corner values of the seeds, before the first children inherit them
+    }
     for (uint32_t d = d0; d <= depth; d++) {
         NodeLevel& L = *levels[d];
         const bool real = d >= startDepth, deepest = d == depth;
         if (L.count > kRefIndexMask) throw Error(SDFB200_ERR_INVALID, "more than 2^27 nodes in one level");
-        levels[d + 1].reset(new NodeLevel());
+        const bool presampled = batched && d <= startDepth && !deepest;
+        const bool childrenExist = batched && d < startDepth;   // geometry made for the batch
+        if (!childrenExist) levels[d + 1].reset(new NodeLevel());
         if (L.count == 0) {
             if (pendingCand) { runFixup(pendingDepth, pendingCand); pendingCand = 0; }
             continue;
@@ -933,13 +986,18 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
         storeTable[d] = L.store(d);
         const uint32_t grid8 = divUp(L.count, kWarpsPerCta);
         // ---- Iter 1
+        float4* midsPtr = presampled ? preMids.p + size_t(preOffset[d]) * 38 : mids.p;
         if (!deepest) {
-            mids.ensure(size_t(L.count) * 38);
-            { const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 2); st.leaves += ran == 0xFFFFFFFFu ? uint64_t(L.count) * 19 : ran; }   // stats.leaves: BVH traversals run
+            if (!presampled) {
+                mids.ensure(size_t(L.count) * 38);
+                midsPtr = mids.p;
+                const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 2);
+                st.leaves += ran == 0xFFFFFFFFu ? uint64_t(L.count) * 19 : ran;   // stats.leaves: BVH traversals run
+            }
             if (pendingCand) { runFixup(pendingDepth, pendingCand); pendingCand = 0; }   // the previous depth's fix-up, under this sampling
             if (real) {
                 coeffs.ensure(size_t(L.count) * 64);
-                contDecideKernel<<<grid8, kWarpsPerCta * 32>>>(L.arrays(), mids.p, coeffs.p, oc.oct.p, rule, sqThreshold, param1);
+                contDecideKernel<<<grid8, kWarpsPerCta * 32>>>(L.arrays(), midsPtr, coeffs.p, oc.oct.p, rule, sqThreshold, param1);
             } else {
                 SDFB_CUDA(cudaMemsetAsync(L.terminal.p, 0, L.count));
             }
@@ -954,7 +1012,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
         if (junctions) {
             candCount.ensure(L.count);
             candWords.ensure(size_t(L.count) * 18);
-            contJunctionKernel<<<grid8, kWarpsPerCta * 32>>>(grid, L.arrays(), d, mids.p, coeffs.p, oc.oct.p, sqThreshold, candCount.p, candWords.p);
+            contJunctionKernel<<<grid8, kWarpsPerCta * 32>>>(grid, L.arrays(), d, midsPtr, coeffs.p, oc.oct.p, sqThreshold, candCount.p, candWords.p);
             candCount32.ensure(L.count);
             candScan.ensure(L.count);
             widenCountsKernel<<<divUp(L.count, 256), 256>>>(candCount.p, candCount32.p, L.count);
@@ -969,8 +1027,8 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
         const uint32_t nSub = scanner.run(sub.p, subScan.p, L.count);
         oc.reserve(words + levelWords);
         NodeLevel& N = *levels[d + 1];
-        N.alloc(nSub * 8);
-        contEmitKernel<<<grid8, kWarpsPerCta * 32>>>(grid, L.arrays(), N.arrays(), d, real, deepest, mids.p, coeffs.p, sizeScan.p, subScan.p,
+        if (!childrenExist) N.alloc(nSub * 8);
+        contEmitKernel<<<grid8, kWarpsPerCta * 32>>>(grid, L.arrays(), N.arrays(), d, real, deepest, midsPtr, coeffs.p, sizeScan.p, subScan.p,
                                                      uint32_t(words), oc.oct.p, oc.leafRef.p, junctions ? candCount.p : nullptr, candWords.p,
                                                      candScan.p, candList.p, scalars.p);
         st.kernel_launches += 8;
