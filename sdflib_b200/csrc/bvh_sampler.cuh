@@ -202,7 +202,7 @@ sampleOwnersKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const
 // (distance, gradient) by a dense second kernel instead of inside the divergent loop.
 __global__ void __launch_bounds__(kBvhThreads)
 sampleOwnersRefillKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const uint32_t* __restrict__ owners, uint32_t first,
-                         uint32_t count, float4* results, uint32_t* counter, int leafBatch) {
+                         uint32_t count, float4* results, uint32_t* counter, int leafBatch, const uint32_t* __restrict__ schedule) {
     constexpr unsigned kFull = 0xffffffffu;
     const BvhStack st = bvhStackOfThread(mesh);
     const unsigned lane = threadIdx.x & 31u;
@@ -224,8 +224,11 @@ sampleOwnersRefillKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf,
                 if (int(lane) == leader) base = atomicAdd(counter, uint32_t(__popc(idle)));
                 base = __shfl_sync(kFull, base, leader);
                 if (!c.active) {
-                    const uint32_t mine = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
-                    if (mine < count) {
+                    const uint32_t slot = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
+                    if (slot < count) {
+                        // `schedule` (optional) is the order in which the samples are STARTED: the expensive ones first, so that
+                        // their long traversals run under everybody else's work instead of after it (LevelSampler::run)
+                        const uint32_t mine = schedule ? schedule[slot] : slot;
                         item = mine;
                         const f3 pf = latticeSamplePosition(centerHalf, owners[first + mine]);
                         c.p = mkd(double(pf.x), double(pf.y), double(pf.z));

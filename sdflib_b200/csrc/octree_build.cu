@@ -419,6 +419,7 @@ struct OctreeBuildState : BuildState {
             if (batched) SDFB_CUDA(cudaEventRecord(seed.done, seed.s));
         }
         DevBuf<float4> preMids, preCentres;
+        DevBuf<float> nodeCost;
         std::vector<uint32_t> preOffset(depth + 2, 0u);
         if (batched) {
             uint32_t total = 0;
@@ -452,8 +453,12 @@ struct OctreeBuildState : BuildState {
             flags.alloc(L.count);
             scan.alloc(L.count);
             const uint32_t grid = divUp(L.count, kWarpsPerCta);
-            if (!presampled)
-            { const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 1); st.leaves += ran == 0xFFFFFFFFu ? uint64_t(L.count) * 19 : ran; }   // stats.leaves: BVH traversals run
+            if (!presampled) {
+                nodeCost.ensure(L.count);   // start order of the traversals: nodes far from the surface first (LevelSampler::run)
+                nodeCostKernel<<<divUp(L.count, 256), 256>>>(L.corners.p, 8, 1, L.count, 1.0f / boxSize, nodeCost.p);
+                const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 1, nodeCost.p);
+                st.leaves += ran == 0xFFFFFFFFu ? uint64_t(L.count) * 19 : ran;   // stats.leaves: BVH traversals run
+            }
             if (d >= startDepth)
                 levelDecideKernel<<<grid, kWarpsPerCta * 32>>>(L.view(), midsPtr, flags.p, rule, param0 * param0, param1);
             else

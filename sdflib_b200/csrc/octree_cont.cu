@@ -950,6 +950,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
     }
     uint32_t pendingDepth = 0, pendingCand = 0;
     DevBuf<float4> preMids, preCentres;
+    DevBuf<float> nodeCost;
     std::vector<uint32_t> preOffset(depth + 2, 0u);
     if (batched) {
         uint32_t total = 0;
@@ -991,7 +992,9 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
             if (!presampled) {
                 mids.ensure(size_t(L.count) * 38);
                 midsPtr = mids.p;
-                const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 2);
+                nodeCost.ensure(L.count);   // start order of the traversals: nodes far from the surface first (LevelSampler::run)
+                nodeCostKernel<<<divUp(L.count, 256), 256>>>(L.values.p, 16, 2, L.count, 1.0f / (out.boxMax[0] - out.boxMin[0]), nodeCost.p);
+                const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 2, nodeCost.p);
                 st.leaves += ran == 0xFFFFFFFFu ? uint64_t(L.count) * 19 : ran;   // stats.leaves: BVH traversals run
             }
             if (pendingCand) { runFixup(pendingDepth, pendingCand); pendingCand = 0; }   // the previous depth's fix-up, under this sampling

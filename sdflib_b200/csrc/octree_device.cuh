@@ -116,6 +116,50 @@ inline bool sampleRefillEnabled() {
     return on;
 }
 
+// ---- start order of a level's traversals -------------------------------------------------------------------------------------
+// A level's launch lasts as long as its longest traversals when those start late: samples far from the surface (deep inside the
+// mesh, or in the corners of the box) visit thousands of nodes — milliseconds of dependent steps — while the bulk takes a few
+// hundred. With the lane-refill schedule the samples are handed out in index order; here they are bucketed by the distance the
+// node's corners already know (min |corner value|, relative to the box) and the far buckets are handed out first.
+__global__ void nodeCostKernel(const float4* __restrict__ cornerValues, int perNode, int perCorner, uint32_t count, float invScale, float* __restrict__ cost) {
+    const uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= count) return;
+    float m = INFINITY;
+    for (int k = 0; k < 8; k++) m = fminf(m, fabsf(cornerValues[size_t(node) * perNode + size_t(k) * perCorner].x));
+    cost[node] = m * invScale;
+}
+__device__ __forceinline__ uint32_t costBucket(float c) { return c > 0.25f ? 0u : (c > 0.12f ? 1u : (c > 0.05f ? 2u : 3u)); }
+__global__ void scheduleCountKernel(const uint32_t* __restrict__ owners, uint32_t n, const float* __restrict__ nodeCost, uint32_t* counts) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = u < n ? costBucket(nodeCost[owners[u] / 19u]) : 4u;
+    for (uint32_t k = 0; k < 4; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, b == k);
+        if (m && (threadIdx.x & 31u) == uint32_t(__ffs(int(m)) - 1)) atomicAdd(counts + k, uint32_t(__popc(m)));
+    }
+}
+__global__ void scheduleOffsetsKernel(uint32_t* counts) {   // counts[0..3] -> cursors[4..7] (exclusive prefix, far buckets first)
+    uint32_t run = 0;
+    for (int k = 0; k < 4; k++) { counts[4 + k] = run; run += counts[k]; }
+}
+__global__ void scheduleScatterKernel(const uint32_t* __restrict__ owners, uint32_t n, const float* __restrict__ nodeCost, uint32_t* counts, uint32_t* __restrict__ schedule) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = u < n ? costBucket(nodeCost[owners[u] / 19u]) : 4u;
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t k = 0; k < 4; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, b == k);
+        if (!m) continue;
+        const int leader = __ffs(int(m)) - 1;
+        uint32_t base = 0;
+        if (int(lane) == leader) base = atomicAdd(counts + 4 + k, uint32_t(__popc(m)));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (b == k) schedule[base + uint32_t(__popc(m & ((1u << lane) - 1u)))] = u;
+    }
+}
+inline bool sampleScheduleEnabled() {   // A/B switch: SDFB200_SAMPLE_SCHEDULE=0 hands the samples out in index order
+    static const bool on = [] { const char* e = std::getenv("SDFB200_SAMPLE_SCHEDULE"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 inline int sampleLeafBatch() {   // lanes of a warp that must hold a leaf before the leaf branch runs (1 = take leaves as they come)
     static const int v = [] { const char* e = std::getenv("SDFB200_LEAF_BATCH"); const int x = e ? std::atoi(e) : 1; return x < 1 ? 1 : (x > 32 ? 32 : x); }();
     return v;
@@ -134,7 +178,8 @@ __global__ void dedupeScatterKernel(const uint32_t* __restrict__ rep, const uint
 struct LevelSampler {
     DevBuf<uint32_t> table, rep, isOwner, pos, owners;
     DevBuf<float4> results, slice;
-    DevBuf<uint32_t> refillCounter;   // EXPERIMENTAL lane-refill schedule: next unassigned sample of the launch
+    DevBuf<uint32_t> refillCounter;   // lane-refill schedule: next unassigned sample of the launch
+    DevBuf<uint32_t> schedule, scheduleCounts;   // ... and the order in which the samples are started (far ones first)
     Scanner scanner;
     SampleExchange exchange;   // world > 1: every rank traverses the BVH for its slice of the distinct positions only
     cudaStream_t stream = nullptr;   // where this sampler's launches go (legacy default stream unless a pass runs on a side stream)
@@ -158,7 +203,8 @@ struct LevelSampler {
         return results.p;   // item u sits at block u / per, offset u % per = index u
     }
 
-    uint32_t run(const DeviceMesh& mesh, const float4* centerHalf, uint32_t count, float4* out, int stride) {
+    // nodeCost (optional): per node, min |corner distance| / box size — decides the start order of the traversals only
+    uint32_t run(const DeviceMesh& mesh, const float4* centerHalf, uint32_t count, float4* out, int stride, const float* nodeCost = nullptr) {
         const uint64_t n64 = uint64_t(count) * 19;
         if (n64 >= (uint64_t(1) << 30)) {   // the table (2 n slots, 32-bit sample indices) would pass 2^31 slots: plain path
             if (exchange.world > 1) throw Error(SDFB200_ERR_INVALID, "more than 2^30 samples on one level of a collective build");
@@ -176,12 +222,21 @@ struct LevelSampler {
         owners.ensure(nUnique);
         dedupeOwnersKernel<<<divUp(n, 256), 256, 0, stream>>>(isOwner.p, pos.p, n, owners.p);
         const uint32_t* ownersPtr = owners.p;
+        const uint32_t* schedulePtr = nullptr;
+        if (nodeCost && nUnique > 8192 && exchange.world <= 1 && sampleRefillEnabled() && sampleScheduleEnabled()) {
+            schedule.ensure(nUnique); scheduleCounts.ensure(8);
+            SDFB_CUDA(cudaMemsetAsync(scheduleCounts.p, 0, 8 * sizeof(uint32_t), stream));
+            scheduleCountKernel<<<divUp(nUnique, 256), 256, 0, stream>>>(owners.p, nUnique, nodeCost, scheduleCounts.p);
+            scheduleOffsetsKernel<<<1, 1, 0, stream>>>(scheduleCounts.p);
+            scheduleScatterKernel<<<divUp(nUnique, 256), 256, 0, stream>>>(owners.p, nUnique, nodeCost, scheduleCounts.p, schedule.p);
+            schedulePtr = schedule.p;
+        }
         const float4* res = shared(nUnique, [&](uint32_t first, uint32_t cnt, float4* dst) {
-            if (sampleRefillEnabled()) {   // EXPERIMENTAL, see sampleOwnersRefillKernel
+            if (sampleRefillEnabled()) {   // see sampleOwnersRefillKernel
                 refillCounter.ensure(1);
                 SDFB_CUDA(cudaMemsetAsync(refillCounter.p, 0, sizeof(uint32_t), stream));
                 const uint32_t blocks = std::min<uint32_t>(divUp(cnt, kBvhThreads), 148u * 8u);
-                sampleOwnersRefillKernel<<<blocks, kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst, refillCounter.p, sampleLeafBatch());
+                sampleOwnersRefillKernel<<<blocks, kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst, refillCounter.p, sampleLeafBatch(), schedulePtr);
                 finishOwnersKernel<<<divUp(cnt, 256), 256, 0, stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst);
                 return;
             }

@@ -5,7 +5,7 @@
 // terminate and give, sample for sample, the bits of the plain one-sample-per-thread kernel (sampleOwnersKernel, the
 // measured default path). Mesh set-up (TriangleData, BVH) comes from the product library's host functions.
 //
-//   simt_sampler_main <isosphere subdivisions> <nodes> [leaf batch]      prints "ok <samples> identical"
+//   simt_sampler_main <isosphere subdivisions> <nodes> [leaf batch] [scheduled: 0|1]      prints "ok <samples> identical"
 #include <algorithm>
 #include <barrier>
 #include <cfloat>
@@ -129,8 +129,11 @@ int main(int argc, char** argv) {
     std::memset(refill.data(), 0xCD, count * sizeof(float4));
     simt::launch((count + 127) / 128, 128, [&] { sampleOwnersKernel(mesh, centerHalf.data(), owners.data(), first, count, plain.data()); });
     uint32_t counter = 0;
+    // optional start order (fifth argument != 0): a permutation of the slots, here simply reversed with a stride
+    std::vector<uint32_t> schedule;
+    if (argc > 4 && std::atoi(argv[4])) { schedule.resize(count); for (uint32_t u = 0; u < count; u++) schedule[u] = uint32_t((uint64_t(count - 1 - u) * 7919u) % count); }
     const unsigned blocks = std::min<unsigned>((count + 127) / 128, 148u * 8u);
-    simt::launch(blocks, 128, [&] { sampleOwnersRefillKernel(mesh, centerHalf.data(), owners.data(), first, count, refill.data(), &counter, leafBatch); });
+    simt::launch(blocks, 128, [&] { sampleOwnersRefillKernel(mesh, centerHalf.data(), owners.data(), first, count, refill.data(), &counter, leafBatch, schedule.empty() ? nullptr : schedule.data()); });
     if (counter < count) { std::fprintf(stderr, "counter %u < count %u\n", counter, count); return 1; }
     for (uint32_t u = 0; u < count; u++) {   // parked nearest triangle must be a valid id before the finishing pass
         int t;

@@ -240,6 +240,7 @@ def test_refill_sampler_source_under_warp_emulation(sdf, tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     # third argument: the leaf-batch threshold of the refill kernel (1 = the default schedule; larger values were measured slower
     # on the GPU but must stay correct: they are reachable through SDFB200_LEAF_BATCH)
-    for subdivisions, nodes, leaf_batch in ((4, 120, 1), (0, 3, 1), (2, 1, 1), (3, 40, 8), (3, 40, 32)):
-        r = subprocess.run([exe, str(subdivisions), str(nodes), str(leaf_batch)], capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0 and "identical" in r.stdout, (subdivisions, nodes, leaf_batch, r.stdout, r.stderr)
+    # fourth argument: 1 = the samples are started in a permuted order (the far-first schedule of LevelSampler::run)
+    for subdivisions, nodes, leaf_batch, scheduled in ((4, 120, 1, 0), (4, 120, 1, 1), (0, 3, 1, 1), (2, 1, 1, 1), (3, 40, 8, 0), (3, 40, 32, 1)):
+        r = subprocess.run([exe, str(subdivisions), str(nodes), str(leaf_batch), str(scheduled)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "identical" in r.stdout, (subdivisions, nodes, leaf_batch, scheduled, r.stdout, r.stderr)
