@@ -122,6 +122,16 @@ __global__ void childGeometryKernel(LevelView lv, float4* nextCenterHalf, uint32
     nextCoord[e] = ix | (iy << 10) | (iz << 20);
 }
 
+// speculative samples of ALL children of a level -> the samples of the children that exist (childOf: first child or kNoChild)
+__global__ void gatherSpeculativeKernel(const uint32_t* __restrict__ childOf, uint32_t parents, const float4* __restrict__ spec, int perNode, float4* __restrict__ mids) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint64_t perParent = uint64_t(8) * perNode;
+    if (i >= uint64_t(parents) * perParent) return;
+    const uint32_t p = uint32_t(i / perParent), r = uint32_t(i % perParent);
+    const uint32_t base = childOf[p];
+    if (base != kNoChild) mids[size_t(base) * perNode + r] = spec[i];
+}
+
 // Children of the subdividing nodes: 8 records each, corner values inherited from the 27-point lattice
 // (child c, corner k  <-  lattice point (c+k) per axis; OctreeSdfDepthFirst.h:225-336).
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
@@ -420,6 +430,9 @@ struct OctreeBuildState : BuildState {
         }
         DevBuf<float4> preMids, preCentres;
         DevBuf<float> nodeCost;
+        DevBuf<uint32_t> specCoord;
+        static const bool speculativeLevel = [] { const char* e = std::getenv("SDFB200_SPECULATIVE_LEVEL"); return !(e && e[0] == '0'); }();
+        bool speculate = false;
         std::vector<uint32_t> preOffset(depth + 2, 0u);
         if (batched) {
             uint32_t total = 0;
@@ -434,9 +447,19 @@ struct OctreeBuildState : BuildState {
                 childGeometryKernel<<<divUp(uint64_t(L.count) * 8, 256), 256>>>(L.view(), N.centerHalf.p, N.coord.p);
                 st.kernel_launches++;
             }
-            preCentres.alloc(total);
+            // ... and, speculatively, of all eight children of every start node: most start nodes subdivide (438 of 512 on the C2 mesh),
+            // and the level below the start depth is still a few hundred CTAs that wait for their far-field traversals
+            speculate = speculativeLevel && world == 1 && startDepth + 1 < depth;
+            const uint32_t nStart = levels[startDepth]->count;
+            preOffset[startDepth + 1] = total;
+            preCentres.alloc(total + (speculate ? nStart * 8 : 0));
             for (uint32_t d = d0; d <= startDepth; d++)
                 SDFB_CUDA(cudaMemcpyAsync(preCentres.p + preOffset[d], levels[d]->centerHalf.p, size_t(levels[d]->count) * sizeof(float4), cudaMemcpyDeviceToDevice));
+            if (speculate) {
+                specCoord.alloc(size_t(nStart) * 8);
+                childGeometryKernel<<<divUp(uint64_t(nStart) * 8, 256), 256>>>(levels[startDepth]->view(), preCentres.p + total, specCoord.p);
+                total += nStart * 8;
+            }
             preMids.alloc(size_t(total) * 19);
             const uint32_t ran = levelSampler.run(dmesh, preCentres.p, total, preMids.p, 1);
             st.leaves += ran == 0xFFFFFFFFu ? uint64_t(total) * 19 : ran;
@@ -448,12 +471,18 @@ struct OctreeBuildState : BuildState {
             if (d == depth) break;
             if (L.count == 0) { levels[d + 1].reset(new Level()); continue; }
             const bool presampled = batched && d <= startDepth;
+            const bool gathered = speculate && d == startDepth + 1;
             if (!presampled) mids.alloc(size_t(L.count) * 19);
+            if (gathered) {
+                const Level& P = *levels[startDepth];
+                gatherSpeculativeKernel<<<divUp(uint64_t(P.count) * 8 * 19, 256), 256>>>(P.childOf.p, P.count, preMids.p + size_t(preOffset[d]) * 19, 19, mids.p);
+                st.leaves += 0;
+            }
             const float4* midsPtr = presampled ? preMids.p + size_t(preOffset[d]) * 19 : mids.p;
             flags.alloc(L.count);
             scan.alloc(L.count);
             const uint32_t grid = divUp(L.count, kWarpsPerCta);
-            if (!presampled) {
+            if (!presampled && !gathered) {
                 nodeCost.ensure(L.count);   // start order of the traversals: nodes far from the surface first (LevelSampler::run)
                 nodeCostKernel<<<divUp(L.count, 256), 256>>>(L.corners.p, 8, 1, L.count, 1.0f / boxSize, nodeCost.p);
                 const uint32_t ran = levelSampler.run(dmesh, L.centerHalf.p, L.count, mids.p, 1, nodeCost.p);

@@ -203,6 +203,16 @@ __global__ void contChildGeometryKernel(uint32_t count, const float4* centerHalf
     nextCoord[e] = ix | (iy << 10) | (iz << 20);
 }
 
+// speculative samples of ALL children of a level -> the samples of the children that exist (sub / subScan of the parents' Iter 2)
+__global__ void contGatherSpeculativeKernel(const uint32_t* __restrict__ sub, const uint32_t* __restrict__ subScan, uint32_t parents, const float4* __restrict__ spec,
+                                            float4* __restrict__ mids) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    constexpr uint64_t perParent = 8 * 38;
+    if (i >= uint64_t(parents) * perParent) return;
+    const uint32_t p = uint32_t(i / perParent), r = uint32_t(i % perParent);
+    if (sub[p]) mids[size_t(subScan[p]) * perParent + r] = spec[i];
+}
+
 // corner samples of the seed nodes (:197-221)
 __global__ void contSeedKernel(DeviceMesh mesh, Grid g, LevelArrays lv, uint32_t depth) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -951,6 +961,9 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
     uint32_t pendingDepth = 0, pendingCand = 0;
     DevBuf<float4> preMids, preCentres;
     DevBuf<float> nodeCost;
+    DevBuf<uint32_t> specCoord;
+    static const bool speculativeLevel = [] { const char* e = std::getenv("SDFB200_SPECULATIVE_LEVEL"); return !(e && e[0] == '0'); }();
+    bool speculate = false;
     std::vector<uint32_t> preOffset(depth + 2, 0u);
     if (batched) {
         uint32_t total = 0;
@@ -965,9 +978,18 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
             contChildGeometryKernel<<<divUp(uint64_t(L.count) * 8, 256), 256>>>(L.count, L.centerHalf.p, L.coord.p, N.centerHalf.p, N.coord.p);
             st.kernel_launches++;
         }
-        preCentres.alloc(total);
+        // ... and, speculatively, of all eight children of every start node (octree_build.cu)
+        speculate = speculativeLevel && exchange.world <= 1 && startDepth + 1 < depth;
+        const uint32_t nStart = levels[startDepth]->count;
+        preOffset[startDepth + 1] = total;
+        preCentres.alloc(total + (speculate ? nStart * 8 : 0));
         for (uint32_t d = d0; d <= startDepth; d++)
             SDFB_CUDA(cudaMemcpyAsync(preCentres.p + preOffset[d], levels[d]->centerHalf.p, size_t(levels[d]->count) * sizeof(float4), cudaMemcpyDeviceToDevice));
+        if (speculate) {
+            specCoord.alloc(size_t(nStart) * 8);
+            contChildGeometryKernel<<<divUp(uint64_t(nStart) * 8, 256), 256>>>(nStart, levels[startDepth]->centerHalf.p, levels[startDepth]->coord.p, preCentres.p + total, specCoord.p);
+            total += nStart * 8;
+        }
         preMids.alloc(size_t(total) * 38);
         const uint32_t ran = levelSampler.run(dmesh, preCentres.p, total, preMids.p, 2);
         st.leaves += ran == 0xFFFFFFFFu ? uint64_t(total) * 19 : ran;
@@ -989,7 +1011,13 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
         // ---- Iter 1
         float4* midsPtr = presampled ? preMids.p + size_t(preOffset[d]) * 38 : mids.p;
         if (!deepest) {
-            if (!presampled) {
+            const bool gathered = speculate && d == startDepth + 1;
+            if (gathered) {   // sub / subScan still hold the start level's Iter 2
+                mids.ensure(size_t(L.count) * 38);
+                midsPtr = mids.p;
+                const uint32_t parents = levels[startDepth]->count;
+                contGatherSpeculativeKernel<<<divUp(uint64_t(parents) * 8 * 38, 256), 256>>>(sub.p, subScan.p, parents, preMids.p + size_t(preOffset[d]) * 38, mids.p);
+            } else if (!presampled) {
                 mids.ensure(size_t(L.count) * 38);
                 midsPtr = mids.p;
                 nodeCost.ensure(L.count);   // start order of the traversals: nodes far from the surface first (LevelSampler::run)
