@@ -165,6 +165,9 @@ static __global__ void __launch_bounds__(kFlagThreads) flagBlockSums(const uint8
     }
 }
 
+// kGroups: out[i / 16] = position of the first flag of every group of 16 only (flagPositionAt recovers any position from it and
+// the flags: the pair passes of the ExactOctreeSdf builder run over billions of pairs, and 4 bytes per pair were half of its memory)
+template <bool kGroups>
 static __global__ void __launch_bounds__(kFlagThreads) flagFinalize(const uint8_t* in, const uint32_t* blockSums, uint32_t* out, uint64_t n) {
     __shared__ uint32_t warpTotals[32];
     const uint64_t i = (uint64_t(blockIdx.x) * kFlagThreads + threadIdx.x) * kFlagsPerThread;
@@ -183,6 +186,7 @@ static __global__ void __launch_bounds__(kFlagThreads) flagFinalize(const uint8_
     uint32_t base = blockSums[blockIdx.x] + inc - mine;
     for (int w = 0; w < warp; w++) base += warpTotals[w];
     if (i >= n) return;
+    if (kGroups) { out[i >> 4] = base; return; }
     const uint32_t words[4] = {f.x, f.y, f.z, f.w};
     uint32_t pos[16];
 #pragma unroll
@@ -208,10 +212,35 @@ struct FlagScanner {
         if (blockSums.n < nBlocks) blockSums.alloc(size_t(nBlocks) + 64);
         flagBlockSums<<<nBlocks, kFlagThreads, 0, st>>>(in, blockSums.p, n);
         scanOfBlockSums<uint32_t><<<1, kScanBlock, 0, st>>>(blockSums.p, nBlocks, total.p);
-        flagFinalize<<<nBlocks, kFlagThreads, 0, st>>>(in, blockSums.p, out, n);
+        flagFinalize<false><<<nBlocks, kFlagThreads, 0, st>>>(in, blockSums.p, out, n);
+        return readScalar<uint32_t>(total.p, st);
+    }
+    // out: (n + 15) / 16 entries, the position of the first flag of each group of 16
+    uint32_t runGroups(const uint8_t* in, uint32_t* outGroups, uint64_t n, cudaStream_t st = 0) {
+        if (!total.p) total.alloc(1);
+        if (n == 0) return 0;
+        const uint32_t nBlocks = divUp(n, kFlagsPerBlock);
+        if (blockSums.n < nBlocks) blockSums.alloc(size_t(nBlocks) + 64);
+        flagBlockSums<<<nBlocks, kFlagThreads, 0, st>>>(in, blockSums.p, n);
+        scanOfBlockSums<uint32_t><<<1, kScanBlock, 0, st>>>(blockSums.p, nBlocks, total.p);
+        flagFinalize<true><<<nBlocks, kFlagThreads, 0, st>>>(in, blockSums.p, outGroups, n);
         return readScalar<uint32_t>(total.p, st);
     }
 };
+
+// position (exclusive count of set flags before i) from the group positions of FlagScanner::runGroups; i < n
+static __device__ __forceinline__ uint32_t flagPositionAt(const uint8_t* flags, const uint32_t* groupPos, uint64_t i, uint64_t n) {
+    const uint64_t g = i & ~uint64_t(15);
+    const uint32_t k = uint32_t(i - g);
+    uint32_t at = groupPos[g >> 4];
+    if (k == 0) return at;
+    const uint4 f = loadFlags16(flags, g, n);
+    const uint32_t w[4] = {f.x, f.y, f.z, f.w};
+    const uint32_t whole = k >> 2, rest = k & 3u;                          // whole words, then the low bytes of the next one
+    for (uint32_t q = 0; q < whole; q++) at += uint32_t(__popc(w[q]));
+    if (rest) at += uint32_t(__popc(w[whole] & ((1u << (8 * rest)) - 1u)));
+    return at;
+}
 
 // 64-bit count of set flags: guards the 32-bit flag scans (their totals would wrap silently) once a pass has
 // more than 2^32 pairs.

@@ -220,21 +220,22 @@ compactKernel(LevelView lv, const uint32_t* __restrict__ parentList, const uint8
     node = __shfl_sync(0xffffffffu, node, 0);
     if (!any) return;
     const uint32_t words[4] = {f.x, f.y, f.z, f.w};
+    uint32_t at = pos[p0 >> 4];                                            // group positions (FlagScanner::runGroups)
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         if (!((words[k >> 2] >> (8 * (k & 3))) & 1u)) continue;
         const uint64_t p = p0 + k;
         while (p >= lv.pairOff[node + 1]) node++;
-        list[pos[p]] = parentList[lv.parentLo[node] + uint32_t(p - lv.pairOff[node])];
+        list[at++] = parentList[lv.parentLo[node] + uint32_t(p - lv.pairOff[node])];
     }
 }
 
-__global__ void listRangeKernel(const uint64_t* pairOff, const uint32_t* pos, uint64_t numPairs, uint32_t total, uint32_t* listLo,
+__global__ void listRangeKernel(const uint64_t* pairOff, const uint8_t* flags, const uint32_t* pos, uint64_t numPairs, uint32_t total, uint32_t* listLo,
                                 uint32_t* listCnt, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t a = pairOff[i], b = pairOff[i + 1];
-    const uint32_t lo = a < numPairs ? pos[a] : total, hi = b < numPairs ? pos[b] : total;
+    const uint32_t lo = a < numPairs ? flagPositionAt(flags, pos, a, numPairs) : total, hi = b < numPairs ? flagPositionAt(flags, pos, b, numPairs) : total;
     listLo[i] = lo;
     listCnt[i] = hi - lo;
 }
@@ -407,7 +408,8 @@ childrenKernel(LevelView lv, const uint32_t* __restrict__ coord, const uint32_t*
 struct MergeChildView {
     const uint64_t* pairOff;     // child level
     const uint8_t* flags;        // child level keep flags per pair
-    const uint32_t* pos;         // child level list position per pair
+    const uint32_t* pos;         // child level list position per group of 16 pairs
+    uint64_t numPairs;           // child level
     const uint32_t* childOf;     // child level: kNone = leaf
     const uint8_t* member;       // child level member bytes (null when the child level is the deepest one)
 };
@@ -430,7 +432,7 @@ memberKernel(const uint32_t* __restrict__ listLo, const uint32_t* __restrict__ c
         for (uint32_t c = 0; c < 8; c++) {
             const uint64_t pp = ch.pairOff[c0 + c] + j;
             bool f = ch.flags[pp] != 0;
-            if (f && ch.member != nullptr && ch.childOf[c0 + c] != kNone) f = ch.member[ch.pos[pp]] != 0;
+            if (f && ch.member != nullptr && ch.childOf[c0 + c] != kNone) f = ch.member[flagPositionAt(ch.flags, ch.pos, pp, ch.numPairs)] != 0;
             m |= f ? (1u << c) : 0u;
         }
     }
@@ -746,18 +748,18 @@ struct ExactBuildState : BuildState {
             if (region.n < size_t(L.count) * 72) region.alloc(size_t(L.count) * 72);
             regionKernel<<<divUp(L.count, 4), 256>>>(dFramesP, L.view(), region.p);
             L.flags.alloc(L.numPairs + 1);
-            L.pos.alloc(L.numPairs + 1);
+            L.pos.alloc(L.numPairs / 16 + 2);   // one position per group of 16 pairs
             if (L.numPairs) filterRefillKernel<<<divUp(L.numPairs, 8 * kFilterChunk), 256>>>(dmesh, L.view(), parentList, region.p, L.flags.p, L.numPairs);
             SDFB_CUDA(cudaGetLastError());
             if (L.numPairs >= (uint64_t(1) << 32)) {   // the 32-bit scan below would wrap silently: count the kept pairs in 64 bits first
                 const uint64_t kept = countFlags64(L.flags.p, L.numPairs);
                 if (kept >= (1ull << 32)) throw Error(SDFB200_ERR_INVALID, "more than 2^32 triangle-list entries on one octree level");
             }
-            L.listTotal = L.numPairs ? scanFlags.run(L.flags.p, L.pos.p, L.numPairs) : 0u;
+            L.listTotal = L.numPairs ? scanFlags.runGroups(L.flags.p, L.pos.p, L.numPairs) : 0u;
             L.list.alloc(size_t(L.listTotal) + 8);   // + 8: the TMA window of the sample kernel may read past the end
             SDFB_CUDA(cudaMemsetAsync(L.list.p + L.listTotal, 0, 8 * sizeof(uint32_t)));
             if (L.numPairs) compactKernel<<<divUp(L.numPairs, 256 * 16), 256>>>(L.view(), parentList, L.flags.p, L.pos.p, L.list.p, L.numPairs);
-            listRangeKernel<<<divUp(L.count, 256), 256>>>(L.pairOff.p, L.pos.p, L.numPairs, L.listTotal, L.listLo.p, L.listCnt.p, L.count);
+            listRangeKernel<<<divUp(L.count, 256), 256>>>(L.pairOff.p, L.flags.p, L.pos.p, L.numPairs, L.listTotal, L.listLo.p, L.listCnt.p, L.count);
             st.kernel_launches += 10;
             st.nodes_processed += L.count;
             st.samples_evaluated += L.numPairs;   // Frank-Wolfe runs
@@ -795,7 +797,7 @@ struct ExactBuildState : BuildState {
             if (L.count == 0) { if (d == 0) break; continue; }
             L.member.alloc(size_t(L.listTotal) + 1); keep.alloc(size_t(L.listTotal) + 1); mpos.alloc(size_t(L.listTotal) + 1);
             if (L.listTotal) {
-                MergeChildView cv{C.pairOff.p, C.flags.p, C.pos.p, C.childOf.p, d + 1 == maxDepth ? nullptr : C.member.p};
+                MergeChildView cv{C.pairOff.p, C.flags.p, C.pos.p, C.numPairs, C.childOf.p, d + 1 == maxDepth ? nullptr : C.member.p};
                 memberKernel<<<divUp(L.listTotal, 256), 256>>>(L.listLo.p, L.childOf.p, L.count, L.listTotal, cv, L.member.p, keep.p);
                 L.mergedTotal = scanFlags.run(keep.p, mpos.p, L.listTotal);
             }
