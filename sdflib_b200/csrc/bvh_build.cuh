@@ -644,10 +644,46 @@ __global__ void __launch_bounds__(256) bvhIotaKernel(int32_t n, int32_t* ids) {
     if (i < int64_t(n)) ids[i] = int32_t(i);
 }
 
+// The longest centre chains on the HOST. A dependent float64 addition takes ~30 cycles on the device and ~1 ns on a host
+// core, and the chains of the top levels are the critical path of the whole build (level 1: half of the triangles each), so a
+// runtime may take them: it gets the order snapshot of the level and fills centres[slot * 3 + axis] (bvhHostCentres: the same
+// serial sum over the same order), which bvhPutCentresKernel stores where bvhCentreKernel would have. The radius pass follows as
+// usual. The sorting — the parallel part — stays on the device, and nothing waits for the host except the radii of those levels.
+template <class Vertex>   // Vertex(triangle, k) -> const float* (x, y, z)
+inline void bvhHostCentres(int32_t n, int level, const int32_t* order, uint32_t slotBegin, uint32_t slotEnd, Vertex vertex, double* centres) {
+    for (uint32_t slot = slotBegin; slot < slotEnd; slot++) {
+        const BvhSeg s = bvhSegOfSlot(n, level, slot);
+        double c[3] = {0.0, 0.0, 0.0};
+        if (s.valid && s.e - s.b > 1) {
+            for (int32_t i = s.b; i < s.e; i++)
+                for (int k = 0; k < 3; k++) {
+                    const float* v = vertex(order[i], k);
+                    c[0] += double(v[0]); c[1] += double(v[1]); c[2] += double(v[2]);
+                }
+            const double count = double(3 * (s.e - s.b));
+            for (int a = 0; a < 3; a++) c[a] /= count;
+        }
+        for (int a = 0; a < 3; a++) centres[size_t(slot) * 3 + a] = c[a];
+    }
+}
+__global__ void bvhPutCentresKernel(int32_t n, int level, const double* __restrict__ centres, BvhNode* nodes) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= (1u << level)) return;
+    const BvhSeg s = bvhSegOfSlot(n, level, slot);
+    if (!s.valid || s.e - s.b <= 1 || s.parent < 0) return;
+    double* out = bvhSphereSlot(nodes, s);
+    for (int a = 0; a < 3; a++) out[a] = centres[size_t(slot) * 3 + a];
+}
+#ifndef BVH_HOST_CHAIN
+#define BVH_HOST_CHAIN 32768
+#endif
+constexpr int32_t kBvhHostChain = BVH_HOST_CHAIN;   // levels whose nodes hold at least this many triangles: centre sums offered to the host
+
 // ---- the build, as a sequence of launches -------------------------------------------------------------------------------------
 // Written against a small runtime interface so that the CPU emulation of tests/cpp/simt_bvh_main.cpp drives the very same
 // sequence: BVH_LAUNCH(kernel, grid, block, stream, args...) and an Rt with
-//   fill(ptr, byte, bytes, stream), copy(dst, src, bytes, stream), mainStream(), sideStream(i), sideWaitsForMain(i), mainWaitsForSides().
+//   fill(ptr, byte, bytes, stream), copy(dst, src, bytes, stream), mainStream(), sideStream(i), sideWaitsForMain(i), mainWaitsForSides(),
+//   hostCentres(level, side, order, n, nodes): true = the runtime queued the centre sums of this level itself (on sideStream(side)).
 struct BvhShape {
     int sortLevels = 0;           // levels 0 .. sortLevels - 1 hold nodes with more than one triangle
     int nodeLevels = 0;           // levels 0 .. nodeLevels - 1 hold nodes at all
@@ -695,7 +731,8 @@ void bvhBuildLevels(Rt& rt, int32_t n, const float4* triVerts, const BvhBuffers&
             auto ss = rt.sideStream(side);
             const int wide = shape.maxSize[l] >= kBvhWarpCentre ? 1 : 0;
             const uint64_t threads = (uint64_t(1) << l) * (wide ? 32u : 1u);
-            BVH_LAUNCH(bvhCentreKernel, uint32_t((threads + 127) / 128), 128, ss, n, l, wide, order, triVerts, B.nodes);
+            if (!(shape.minSize[l] >= kBvhHostChain && rt.hostCentres(l, side, order, n, B.nodes)))
+                BVH_LAUNCH(bvhCentreKernel, uint32_t((threads + 127) / 128), 128, ss, n, l, wide, order, triVerts, B.nodes);
             BVH_LAUNCH(bvhRadiusKernel, perElement, 256, ss, n, l, order, triVerts, B.nodes);
         }
         const size_t boxBytes = (size_t(3) << l) * 4;

@@ -317,7 +317,7 @@ std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bo
     if (withBvh && !hostBvh) {
         t0 = std::chrono::steady_clock::now();
         gatherTriVerts(pm->dev);
-        buildBvhOnDevice(pm->dev);
+        buildBvhOnDevice(pm->dev, &mesh);
         pm->hasBvh = true;
         bvhMs = msSince(t0);
     }

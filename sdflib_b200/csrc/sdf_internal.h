@@ -139,7 +139,7 @@ struct PreparedMesh {
 };
 std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bool withExactParts);
 void attachBvh(PreparedMesh& pm, const RawVec<BvhNode>& bvh, double bvhMs);   // a BVH built once on the host, uploaded to pm's device
-void buildBvhOnDevice(MeshOnDevice& m);   // bvh_device.cu: m.triVerts in place -> m.bvh, rootLink, stackDepth (synchronous)
+void buildBvhOnDevice(MeshOnDevice& m, const HostMesh* host = nullptr);   // bvh_device.cu: m.triVerts in place -> m.bvh, rootLink, stackDepth (synchronous); host: the caller's arrays, for the centre sums of the top levels
 bool hostBvhRequested();                  // SDFB200_HOST_BVH: the host builder of mesh_host.cpp instead (A/B)
 uint64_t meshBlobBytes(const PreparedMesh& pm);
 void meshBlobExport(const PreparedMesh& pm, void* dDst, uint64_t capacity, cudaStream_t st);

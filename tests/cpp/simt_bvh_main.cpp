@@ -123,6 +123,15 @@ namespace {
 #include "bvh_build.cuh"
 
 struct HostRt {   // every "stream" is the calling thread
+    const float4* triVerts = nullptr;   // set: the centre sums of the top levels take the host path (bvhHostCentres + bvhPutCentresKernel)
+    int32_t hostChainMin = kBvhHostChain;
+    bool hostCentres(int level, int, const int32_t* order, int32_t n, BvhNode* nodes) {
+        if (!triVerts || (level & 1) == 0) return false;   // odd levels on the host path, even ones through bvhCentreKernel: both are checked
+        std::vector<double> centres(size_t(3) << level);
+        bvhHostCentres(n, level, order, 0u, 1u << level, [&](int32_t t, int k) { return &triVerts[size_t(t) * 3 + k].x; }, centres.data());
+        simt::launch(((1u << level) + 63) / 64, 64, [&] { bvhPutCentresKernel(n, level, centres.data(), nodes); });
+        return true;
+    }
     int mainStream() { return 0; }
     int sideStream(int) { return 0; }
     void sideWaitsForMain(int) {}
@@ -164,6 +173,7 @@ static int runMesh(uint32_t subdivisions, bool displaced, uint32_t keep) {
     BvhBuffers B{keys.data(), ids.data(), lpos.data(), rpos.data(), orders.data(), boxMin.data(), boxMax.data(), {bigA.data(), bigB.data()}, small.data(),
                  counters.data(), nodes.data()};
     HostRt rt;
+    rt.triVerts = triVerts.data();   // (kBvhHostChain is lowered by the build flags of the test, so small meshes reach the host path)
     bvhBuildLevels(rt, n, triVerts.data(), B, 3u);
 
     long bad = 0;

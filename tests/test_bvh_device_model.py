@@ -17,9 +17,10 @@ def exe(tmp_path_factory, sdf):
     out = str(tmp_path_factory.mktemp("simt_bvh") / "simt_bvh_main")
     lib_dir = os.path.join(ROOT, "sdflib_b200")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    # small CTAs and a 256-element shared-memory limit: meshes of a few thousand triangles reach the global partition rounds
+    # small CTAs and a 256-element shared-memory limit: meshes of a few thousand triangles reach the global partition rounds;
+    # BVH_HOST_CHAIN=100: the centre sums of levels with >= 100 triangles per node are offered to the host path (odd levels take it)
     cmd = [cxx, "-std=c++20", "-O1", "-ffp-contract=off", "-w", "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "include"),
-           "-I" + os.path.join(lib_dir, "csrc"), "-DBVH_SMALL_MAX=256", "-DBVH_BIG_THREADS=64", "-DBVH_SMALL_THREADS=64", "-x", "c++",
+           "-I" + os.path.join(lib_dir, "csrc"), "-DBVH_SMALL_MAX=256", "-DBVH_BIG_THREADS=64", "-DBVH_SMALL_THREADS=64", "-DBVH_HOST_CHAIN=100", "-x", "c++",
            os.path.join(ROOT, "tests", "cpp", "simt_bvh_main.cpp"), "-o", out, "-L" + lib_dir, "-lsdfb200", "-Wl,-rpath," + lib_dir, "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]

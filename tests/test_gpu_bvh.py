@@ -64,6 +64,23 @@ def test_quantised_mesh_with_massive_ties(sdf):
     assert_same_tree(device_tree(sdf, v, i), sdf.bvh_host(v, i), "quantised icosphere 6")
 
 
+def test_coordinates_of_mixed_magnitude(sdf):
+    """Centre sums are sequential float64 sums whose roundings depend on the running magnitude: a few coordinates ten orders of
+    magnitude below the rest, meshes far from the origin and extreme scales, with the top levels' sums on the host threads
+    (default) — both must give the host builder's bits."""
+    v, i = displaced_sphere(6)
+    cases = []
+    for every in (7, 1000):
+        w = v.copy()
+        k = np.arange(0, len(w), every)
+        w[k, k % 3] *= np.float32(1e-10)
+        cases.append((f"tiny coordinate every {every} vertices", w))
+    for offset, scale in ((123456.7, 1.0), (0.0, 1e-20), (0.0, 1e20), (-3.3, 1e-3)):
+        cases.append((f"offset {offset} scale {scale}", (v * np.float32(scale) + np.float32(offset)).astype(np.float32)))
+    for what, w in cases:
+        assert_same_tree(device_tree(sdf, w, i), sdf.bvh_host(w, i), what)
+
+
 @pytest.mark.parametrize("name", ["M1", "M2"])
 def test_benchmark_meshes_at_full_size(sdf, name):
     v, i = sdf.meshes.config_mesh(name)
