@@ -44,6 +44,8 @@ void prepareOctreeQuery(sdfb200_sdf& s) {
     s.topLevels = -1;
     const char* plain = std::getenv("SDFB200_QUERY_PLAIN");   // read once per structure, not per query
     s.forcePlainQuery = plain && plain[0] == '1';
+    const char* packed = std::getenv("SDFB200_QUERY_PACKED");   // A/B switch: 0 = scalar FFMA / FADD in the tile kernel
+    s.packedQuery = !(packed && packed[0] == '0');
     if (s.format != SDFB200_FORMAT_OCTREE || !s.dOctree.p) return;
     int startDepth = 0;
     while ((1 << startDepth) < s.startGridSize) startDepth++;
@@ -117,8 +119,13 @@ void launchOctreeQueryFast(
         (void)hostMapped;
         const uint64_t tiles = (n + 31) / 32;
         const uint32_t ctas = uint32_t(std::min<uint64_t>((tiles + kTileWarps - 1) / kTileWarps, uint64_t(smCount(s.device)) * 6));   // persistent: 6 CTAs per SM
-        if (dGrad) octreeQueryTileKernel<true><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, dGrad);
-        else octreeQueryTileKernel<false><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, nullptr);
+        if (s.packedQuery) {
+            if (dGrad) octreeQueryTileKernel<true, true><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, dGrad);
+            else octreeQueryTileKernel<false, true><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, nullptr);
+        } else {
+            if (dGrad) octreeQueryTileKernel<true, false><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, dGrad);
+            else octreeQueryTileKernel<false, false><<<ctas, kTileWarps * 32, 0, st>>>(s.dOctree.p, s.dTopIndex.p, q, tq, dXyz, n, dDist, nullptr);
+        }
         SDFB_CUDA(cudaGetLastError());
         return;
     }

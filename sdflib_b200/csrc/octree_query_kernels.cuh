@@ -273,13 +273,43 @@ __device__ __forceinline__ float fractSmall(float v) {
     return __fadd_rn(v, -__fadd_rn(__fadd_rd(v, 8388608.0f), -8388608.0f));
 }
 
+// Packed float32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 — one issue slot for two IEEE operations, each half rounded exactly
+// like its scalar instruction, so a packed evaluation has the bits of the scalar one). The tile kernel is issue bound.
+struct P2 { float x, y; };
+__device__ __forceinline__ P2 mkp(float x, float y) { P2 r; r.x = x; r.y = y; return r; }
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned long long p2Bits(P2 v) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y)); return r; }
+__device__ __forceinline__ P2 p2From(unsigned long long b) { P2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(b)); return r; }
+__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b)), "l"(p2Bits(c))); return p2From(r); }
+__device__ __forceinline__ P2 mul2(P2 a, P2 b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b))); return p2From(r); }
+__device__ __forceinline__ P2 add2(P2 a, P2 b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b))); return p2From(r); }
+__device__ __forceinline__ P2 add2Down(P2 a, P2 b) { unsigned long long r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b))); return p2From(r); }
+#else   // the warp emulation of tests/cpp/simt_query_main.cpp runs this source on the CPU
+__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) { return mkp(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+__device__ __forceinline__ P2 mul2(P2 a, P2 b) { return mkp(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ P2 add2(P2 a, P2 b) { return mkp(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ P2 add2Down(P2 a, P2 b) { return mkp(__fadd_rd(a.x, b.x), __fadd_rd(a.y, b.y)); }
+#endif
+// cellCoordinate / fractSmall for two coordinates at once (same operations per half)
+__device__ __forceinline__ P2 cellCoordinate2(P2 x, P2 cell, P2 rc) {
+    const P2 ncell = mkp(-cell.x, -cell.y);
+    P2 qv = mul2(x, rc);
+    qv = fma2(fma2(qv, ncell, x), rc, qv);      // fma(-q, cell, x) == fma(q, -cell, x): the product is exact either way
+    return fma2(fma2(qv, ncell, x), rc, qv);
+}
+__device__ __forceinline__ P2 fractSmall2(P2 v) {
+    const P2 big = mkp(8388608.0f, 8388608.0f), nbig = mkp(-8388608.0f, -8388608.0f);
+    const P2 fl = add2(add2Down(v, big), nbig);
+    return add2(v, mkp(-fl.x, -fl.y));
+}
+
 constexpr int kTileWarps = 8;   // warps per CTA of the tile kernel
 
 // 6 resident CTAs per SM = 40 registers: measured faster than 8 x 32 registers (which spills 36 bytes): 0.162 vs 0.174 ms.
 // Also measured and dropped: issuing the top-index load one tile ahead (a two-stage software pipeline, 48 registers,
 // 5 CTAs per SM): 0.160 vs 0.163 ms — the kernel sits on a balance of issue slots (71 %), LSU wavefronts (61 %) and
 // exposed L2 latency, and moving one of the three does not move the total.
-template <bool kGrad>
+template <bool kGrad, bool kPacked>   // kPacked: the value part and the x / y front end use the packed float32 instructions
 __global__ void __launch_bounds__(kTileWarps * 32, 6)
 octreeQueryTileKernel(const uint32_t* __restrict__ oct, const uint32_t* __restrict__ top, const QueryParams q, const TileQuery tq,
                       const float* __restrict__ xyz, uint64_t n, float* __restrict__ dist, float* __restrict__ grad) {
@@ -300,8 +330,14 @@ octreeQueryTileKernel(const uint32_t* __restrict__ oct, const uint32_t* __restri
         if (tNext < tiles && iNext < n) pNext = mk3(__ldg(xyz + 3 * iNext), __ldg(xyz + 3 * iNext + 1), __ldg(xyz + 3 * iNext + 2));
 
         // u = (p - min) / cell * 2^L: integer part = cell of the top index, fraction = position inside it
-        const float ux = cellCoordinate(__fadd_rn(p.x, -q.minx), tq.cellL, tq.rcellL), uy = cellCoordinate(__fadd_rn(p.y, -q.miny), tq.cellL, tq.rcellL),
-                    uz = cellCoordinate(__fadd_rn(p.z, -q.minz), tq.cellL, tq.rcellL);
+        float ux, uy;
+        if (kPacked) {
+            const P2 u = cellCoordinate2(add2(mkp(p.x, p.y), mkp(-q.minx, -q.miny)), mkp(tq.cellL, tq.cellL), mkp(tq.rcellL, tq.rcellL));
+            ux = u.x; uy = u.y;
+        } else {
+            ux = cellCoordinate(__fadd_rn(p.x, -q.minx), tq.cellL, tq.rcellL); uy = cellCoordinate(__fadd_rn(p.y, -q.miny), tq.cellL, tq.rcellL);
+        }
+        const float uz = cellCoordinate(__fadd_rn(p.z, -q.minz), tq.cellL, tq.rcellL);
         // 0 <= u < N as one unsigned compare of the bit pattern (negative values and NaN compare larger; -0 never occurs)
         const bool inside = valid && __float_as_uint(ux) < tq.limitBits && __float_as_uint(uy) < tq.limitBits && __float_as_uint(uz) < tq.limitBits;
         f3 g = mk3(0.0f, 0.0f, 0.0f);
@@ -328,7 +364,13 @@ octreeQueryTileKernel(const uint32_t* __restrict__ oct, const uint32_t* __restri
                 }
             }
             const float scale = __int_as_float((127 + k - tq.topLevels) << 23);   // 2^(k - L): leaf-local fraction = frac(f * 2^k)
-            fx = fractSmall(__fmul_rn(ux, scale)); fy = fractSmall(__fmul_rn(uy, scale)); fz = fractSmall(__fmul_rn(uz, scale));
+            if (kPacked) {
+                const P2 fr = fractSmall2(mul2(mkp(ux, uy), mkp(scale, scale)));
+                fx = fr.x; fy = fr.y;
+            } else {
+                fx = fractSmall(__fmul_rn(ux, scale)); fy = fractSmall(__fmul_rn(uy, scale));
+            }
+            fz = fractSmall(__fmul_rn(uz, scale));
         }
         bool pending = inside;
         for (;;) {
@@ -346,9 +388,19 @@ octreeQueryTileKernel(const uint32_t* __restrict__ oct, const uint32_t* __restri
                 const float4 c0 = __ldg(c), c1 = __ldg(c + 4), c2 = __ldg(c + 8), c3 = __ldg(c + 12);
                 const float yy = ly * ly;
                 const float yr = ((r & 1u) ? ly : 1.0f) * ((r & 2u) ? yy : 1.0f);                     // y^r
-                const float h0 = fmaf(fmaf(fmaf(c3.x, lz, c2.x), lz, c1.x), lz, c0.x), h1 = fmaf(fmaf(fmaf(c3.y, lz, c2.y), lz, c1.y), lz, c0.y);
-                const float h2 = fmaf(fmaf(fmaf(c3.z, lz, c2.z), lz, c1.z), lz, c0.z), h3 = fmaf(fmaf(fmaf(c3.w, lz, c2.w), lz, c1.w), lz, c0.w);
-                a0 = yr * h0; a1 = yr * h1; a2 = yr * h2; a3 = yr * h3;
+                float h0, h1, h2, h3;
+                if (kPacked) {
+                    const P2 z2 = mkp(lz, lz), y2 = mkp(yr, yr);
+                    const P2 h01 = fma2(fma2(fma2(mkp(c3.x, c3.y), z2, mkp(c2.x, c2.y)), z2, mkp(c1.x, c1.y)), z2, mkp(c0.x, c0.y));
+                    const P2 h23 = fma2(fma2(fma2(mkp(c3.z, c3.w), z2, mkp(c2.z, c2.w)), z2, mkp(c1.z, c1.w)), z2, mkp(c0.z, c0.w));
+                    const P2 a01 = mul2(y2, h01), a23 = mul2(y2, h23);
+                    h0 = h01.x; h1 = h01.y; h2 = h23.x; h3 = h23.y;
+                    a0 = a01.x; a1 = a01.y; a2 = a23.x; a3 = a23.y;
+                } else {
+                    h0 = fmaf(fmaf(fmaf(c3.x, lz, c2.x), lz, c1.x), lz, c0.x); h1 = fmaf(fmaf(fmaf(c3.y, lz, c2.y), lz, c1.y), lz, c0.y);
+                    h2 = fmaf(fmaf(fmaf(c3.z, lz, c2.z), lz, c1.z), lz, c0.z); h3 = fmaf(fmaf(fmaf(c3.w, lz, c2.w), lz, c1.w), lz, c0.w);
+                    a0 = yr * h0; a1 = yr * h1; a2 = yr * h2; a3 = yr * h3;
+                }
                 if (kGrad) {
                     const float dyr = r == 0 ? 0.0f : (r == 1 ? 1.0f : (r == 2 ? 2.0f * ly : 3.0f * yy));   // d y^r / dy
                     y0 = dyr * h0; y1 = dyr * h1; y2 = dyr * h2; y3 = dyr * h3;
@@ -360,8 +412,14 @@ octreeQueryTileKernel(const uint32_t* __restrict__ oct, const uint32_t* __restri
             }
 #pragma unroll
             for (int m = 1; m <= 2; m <<= 1) {                     // butterfly over the quad: all four lanes end with the same sums
-                a0 += __shfl_xor_sync(kFull, a0, m); a1 += __shfl_xor_sync(kFull, a1, m);
-                a2 += __shfl_xor_sync(kFull, a2, m); a3 += __shfl_xor_sync(kFull, a3, m);
+                if (kPacked) {
+                    const P2 s01 = add2(mkp(a0, a1), mkp(__shfl_xor_sync(kFull, a0, m), __shfl_xor_sync(kFull, a1, m)));
+                    const P2 s23 = add2(mkp(a2, a3), mkp(__shfl_xor_sync(kFull, a2, m), __shfl_xor_sync(kFull, a3, m)));
+                    a0 = s01.x; a1 = s01.y; a2 = s23.x; a3 = s23.y;
+                } else {
+                    a0 += __shfl_xor_sync(kFull, a0, m); a1 += __shfl_xor_sync(kFull, a1, m);
+                    a2 += __shfl_xor_sync(kFull, a2, m); a3 += __shfl_xor_sync(kFull, a3, m);
+                }
                 if (kGrad) {
                     y0 += __shfl_xor_sync(kFull, y0, m); y1 += __shfl_xor_sync(kFull, y1, m);
                     y2 += __shfl_xor_sync(kFull, y2, m); y3 += __shfl_xor_sync(kFull, y3, m);

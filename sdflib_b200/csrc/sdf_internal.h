@@ -231,6 +231,7 @@ struct sdfb200_sdf {
     sdfb200::DevBuf<uint32_t> dTopIndex;
     int topLevels = -1, gridShift = 0;
     bool forcePlainQuery = false;    // SDFB200_QUERY_PLAIN=1 at build / load time: one-query-per-thread kernel (A/B measurements)
+    bool packedQuery = true;         // SDFB200_QUERY_PACKED=0 at build / load time: tile kernel without the packed float32 instructions (A/B)
     // staging of host-pointer queries (query_host.cpp), created on first use under stageMutex
     std::unique_ptr<sdfb200::QueryStage, sdfb200::QueryStageDeleter> stage;
     std::mutex stageMutex;

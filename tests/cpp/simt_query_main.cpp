@@ -197,11 +197,16 @@ int main(int argc, char** argv) {
 #ifndef SDFB_QUERY_EXACT   // compiled with -DSDFB_QUERY_EXACT the header holds the reference-order kernel only
     // tile kernel (plain loads instead of the TMA staging): 3 CTAs of 8 warps, so every warp loops over several tiles
     std::fill(dist.begin(), dist.end(), -123.0f);
-    simt::launch(3, 256, [&] { octreeQueryTileKernel<false>(oct.data(), index.data(), q, tq, pts, n, dist.data(), nullptr); });
+    simt::launch(3, 256, [&] { octreeQueryTileKernel<false, true>(oct.data(), index.data(), q, tq, pts, n, dist.data(), nullptr); });
     emit(false);
+    {   // the scalar form of the same kernel (SDFB200_QUERY_PACKED=0) gives the same bits: packing only pairs up operations
+        std::vector<float> scalar(n, -123.0f);
+        simt::launch(3, 256, [&] { octreeQueryTileKernel<false, false>(oct.data(), index.data(), q, tq, pts, n, scalar.data(), nullptr); });
+        if (std::memcmp(scalar.data(), dist.data(), n * 4) != 0) { std::fprintf(stderr, "packed and scalar tile kernels differ\n"); return 1; }
+    }
     std::fill(dist.begin(), dist.end(), -123.0f);
     std::fill(grad.begin(), grad.end(), -123.0f);
-    simt::launch(3, 256, [&] { octreeQueryTileKernel<true>(oct.data(), index.data(), q, tq, pts, n, dist.data(), grad.data()); });
+    simt::launch(3, 256, [&] { octreeQueryTileKernel<true, true>(oct.data(), index.data(), q, tq, pts, n, dist.data(), grad.data()); });
     emit(true);
 #endif
     std::fclose(o);
