@@ -1,7 +1,8 @@
 """A/B of the two late round-2 changes, one process per setting (the switches are read once per process / structure):
 
-  SDFB200_SAMPLE_FAST=0|1 (+ SDFB200_SAMPLE_CTAS=6|7)   float-screened BVH traversal of the OctreeSdf builders: best-of-4 GPU phase
-                                                         of the C2 builds (both algorithms) + sha1 of the array (must not move)
+  build switches (any ENV=VALUE of the builders)         best-of-4 GPU phase of the C2 builds (both algorithms) + sha1 of the array (must
+                                                         not move); profiles/r2_ab_screened_sampler_packed_query.log holds the float-screened
+                                                         BVH traversal measured this way (dropped: bvh_sampler.cuh)
   SDFB200_QUERY_PACKED=0|1                               packed float32 instructions in the tile query kernel: kernel times on the
                                                          256^3 grid / 2^24 random points (value, value + gradient) + sha1 of the results
 
@@ -52,8 +53,7 @@ if len(sys.argv) > 1 and sys.argv[1] == 'run':
                 print(sys.argv[3:], name, 'grad=%d' % gradient, 'best %.4f ms mean %.4f ms (%.1f Gq/s)' % (best, total / 20, pts.shape[0] / best / 1e6), h, flush=True)
         sdf.close()
 else:
-    runs = [('build', {'SDFB200_SAMPLE_FAST': '0'}), ('build', {'SDFB200_SAMPLE_FAST': '1', 'SDFB200_SAMPLE_CTAS': '7'}),
-            ('build', {'SDFB200_SAMPLE_FAST': '1', 'SDFB200_SAMPLE_CTAS': '6'}),
-            ('query', {'SDFB200_QUERY_PACKED': '0'}), ('query', {'SDFB200_QUERY_PACKED': '1'})]
+    # (the SDFB200_SAMPLE_FAST / SDFB200_SAMPLE_CTAS settings of the committed log existed at commit 12a8917 only)
+    runs = [('build', {'SDFB200_SAMPLE_REFILL': '1'}), ('query', {'SDFB200_QUERY_PACKED': '0'}), ('query', {'SDFB200_QUERY_PACKED': '1'})]
     for what, env in runs:
         subprocess.run([sys.executable, __file__, 'run', what] + ['%s=%s' % kv for kv in env.items()], env=dict(os.environ, **env))

@@ -254,163 +254,14 @@ sampleOwnersRefillKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf,
     }
 }
 
-// ---- float-screened schedule (default; SDFB200_SAMPLE_FAST=0 selects sampleOwnersRefillKernel above) ---------------------------
-// What bounds a traversal is the dependent chain of one visit (profiles/r2_summary.md): node load -> two float64 square
-// roots (MUFU.RSQ64H + eight dependent DMUL / DFMA each, serialised by their slow-path branches) -> compares -> next load:
-// ~23 dependent float64 operations between two loads, and all a visit needs from them is three DECISIONS (which child is
-// nearer, does the near one beat the running best, does the far one). Here the decisions are taken from float32 images —
-// s~ = sqrt.approx(float(q)) is within 2^-22 of sqrt(q) (conversion 2^-25, MUFU.SQRT 1 ulp), a~ = s~ - float(r) within
-// 2^-21.5 (s + r) of the reference's float64 value — and are final whenever they clear an error margin of 2^-20 (s + r)
-// (almost three times the bound; the running best carries its own 2^-20 margin against the 2^-23 of its float image); a visit that does not clear it (a relative near-tie of 1e-6: one visit in ~1e4) takes the reference's
-// float64 path, so every decision is the reference's and the results keep their bits. The exact distance of the far child
-// is only needed when it is pushed; it is computed AFTER the next node's load has been issued (the node a lane works on
-// is held in registers and fetched as soon as the lane knows it), in the shadow of that load.
-constexpr float kScreenEps = 9.5367431640625e-07f;   // 2^-20
-
-struct BvhFastCursor {
-    BvhCursor c;
-    float bestF;            // float(best): a~ + e < bestF (1 - 2^-20) => d < best, a~ - e > bestF (1 + 2^-20) => d >= best
-    BvhNode nd;             // m.bvh[c.cur] while the lane is active at an inner node
-};
-
-// square root for the screen only: one MUFU.SQRT (1 ulp) on the device — the margins below have room for it
-__device__ __forceinline__ float screenSqrt(float x) {
-#ifdef __CUDA_ARCH__
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-#else
-    return sqrtf(x);
-#endif
-}
-
-__device__ __forceinline__ void bvhFastSetBest(BvhFastCursor& f, double best) {
-    f.c.best = best;
-    f.bestF = best < 1e30 ? float(best) : INFINITY;
-}
-__device__ __forceinline__ void bvhFastFetch(const DeviceMesh& m, BvhFastCursor& f) {
-    if (f.c.active && f.c.cur >= 0) f.nd = m.bvh[f.c.cur];
-}
-__device__ __forceinline__ void bvhFastStart(const DeviceMesh& m, BvhFastCursor& f, f3 pf) {
-    f.c.p = mkd(double(pf.x), double(pf.y), double(pf.z));
-    f.c.bestTri = -1; f.c.sp = 0; f.c.cur = m.rootLink; f.c.active = true;
-    bvhFastSetBest(f, DBL_MAX);
-    bvhFastFetch(m, f);
-}
-
-__device__ __forceinline__ void bvhFastInnerStep(const DeviceMesh& m, BvhFastCursor& f, const BvhStack& st) {
-    BvhCursor& c = f.c;
-    const d3 dl3 = c.p - mkd(f.nd.lc[0], f.nd.lc[1], f.nd.lc[2]);
-    const d3 dr3 = c.p - mkd(f.nd.rc[0], f.nd.rc[1], f.nd.rc[2]);
-    const double ql = ddot(dl3, dl3), qr = ddot(dr3, dr3);
-    const double lr = f.nd.lr, rr = f.nd.rr;
-    const int left = f.nd.left, right = f.nd.right;
-    const float qlf = float(ql), qrf = float(qr), rlf = float(lr), rrf = float(rr);
-    const float sl = screenSqrt(qlf), sr = screenSqrt(qrf);
-    const float bestLo = f.bestF * (1.0f - kScreenEps), bestHi = f.bestF * (1.0f + kScreenEps);
-    const float al = sl - rlf, ar = sr - rrf;
-    const float el = kScreenEps * (sl + rlf), er = kScreenEps * (sr + rrf);
-    const bool leftFirstF = al < ar;
-    const float aF = leftFirstF ? al : ar, eF = leftFirstF ? el : er, aS = leftFirstF ? ar : al, eS = leftFirstF ? er : el;
-    const bool firstIn = aF + eF < bestLo, firstOut = aF - eF > bestHi;
-    // float images are only trusted inside the normal range (a sample on a sphere centre, absurd coordinates: exact path)
-    const bool sure = fminf(qlf, qrf) > 1e-30f && fmaxf(qlf, qrf) < 1e30f && fabsf(al - ar) > el + er && (firstIn || firstOut);
-    if (sure) {
-        const int second = leftFirstF ? right : left;
-        if (firstIn) {
-            c.cur = leftFirstF ? left : right;
-            bvhFastFetch(m, f);                      // next node on its way before the far child's square root
-        }
-        if (!(aS - eS > bestHi)) {                 // the far child may beat the best: its exact distance decides and is what the stack keeps
-            const double dSecond = sqrt(leftFirstF ? qr : ql) - (leftFirstF ? rr : lr);
-            if (dSecond < c.best) {
-                st.node[c.sp * st.stride] = second;
-                st.dist[c.sp * st.stride] = dSecond;
-                c.sp++;
-            }
-        }
-        if (!firstIn) { bvhPop(c, st); bvhFastFetch(m, f); }
-        return;
-    }
-    // the reference's arithmetic (bvhInnerStep)
-#ifdef SDFB_BVH_SCREEN_STATS
-    SDFB_BVH_SCREEN_STATS;   // tests/cpp/bvh_screen_main.cpp counts the visits that end up here
-#endif
-    const double dl = sqrt(ql) - lr, dr = sqrt(qr) - rr;
-    const bool leftFirst = dl < dr;
-    const int first = leftFirst ? left : right, second = leftFirst ? right : left;
-    const double dFirst = leftFirst ? dl : dr, dSecond = leftFirst ? dr : dl;
-    if (dSecond < c.best) {
-        st.node[c.sp * st.stride] = second;
-        st.dist[c.sp * st.stride] = dSecond;
-        c.sp++;
-    }
-    if (dFirst < c.best) c.cur = first;
-    else bvhPop(c, st);
-    bvhFastFetch(m, f);
-}
-
-__device__ __forceinline__ void bvhFastLeafStep(const DeviceMesh& m, BvhFastCursor& f, const BvhStack& st) {
-    BvhCursor& c = f.c;
-    const int t = ~c.cur;
-    const float4 a = m.triVerts[3 * size_t(t)], b = m.triVerts[3 * size_t(t) + 1], v = m.triVerts[3 * size_t(t) + 2];
-    // The stack is popped BEFORE the point-triangle test: most leaves do not improve the best, and then the next node is the
-    // first stack entry below the (unchanged) best — its node is fetched under the test. When the best does shrink, the
-    // entries this pop skipped fail the smaller best as well, so only the popped entry is re-tested and the pop continues
-    // from there: the same entry the reference's order (test, then pop) ends on.
-    bvhPop(c, st);
-    const double popped = c.active ? st.dist[c.sp * st.stride] : 0.0;
-    bvhFastFetch(m, f);
-    const double d2 = eberlySqDistConverged(c.p, mkd(double(a.x), double(a.y), double(a.z)), mkd(double(b.x), double(b.y), double(b.z)),
-                                            mkd(double(v.x), double(v.y), double(v.z)));
-    if (d2 < c.best * c.best) {
-        bvhFastSetBest(f, sqrt(d2));
-        c.bestTri = t;
-        if (c.active && !(popped < c.best)) { bvhPop(c, st); bvhFastFetch(m, f); }
-    }
-}
-
-template <int kMinCtas>   // resident CTAs per SM the register budget is cut for (7 = what the shared-memory stacks of the C2 mesh allow: 72 registers)
-__global__ void __launch_bounds__(kBvhThreads, kMinCtas)
-sampleOwnersFastKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const uint32_t* __restrict__ owners, uint32_t first,
-                       uint32_t count, float4* results, uint32_t* counter, const uint32_t* __restrict__ schedule) {
-    constexpr unsigned kFull = 0xffffffffu;
-    const BvhStack st = bvhStackOfThread(mesh);
-    const unsigned lane = threadIdx.x & 31u;
-    BvhFastCursor f;
-    f.c.active = false;
-    f.c.bestTri = -1; f.c.best = DBL_MAX; f.c.sp = 0; f.c.cur = mesh.rootLink; f.c.p = mkd(0.0, 0.0, 0.0);
-    f.bestF = INFINITY;
-    uint32_t item = 0xFFFFFFFFu;   // sample this lane is traversing for
-    bool drained = false;          // warp-uniform: the counter has passed `count`
-    for (;;) {
-        const unsigned idle = __ballot_sync(kFull, !f.c.active);
-        if (idle) {
-            if (!f.c.active && item != 0xFFFFFFFFu) {
-                results[item] = make_float4(__int_as_float(f.c.bestTri), 0.f, 0.f, 0.f);
-                item = 0xFFFFFFFFu;
-            }
-            if (!drained) {
-                const int leader = __ffs(int(idle)) - 1;
-                uint32_t base = 0;
-                if (int(lane) == leader) base = atomicAdd(counter, uint32_t(__popc(idle)));
-                base = __shfl_sync(kFull, base, leader);
-                if (!f.c.active) {
-                    const uint32_t slot = base + uint32_t(__popc(idle & ((1u << lane) - 1u)));
-                    if (slot < count) {
-                        const uint32_t mine = schedule ? schedule[slot] : slot;
-                        item = mine;
-                        bvhFastStart(mesh, f, latticeSamplePosition(centerHalf, owners[first + mine]));
-                    }
-                }
-                drained = base + uint32_t(__popc(idle)) >= count;
-            }
-            if (drained && __ballot_sync(kFull, f.c.active) == 0) break;
-        }
-        if (f.c.active && f.c.cur >= 0) bvhFastInnerStep(mesh, f, st);
-        if (f.c.active && f.c.cur < 0) bvhFastLeafStep(mesh, f, st);
-    }
-}
+// Measured and dropped (profiles/r2_summary.md, r2_ab_screened_sampler_packed_query.log; the code is in the history at commit
+// 12a8917): a float-screened visit — the three decisions of an inner step (nearer child, near child against the best, far
+// child against the best) taken from float32 images inside a rigorous error margin with the float64 path as fallback (one
+// visit in 2000), the node a lane works on held in registers and fetched as soon as the lane knows it, the far child's exact
+// square root and the leaf's point-triangle test run in the shadow of that load (speculative pop). Bit-identical (3 M samples
+// against bvhNearest on the CPU, full-size hashes on the GPU) and no faster: C2 levels 57.1 -> 56.7 ms at 72 registers / 7
+// CTAs per SM, 57.4 ms at 78 registers / 6 CTAs. Shortening a visit's dependent chain does not move the kernel: it trades
+// ~16 float64 instructions for ~25 float32 ones, and the warp's issue slots (61 % busy at 10 of 32 lanes) are what is spent.
 
 __global__ void finishOwnersKernel(DeviceMesh mesh, const float4* __restrict__ centerHalf, const uint32_t* __restrict__ owners, uint32_t first,
                                    uint32_t count, float4* results) {

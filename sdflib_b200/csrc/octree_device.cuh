@@ -160,16 +160,6 @@ inline bool sampleScheduleEnabled() {   // A/B switch: SDFB200_SAMPLE_SCHEDULE=0
     return on;
 }
 
-inline bool sampleFastEnabled() {   // A/B switch: SDFB200_SAMPLE_FAST=0 keeps every decision of a visit in float64 (sampleOwnersRefillKernel)
-    static const bool on = [] { const char* e = std::getenv("SDFB200_SAMPLE_FAST"); return !(e && e[0] == '0'); }();
-    return on;
-}
-
-inline int sampleFastCtas() {   // A/B switch: SDFB200_SAMPLE_CTAS=6 runs the float-screened kernel with 80 registers at 6 CTAs per SM
-    static const int v = [] { const char* e = std::getenv("SDFB200_SAMPLE_CTAS"); return e && e[0] == '6' ? 6 : 7; }();
-    return v;
-}
-
 inline int sampleLeafBatch() {   // lanes of a warp that must hold a leaf before the leaf branch runs (1 = take leaves as they come)
     static const int v = [] { const char* e = std::getenv("SDFB200_LEAF_BATCH"); const int x = e ? std::atoi(e) : 1; return x < 1 ? 1 : (x > 32 ? 32 : x); }();
     return v;
@@ -246,14 +236,7 @@ struct LevelSampler {
                 refillCounter.ensure(1);
                 SDFB_CUDA(cudaMemsetAsync(refillCounter.p, 0, sizeof(uint32_t), stream));
                 const uint32_t blocks = std::min<uint32_t>(divUp(cnt, kBvhThreads), 148u * 8u);
-                if (sampleFastEnabled() && sampleLeafBatch() == 1) {
-                    if (sampleFastCtas() == 6)
-                        sampleOwnersFastKernel<6><<<blocks, kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst, refillCounter.p, schedulePtr);
-                    else
-                        sampleOwnersFastKernel<7><<<blocks, kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst, refillCounter.p, schedulePtr);
-                }
-                else
-                    sampleOwnersRefillKernel<<<blocks, kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst, refillCounter.p, sampleLeafBatch(), schedulePtr);
+                sampleOwnersRefillKernel<<<blocks, kBvhThreads, bvhStackBytes(mesh), stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst, refillCounter.p, sampleLeafBatch(), schedulePtr);
                 finishOwnersKernel<<<divUp(cnt, 256), 256, 0, stream>>>(mesh, centerHalf, ownersPtr, first, cnt, dst);
                 return;
             }

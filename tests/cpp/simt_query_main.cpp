@@ -206,7 +206,7 @@ int main(int argc, char** argv) {
     }
     std::fill(dist.begin(), dist.end(), -123.0f);
     std::fill(grad.begin(), grad.end(), -123.0f);
-    simt::launch(3, 256, [&] { octreeQueryTileKernel<true, true>(oct.data(), index.data(), q, tq, pts, n, dist.data(), grad.data()); });
+    simt::launch(3, 256, [&] { octreeQueryTileKernel<true, false>(oct.data(), index.data(), q, tq, pts, n, dist.data(), grad.data()); });
     emit(true);
 #endif
     std::fclose(o);
