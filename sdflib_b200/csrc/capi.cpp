@@ -36,6 +36,11 @@ template <class F> int guarded(F&& f) {
     }
 }
 
+template <class F> int guarded(const char* range, F&& f) {   // the same inside an NVTX range named after the entry point
+    NvtxRange nvtx(range);
+    return guarded(static_cast<F&&>(f));
+}
+
 void requireDevice() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -109,7 +114,7 @@ extern "C" {
 // ---- prepared meshes ---------------------------------------------------------------------------------------------
 int sdfb200_mesh_create(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices, int parts,
                         sdfb200_mesh** out) {
-    return guarded([&] {
+    return guarded("sdfb200:mesh_create", [&] {
         if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
         *out = nullptr;
         HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
@@ -137,14 +142,14 @@ int sdfb200_mesh_blob_bytes(const sdfb200_mesh* mesh, uint64_t* outBytes) {
 }
 
 int sdfb200_mesh_export(const sdfb200_mesh* mesh, void* devicePtr, uint64_t capacityBytes) {
-    return guarded([&] {
+    return guarded("sdfb200:mesh_export", [&] {
         if (!devicePtr) throw Error(SDFB200_ERR_INVALID, "null argument");
         meshBlobExport(meshOnCurrentDevice(mesh), devicePtr, capacityBytes, cudaStream_t(0));
     });
 }
 
 int sdfb200_mesh_import(const void* devicePtr, uint64_t bytes, sdfb200_mesh** out) {
-    return guarded([&] {
+    return guarded("sdfb200:mesh_import", [&] {
         if (!devicePtr || !out) throw Error(SDFB200_ERR_INVALID, "null argument");
         *out = nullptr;
         requireDevice();
@@ -166,7 +171,7 @@ int sdfb200_mesh_stats(const sdfb200_mesh* mesh, double* triangleDataMs, double*
 int sdfb200_build_octree_from_mesh(const sdfb200_mesh* mesh, const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule,
                                    float param0, float param1, int initAlgorithm, uint32_t numThreads, uint32_t rank, uint32_t worldSize,
                                    sdfb200_sdf** out) {
-    return guarded([&] {
+    return guarded("sdfb200:build_octree_from_mesh", [&] {
         if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
         *out = nullptr;
         checkBox(box6);
@@ -185,7 +190,7 @@ int sdfb200_build_octree_from_mesh(const sdfb200_mesh* mesh, const float* box6, 
 int sdfb200_build_octree_collective_from_mesh(const sdfb200_mesh* mesh, const float* box6, uint32_t depth, uint32_t startDepth,
                                               int terminationRule, float param0, float param1, uint32_t rank, uint32_t worldSize,
                                               sdfb200_allgather_fn allgather, void* user, sdfb200_sdf** out) {
-    return guarded([&] {
+    return guarded("sdfb200:build_octree_collective_from_mesh", [&] {
         if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
         *out = nullptr;
         checkBox(box6);
@@ -203,7 +208,7 @@ int sdfb200_build_octree_collective_from_mesh(const sdfb200_mesh* mesh, const fl
 
 int sdfb200_build_exact_from_mesh(const sdfb200_mesh* mesh, const float* box6, uint32_t maxDepth, uint32_t startDepth,
                                   uint32_t minTrianglesPerNode, uint32_t numThreads, uint32_t rank, uint32_t worldSize, sdfb200_sdf** out) {
-    return guarded([&] {
+    return guarded("sdfb200:build_exact_from_mesh", [&] {
         if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
         *out = nullptr;
         checkBox(box6);
@@ -221,7 +226,7 @@ int sdfb200_nccl_available(void) { return ncclAvailable() ? 1 : 0; }
 int sdfb200_build_octree_multi(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
                                const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule, float param0, float param1,
                                int initAlgorithm, uint32_t numThreads, const int* devices, uint32_t nDevices, sdfb200_sdf** outHandles) {
-    return guarded([&] {
+    return guarded("sdfb200:build_octree_multi", [&] {
         HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
         checkBox(box6);
         checkOctreeOptions(initAlgorithm, terminationRule);
@@ -233,7 +238,7 @@ int sdfb200_build_octree_multi(const float* vertices, uint32_t numVertices, cons
 int sdfb200_build_exact_multi(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
                               const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode, uint32_t numThreads,
                               const int* devices, uint32_t nDevices, sdfb200_sdf** outHandles) {
-    return guarded([&] {
+    return guarded("sdfb200:build_exact_multi", [&] {
         HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
         checkBox(box6);
         MultiBuildRequest req{SDFB200_FORMAT_EXACT_OCTREE, box6, maxDepth, startDepth, numThreads, 0, 0.0f, 0.0f, 0, minTrianglesPerNode};
@@ -267,7 +272,7 @@ int sdfb200_build_octree_shard(const float* vertices, uint32_t numVertices, cons
                                const float* box6, uint32_t depth, uint32_t startDepth, int terminationRule, float param0,
                                float param1, int initAlgorithm, uint32_t numThreads, uint32_t rank, uint32_t worldSize,
                                sdfb200_sdf** out) {
-    return guarded([&] {
+    return guarded("sdfb200:build_octree_shard", [&] {
         if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
         *out = nullptr;
         HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
@@ -298,7 +303,7 @@ int sdfb200_build_octree_collective(const float* vertices, uint32_t numVertices,
                                     float param1, int initAlgorithm, uint32_t numThreads, uint32_t rank, uint32_t worldSize,
                                     sdfb200_allgather_fn allgather, void* user, sdfb200_sdf** out) {
     (void)numThreads;   // the CONTINUITY layout does not depend on it
-    return guarded([&] {
+    return guarded("sdfb200:build_octree_collective", [&] {
         if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
         *out = nullptr;
         HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
@@ -332,7 +337,7 @@ int sdfb200_build_octree(const float* vertices, uint32_t numVertices, const uint
 int sdfb200_build_exact_shard(const float* vertices, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices,
                               const float* box6, uint32_t maxDepth, uint32_t startDepth, uint32_t minTrianglesPerNode,
                               uint32_t numThreads, uint32_t rank, uint32_t worldSize, sdfb200_sdf** out) {
-    return guarded([&] {
+    return guarded("sdfb200:build_exact_shard", [&] {
         if (!out) throw Error(SDFB200_ERR_INVALID, "null output handle");
         *out = nullptr;
         HostMesh mesh = checkedMesh(vertices, numVertices, indices, numIndices);
@@ -357,7 +362,7 @@ int sdfb200_build_exact(const float* vertices, uint32_t numVertices, const uint3
 }
 
 int sdfb200_save(const sdfb200_sdf* sdf, const char* path) {
-    return guarded([&] {
+    return guarded("sdfb200:save", [&] {
         if (!sdf || !path) throw Error(SDFB200_ERR_INVALID, "null argument");
         if (sdf->isShard) throw Error(SDFB200_ERR_INVALID, "handle is an unassembled shard (sdfb200_assemble not called yet)");
         ensureHostMirror(*const_cast<sdfb200_sdf*>(sdf));
@@ -366,7 +371,7 @@ int sdfb200_save(const sdfb200_sdf* sdf, const char* path) {
 }
 
 int sdfb200_load(const char* path, sdfb200_sdf** out) {
-    return guarded([&] {
+    return guarded("sdfb200:load", [&] {
         if (!out || !path) throw Error(SDFB200_ERR_INVALID, "null argument");
         *out = nullptr;
         std::unique_ptr<sdfb200_sdf> s(new sdfb200_sdf());
@@ -443,7 +448,7 @@ int sdfb200_get_device_octree(const sdfb200_sdf* s, const uint32_t** outDevicePt
 }
 
 int sdfb200_query(sdfb200_sdf* s, const float* xyz, uint64_t n, float* dist, float* grad, int flags, void* cudaStream) {
-    return guarded([&] {
+    return guarded("sdfb200:query", [&] {
         if (!s || (n && (!xyz || !dist))) throw Error(SDFB200_ERR_INVALID, "null argument");
         if (n == 0) return;
         if (!s->dOctree.p) throw Error(SDFB200_ERR_CUDA, "structure is not resident on a CUDA device");
@@ -457,7 +462,7 @@ int sdfb200_query(sdfb200_sdf* s, const float* xyz, uint64_t n, float* dist, flo
 
 int sdfb200_sphere_trace(sdfb200_sdf* s, const float* origins, const float* directions, uint64_t n, float epsilon, float farDistance,
                          uint32_t maxIterations, float* outHit, float* outTravelled, uint32_t* outIterations, int flags, void* cudaStream) {
-    return guarded([&] {
+    return guarded("sdfb200:sphere_trace", [&] {
         if (!s || (n && (!origins || !directions || !outHit || !outTravelled))) throw Error(SDFB200_ERR_INVALID, "null argument");
         if (n == 0) return;
         if (s->format != SDFB200_FORMAT_OCTREE) throw Error(SDFB200_ERR_UNSUPPORTED, "sphere tracing is built for OctreeSdf structures");
@@ -494,7 +499,7 @@ int sdfb200_shard_sizes(const sdfb200_sdf* s, uint32_t* outSizes, uint64_t capac
 }
 
 int sdfb200_shard_finish(sdfb200_sdf* s, const uint32_t* allSizes, uint64_t count) {
-    return guarded([&] {
+    return guarded("sdfb200:shard_finish", [&] {
         if (!s || !allSizes) throw Error(SDFB200_ERR_INVALID, "null argument");
         if (!s->build) throw Error(SDFB200_ERR_INVALID, "handle is not a shard in phase 1 (built with worldSize > 1)");
         if (count != s->shardSizes.size()) throw Error(SDFB200_ERR_INVALID, "size vector length differs from sdfb200_shard_sizes");
@@ -514,7 +519,7 @@ int sdfb200_shard_words(const sdfb200_sdf* s, uint64_t* outWords) {
 }
 
 int sdfb200_shard_export(const sdfb200_sdf* s, uint32_t* devicePtr, uint64_t capacityWords) {
-    return guarded([&] {
+    return guarded("sdfb200:shard_export", [&] {
         if (!s || !devicePtr) throw Error(SDFB200_ERR_INVALID, "null argument");
         SDFB_CUDA(cudaSetDevice(s->device));
         shardExport(*s, devicePtr, capacityWords);
@@ -523,7 +528,7 @@ int sdfb200_shard_export(const sdfb200_sdf* s, uint32_t* devicePtr, uint64_t cap
 
 int sdfb200_assemble(sdfb200_sdf* s, const uint32_t* gatheredDevicePtr, const uint64_t* wordsPerRank, uint64_t strideWords,
                      uint32_t worldSize) {
-    return guarded([&] {
+    return guarded("sdfb200:assemble", [&] {
         if (!s || !gatheredDevicePtr || !wordsPerRank) throw Error(SDFB200_ERR_INVALID, "null argument");
         SDFB_CUDA(cudaSetDevice(s->device));
         shardAssemble(*s, gatheredDevicePtr, wordsPerRank, strideWords, worldSize);

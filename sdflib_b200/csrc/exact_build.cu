@@ -659,6 +659,7 @@ struct ExactBuildState : BuildState {
         const uint32_t numAll = mesh.numValid;
         const DeviceMesh dmesh{mesh.dev.verts.p, mesh.dev.idx.p, nullptr, nullptr, nT};
 
+        NvtxRange nvtx("sdfb200:exact:levels");
         auto t0 = std::chrono::steady_clock::now();
         const uint32_t d0 = std::min(startDepth, 1u);
         const f3 boxMin = mk3(out.boxMin[0], out.boxMin[1], out.boxMin[2]);
@@ -787,6 +788,7 @@ struct ExactBuildState : BuildState {
         st.levels_ms = msSince(t0);
 
         // ---- post-order merge: levels maxDepth-1, then maxDepth-2 ------------------------------------------------
+        nvtx.next("sdfb200:exact:merge_and_layout");
         t0 = std::chrono::steady_clock::now();
         DevBuf<uint8_t> keep;
         DevBuf<uint32_t> mpos;
@@ -852,6 +854,7 @@ struct ExactBuildState : BuildState {
 
     void finish(sdfb200_sdf& out, const uint32_t* allSizesBySlot) override {
         sdfb200_build_stats& st = out.stats;
+        NvtxRange nvtx("sdfb200:exact:emit");
         auto t0 = std::chrono::steady_clock::now();
         const RootPlan& plan = out.plan;
         const uint32_t G3 = plan.G3;
@@ -918,6 +921,7 @@ struct ExactBuildState : BuildState {
         if (plan.world == 1) {
             out.maxTrisInLeafs = out.shardScalars[0];
             out.maxTrisEncoded = out.shardScalars[1];
+            nvtx.next("sdfb200:exact:download");
             t0 = std::chrono::steady_clock::now();
             ensureHostMirror(out);
             st.download_ms = msSince(t0);

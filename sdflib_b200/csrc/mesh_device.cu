@@ -288,6 +288,7 @@ std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bo
     double bvhMs = 0.0;
     const bool hostBvh = withBvh && hostBvhRequested();
     t0 = std::chrono::steady_clock::now();
+    NvtxRange nvtx("sdfb200:mesh:triangle_data");
     static const bool hostTriangleData = std::getenv("SDFB200_HOST_TRIANGLE_DATA") != nullptr;   // A/B switch: the round-1 host path
     if (hostTriangleData) {
         pm->hostTris = computeTriangleData(mesh);
@@ -314,6 +315,7 @@ std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bo
         triangleDataOnDevice(*pm, mesh);
         pm->triangleDataMs = msSince(t0);
     }
+    nvtx.next("sdfb200:mesh:bvh");
     if (withBvh && !hostBvh) {
         t0 = std::chrono::steady_clock::now();
         gatherTriVerts(pm->dev);
@@ -322,6 +324,7 @@ std::shared_ptr<PreparedMesh> prepareMesh(const HostMesh& mesh, bool withBvh, bo
         bvhMs = msSince(t0);
     }
     pm->bvhMs = bvhMs;
+    nvtx.next("sdfb200:mesh:exact_parts");
     t0 = std::chrono::steady_clock::now();
     if (hostBvh) uploadBvh(*pm, bvh);
     if (withExactParts) exactPartsOnDevice(*pm);

@@ -374,6 +374,7 @@ struct OctreeBuildState : BuildState {
         meshStats(mesh, st);
         const DeviceMesh dmesh = mesh.dev.view();
 
+        NvtxRange nvtx("sdfb200:octree:levels");
         auto t0 = std::chrono::steady_clock::now();
         const uint32_t d0 = std::min(startDepth, 1u);
         const f3 boxMin = mk3(out.boxMin[0], out.boxMin[1], out.boxMin[2]);
@@ -515,6 +516,7 @@ struct OctreeBuildState : BuildState {
         st.levels_ms = msSince(t0);
 
         // subtree sizes, bottom-up
+        nvtx.next("sdfb200:octree:layout");
         t0 = std::chrono::steady_clock::now();
         {
             Level& D = *levels[depth];
@@ -563,6 +565,7 @@ struct OctreeBuildState : BuildState {
     // phase 2: global offsets, node words + leaf blocks of the own roots at their final positions
     void finish(sdfb200_sdf& out, const uint32_t* allSizesBySlot) override {
         sdfb200_build_stats& st = out.stats;
+        NvtxRange nvtx("sdfb200:octree:emit");
         auto t0 = std::chrono::steady_clock::now();
         const RootPlan& plan = out.plan;
         const uint32_t G3 = plan.G3;
@@ -611,6 +614,7 @@ struct OctreeBuildState : BuildState {
         levels.clear();
         if (plan.world == 1) {
             finalizeOctreeScalars(out);
+            nvtx.next("sdfb200:octree:query_index_and_download");
             t0 = std::chrono::steady_clock::now();
             prepareOctreeQuery(out);
             ensureHostMirror(out);

@@ -785,6 +785,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
     meshStats(mesh, st);
     const DeviceMesh dmesh = mesh.dev.view();
 
+    NvtxRange nvtx("sdfb200:continuity:levels");
     auto t0 = std::chrono::steady_clock::now();
     const uint32_t G = uint32_t(out.startGridSize), G3 = G * G * G;
     Grid grid{G, startDepth, {out.boxMin[0], out.boxMin[1], out.boxMin[2]}, out.cellSize};
@@ -1087,6 +1088,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
     st.levels_ms = msSince(t0);
     finalizeOctreeScalars(out);
 
+    nvtx.next("sdfb200:continuity:finish");
     t0 = std::chrono::steady_clock::now();
     levels.clear(); pools.clear();
     // keep exactly `words` entries on the device for the query kernels

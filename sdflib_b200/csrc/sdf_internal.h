@@ -30,6 +30,28 @@ void setLastError(const std::string& msg);
             throw ::sdfb200::Error(SDFB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+// ---- NVTX ranges ---------------------------------------------------------------------------------
+// Entry points and build phases show up as named ranges ("sdfb200:...") in Nsight Systems / Compute timelines. nvtx3 is
+// header-only and resolves the tool's injection library at the first call: without a tool attached a range costs a
+// function-pointer test.
+}  // namespace sdfb200
+#ifndef SDFB_NO_NVTX
+#include <nvtx3/nvToolsExt.h>
+#define SDFB_NVTX_PUSH(name) nvtxRangePushA(name)
+#define SDFB_NVTX_POP() nvtxRangePop()
+#else
+#define SDFB_NVTX_PUSH(name) ((void)0)
+#define SDFB_NVTX_POP() ((void)0)
+#endif
+namespace sdfb200 {
+struct NvtxRange {   // scoped range; next() closes the current phase and opens another one
+    explicit NvtxRange(const char* name) { SDFB_NVTX_PUSH(name); }
+    void next(const char* name) { SDFB_NVTX_POP(); SDFB_NVTX_PUSH(name); }
+    ~NvtxRange() { SDFB_NVTX_POP(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 // ---- device buffer -----------------------------------------------------------------------------
 // Device blocks: rounded to a size class and recycled through per-class free lists. Every kernel that touches a
 // DevBuf runs on the legacy default stream (or is synchronised before the buffer is released), so handing a freed
