@@ -508,6 +508,7 @@ int sdfb200_shard_finish(sdfb200_sdf* s, const uint32_t* allSizes, uint64_t coun
                 throw Error(SDFB200_ERR_INVALID, "all-reduced sizes disagree with this rank's own roots (ownership overlap?)");
         SDFB_CUDA(cudaSetDevice(s->device));
         s->build->finish(*s, allSizes);
+        settleDeviceCache(s->device);
     });
 }
 

@@ -951,6 +951,7 @@ void buildExactOnDevice(sdfb200_sdf& out, const std::shared_ptr<PreparedMesh>& m
     out.slotWords = 2;
     cubifyBox(out, box6, startDepth);
     SDFB_CUDA(cudaGetDevice(&out.device));
+    DeviceCacheSettle settle(out.device);
     std::unique_ptr<ExactBuildState> state(new ExactBuildState());
     state->maxDepth = maxDepth; state->startDepth = startDepth; state->minTris = minTris; state->bitEnc = maxDepth - 2;
     out.isShard = true;

@@ -73,17 +73,13 @@ void hostBlockFree(void* p, size_t capacity, bool pinned) {
 // sizes, and whenever the pool has no contiguous range for one of them it maps physical pages into a new range —
 // tens to hundreds of milliseconds, at random (a 0.21 s CONTINUITY build took 0.9 s one time in five). Requests are
 // therefore rounded to size classes (1/8 steps above 1 MiB) and freed blocks go to per-(device, class) lists, so a
-// repeated build gets exactly the blocks of the previous one. Blocks above 32 GiB, or beyond 96 GiB of cached bytes per
-// device, go back to the stream-ordered allocator. (Round 2 started with 1 GiB / 16 GiB: the Dragon-class ExactOctreeSdf
-// build allocates a dozen blocks of 1-12 GiB per build, which then still went through the pool — best 0.49 s at 2 GPUs,
-// but 0.74 s and 1.33 s for the next two builds of the same process, profiles/r2_bench_2gpu_final.json. The pool keeps
-// freed memory either way (release threshold = max), so caching the blocks themselves takes nothing away from other
-// users of the device; sdfb200_release_cached_memory hands everything back.)
+// repeated build gets exactly the blocks of the previous one. Blocks above 1 GiB, or beyond 16 GiB of cached bytes,
+// go back to the stream-ordered allocator.
 namespace {
 std::mutex gDevMutex;
 std::map<std::pair<int, size_t>, std::vector<void*>> gFreeDevice;
-std::map<int, size_t> gDevCachedBytes;   // per device
-constexpr size_t kMaxDevCachedBytes = size_t(96) << 30, kMaxDevCachedBlock = size_t(32) << 30, kTrimOnMissBytes = size_t(2) << 30;
+size_t gDevCachedBytes = 0;
+constexpr size_t kMaxDevCachedBytes = size_t(16) << 30, kMaxDevCachedBlock = size_t(1) << 30, kTrimOnMissBytes = size_t(2) << 30;
 
 size_t roundDeviceBlock(size_t bytes) {
     if (bytes <= 4096) return 4096;
@@ -95,7 +91,7 @@ size_t roundDeviceBlock(size_t bytes) {
 void trimDeviceCache(int device) {   // gDevMutex held
     for (auto& kv : gFreeDevice) {
         if (kv.first.first != device) continue;
-        for (void* p : kv.second) { cudaFreeAsync(p, cudaStream_t(0)); gDevCachedBytes[kv.first.first] -= kv.first.second; }
+        for (void* p : kv.second) { cudaFreeAsync(p, cudaStream_t(0)); gDevCachedBytes -= kv.first.second; }
         kv.second.clear();
     }
 }
@@ -131,7 +127,7 @@ void* deviceBlockAlloc(size_t bytes, size_t* outCapacity) {
         if (it != gFreeDevice.end() && !it->second.empty()) {
             void* p = it->second.back();
             it->second.pop_back();
-            gDevCachedBytes[device] -= cap;
+            gDevCachedBytes -= cap;
             return p;
         }
     }
@@ -139,7 +135,7 @@ void* deviceBlockAlloc(size_t bytes, size_t* outCapacity) {
         // cached blocks back to the stream-ordered pool so that it can serve this request from their memory instead of
         // mapping fresh pages (first build of the 5.2 M-triangle ExactOctreeSdf: 8.9 s without this, 101 GB touched).
         std::lock_guard<std::mutex> lock(gDevMutex);
-        if (gDevCachedBytes[device] > kTrimOnMissBytes) trimDeviceCache(device);
+        if (gDevCachedBytes > kTrimOnMissBytes) trimDeviceCache(device);
     }
     void* p = nullptr;
     cudaError_t e = cudaMallocAsync(&p, cap, tBlockStream);
@@ -156,6 +152,22 @@ void* deviceBlockAlloc(size_t bytes, size_t* outCapacity) {
     return p;
 }
 
+// End of a top-level build: a cache that holds more than kTrimOnMissBytes goes back to the stream-ordered pool, so that the
+// next build starts from the same state as this one did (an empty cache and a pool whose free ranges have coalesced)
+// instead of from whatever the last levels of this build happened to leave: a series of identical large builds then
+// repeats itself (before: 0.75 / 0.98 / 1.39 / 1.41 s for the same Dragon-class build, depending on its predecessor).
+// Small builds keep their blocks (a C2 / C3 build caches well under the threshold) and stay exact-reuse.
+void settleDeviceCache(int device) {
+    std::lock_guard<std::mutex> lock(gDevMutex);
+    if (gDevCachedBytes <= kTrimOnMissBytes) return;
+    int current = 0;
+    cudaGetDevice(&current);
+    if (current != device) cudaSetDevice(device);
+    trimDeviceCache(device);
+    if (current != device) cudaSetDevice(current);
+    cudaGetLastError();
+}
+
 void deviceBlockFree(void* p, size_t capacity) {
     if (!p) return;
     if (blockCacheOff()) { cudaFreeAsync(p, tBlockStream); return; }
@@ -164,9 +176,9 @@ void deviceBlockFree(void* p, size_t capacity) {
     if (cudaPointerGetAttributes(&attr, p) == cudaSuccess) device = attr.device; else cudaGetLastError();
     if (capacity <= kMaxDevCachedBlock) {
         std::lock_guard<std::mutex> lock(gDevMutex);
-        if (gDevCachedBytes[device] + capacity <= kMaxDevCachedBytes) {
+        if (gDevCachedBytes + capacity <= kMaxDevCachedBytes) {
             gFreeDevice[std::make_pair(device, capacity)].push_back(p);
-            gDevCachedBytes[device] += capacity;
+            gDevCachedBytes += capacity;
             return;
         }
     }
@@ -184,7 +196,7 @@ void releaseCachedMemory() {
             if (kv.second.empty()) continue;
             cudaSetDevice(kv.first.first);
             cudaDeviceSynchronize();
-            for (void* p : kv.second) { cudaFreeAsync(p, cudaStream_t(0)); gDevCachedBytes[kv.first.first] -= kv.first.second; }
+            for (void* p : kv.second) { cudaFreeAsync(p, cudaStream_t(0)); gDevCachedBytes -= kv.first.second; }
             kv.second.clear();
         }
     }

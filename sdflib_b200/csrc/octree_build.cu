@@ -649,6 +649,7 @@ void buildOctreeOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, const float
     cubifyBox(out, box6, startDepth);
     SDFB_CUDA(cudaGetDevice(&out.device));
     uploadHermite();
+    DeviceCacheSettle settle(out.device);
     std::unique_ptr<OctreeBuildState> state(new OctreeBuildState());
     state->depth = depth;
     state->startDepth = startDepth;

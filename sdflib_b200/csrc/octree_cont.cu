@@ -756,6 +756,7 @@ void buildOctreeContinuityOnDevice(sdfb200_sdf& out, const PreparedMesh& mesh, c
     out.slotWords = 1;
     cubifyBox(out, box6, startDepth);
     SDFB_CUDA(cudaGetDevice(&out.device));
+    DeviceCacheSettle settle(out.device);
     uploadHermite();
     {   // face/edge sample table (:139-176), derived: sample s is on the shared face iff rel[a] == side for every axis of dir
         static const int lat[19] = {1, 3, 4, 5, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 19, 21, 22, 23, 25};

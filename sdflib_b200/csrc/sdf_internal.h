@@ -58,6 +58,12 @@ struct NvtxRange {   // scoped range; next() closes the current phase and opens 
 // block to the next allocation is ordered by the stream itself.
 void* deviceBlockAlloc(size_t bytes, size_t* outCapacity);
 void deviceBlockFree(void* p, size_t capacity);
+void settleDeviceCache(int device);          // end of a top-level build (see host_mem.cpp)
+struct DeviceCacheSettle {                  // declare BEFORE the build state it should outlive
+    int device;
+    explicit DeviceCacheSettle(int d) : device(d) {}
+    ~DeviceCacheSettle() { settleDeviceCache(device); }
+};
 void setDeviceBlockStream(cudaStream_t s);   // thread-local: stream that cache misses / overflows are ordered on (default: legacy stream)
 
 template <class T> struct DevBuf {
