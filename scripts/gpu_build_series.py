@@ -7,6 +7,7 @@ import sdflib_b200 as S
 from sdflib_b200 import meshes
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+only_c4 = len(sys.argv) > 2 and sys.argv[2] == "c4"   # with SDFB200_TIMING=1 the per-depth times of every build go to stderr
 
 
 def series(name, make):
@@ -16,17 +17,19 @@ def series(name, make):
         s = make()
         dt = time.perf_counter() - t0
         st = s.build_stats()
-        out.append("%.3f (levels %.0f, layout %.0f)" % (dt, st["levels_ms"], st["layout_ms"]))
+        out.append("%.3f (total %.0f: levels %.0f, layout %.0f, download %.0f, mesh %.0f)" % (dt, st["total_ms"], st["levels_ms"], st["layout_ms"], st["download_ms"],
+                                                                                               st["triangle_data_ms"] + st["bvh_ms"] + st["upload_ms"]))
         s.close()
     print(name, " | ".join(out), flush=True)
 
 
-v, i = meshes.config_mesh("M1"); box = meshes.bounding_box_with_margin(v)
-mesh, bb = S.Mesh(v, i), S.BoundingBox(box[:3], box[3:])
-series("octree_c2", lambda: S.OctreeSdf(mesh, bb, 8, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 2))
-series("octree_c2_continuity", lambda: S.OctreeSdf(mesh, bb, 8, 3, 1e-3, S.OctreeSdf.CONTINUITY, 2))
-series("exact_c3", lambda: S.ExactOctreeSdf(mesh, bb, 7, 3, 128, 2))
-S.lib().sdfb200_release_cached_memory()
+if not only_c4:
+    v, i = meshes.config_mesh("M1"); box = meshes.bounding_box_with_margin(v)
+    mesh, bb = S.Mesh(v, i), S.BoundingBox(box[:3], box[3:])
+    series("octree_c2", lambda: S.OctreeSdf(mesh, bb, 8, 3, 1e-3, S.OctreeSdf.NO_CONTINUITY, 2))
+    series("octree_c2_continuity", lambda: S.OctreeSdf(mesh, bb, 8, 3, 1e-3, S.OctreeSdf.CONTINUITY, 2))
+    series("exact_c3", lambda: S.ExactOctreeSdf(mesh, bb, 7, 3, 128, 2))
+    S.lib().sdfb200_release_cached_memory()
 v, i = meshes.config_mesh("M2"); box = meshes.bounding_box_with_margin(v)
 mesh, bb = S.Mesh(v, i), S.BoundingBox(box[:3], box[3:])
 series("exact_c4", lambda: S.ExactOctreeSdf(mesh, bb, 8, 3, 128, 2))

@@ -5,6 +5,7 @@
 //   * the device side uses the CUDA stream-ordered allocator (cudaMallocAsync) with the pool's release threshold
 //     raised, so the hundreds of per-level temporaries of a build are recycled instead of hitting cudaMalloc/cudaFree.
 // Without a CUDA device (loading a .bin only to report a file error) host blocks fall back to malloc.
+#include <chrono>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -88,7 +89,16 @@ size_t roundDeviceBlock(size_t bytes) {
     return (bytes + step - 1) / step * step;
 }
 
+// SDFB200_TIMING: host time spent in the allocator since the last report (misses served by cudaMallocAsync, trims)
+struct AllocClock {
+    double missMs = 0, trimMs = 0;
+    uint64_t misses = 0, hits = 0, trims = 0, missBytes = 0;
+} gAllocClock;
+inline double nowMs() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 void trimDeviceCache(int device) {   // gDevMutex held
+    const double t0 = nowMs();
+    struct Done { double t0; ~Done() { gAllocClock.trimMs += nowMs() - t0; gAllocClock.trims++; } } done{t0};
     for (auto& kv : gFreeDevice) {
         if (kv.first.first != device) continue;
         for (void* p : kv.second) { cudaFreeAsync(p, cudaStream_t(0)); gDevCachedBytes -= kv.first.second; }
@@ -128,6 +138,7 @@ void* deviceBlockAlloc(size_t bytes, size_t* outCapacity) {
             void* p = it->second.back();
             it->second.pop_back();
             gDevCachedBytes -= cap;
+            gAllocClock.hits++;
             return p;
         }
     }
@@ -138,6 +149,8 @@ void* deviceBlockAlloc(size_t bytes, size_t* outCapacity) {
         if (gDevCachedBytes > kTrimOnMissBytes) trimDeviceCache(device);
     }
     void* p = nullptr;
+    const double tMiss = nowMs();
+    struct Miss { double t0; size_t cap; ~Miss() { std::lock_guard<std::mutex> lock(gDevMutex); gAllocClock.missMs += nowMs() - t0; gAllocClock.misses++; gAllocClock.missBytes += cap; } } miss{tMiss, cap};
     cudaError_t e = cudaMallocAsync(&p, cap, tBlockStream);
     if (e == cudaErrorMemoryAllocation) {   // give the cached blocks back and try once more
         cudaGetLastError();
@@ -159,6 +172,14 @@ void* deviceBlockAlloc(size_t bytes, size_t* outCapacity) {
 // Small builds keep their blocks (a C2 / C3 build caches well under the threshold) and stay exact-reuse.
 void settleDeviceCache(int device) {
     std::lock_guard<std::mutex> lock(gDevMutex);
+    static const bool timing = std::getenv("SDFB200_TIMING") != nullptr;
+    struct Report { ~Report() {
+        if (!timing) return;
+        std::fprintf(stderr, "[sdfb200] allocator: %llu hits, %llu misses (%.1f GB, %.2f ms in cudaMallocAsync), %llu trims (%.2f ms), %.1f GB cached\n",
+                     (unsigned long long)gAllocClock.hits, (unsigned long long)gAllocClock.misses, double(gAllocClock.missBytes) / 1e9, gAllocClock.missMs,
+                     (unsigned long long)gAllocClock.trims, gAllocClock.trimMs, double(gDevCachedBytes) / 1e9);
+        gAllocClock = AllocClock();
+    } } report;
     if (gDevCachedBytes <= kTrimOnMissBytes) return;
     int current = 0;
     cudaGetDevice(&current);
