@@ -54,31 +54,37 @@ __device__ __forceinline__ float monomialExact(float c, int i, int j, int k, flo
     for (int a = 0; a < k; a++) t *= z;
     return t;
 }
-__device__ __forceinline__ float polyValue(const float* c, float x, float y, float z) {
-    float acc = 0.0f;
-#pragma unroll
-    for (int n = 0; n < 64; n++) acc += monomialExact(c[n], n & 3, (n >> 2) & 3, n >> 4, x, y, z);
-    return acc;
-}
-// interpolateGradient (InterpolationMethods.h:442-455): per component, terms in ascending n, the
-// integer factor multiplies the coefficient first, no leading zero.
-template <int AX> __device__ __forceinline__ float polyDerivative(const float* c, float x, float y, float z) {
-    float acc = 0.0f;
-    bool first = true;
-#pragma unroll
-    for (int n = 0; n < 64; n++) {
-        const int i = n & 3, j = (n >> 2) & 3, k = n >> 4;
-        const int p = AX == 0 ? i : (AX == 1 ? j : k);
-        if (p == 0) continue;
-        const float t = monomialExact(float(p) * c[n], i - (AX == 0), j - (AX == 1), k - (AX == 2), x, y, z);
-        acc = first ? t : acc + t;
-        first = false;
-    }
-    return acc;
-}
+// interpolateValue (InterpolationMethods.h:432-439, scalar branch): acc = 0 + sum over n ascending of ((c_n * x^i) * y^j) * z^k,
+// every product left to right. interpolateGradient (:442-455): per component the terms with a non-zero exponent in ascending
+// n, the integer factor multiplies the coefficient first, no leading zero. The four sums are independent chains, so one pass
+// over the coefficients feeds all of them without changing any sum's order; kVec: the coefficients arrive as 16 x 128-bit
+// read-only loads instead of 64 (+ 3 x 48 with gradients) scalar ones — the one-load-per-term form sat on the L1 data pipe
+// (a wavefront per distinct leaf and load), same bits.
 template <bool kGrad, bool kVec> __device__ __forceinline__ float evalLeaf(const float* c, float x, float y, float z, f3& g) {
-    if (kGrad) g = normalize3(mk3(polyDerivative<0>(c, x, y, z), polyDerivative<1>(c, x, y, z), polyDerivative<2>(c, x, y, z)));
-    return polyValue(c, x, y, z);
+    float acc = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+        float cc[4];
+        if (kVec) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(c) + m);
+            cc[0] = q.x; cc[1] = q.y; cc[2] = q.z; cc[3] = q.w;
+        } else {
+            cc[0] = __ldg(c + 4 * m); cc[1] = __ldg(c + 4 * m + 1); cc[2] = __ldg(c + 4 * m + 2); cc[3] = __ldg(c + 4 * m + 3);
+        }
+        const int j = m & 3, k = m >> 2;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int n = 4 * m + i;
+            acc += monomialExact(cc[i], i, j, k, x, y, z);
+            if (kGrad) {
+                if (i > 0) { const float t = monomialExact(float(i) * cc[i], i - 1, j, k, x, y, z); gx = n == 1 ? t : gx + t; }
+                if (j > 0) { const float t = monomialExact(float(j) * cc[i], i, j - 1, k, x, y, z); gy = n == 4 ? t : gy + t; }
+                if (k > 0) { const float t = monomialExact(float(k) * cc[i], i, j, k - 1, x, y, z); gz = n == 16 ? t : gz + t; }
+            }
+        }
+    }
+    if (kGrad) g = normalize3(mk3(gx, gy, gz));
+    return acc;
 }
 #else
 // Horner in x, then y, then z with derivative recurrences; all FMA. kVec: the 64 coefficients are
