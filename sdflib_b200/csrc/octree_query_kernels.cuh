@@ -46,6 +46,23 @@ __device__ __forceinline__ float boxDistanceGrad(const QueryParams& q, f3 p, f3&
     return boxDistance(q, p);
 }
 
+// Packed float32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 — one issue slot for two IEEE operations, each half rounded exactly
+// like its scalar instruction, so a packed evaluation has the bits of the scalar one). The tile kernel is issue bound.
+struct P2 { float x, y; };
+__device__ __forceinline__ P2 mkp(float x, float y) { P2 r; r.x = x; r.y = y; return r; }
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ unsigned long long p2Bits(P2 v) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y)); return r; }
+__device__ __forceinline__ P2 p2From(unsigned long long b) { P2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(b)); return r; }
+__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b)), "l"(p2Bits(c))); return p2From(r); }
+__device__ __forceinline__ P2 mul2(P2 a, P2 b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b))); return p2From(r); }
+__device__ __forceinline__ P2 add2(P2 a, P2 b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b))); return p2From(r); }
+__device__ __forceinline__ P2 add2Down(P2 a, P2 b) { unsigned long long r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b))); return p2From(r); }
+#else   // the warp emulation of tests/cpp/simt_query_main.cpp runs this source on the CPU
+__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) { return mkp(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+__device__ __forceinline__ P2 mul2(P2 a, P2 b) { return mkp(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ P2 add2(P2 a, P2 b) { return mkp(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ P2 add2Down(P2 a, P2 b) { return mkp(__fadd_rd(a.x, b.x), __fadd_rd(a.y, b.y)); }
+#endif
 #ifdef SDFB_QUERY_EXACT
 __device__ __forceinline__ float monomialExact(float c, int i, int j, int k, float x, float y, float z) {
     float t = c;
@@ -60,7 +77,30 @@ __device__ __forceinline__ float monomialExact(float c, int i, int j, int k, flo
 // over the coefficients feeds all of them without changing any sum's order; kVec: the coefficients arrive as 16 x 128-bit
 // read-only loads instead of 64 (+ 3 x 48 with gradients) scalar ones — the one-load-per-term form sat on the L1 data pipe
 // (a wavefront per distinct leaf and load), same bits.
+// Value only: the four product chains of a coefficient vector (i = 0..3, same j and k) are multiplied in PAIRS by the packed
+// float32 multiply of sm_100 (FMUL2: two IEEE products per issue slot) — (c0, c1 x) and (c2, c3 x) after one scalar product each,
+// then x, x for the second pair and y^j, z^k for both — 160 multiply instructions instead of 288; the 64 additions stay one
+// serial chain in the reference's order. Every product is the same IEEE operation on the same operands as in monomialExact.
+template <bool kVec> __device__ __forceinline__ float evalLeafValuePacked(const float* c, float x, float y, float z) {
+    const P2 xx = mkp(x, x), yy = mkp(y, y), zz = mkp(z, z);
+    float acc = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(c) + m);
+        const int j = m & 3, k = m >> 2;
+        P2 lo = mkp(q.x, __fmul_rn(q.y, x));                           // i = 0, 1
+        P2 hi = mul2(mul2(mkp(q.z, __fmul_rn(q.w, x)), xx), xx);      // i = 2, 3
+#pragma unroll
+        for (int a = 0; a < j; a++) { lo = mul2(lo, yy); hi = mul2(hi, yy); }
+#pragma unroll
+        for (int a = 0; a < k; a++) { lo = mul2(lo, zz); hi = mul2(hi, zz); }
+        acc = __fadd_rn(acc, lo.x); acc = __fadd_rn(acc, lo.y); acc = __fadd_rn(acc, hi.x); acc = __fadd_rn(acc, hi.y);
+    }
+    return acc;
+}
+
 template <bool kGrad, bool kVec> __device__ __forceinline__ float evalLeaf(const float* c, float x, float y, float z, f3& g) {
+    if (!kGrad && kVec) return evalLeafValuePacked<kVec>(c, x, y, z);
     float acc = 0.0f, gx = 0.0f, gy = 0.0f, gz = 0.0f;
 #pragma unroll
     for (int m = 0; m < 16; m++) {
@@ -279,23 +319,6 @@ __device__ __forceinline__ float fractSmall(float v) {
     return __fadd_rn(v, -__fadd_rn(__fadd_rd(v, 8388608.0f), -8388608.0f));
 }
 
-// Packed float32 pairs (sm_100: FFMA2 / FMUL2 / FADD2 — one issue slot for two IEEE operations, each half rounded exactly
-// like its scalar instruction, so a packed evaluation has the bits of the scalar one). The tile kernel is issue bound.
-struct P2 { float x, y; };
-__device__ __forceinline__ P2 mkp(float x, float y) { P2 r; r.x = x; r.y = y; return r; }
-#ifdef __CUDA_ARCH__
-__device__ __forceinline__ unsigned long long p2Bits(P2 v) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y)); return r; }
-__device__ __forceinline__ P2 p2From(unsigned long long b) { P2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(b)); return r; }
-__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b)), "l"(p2Bits(c))); return p2From(r); }
-__device__ __forceinline__ P2 mul2(P2 a, P2 b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b))); return p2From(r); }
-__device__ __forceinline__ P2 add2(P2 a, P2 b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b))); return p2From(r); }
-__device__ __forceinline__ P2 add2Down(P2 a, P2 b) { unsigned long long r; asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(p2Bits(a)), "l"(p2Bits(b))); return p2From(r); }
-#else   // the warp emulation of tests/cpp/simt_query_main.cpp runs this source on the CPU
-__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) { return mkp(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
-__device__ __forceinline__ P2 mul2(P2 a, P2 b) { return mkp(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
-__device__ __forceinline__ P2 add2(P2 a, P2 b) { return mkp(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
-__device__ __forceinline__ P2 add2Down(P2 a, P2 b) { return mkp(__fadd_rd(a.x, b.x), __fadd_rd(a.y, b.y)); }
-#endif
 // cellCoordinate / fractSmall for two coordinates at once (same operations per half)
 __device__ __forceinline__ P2 cellCoordinate2(P2 x, P2 cell, P2 rc) {
     const P2 ncell = mkp(-cell.x, -cell.y);
